@@ -1,0 +1,193 @@
+/* uwcuda.h -- C ABI of the B200-native chunk builder (libuwcuda.so).
+ *
+ * Drop-in boundary for UnderwaterWorld's chunk-build hot path.  The reference has NO
+ * FFI/plugin interface for this path -- the path is plain Rust methods on `Chunk`
+ * (underwater_world/src/chunk.rs:88-349) called from `World::build_full_step` /
+ * `World::build_step` (src/world.rs:113-145).  The entry points below are therefore what a
+ * Rust `extern "C"` shim for that path binds (see INTEGRATION.md for the shim); each cites
+ * the reference interface it replaces.
+ *
+ * No torch / C++ types cross this boundary: plain pointers, sizes and POD structs only.
+ * Errors: integer status; message through uw_last_error().  Nothing throws or unwinds.
+ * There is no CPU fallback: every build call needs a CUDA device (sm_100a).
+ *
+ * Threading: a uw_ctx is not thread-safe -- one per caller thread (the reference is
+ * single-threaded: README.md:19, src/lib.rs:88-90).
+ */
+#ifndef UWCUDA_H
+#define UWCUDA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UW_ABI_VERSION 1
+
+typedef enum uw_status {
+    UW_OK              = 0,
+    UW_ERR_INVALID     = 1,   /* bad argument / unsupported configuration            */
+    UW_ERR_CUDA        = 2,   /* a CUDA runtime call failed (see uw_last_error)       */
+    UW_ERR_NO_DEVICE   = 3,   /* no usable CUDA device -- there is no CPU fallback    */
+    UW_ERR_OOM         = 4,   /* host or device allocation failed                     */
+    UW_ERR_NOT_READY   = 5,   /* uw_batch_view before uw_batch_wait on an async batch */
+    UW_ERR_UNSUPPORTED = 6
+} uw_status;
+
+/* uw_config.flags */
+#define UW_FLAG_EXACT_F64   0x1u  /* evaluate EVERY density sample with the f64 reference-order path
+                                     (verification mode; default = FP32 fast path + f64 guard band) */
+#define UW_FLAG_INDEX32     0x2u  /* also emit u32 indices (forced when internal_size > 22, where the
+                                     reference's `ind as u16` (chunk.rs:243) could wrap)            */
+#define UW_FLAG_KEEP_DENSITIES 0x4u /* keep per-chunk densities/cases of the last batch readable
+                                     through uw_batch_densities / uw_batch_cases (debug taps)      */
+#define UW_FLAG_TRIS        0x8u  /* also emit the per-cell collision triangle lists (chunk.rs:167-174,
+                                     245-250) -- SURVEY §8f-1                                       */
+
+/* Compile-time constants of the reference made runtime.  uw_config_default() fills the
+ * reference's values: src/chunk.rs:5-17, src/world.rs:11-12. */
+typedef struct uw_config {
+    int32_t  internal_size;  /* INTERNAL_SIZE   chunk.rs:6   = 12 (cells per axis, S)          */
+    int32_t  chunk_size;     /* CHUNK_SIZE      chunk.rs:5   = 16 (world units per chunk)      */
+    uint32_t octaves;        /* PERLIN_OCTAVES  chunk.rs:9   = 3  (1..4 supported)             */
+    float    iso_level;      /* ISO_LEVEL       chunk.rs:10  = -0.1                            */
+    float    max_height;     /* MAX_HEIGHT      chunk.rs:11  = 32                              */
+    float    adj_z_mod;      /* ADJ_Z_MOD       chunk.rs:12  = 0.25                            */
+    float    min_hue;        /* MIN_HUE         chunk.rs:14  = -150                            */
+    float    max_hue;        /* MAX_HUE         chunk.rs:15  = 60                              */
+    float    saturation;     /* SATURATION      chunk.rs:16  = 0.6                             */
+    float    base_value;     /* BASE_VALUE      chunk.rs:17  = 0.4                             */
+    float    min_z;          /* world::MIN_Z as f32, world.rs:12 = -2                          */
+    float    max_z;          /* world::MAX_Z as f32, world.rs:11 =  2                          */
+    uint32_t seed;           /* noise::Perlin::new(seed), state.rs:358-359 (reference: wall clock) */
+    int32_t  device;         /* CUDA device ordinal; -1 = current device                       */
+    uint32_t flags;          /* UW_FLAG_*                                                      */
+    float    guard_eps;      /* guard band: samples with |iso - iso_level| < guard_eps are
+                                re-evaluated in f64 reference order.  0 -> default 1e-5        */
+    uint32_t reserved[4];
+} uw_config;
+
+/* == draw::VertColor, src/draw.rs:4-9: #[repr(C)] {pos:[f32;3], color:[f32;3]}, stride 24 */
+typedef struct uw_vert {
+    float pos[3];
+    float color[3];
+} uw_vert;
+
+/* == util::Tri, src/util.rs:7-10 (cgmath Vector3<f32> x4), 48 bytes */
+typedef struct uw_tri {
+    float verts[3][3];
+    float normal[3];
+} uw_tri;
+
+/* uw_chunk_desc.flags */
+#define UW_CHUNK_BLANK_EARLY  0x1u  /* early_blank_check() was true, chunk.rs:131-133,276-280      */
+#define UW_CHUNK_HAS_MESH     0x2u  /* num_inds > 0  <=>  Chunk::not_blank(), chunk.rs:291,344     */
+#define UW_CHUNK_U16_OVERFLOW 0x4u  /* vert_count > 65536: the u16 view would wrap (chunk.rs:243)  */
+
+/* One per requested chunk, in request order.  Offsets index the batch-wide packed arrays;
+ * index VALUES are chunk-local (start at 0), exactly as the reference's per-chunk buffers. */
+typedef struct uw_chunk_desc {
+    int32_t  pos[3];        /* chunk position as passed to Chunk::new, chunk.rs:89             */
+    uint32_t flags;
+    uint32_t vert_offset;   /* first vertex of this chunk in verts[]                           */
+    uint32_t vert_count;    /* == build.verts.len()                                            */
+    uint32_t index_offset;  /* first index of this chunk in inds16[] / inds32[]                */
+    uint32_t index_count;   /* == Chunk::num_inds(), chunk.rs:348                              */
+} uw_chunk_desc;
+
+/* Host-side view of a finished batch.  Pointers are into a pinned host arena owned by the
+ * batch and stay valid until uw_batch_free().  The caller copies out, which mirrors the
+ * reference's create_buffer_init copy (chunk.rs:292-304). */
+typedef struct uw_batch_view {
+    uint32_t             n_chunks;
+    uint64_t             n_verts;
+    uint64_t             n_inds;
+    const uw_chunk_desc* descs;    /* [n_chunks]                                               */
+    const uw_vert*       verts;    /* [n_verts]                                                */
+    const uint16_t*      inds16;   /* [n_inds]  NULL when only u32 indices were emitted        */
+    const uint32_t*      inds32;   /* [n_inds]  NULL unless UW_FLAG_INDEX32 / internal_size>22 */
+    const uw_tri*        tris;     /* [n_inds/3] in index order, NULL unless UW_FLAG_TRIS      */
+    const uint32_t*      tri_cell_start; /* [n_chunks*(S^3+1)] per-cell offsets (chunk-local), or NULL */
+} uw_batch_view;
+
+/* Device-resident result (no host copies): raw device pointers for interop / benchmarking.
+ * Valid until the next build on the same context. */
+typedef struct uw_device_view {
+    uint32_t n_chunks;
+    uint64_t n_verts;        /* valid after uw_sync()                                          */
+    uint64_t n_inds;
+    const void* d_descs;     /* uw_chunk_desc[n_chunks]                                        */
+    const void* d_verts;     /* uw_vert[n_verts]                                               */
+    const void* d_inds16;    /* uint16_t[n_inds] or NULL                                       */
+    const void* d_inds32;    /* uint32_t[n_inds] or NULL                                       */
+    const void* d_densities; /* float[n_chunks][density_stride], idx = x*L*L + y*L + z (chunk.rs:351-353) */
+    uint32_t    density_stride; /* floats per chunk (>= L^3, padded to 16 B)                   */
+} uw_device_view;
+
+/* Per-stage device times of the last build (CUDA events on the context's stream). */
+typedef struct uw_stage_times {
+    float noise_ms;      /* K1  density sampling                 (chunk.rs:105-129)            */
+    float classify_ms;   /* K2  blank/solid vote + case counts   (chunk.rs:131-133,141-164)    */
+    float scan_ms;       /* K3  chunk-level prefix sums          (order of chunk.rs:233-243)   */
+    float emit_ms;       /* K4  vertex + index emission          (chunk.rs:178-243)            */
+    float total_ms;
+    uint32_t launches;   /* kernels launched by the last build                                 */
+} uw_stage_times;
+
+typedef struct uw_ctx   uw_ctx;
+typedef struct uw_batch uw_batch;
+
+/* ---- lifecycle ------------------------------------------------------------------------ */
+uint32_t    uw_abi_version(void);
+void        uw_config_default(uw_config* cfg);                      /* chunk.rs:5-17 defaults, seed 0 */
+uw_status   uw_create(const uw_config* cfg, uw_ctx** out);          /* replaces noise::Perlin::new (state.rs:359) + consts */
+void        uw_destroy(uw_ctx* ctx);
+const char* uw_last_error(const uw_ctx* ctx);                       /* ctx may be NULL: last create error */
+
+/* The permutation table of noise::Perlin::new(cfg.seed) (noise-0.8.2). */
+uw_status   uw_perm_table(const uw_ctx* ctx, uint8_t out[256]);
+
+/* ---- the hot path: Chunk::new + Chunk::build_full for n chunks (chunk.rs:89-103,266-313) -- */
+/* chunk_pos_xyz: n x 3 int32, HOST memory.  Blocking: returns with the batch complete. */
+uw_status   uw_build(uw_ctx* ctx, const int32_t* chunk_pos_xyz, uint32_t n, uw_batch** out);
+/* Same, but returns once work is enqueued; uw_batch_wait() completes it. */
+uw_status   uw_build_async(uw_ctx* ctx, const int32_t* chunk_pos_xyz, uint32_t n, uw_batch** out);
+uw_status   uw_batch_wait(uw_batch* b);
+uw_status   uw_batch_view_get(const uw_batch* b, uw_batch_view* out);
+void        uw_batch_free(uw_batch* b);
+
+/* Device-resident variant: positions already on the device, outputs stay on the device.
+ * Enqueues on the context's stream and does NOT synchronise; call uw_sync() before reading
+ * n_verts / n_inds through uw_device_view_get(). */
+uw_status   uw_build_device(uw_ctx* ctx, const int32_t* d_chunk_pos_xyz, uint32_t n);
+uw_status   uw_sync(uw_ctx* ctx);
+uw_status   uw_device_view_get(uw_ctx* ctx, uw_device_view* out);
+
+/* ---- parity taps (debug): stage outputs for n chunks into HOST buffers ---------------- */
+/* densities: n * L^3 floats, idx = x*L*L + y*L + z  (build.isos, chunk.rs:119,351-353) */
+uw_status   uw_debug_densities(uw_ctx* ctx, const int32_t* chunk_pos_xyz, uint32_t n, float* out);
+/* cases: n * S^3 bytes, cell scan order x,y,z (triangulation_idx, chunk.rs:155-162) */
+uw_status   uw_debug_cases(uw_ctx* ctx, const int32_t* chunk_pos_xyz, uint32_t n, uint8_t* out);
+/* Run ONLY the extraction stages (K2-K4) on caller-supplied HOST densities (n * L^3 floats).
+ * Lets tests feed oracle densities and demand bit-exact topology. */
+uw_status   uw_build_from_densities(uw_ctx* ctx, const int32_t* chunk_pos_xyz, const float* densities,
+                                    uint32_t n, uw_batch** out);
+/* Batched density point queries: perlin_util::iso_at (perlin_util.rs:24-29) on n points
+ * (x,y,z f64 triples, HOST) -> n floats (HOST).  SURVEY §8f-3. */
+uw_status   uw_iso_at(uw_ctx* ctx, const double* points_xyz, uint32_t n, float* out);
+
+/* ---- plumbing ------------------------------------------------------------------------- */
+/* Run on an existing CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */
+uw_status   uw_set_stream(uw_ctx* ctx, void* cuda_stream);
+uw_status   uw_get_stage_times(uw_ctx* ctx, uw_stage_times* out);
+/* Enable/disable per-stage event timing (adds event records between stages). Default off. */
+uw_status   uw_set_profiling(uw_ctx* ctx, int enabled);
+/* Number of f64 guard-band re-evaluations in the last build (valid after sync). */
+uw_status   uw_get_guard_count(uw_ctx* ctx, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UWCUDA_H */

@@ -1,0 +1,336 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every test calls the CUDA path through the
+C ABI (libuwcuda.so via underwaterworld_b200.ChunkBuilder) and checks it against the CPU oracle
+or the committed golden vectors.  Nothing here reads /root/reference.
+
+Bars (BASELINE.json north_star / SURVEY §8d):
+  * case indices, per-chunk counts, index buffers ........ bit-exact, every chunk
+  * densities (FP32 fast path) ........................... |d| <= DENS_TOL;  exact-f64 mode: bit-exact
+  * vertex positions ..................................... bit-exact given identical densities;
+                                                           else |d| <= POS_TOL(edge) (see below)
+  * vertex colours ....................................... |d| <= COL_TOL (CUDA powf vs glibc powf)
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import MODE_FAITHFUL, MODE_FAST, FLAG_BLANK_EARLY, FLAG_HAS_MESH  # noqa: E402
+
+DENS_TOL = 2e-6       # FP32 factorised noise vs f64 reference (measured max ~3e-7)
+COL_TOL = 1e-6        # one powf per vertex: CUDA powf (<= 2 ulp here) vs glibc powf
+GUARD_EPS = 1e-5      # default guard band of the library
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def uw():
+    import underwaterworld_b200 as m
+    m.load_library()          # fails loudly if the CUDA library has not been built
+    return m
+
+
+@pytest.fixture(scope="module")
+def builder12(uw):
+    b = uw.ChunkBuilder(uw.Perlin(0), internal_size=12)
+    yield b
+    b.close()
+
+
+def _oracle_batch(o, perm, positions, mode=MODE_FAST, isos=None):
+    return [o.build_chunk(perm, tuple(int(v) for v in p), mode, isos=None if isos is None else isos[i])
+            for i, p in enumerate(positions)]
+
+
+def _check_batch(batch, refs, *, exact_positions, dens_pairs=None):
+    """Compare a GPU batch with per-chunk oracle results."""
+    assert len(batch) == len(refs)
+    vo = io = 0
+    for i, r in enumerate(refs):
+        m = batch.chunk(i)
+        d = batch.descs[i]
+        assert int(d["vert_offset"]) == vo and int(d["index_offset"]) == io, f"packing chunk {i}"
+        assert m.flags & 0x3 == r["flags"] & 0x3, f"flags chunk {i}: {m.flags} vs {r['flags']}"
+        assert len(m.inds) == len(r["inds"]), f"index count chunk {i}"
+        assert len(m.verts) == len(r["verts"]), f"vertex count chunk {i}"
+        assert np.array_equal(m.inds.astype(np.uint32), r["inds"]), f"indices chunk {i}"
+        if len(r["verts"]):
+            if exact_positions:
+                assert np.array_equal(_bits(m.verts["pos"]), _bits(r["verts"]["pos"])), f"positions chunk {i}"
+            else:
+                np.testing.assert_allclose(m.verts["pos"], r["verts"]["pos"], rtol=0, atol=5e-2)
+            np.testing.assert_allclose(m.verts["color"], r["verts"]["color"], rtol=0, atol=COL_TOL if exact_positions else 5e-3)
+        vo += len(r["verts"])
+        io += len(r["inds"])
+    assert batch.n_verts == vo and batch.n_inds == io
+
+
+# ---------------------------------------------------------------------------------------------
+def test_perm_table(uw, oracle12, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_wasm_perm.npz"))
+    for seed, perm in zip(g["seeds"][:4], g["perms"][:4]):
+        with uw.ChunkBuilder(uw.Perlin(int(seed))) as b:
+            assert np.array_equal(b.perm_table(), perm)
+
+
+def test_iso_at_points_bit_exact(builder12, oracle12):
+    perm = oracle12.perm_table(0)
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-50, 50, size=(4000, 3))
+    pts[::9] = np.round(pts[::9])
+    got = builder12.iso_at(pts)
+    want = np.array([oracle12.iso_at(perm, *p) for p in pts], dtype=np.float32)
+    assert np.array_equal(_bits(got), _bits(want))
+
+
+@pytest.mark.parametrize("seed", [0, 42])
+def test_densities_exact_mode_bit_exact(uw, oracle12, seed):
+    pos = np.array([[0, 0, 0], [0, 0, -1], [-8, 7, -2], [63, -64, -1], [1000, -2000, -3], [5, 5, 1]], dtype=np.int32)
+    perm = oracle12.perm_table(seed)
+    with uw.ChunkBuilder(uw.Perlin(seed), exact_f64=True) as b:
+        got = b.debug_densities(pos)
+    want = np.stack([oracle12.densities(perm, p) for p in pos])
+    assert np.array_equal(_bits(got), _bits(want))
+
+
+def test_densities_fast_path_within_tolerance(uw, builder12, oracle12):
+    pos = uw.region.box_region((-3, 3), (-3, 3), (-4, 3))         # 252 chunks
+    pos = np.concatenate([pos, np.array([[100000, -70000, -1], [-(1 << 24), (1 << 24), 0]], dtype=np.int32)])
+    perm = oracle12.perm_table(0)
+    got = builder12.debug_densities(pos)
+    want = np.stack([oracle12.densities(perm, p) for p in pos])
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    assert err.max() <= DENS_TOL, err.max()
+    # guard band: every sample within GUARD_EPS/2 of the isovalue was re-evaluated in f64 -> bit-exact
+    near = np.abs(want - np.float32(-0.1)) < GUARD_EPS / 2
+    assert np.array_equal(_bits(got[near]), _bits(want[near]))
+    # and the classification is identical everywhere
+    iso = np.float32(-0.1)
+    assert np.array_equal(got < iso, want < iso) and np.array_equal(got > iso, want > iso)
+
+
+def test_cases_bit_exact(uw, builder12, oracle12):
+    pos = uw.region.box_region((-2, 2), (-2, 2), (-4, 3))
+    perm = oracle12.perm_table(0)
+    got = builder12.debug_cases(pos)
+    for i, p in enumerate(pos):
+        want = oracle12.build_chunk(perm, tuple(int(v) for v in p), MODE_FAST)["cases"]
+        assert np.array_equal(got[i], want), f"chunk {p}"
+
+
+def test_extraction_bit_exact_from_oracle_densities(uw, builder12, oracle12):
+    """K2-K4 fed with the oracle's densities: topology, indices AND positions must be bit-exact."""
+    pos = uw.region.box_region((-2, 2), (-2, 2), (-3, 2))
+    perm = oracle12.perm_table(0)
+    dens = np.stack([oracle12.densities(perm, p) for p in pos])
+    batch = builder12.build_from_densities(pos, dens)
+    refs = _oracle_batch(oracle12, perm, pos, MODE_FAST, isos=dens)
+    assert sum(len(r["inds"]) for r in refs) > 10000
+    _check_batch(batch, refs, exact_positions=True)
+
+
+def test_extraction_worst_case_random_fields(uw, builder12, oracle12):
+    """Pure-noise densities: every cell is a surface cell (max vertices/indices per chunk), plus
+    corners exactly at the isovalue, all-solid, all-blank and almost-blank chunks."""
+    rng = np.random.default_rng(11)
+    L3 = 13 ** 3
+    fields = [rng.uniform(-1, 1, L3).astype(np.float32) for _ in range(6)]
+    f = rng.uniform(-1, 1, L3).astype(np.float32); f[::5] = np.float32(-0.1); fields.append(f)
+    fields.append(np.full(L3, -1.0, np.float32))
+    fields.append(np.full(L3, 1.0, np.float32))
+    f = np.full(L3, 1.0, np.float32); f[1000] = np.float32(-0.1); fields.append(f)     # not blank, no surface
+    f = np.full(L3, 1.0, np.float32); f[0] = -1.0; f[-1] = -1.0; fields.append(f)       # two corner tetrahedra
+    f = np.full(L3, -1.0, np.float32); f[777] = 1.0; fields.append(f)
+    dens = np.stack(fields)
+    pos = np.array([[i, -i, i % 3 - 1] for i in range(len(fields))], dtype=np.int32)
+    perm = oracle12.perm_table(0)
+    batch = builder12.build_from_densities(pos, dens)
+    refs = _oracle_batch(oracle12, perm, pos, MODE_FAST, isos=dens)
+    assert max(len(r["verts"]) for r in refs) > 5000
+    _check_batch(batch, refs, exact_positions=True)
+    assert batch.chunk(8).flags == 1 and batch.chunk(7).flags == 0 and batch.chunk(9).flags == 0
+
+
+def test_full_build_exact_mode_matches_oracle_bitwise(uw, oracle12):
+    pos = uw.region.box_region((-1, 2), (-2, 1), (-3, 2))
+    perm = oracle12.perm_table(42)
+    with uw.ChunkBuilder(uw.Perlin(42), exact_f64=True) as b:
+        batch = b.build(pos)
+    refs = _oracle_batch(oracle12, perm, pos, MODE_FAST)
+    _check_batch(batch, refs, exact_positions=True)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 0xDEADBEEF])
+def test_full_build_fast_path_topology_bit_exact(uw, oracle12, seed):
+    """The shipped path (FP32 noise + f64 guard band).
+    (1) indices / counts / flags bit-exact for EVERY chunk against the oracle's own f64 densities;
+    (2) fed with the GPU's densities, the oracle reproduces the GPU mesh bit for bit (positions too),
+        i.e. the only deviation is the stated density tolerance;
+    (3) position error is small in bulk and bounded for ill-conditioned edges (|b - a| ~ guard band)."""
+    pos = uw.region.box_region((-3, 3), (-3, 3), (-4, 3))
+    perm = oracle12.perm_table(seed)
+    with uw.ChunkBuilder(uw.Perlin(seed)) as b:
+        batch = b.build(pos)
+        guards = b.guard_count()
+        gdens = b.debug_densities(pos)
+    refs = _oracle_batch(oracle12, perm, pos, MODE_FAST)
+    assert sum(len(r["inds"]) for r in refs) > 20000
+    for i, r in enumerate(refs):
+        m = batch.chunk(i)
+        assert m.flags & 3 == r["flags"] & 3
+        assert np.array_equal(m.inds.astype(np.uint32), r["inds"]), f"indices chunk {pos[i]}"
+        assert len(m.verts) == len(r["verts"])
+    refs_g = _oracle_batch(oracle12, perm, pos, MODE_FAST, isos=gdens)
+    _check_batch(batch, refs_g, exact_positions=True)
+    errs = np.concatenate([np.abs(batch.chunk(i).verts["pos"] - r["verts"]["pos"]).max(axis=1)
+                           for i, r in enumerate(refs) if len(r["verts"])])
+    cerr = np.concatenate([np.abs(batch.chunk(i).verts["color"] - r["verts"]["color"]).max(axis=1)
+                           for i, r in enumerate(refs) if len(r["verts"])])
+    assert np.median(errs) < 5e-6 and np.quantile(errs, 0.99) < 1e-4 and errs.max() < 5e-2
+    assert np.quantile(cerr, 0.99) < 1e-5 and cerr.max() < 5e-3
+    assert guards < 0.001 * len(pos) * 2197
+
+
+def test_spawn_config_config2(uw, builder12, oracle12):
+    """BASELINE config 2: the 16x16x8 spawn neighbourhood in ONE batched call."""
+    pos = uw.region.config_positions("spawn")
+    perm = oracle12.perm_table(0)
+    batch = builder12.build(pos)
+    assert len(batch) == 2048
+    # bit-exact topology for every chunk against the oracle
+    n_mesh = 0
+    io = vo = 0
+    for i, p in enumerate(pos):
+        r = oracle12.build_chunk(perm, tuple(int(v) for v in p), MODE_FAST)
+        m = batch.chunk(i)
+        assert m.flags & 3 == r["flags"] & 3
+        assert np.array_equal(m.inds.astype(np.uint32), r["inds"]), f"chunk {p}"
+        assert len(m.verts) == len(r["verts"])
+        n_mesh += m.not_blank()
+        io += len(r["inds"]); vo += len(r["verts"])
+    assert batch.n_inds == io and batch.n_verts == vo and n_mesh > 100
+    # provably trivial layers
+    z = pos[:, 2]
+    assert all(batch.descs["flags"][z >= 2] == 1) and all(batch.descs["index_count"][z <= -4] == 0)
+
+
+def test_golden_reference_binary_chunks_s10(uw, golden_dir):
+    """The reference's own shipped binary (INTERNAL_SIZE=10): GPU vs tests/golden/ref_wasm_chunks_s10.npz."""
+    g = np.load(os.path.join(golden_dir, "ref_wasm_chunks_s10.npz"))
+    for exact in (True, False):
+        for ci, (seed, x, y, z, finished, at_buffer, num_inds, calls) in enumerate(g["meta"]):
+            with uw.ChunkBuilder(uw.Perlin(int(seed)), internal_size=10, exact_f64=exact) as b:
+                m = b.build([(int(x), int(y), int(z))]).chunk(0)
+                dens = b.debug_densities([(int(x), int(y), int(z))])[0]
+            if f"isos_{ci}" in g:
+                if exact:
+                    assert np.array_equal(_bits(dens), _bits(g[f"isos_{ci}"]))
+                else:
+                    assert np.abs(dens - g[f"isos_{ci}"]).max() <= DENS_TOL
+            if at_buffer:
+                want_v, want_i = g[f"verts_{ci}"], g[f"inds_{ci}"]
+                assert np.array_equal(m.inds, want_i)
+                assert len(m.verts) == len(want_v)
+                if exact:
+                    assert np.array_equal(_bits(m.verts["pos"]), _bits(want_v[:, :3]))
+                    np.testing.assert_allclose(m.verts["color"], want_v[:, 3:], rtol=0, atol=COL_TOL)
+                else:
+                    np.testing.assert_allclose(m.verts["pos"], want_v[:, :3], rtol=0, atol=5e-2)
+            else:
+                assert m.num_inds() == 0 and not m.not_blank()
+                assert m.blank_early == (calls == 1)
+
+
+def test_golden_oracle_kats_s12(uw, golden_dir):
+    g = np.load(os.path.join(golden_dir, "oracle_kat_s12.npz"))
+    for ci, (seed, x, y, z, flags, nv, ni) in enumerate(g["meta"]):
+        with uw.ChunkBuilder(uw.Perlin(int(seed)), exact_f64=True) as b:
+            m = b.build([(int(x), int(y), int(z))]).chunk(0)
+            cases = b.debug_cases([(int(x), int(y), int(z))])[0]
+        assert m.flags & 3 == flags & 3 and len(m.verts) == nv and len(m.inds) == ni
+        assert np.array_equal(cases, g[f"cases_{ci}"])
+        assert np.array_equal(m.inds, g[f"inds_{ci}"])
+        if nv:
+            assert np.array_equal(_bits(m.verts["pos"]), _bits(g[f"verts_{ci}"][:, :3]))
+            np.testing.assert_allclose(m.verts["color"], g[f"verts_{ci}"][:, 3:], rtol=0, atol=COL_TOL)
+
+
+def test_edge_cases(uw, builder12, oracle12):
+    # empty batch
+    b0 = builder12.build(np.zeros((0, 3), dtype=np.int32))
+    assert len(b0) == 0 and b0.n_verts == 0 and b0.n_inds == 0
+    # single chunk == the same chunk inside a batch (chunk-local indices, independent chunks)
+    pos = uw.region.box_region((-1, 1), (-1, 1), (-2, 1))
+    whole = builder12.build(pos)
+    for i in (0, 3, len(pos) - 1):
+        one = builder12.build(pos[i:i + 1]).chunk(0)
+        m = whole.chunk(i)
+        assert np.array_equal(one.inds, m.inds) and np.array_equal(one.verts.view(np.uint8), m.verts.view(np.uint8))
+    # duplicates and ragged ordering are fine: every chunk is a pure function of its position
+    dup = builder12.build(np.concatenate([pos[::-1], pos[:2]]))
+    assert np.array_equal(dup.chunk(len(pos)).inds, whole.chunk(0).inds)
+    # idempotence: same batch twice -> identical bytes
+    again = builder12.build(pos)
+    assert np.array_equal(again.inds, whole.inds) and np.array_equal(again.verts.view(np.uint8), whole.verts.view(np.uint8))
+    # out-of-range position is rejected, not mis-built
+    with pytest.raises(uw.UwError):
+        builder12.build([(1 << 25, 0, 0)])
+    # Chunk mirror API
+    c = uw.Chunk.new((0, 0, -1))
+    c.build_full(builder12)
+    r = oracle12.build_chunk(oracle12.perm_table(0), (0, 0, -1), MODE_FAST)
+    assert c.not_blank() and c.num_inds() == len(r["inds"]) and len(c.verts_buffer_slice()) == len(r["verts"])
+    assert c.inds_buffer_slice().dtype == np.uint16            # IndexFormat::Uint16, state.rs:506
+
+
+def test_index32_and_async(uw, oracle12):
+    pos = uw.region.box_region((0, 2), (0, 2), (-2, 0))
+    perm = oracle12.perm_table(0)
+    with uw.ChunkBuilder(uw.Perlin(0), index32=True) as b:
+        h = b.build_async(pos)
+        batch = b.wait(h)
+    assert batch.inds.dtype == np.uint32
+    refs = _oracle_batch(oracle12, perm, pos, MODE_FAST)
+    assert np.array_equal(batch.inds, np.concatenate([r["inds"] for r in refs]))
+
+
+def test_large_batch_properties(uw, builder12):
+    """Config-3-sized slab properties that need no oracle: index range, packing, determinism,
+    triangle soup equality between FP32 and exact-f64 topology."""
+    pos = uw.region.box_region((-16, 16), (-16, 16), (-4, 3))     # 7168 chunks
+    batch = builder12.build(pos)
+    d = batch.descs
+    assert np.array_equal(d["pos"], pos)
+    assert np.array_equal(d["vert_offset"][1:], np.cumsum(d["vert_count"])[:-1])
+    assert np.array_equal(d["index_offset"][1:], np.cumsum(d["index_count"])[:-1])
+    assert batch.n_inds % 3 == 0 and np.all(d["index_count"] % 3 == 0)
+    # every index addresses a vertex of its own chunk, and every vertex is referenced
+    owner = np.repeat(np.arange(len(d)), d["index_count"])
+    assert np.all(batch.inds < d["vert_count"][owner])
+    used = np.zeros(batch.n_verts, dtype=bool)
+    used[batch.inds.astype(np.int64) + d["vert_offset"][owner]] = True
+    assert used.all()
+    # vertices lie inside their chunk's bounding box (chunk.rs:224-229)
+    vown = np.repeat(np.arange(len(d)), d["vert_count"])
+    lo = (d["pos"][vown] * 16).astype(np.float32)
+    p = batch.verts["pos"]
+    assert np.all(p >= lo - 1e-4) and np.all(p <= lo + 16.0 + 1e-4)
+    with uw.ChunkBuilder(uw.Perlin(0), exact_f64=True) as bx:
+        exact = bx.build(pos)
+    assert np.array_equal(exact.inds, batch.inds) and np.array_equal(exact.descs, batch.descs)
+    np.testing.assert_allclose(batch.verts["pos"], exact.verts["pos"], rtol=0, atol=5e-2)
+
+
+def test_device_resident_build_matches_host_build(uw, builder12):
+    import torch
+    pos = uw.region.box_region((-2, 2), (-2, 2), (-2, 1))
+    host = builder12.build(pos)
+    t = torch.from_numpy(pos).cuda()
+    builder12.build_device(t.data_ptr(), len(pos))
+    builder12.sync()
+    v = builder12.device_view()
+    assert v.n_verts == host.n_verts and v.n_inds == host.n_inds and v.n_chunks == len(pos)

@@ -1,0 +1,160 @@
+"""CPU tests: the oracle against outputs of the reference's own shipped binary (tests/golden/
+ref_wasm_*.npz, produced by oracle/gen_golden.py), its frozen KATs, and analytic invariants."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import MODE_FAITHFUL, MODE_FAST, MODE_RULE, FLAG_BLANK_EARLY, FLAG_HAS_MESH
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def test_perm_table_matches_reference_binary(oracle12, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_wasm_perm.npz"))
+    for seed, perm in zip(g["seeds"], g["perms"]):
+        got = oracle12.perm_table(int(seed))
+        assert np.array_equal(got, perm), f"seed {seed}"
+        assert sorted(got.tolist()) == list(range(256))
+
+
+def test_perlin3_bit_exact_vs_reference_binary(oracle12, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_wasm_perlin3.npz"))
+    perms = {}
+    bad = 0
+    for seed, pt, want in zip(g["seeds"], g["points"], g["values"]):
+        seed = int(seed)
+        if seed not in perms:
+            perms[seed] = oracle12.perm_table(seed)
+        got = oracle12.perlin3(perms[seed], *pt.tolist())
+        bad += np.float64(got).view(np.uint64) != np.float64(want).view(np.uint64)
+    assert bad == 0
+    assert len(g["values"]) == 4000
+
+
+def test_perlin3_is_zero_on_the_integer_lattice(oracle12):
+    perm = oracle12.perm_table(42)
+    rng = np.random.default_rng(0)
+    for p in rng.integers(-300, 300, size=(200, 3)):
+        assert oracle12.perlin3(perm, float(p[0]), float(p[1]), float(p[2])) == 0.0
+
+
+def test_chunk_build_matches_reference_binary_s10(oracle10, golden_dir):
+    """Whole Chunk::build_full (S=10 as compiled into the shipped wasm): densities, positions and
+    indices bit-exact; colours within 1 ulp (the wasm links Rust's libm port for powf, the oracle
+    glibc's -- the reference itself differs between its web and native builds there)."""
+    g = np.load(os.path.join(golden_dir, "ref_wasm_chunks_s10.npz"))
+    meta = g["meta"]
+    assert len(meta) >= 9
+    n_mesh = 0
+    for ci, (seed, x, y, z, finished, at_buffer, num_inds, calls) in enumerate(meta):
+        perm = oracle10.perm_table(int(seed))
+        r = oracle10.build_chunk(perm, (int(x), int(y), int(z)), MODE_FAITHFUL)
+        if f"isos_{ci}" in g:
+            assert np.array_equal(_bits(r["isos"]), _bits(g[f"isos_{ci}"])), f"densities chunk {ci}"
+        if at_buffer:
+            n_mesh += 1
+            assert r["flags"] & FLAG_HAS_MESH
+            want_v, want_i = g[f"verts_{ci}"], g[f"inds_{ci}"]
+            assert len(r["inds"]) == num_inds == len(want_i)
+            assert np.array_equal(r["inds"].astype(np.uint16), want_i), f"indices chunk {ci}"
+            assert len(r["verts"]) == len(want_v)
+            assert np.array_equal(_bits(r["verts"]["pos"]), _bits(want_v[:, :3])), f"positions chunk {ci}"
+            np.testing.assert_allclose(r["verts"]["color"], want_v[:, 3:], rtol=0, atol=6e-8)
+        else:
+            assert finished and num_inds == 0
+            assert len(r["inds"]) == 0 and not (r["flags"] & FLAG_HAS_MESH)
+            if calls == 1:      # finished inside the Iso step -> early blank
+                assert r["flags"] & FLAG_BLANK_EARLY
+            else:               # went through the mesh stage and emitted nothing (all solid)
+                assert not (r["flags"] & FLAG_BLANK_EARLY)
+    assert n_mesh >= 6
+
+
+def test_oracle_kats_s12(oracle12, golden_dir):
+    g = np.load(os.path.join(golden_dir, "oracle_kat_s12.npz"))
+    for ci, (seed, x, y, z, flags, nv, ni) in enumerate(g["meta"]):
+        perm = oracle12.perm_table(int(seed))
+        r = oracle12.build_chunk(perm, (int(x), int(y), int(z)), MODE_FAITHFUL)
+        assert r["flags"] == flags and len(r["verts"]) == nv and len(r["inds"]) == ni
+        assert np.array_equal(_bits(r["isos"]), _bits(g[f"isos_{ci}"]))
+        assert np.array_equal(r["cases"], g[f"cases_{ci}"])
+        assert np.array_equal(r["inds"].astype(np.uint16), g[f"inds_{ci}"])
+        got = np.concatenate([r["verts"]["pos"], r["verts"]["color"]], axis=1)
+        assert np.array_equal(_bits(got), _bits(g[f"verts_{ci}"]))
+
+
+@pytest.mark.parametrize("S", [3, 5, 10, 12])
+def test_modes_agree_on_random_fields(S):
+    """faithful (linear-search dedup) == fast (edge map) == rule (static ownership + prefix sums,
+    SURVEY App. B.4 -- the numbering the CUDA kernels implement), on terrain and on pure noise."""
+    from oracle import Oracle
+    o = Oracle(S)
+    perm = o.perm_table(3)
+    rng = np.random.default_rng(S)
+    L = S + 1
+    fields = [rng.uniform(-1, 1, L ** 3).astype(np.float32) for _ in range(4)]
+    fields.append(np.where(rng.uniform(size=L ** 3) < 0.05, -1.0, 1.0).astype(np.float32))
+    fields.append(np.where(rng.uniform(size=L ** 3) < 0.95, -1.0, 1.0).astype(np.float32))
+    f = rng.uniform(-1, 1, L ** 3).astype(np.float32)
+    f[::7] = np.float32(-0.1)           # corners exactly at the isovalue: "outside" for classify
+    fields.append(f)
+    for pos in [(0, 0, -1), (2, -3, 0)]:
+        fields.append(o.densities(perm, pos))
+    for f in fields:
+        a = o.build_chunk(perm, (1, -2, 0), MODE_FAITHFUL, isos=f)
+        for mode in (MODE_FAST, MODE_RULE):
+            b = o.build_chunk(perm, (1, -2, 0), mode, isos=f)
+            assert a["flags"] == b["flags"]
+            assert np.array_equal(a["cases"], b["cases"])
+            assert np.array_equal(a["inds"], b["inds"])
+            assert np.array_equal(a["verts"].view(np.uint8), b["verts"].view(np.uint8))
+
+
+def test_blank_uses_gt_and_classify_uses_lt(oracle12):
+    """chunk.rs:132 vs :159 -- a corner exactly at ISO_LEVEL defeats the early-out but is 'outside'."""
+    L = 13
+    perm = oracle12.perm_table(0)
+    iso = np.float32(-0.1)
+    f = np.full(L ** 3, 1.0, dtype=np.float32)
+    r = oracle12.build_chunk(perm, (0, 0, 0), MODE_FAITHFUL, isos=f)
+    assert r["flags"] == FLAG_BLANK_EARLY
+    f[100] = iso
+    r = oracle12.build_chunk(perm, (0, 0, 0), MODE_FAITHFUL, isos=f)
+    assert r["flags"] == 0 and len(r["inds"]) == 0 and not r["cases"].any()
+    f[:] = -1.0                                    # all solid: mesh stage runs, emits nothing
+    r = oracle12.build_chunk(perm, (0, 0, 0), MODE_FAITHFUL, isos=f)
+    assert r["flags"] == 0 and len(r["inds"]) == 0 and (r["cases"] == 255).all()
+
+
+def test_provably_trivial_layers(oracle12):
+    """chunk z >= 2 is always blank, z <= -4 always solid (|noise| <= 1)."""
+    perm = oracle12.perm_table(1)
+    for z in (2, 3, 9):
+        assert oracle12.build_chunk(perm, (3, -1, z), MODE_FAST)["flags"] == FLAG_BLANK_EARLY
+    for z in (-4, -5, -11):
+        r = oracle12.build_chunk(perm, (3, -1, z), MODE_FAST)
+        assert r["flags"] == 0 and (r["cases"] == 255).all()
+
+
+def test_colour_helpers(oracle12):
+    # util.rs:122-153: pure hues; util.rs:106-112: srgb of 255 -> 1.0
+    np.testing.assert_allclose(oracle12.hsv_to_rgb(0.0, 1.0, 1.0), [255, 0, 0], atol=1e-4)
+    np.testing.assert_allclose(oracle12.hsv_to_rgb(120.0, 1.0, 1.0), [0, 255, 0], atol=1e-4)
+    np.testing.assert_allclose(oracle12.hsv_to_rgb(-120.0, 1.0, 1.0), [0, 0, 255], atol=1e-4)   # rem_euclid
+    np.testing.assert_allclose(oracle12.to_srgb([255.0, 255.0, 255.0]), [1, 1, 1], atol=1e-6)
+    c = oracle12.vertex_color(-8.0, 5)
+    assert c.shape == (3,) and np.all(c > 0) and np.all(c < 1)
+
+
+def test_tri_lists_cover_every_triangle(oracle12):
+    perm = oracle12.perm_table(0)
+    r = oracle12.build_chunk(perm, (0, 0, -1), MODE_FAITHFUL, want_tris=True)
+    assert len(r["tris"]) == len(r["inds"]) // 3
+    assert r["tri_cell_start"][-1] == len(r["tris"])
+    v = r["verts"]["pos"][r["inds"].reshape(-1, 3)]
+    assert np.array_equal(v.view(np.uint32), r["tris"]["verts"].view(np.uint32))
+    n = np.linalg.norm(r["tris"]["normal"], axis=1)
+    assert np.all((np.abs(n - 1) < 1e-5) | (n == 0))

@@ -1,0 +1,778 @@
+// uw_kernels.cuh -- sm_100a kernels of the chunk-build hot path (K1 noise, K2 classify,
+// K3 scan, K4 emit).  Included once by uwcuda.cu.  See DESIGN.md for layout and rooflines.
+//
+// Reference semantics reproduced here (file:line under /root/reference/underwater_world/src):
+//   K1  chunk.rs:105-129 (build_iso) + perlin_util.rs:6-29 + noise-0.8.2 perlin_3d
+//   K2  chunk.rs:131-133 (early_blank_check), chunk.rs:141-164 (triangulation_idx)
+//   K3  implicit order of the sequential pushes, chunk.rs:233-243
+//   K4  chunk.rs:178-243 (edge lerp, colour, ordered-pair dedup, index emission)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mc_tables.h"
+#include "../../include/uwcuda.h"
+
+#define UW_MAX_OCT 4
+#define UW_SMALL_MAX_L 16        // small path: whole chunk per CTA, L = S+1 <= 16
+#define UW_AXIS_PAD 20
+
+// ---------------------------------------------------------------------------------------
+// Parameter blocks (passed by value -> constant bank, uniform access)
+// ---------------------------------------------------------------------------------------
+struct DevCfg {
+    int S, L, L2, L3, chunk_size, octaves;
+    float iso_level, max_height, adj_z_mod, size_scale;
+    float min_hue, max_hue, min_z, max_z;
+    float guard_eps;
+    float hsv_c[3], hsv_m[3];          // c = value*saturation, m = value - c per value level (util.rs:129,132)
+    float srgb_hi[3], srgb_lo[3];      // to_srgb((c+m)*255), to_srgb((0+m)*255) per value level (host powf)
+    uint32_t dens_stride;              // floats per chunk in the density array (multiple of 4)
+    int G[UW_MAX_OCT];                 // lattice points per axis per octave = 2^o + 2
+    int lat_base[UW_MAX_OCT + 1];      // prefix of G^3
+    int x_base[UW_MAX_OCT + 1];        // prefix of L*G^2
+};
+
+// Chunk-independent per-axis tables: for octave o and lattice index i,
+// p = 2^o * u_i with u_i = (i * f64(size_scale_f32)) / chunk_size; c = floor(p), d = p - c,
+// d1 = d - 1, w = fade(d).  Computed on the host in f64 in the reference's operation order.
+struct AxisTables {
+    float d[UW_MAX_OCT][UW_AXIS_PAD];
+    float d1[UW_MAX_OCT][UW_AXIS_PAD];
+    float w[UW_MAX_OCT][UW_AXIS_PAD];
+    int   c[UW_MAX_OCT][UW_AXIS_PAD];
+};
+
+// MC tables in device global memory (L1/L2 resident, divergent lookups)
+struct McTables {
+    uint64_t rows[256];        // nibble-packed edge rows, 0xF terminated
+    uint16_t crossed[256];     // edges present in the row
+    uint16_t before[256][12];  // edges first-appearing before edge e in the row
+    uint8_t  ninds[256];       // indices per case
+};
+
+__device__ __constant__ uint8_t c_edge_a[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3};
+__device__ __constant__ uint8_t c_edge_b[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+
+// corner offsets, chunk.rs:144-153: bit0 = dx, bit1 = dy, bit2 = dz packed per corner
+// corners: 0(0,0,0) 1(1,0,0) 2(1,0,1) 3(0,0,1) 4(0,1,0) 5(1,1,0) 6(1,1,1) 7(0,1,1)
+__device__ __forceinline__ void corner_off(int c, int& dx, int& dy, int& dz) {
+    const uint32_t DX = 0x66u, DY = 0xF0u, DZ = 0xCCu;   // bit c of each = offset of corner c
+    dx = (DX >> c) & 1; dy = (DY >> c) & 1; dz = (DZ >> c) & 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact f64 density: the reference's operation order, no fused operations.
+//   coords chunk.rs:107-116; iso_at perlin_util.rs:24-29; octaves perlin_util.rs:6-22;
+//   perlin_3d SURVEY App. A.4.  Bit-identical to the reference arithmetic by construction
+//   (IEEE add/sub/mul/div in the same order; __d*_rn intrinsics are never contracted).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double x_grad3(uint32_t h, double x, double y, double z) {
+    switch (h & 15u) {
+        case 0: case 12: return __dadd_rn(x, y);
+        case 1: case 13: return __dsub_rn(y, x);
+        case 2:          return __dsub_rn(x, y);
+        case 3:          return __dsub_rn(-x, y);
+        case 4:          return __dadd_rn(x, z);
+        case 5:          return __dsub_rn(z, x);
+        case 6:          return __dsub_rn(x, z);
+        case 7:          return __dsub_rn(-x, z);
+        case 8:          return __dadd_rn(y, z);
+        case 9: case 14: return __dsub_rn(z, y);
+        case 10:         return __dsub_rn(y, z);
+        default:         return __dsub_rn(-y, z);
+    }
+}
+
+__device__ __forceinline__ double x_fade(double t) {
+    double c = t < 0.0 ? 0.0 : t;
+    c = c > 1.0 ? 1.0 : c;
+    const double c3 = __dmul_rn(__dmul_rn(c, c), c);
+    const double in = __dadd_rn(__dmul_rn(c, __dadd_rn(__dmul_rn(c, 6.0), -15.0)), 10.0);
+    return __dmul_rn(c3, in);
+}
+
+__device__ __forceinline__ uint32_t x_hash(const uint8_t* perm, int ix, int iy, int iz) {
+    return perm[perm[perm[ix & 255] ^ (iy & 255)] ^ (iz & 255)];
+}
+
+__device__ __noinline__ double x_perlin3(const uint8_t* perm, double px, double py, double pz) {
+    const double fx = floor(px), fy = floor(py), fz = floor(pz);
+    const double dx = __dsub_rn(px, fx), dy = __dsub_rn(py, fy), dz = __dsub_rn(pz, fz);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    const double dx1 = __dadd_rn(dx, -1.0), dy1 = __dadd_rn(dy, -1.0), dz1 = __dadd_rn(dz, -1.0);
+    const double g000 = x_grad3(x_hash(perm, ix,     iy,     iz    ), dx,  dy,  dz );
+    const double g100 = x_grad3(x_hash(perm, ix + 1, iy,     iz    ), dx1, dy,  dz );
+    const double g010 = x_grad3(x_hash(perm, ix,     iy + 1, iz    ), dx,  dy1, dz );
+    const double g110 = x_grad3(x_hash(perm, ix + 1, iy + 1, iz    ), dx1, dy1, dz );
+    const double g001 = x_grad3(x_hash(perm, ix,     iy,     iz + 1), dx,  dy,  dz1);
+    const double g101 = x_grad3(x_hash(perm, ix + 1, iy,     iz + 1), dx1, dy,  dz1);
+    const double g011 = x_grad3(x_hash(perm, ix,     iy + 1, iz + 1), dx,  dy1, dz1);
+    const double g111 = x_grad3(x_hash(perm, ix + 1, iy + 1, iz + 1), dx1, dy1, dz1);
+    const double a = x_fade(dx), b = x_fade(dy), c = x_fade(dz);
+    const double k0 = g000;
+    const double k1 = __dsub_rn(g100, g000);
+    const double k2 = __dsub_rn(g010, g000);
+    const double k3 = __dsub_rn(g001, g000);
+    const double k4 = __dsub_rn(__dsub_rn(__dadd_rn(g000, g110), g100), g010);
+    const double k5 = __dsub_rn(__dsub_rn(__dadd_rn(g000, g101), g100), g001);
+    const double k6 = __dsub_rn(__dsub_rn(__dadd_rn(g000, g011), g010), g001);
+    const double k7 = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(
+                        __dadd_rn(__dadd_rn(__dadd_rn(g100, g010), g001), g111), g000), g110), g101), g011);
+    double r = __dadd_rn(k0, __dmul_rn(k1, a));
+    r = __dadd_rn(r, __dmul_rn(k2, b));
+    r = __dadd_rn(r, __dmul_rn(k3, c));
+    r = __dadd_rn(r, __dmul_rn(__dmul_rn(k4, a), b));
+    r = __dadd_rn(r, __dmul_rn(__dmul_rn(k5, a), c));
+    r = __dadd_rn(r, __dmul_rn(__dmul_rn(k6, b), c));
+    r = __dadd_rn(r, __dmul_rn(__dmul_rn(__dmul_rn(k7, a), b), c));
+    r = __dmul_rn(r, 1.1547005383792515);
+    return r < -1.0 ? -1.0 : (r > 1.0 ? 1.0 : r);
+}
+
+// perlin_util.rs:24-29 on an arbitrary f64 point
+__device__ __forceinline__ float x_iso_at(const DevCfg& cfg, const uint8_t* perm, double x, double y, double z) {
+    double total = 0.0, freq = 1.0, amp = 1.0, maxv = 0.0;
+    for (int o = 0; o < cfg.octaves; ++o) {
+        const double v = x_perlin3(perm, __dmul_rn(x, freq), __dmul_rn(y, freq), __dmul_rn(z, freq));
+        total = __dadd_rn(total, __dmul_rn(v, amp));
+        maxv = __dadd_rn(maxv, amp);
+        amp = __dmul_rn(amp, 0.5);
+        freq = __dmul_rn(freq, 2.0);
+    }
+    const float p = __double2float_rn(__ddiv_rn(total, maxv));
+    const float adj_z = __fdiv_rn(__fmul_rn(__double2float_rn(z), (float)cfg.chunk_size), cfg.max_height);
+    return __fsub_rn(__fadd_rn(adj_z, p), fmodf(adj_z, cfg.adj_z_mod));
+}
+
+// chunk.rs:107-116: lattice index -> f64 sample coordinate
+__device__ __forceinline__ double x_coord(const DevCfg& cfg, int i, int chunk_pos) {
+    const double local = __dmul_rn((double)i, (double)cfg.size_scale);
+    const int off = chunk_pos * cfg.chunk_size;                       // chunk.rs:90-94
+    return __ddiv_rn(__dadd_rn(local, (double)off), (double)cfg.chunk_size);
+}
+
+__device__ __noinline__ float x_iso_lattice(const DevCfg& cfg, const uint8_t* perm,
+                                            int px, int py, int pz, int i, int j, int k) {
+    return x_iso_at(cfg, perm, x_coord(cfg, i, px), x_coord(cfg, j, py), x_coord(cfg, k, pz));
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 (exact mode): one thread per sample, f64 everywhere.  UW_FLAG_EXACT_F64.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_noise_exact(DevCfg cfg, const uint8_t* __restrict__ g_perm,
+                                                     const int32_t* __restrict__ pos, uint32_t n,
+                                                     float* __restrict__ dens) {
+    __shared__ uint8_t s_perm[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) s_perm[t] = g_perm[t];
+    __syncthreads();
+    const uint64_t total = (uint64_t)n * cfg.L3;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t chunk = (uint32_t)(idx / cfg.L3);
+        const int r = (int)(idx - (uint64_t)chunk * cfg.L3);
+        const int i = r / cfg.L2, j = (r / cfg.L) % cfg.L, k = r % cfg.L;
+        const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];
+        dens[(size_t)chunk * cfg.dens_stride + r] = x_iso_lattice(cfg, s_perm, px, py, pz, i, j, k);
+    }
+}
+
+// Batched point queries, perlin_util.rs:24-29 (boid.rs:132,324 callers).  SURVEY §8f-3.
+__global__ void __launch_bounds__(256) k_iso_points(DevCfg cfg, const uint8_t* __restrict__ g_perm,
+                                                    const double* __restrict__ pts, uint32_t n,
+                                                    float* __restrict__ out) {
+    __shared__ uint8_t s_perm[256];
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) s_perm[t] = g_perm[t];
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = x_iso_at(cfg, s_perm, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 (fast path, small chunks): one CTA builds one chunk's L^3 lattice.
+//
+// Tensor-product factorisation of gradient noise.  Inside one noise cell the value is
+//   n = lerp_z( lerp_y( lerp_x( g.(d - corner) ) ) )
+// and the sample lattice is a tensor product (x index i, y index j, z index k) whose
+// fractional offsets and fade weights depend only on the per-axis index (App. A.6).  So:
+//   stage H : hash every noise-lattice point the chunk touches once  (sum_o G_o^3  <= 307)
+//   stage X : lerp the two x-neighbours for every (i, cy, cz)         (sum_o L*G_o^2 = 793)
+//             -> (Q, Py, Pz) with value-at-corner = Q + Py*dyc + Pz*dzc
+//   stage YZ: thread (i,j) walks its z column; per lattice cz it lerps in y -> (R, Sz),
+//             per sample it lerps in z: 4 FP32 ops per octave-sample.
+// FP32 error vs the f64 reference is ~1e-7; samples that land within guard_eps of the
+// isovalue are re-evaluated by the exact f64 path so that classification is bit-exact.
+// ---------------------------------------------------------------------------------------
+__device__ __constant__ float c_grad_vec[16][4] = {
+    { 1,  1,  0, 0}, {-1,  1,  0, 0}, { 1, -1,  0, 0}, {-1, -1,  0, 0},
+    { 1,  0,  1, 0}, {-1,  0,  1, 0}, { 1,  0, -1, 0}, {-1,  0, -1, 0},
+    { 0,  1,  1, 0}, { 0, -1,  1, 0}, { 0,  1, -1, 0}, { 0, -1, -1, 0},
+    { 1,  1,  0, 0}, {-1,  1,  0, 0}, { 0, -1,  1, 0}, { 0, -1, -1, 0}};
+
+struct NoiseSmem {   // dynamic shared memory carve-up (offsets in bytes computed by host+device identically)
+    uint8_t* perm; float4* grad; float4* lat; float4* X; float* dens; float* adjz; float* fm; int* red;
+};
+
+__host__ __device__ inline size_t noise_smem_bytes(const DevCfg& cfg) {
+    size_t b = 256 + 16 * 16;
+    b += (size_t)cfg.lat_base[cfg.octaves] * 16;
+    b += (size_t)cfg.x_base[cfg.octaves] * 16;
+    b += (size_t)cfg.dens_stride * 4;
+    b += (size_t)UW_AXIS_PAD * 4 * 2;
+    b += 64 * 4;
+    return b;
+}
+
+__device__ __forceinline__ NoiseSmem noise_smem_carve(const DevCfg& cfg, unsigned char* base) {
+    NoiseSmem s;
+    s.perm = base;                          base += 256;
+    s.grad = (float4*)base;                 base += 16 * 16;
+    s.lat  = (float4*)base;                 base += (size_t)cfg.lat_base[cfg.octaves] * 16;
+    s.X    = (float4*)base;                 base += (size_t)cfg.x_base[cfg.octaves] * 16;
+    s.dens = (float*)base;                  base += (size_t)cfg.dens_stride * 4;
+    s.adjz = (float*)base;                  base += UW_AXIS_PAD * 4;
+    s.fm   = (float*)base;                  base += UW_AXIS_PAD * 4;
+    s.red  = (int*)base;
+    return s;
+}
+
+// per-chunk flags written by K1/K2
+#define CF_ALL_GT   1u   // every sample >  iso_level  -> early blank (chunk.rs:131-133)
+#define CF_ANY_LT   2u   // some sample  <  iso_level  -> mesh stage may emit
+
+template <int LT, int NOCT>
+__global__ void __launch_bounds__(256) k_noise_small(const __grid_constant__ DevCfg cfg,
+                                                     const __grid_constant__ AxisTables tab,
+                                                     const uint8_t* __restrict__ g_perm,
+                                                     const int32_t* __restrict__ pos, uint32_t n,
+                                                     float* __restrict__ dens,
+                                                     unsigned long long* __restrict__ guard_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const NoiseSmem s = noise_smem_carve(cfg, smem_raw);
+    const int L = LT > 0 ? LT : cfg.L;
+    const int noct = NOCT > 0 ? NOCT : cfg.octaves;
+    const int tid = threadIdx.x, NT = blockDim.x;
+
+    for (int t = tid; t < 256; t += NT) s.perm[t] = g_perm[t];
+    if (tid < 16) s.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
+    __syncthreads();
+
+    const int lat_total = cfg.lat_base[noct], x_total = cfg.x_base[noct];
+
+    for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];
+
+        // ---- stage H: gradient vector of every touched noise-lattice point -----------------
+        for (int t = tid; t < lat_total; t += NT) {
+            int o = 0;
+#pragma unroll
+            for (int q = 1; q < UW_MAX_OCT; ++q) if (q < noct && t >= cfg.lat_base[q]) o = q;
+            const int G = cfg.G[o];
+            const int r = t - cfg.lat_base[o];
+            const int cx = r / (G * G), cy = (r / G) % G, cz = r % G;
+            const int F = 1 << o;
+            const uint32_t h = s.perm[s.perm[s.perm[(F * px + cx) & 255] ^ ((F * py + cy) & 255)] ^ ((F * pz + cz) & 255)];
+            s.lat[t] = s.grad[h & 15u];
+        }
+        // terrace term, perlin_util.rs:27-28: exact (f64 coordinate -> f32), per (chunk, k)
+        if (tid < L) {
+            const float zf = __double2float_rn(x_coord(cfg, tid, pz));
+            const float adj = __fdiv_rn(__fmul_rn(zf, (float)cfg.chunk_size), cfg.max_height);
+            s.adjz[tid] = adj;
+            s.fm[tid] = fmodf(adj, cfg.adj_z_mod);
+        }
+        __syncthreads();
+
+        // ---- stage X: x-lerp for every (octave, i, cy, cz) -----------------------------------
+        for (int t = tid; t < x_total; t += NT) {
+            int o = 0;
+#pragma unroll
+            for (int q = 1; q < UW_MAX_OCT; ++q) if (q < noct && t >= cfg.x_base[q]) o = q;
+            const int G = cfg.G[o];
+            const int r = t - cfg.x_base[o];
+            const int i = r / (G * G), cy = (r / G) % G, cz = r % G;
+            const int c = tab.c[o][i];
+            const float4 g0 = s.lat[cfg.lat_base[o] + (c * G + cy) * G + cz];
+            const float4 g1 = s.lat[cfg.lat_base[o] + ((c + 1) * G + cy) * G + cz];
+            const float d = tab.d[o][i], d1 = tab.d1[o][i], w = tab.w[o][i];
+            const float q0 = g0.x * d, q1 = g1.x * d1;
+            float4 e;
+            e.x = fmaf(w, q1 - q0, q0);
+            e.y = fmaf(w, g1.y - g0.y, g0.y);
+            e.z = fmaf(w, g1.z - g0.z, g0.z);
+            e.w = 0.f;
+            s.X[t] = e;
+        }
+        __syncthreads();
+
+        // ---- stage YZ: one thread per (i, j) column ------------------------------------------
+        uint32_t my_flags_allgt = 1u, my_flags_anylt = 0u;
+        if (tid < L * L) {
+            const int i = tid / L, j = tid - i * L;
+            float R0[UW_MAX_OCT], S0[UW_MAX_OCT], R1[UW_MAX_OCT], S1[UW_MAX_OCT];
+            const float inv_max = 1.0f / (2.0f - ldexpf(1.0f, 1 - noct));   // 1 / sum_{o<noct} 2^-o
+            float* out = s.dens + (size_t)tid * L;
+
+            auto ystage = [&](int o, int cz, float& R, float& Sz) {
+                const int G = cfg.G[o];
+                const int cyj = tab.c[o][j];
+                const float4 E0 = s.X[cfg.x_base[o] + (i * G + cyj) * G + cz];
+                const float4 E1 = s.X[cfg.x_base[o] + (i * G + cyj + 1) * G + cz];
+                const float dy = tab.d[o][j], dy1 = tab.d1[o][j], wy = tab.w[o][j];
+                const float A0 = fmaf(E0.y, dy, E0.x);
+                const float A1 = fmaf(E1.y, dy1, E1.x);
+                R = fmaf(wy, A1 - A0, A0);
+                Sz = fmaf(wy, E1.z - E0.z, E0.z);
+            };
+
+#pragma unroll
+            for (int k = 0; k < (LT > 0 ? LT : UW_SMALL_MAX_L); ++k) {
+                if (LT == 0 && k >= L) break;
+                float total = 0.f;
+#pragma unroll
+                for (int o = 0; o < UW_MAX_OCT; ++o) {
+                    if (o >= noct) break;
+                    const int c = tab.c[o][k];
+                    if (k == 0) {
+                        ystage(o, c, R0[o], S0[o]);
+                        ystage(o, c + 1, R1[o], S1[o]);
+                    } else if (c != tab.c[o][k - 1]) {      // warp-uniform: depends on k and tables only
+                        R0[o] = R1[o]; S0[o] = S1[o];
+                        ystage(o, c + 1, R1[o], S1[o]);
+                    }
+                    const float a0 = fmaf(S0[o], tab.d[o][k], R0[o]);
+                    const float a1 = fmaf(S1[o], tab.d1[o][k], R1[o]);
+                    float v = fmaf(tab.w[o][k], a1 - a0, a0) * 1.1547005383792515f;
+                    v = fminf(fmaxf(v, -1.0f), 1.0f);
+                    total = fmaf(v, ldexpf(1.0f, -o), total);
+                }
+                const float pf = total * inv_max;
+                float iso = (s.adjz[k] + pf) - s.fm[k];
+                if (fabsf(iso - cfg.iso_level) < cfg.guard_eps) {
+                    iso = x_iso_lattice(cfg, s.perm, px, py, pz, i, j, k);
+                    atomicAdd(guard_count, 1ull);
+                }
+                out[k] = iso;
+                my_flags_allgt &= (iso > cfg.iso_level) ? 1u : 0u;
+                my_flags_anylt |= (iso < cfg.iso_level) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+
+        // ---- coalesced write-out (float4; per-chunk stride is a multiple of 4 floats) ---------
+        {
+            float4* dst = reinterpret_cast<float4*>(dens + (size_t)chunk * cfg.dens_stride);
+            const float4* src = reinterpret_cast<const float4*>(s.dens);
+            const int n4 = (int)(cfg.dens_stride >> 2);
+            for (int t = tid; t < n4; t += NT) dst[t] = src[t];
+        }
+        __syncthreads();   // s.dens / s.lat / s.X reused by the next chunk
+        (void)my_flags_allgt; (void)my_flags_anylt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Shared extraction helpers (small path): sign bits -> per-column masks -> cases
+// ---------------------------------------------------------------------------------------
+struct ChunkCounts { uint32_t n_verts, n_inds, flags, pad; };
+
+__device__ __forceinline__ uint32_t own_mask_of(int x, int y, int z) {
+    // SURVEY App. B.4 ownership table: edges this cell is the FIRST (scan order) holder of
+    uint32_t m = 0x4F0u;                       // 4,5,6,7,10 always
+    if (y == 0) m |= 0x00Fu;                   // 0,1,2,3
+    if (z == 0) m |= 0x200u;                   // 9
+    if (x == 0) m |= 0x800u;                   // 11
+    if (x == 0 && z == 0) m |= 0x100u;         // 8
+    return m;
+}
+
+// column (x,y) sign mask: bit z = (iso[x][y][z] < iso_level)
+__device__ __forceinline__ uint32_t col_mask(const uint32_t* bits, int col, int L) {
+    const int b = col * L;
+    const uint32_t lo = bits[b >> 5], hi = bits[(b >> 5) + 1];
+    return __funnelshift_r(lo, hi, b & 31) & ((1u << L) - 1u);
+}
+
+__device__ __forceinline__ uint32_t case_of(uint32_t m00, uint32_t m10, uint32_t m01, uint32_t m11, int z) {
+    const uint32_t a = (m00 >> z) & 3u, b = (m10 >> z) & 3u, c = (m01 >> z) & 3u, d = (m11 >> z) & 3u;
+    return (a & 1u) | ((b & 1u) << 1) | ((b >> 1) << 2) | ((a >> 1) << 3)
+         | ((c & 1u) << 4) | ((d & 1u) << 5) | ((d >> 1) << 6) | ((c >> 1) << 7);
+}
+
+// Loads one chunk's densities into shared memory (optional) and builds the sign bit array.
+// Returns block-uniform flags (CF_ALL_GT, CF_ANY_LT).  All threads must call.
+template <bool KEEP>
+__device__ __forceinline__ uint32_t load_signs(const DevCfg& cfg, const float* __restrict__ src,
+                                               float* s_dens, uint32_t* s_bits, int* s_red) {
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+    const int L3 = cfg.L3;
+    if (tid < 2) s_red[tid] = (tid == 0) ? 1 : 0;   // [0] = all_gt (and), [1] = any_lt (or)
+    __syncthreads();
+    bool all_gt = true, any_lt = false;
+    for (int base = tid - lane; base < L3; base += NT) {
+        const int idx = base + lane;
+        float v = 0.f;
+        const bool ok = idx < L3;
+        if (ok) { v = __ldg(src + idx); if (KEEP) s_dens[idx] = v; }
+        const bool lt = ok && (v < cfg.iso_level);
+        const bool gt = !ok || (v > cfg.iso_level);
+        const uint32_t w = __ballot_sync(0xFFFFFFFFu, lt);
+        if (lane == 0) s_bits[base >> 5] = w;
+        all_gt &= gt; any_lt |= lt;
+    }
+    if (tid == 0) s_bits[(L3 + 31) >> 5] = 0;       // padding word read by col_mask's funnel shift
+    const bool w_all = __all_sync(0xFFFFFFFFu, all_gt);
+    const bool w_any = __any_sync(0xFFFFFFFFu, any_lt);
+    if (lane == 0) { if (!w_all) atomicAnd(&s_red[0], 0); if (w_any) atomicOr(&s_red[1], 1); }
+    __syncthreads();
+    return (s_red[0] ? CF_ALL_GT : 0u) | (s_red[1] ? CF_ANY_LT : 0u);
+}
+
+// block-wide exclusive scan of two 32-bit counters packed per thread; returns this thread's
+// exclusive prefix and the block totals.  NT <= 1024.
+__device__ __forceinline__ void block_scan2(uint32_t v, uint32_t i, uint32_t& ev, uint32_t& ei,
+                                            uint32_t& tv, uint32_t& ti, uint32_t* s_w /*[64]*/) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t sv = v, si = i;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, sv, d), b = __shfl_up_sync(0xFFFFFFFFu, si, d);
+        if (lane >= d) { sv += a; si += b; }
+    }
+    if (lane == 31) { s_w[warp] = sv; s_w[32 + warp] = si; }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t a = lane < nw ? s_w[lane] : 0u, b = lane < nw ? s_w[32 + lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, a, d), y = __shfl_up_sync(0xFFFFFFFFu, b, d);
+            if (lane >= d) { a += x; b += y; }
+        }
+        s_w[lane] = a; s_w[32 + lane] = b;           // inclusive warp totals
+    }
+    __syncthreads();
+    const uint32_t wv = warp ? s_w[warp - 1] : 0u, wi = warp ? s_w[32 + warp - 1] : 0u;
+    ev = wv + sv - v; ei = wi + si - i;
+    tv = s_w[nw - 1]; ti = s_w[32 + nw - 1];
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: classify + count.  One CTA per chunk.  Ballot-based blank (all > iso) / no-surface
+// skip; optional coalesced case-byte output (debug tap).  Writes per-chunk (V, I, flags).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_classify_small(const __grid_constant__ DevCfg cfg,
+                                                        const McTables* __restrict__ mc,
+                                                        const float* __restrict__ dens, uint32_t n,
+                                                        ChunkCounts* __restrict__ counts,
+                                                        uint8_t* __restrict__ cases_out /*nullable*/) {
+    __shared__ uint32_t s_bits[(UW_SMALL_MAX_L * UW_SMALL_MAX_L * UW_SMALL_MAX_L + 31) / 32 + 2];
+    __shared__ int s_red[2];
+    __shared__ uint32_t s_w[64];
+    __shared__ __align__(16) uint8_t s_cases[(UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1) + 16];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int S = cfg.S, L = cfg.L, S3 = S * S * S;
+
+    for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const uint32_t fl = load_signs<false>(cfg, dens + (size_t)chunk * cfg.dens_stride, nullptr, s_bits, s_red);
+        uint32_t nv = 0, ni = 0;
+        if (fl & CF_ANY_LT) {             // block-uniform: otherwise every case is 0 -> nothing to count
+            for (int col = tid; col < S * S; col += NT) {
+                const int x = col / S, y = col - x * S;
+                const uint32_t m00 = col_mask(s_bits, x * L + y, L), m10 = col_mask(s_bits, (x + 1) * L + y, L);
+                const uint32_t m01 = col_mask(s_bits, x * L + y + 1, L), m11 = col_mask(s_bits, (x + 1) * L + y + 1, L);
+                const uint32_t any = m00 | m10 | m01 | m11, all = m00 & m10 & m01 & m11;
+                const bool trivial = (any == 0u) || (all == ((1u << L) - 1u));
+                for (int z = 0; z < S; ++z) {
+                    uint32_t cs = 0;
+                    if (!trivial) {
+                        cs = case_of(m00, m10, m01, m11, z);
+                        if (cs != 0u && cs != 255u) {
+                            ni += mc->ninds[cs];
+                            nv += __popc((uint32_t)mc->crossed[cs] & own_mask_of(x, y, z));
+                        }
+                    } else if (any) cs = 255u;
+                    if (cases_out) s_cases[col * S + z] = (uint8_t)cs;
+                }
+            }
+        } else if (cases_out) {
+            for (int t = tid; t < S3; t += NT) s_cases[t] = 0;
+        }
+        uint32_t ev, ei, tv, ti;
+        block_scan2(nv, ni, ev, ei, tv, ti, s_w);
+        if (tid == 0) {
+            ChunkCounts c;
+            c.n_verts = tv; c.n_inds = ti; c.flags = fl; c.pad = 0;
+            counts[chunk] = c;
+        }
+        if (cases_out) {
+            __syncthreads();
+            uint8_t* dst = cases_out + (size_t)chunk * S3;
+            if ((S3 & 15) == 0 && ((size_t)dst & 15) == 0) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(s_cases);
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+                for (int t = tid; t < (S3 >> 4); t += NT) d4[t] = s4[t];
+            } else {
+                for (int t = tid; t < S3; t += NT) dst[t] = s_cases[t];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: chunk-level exclusive scan of (V, I) -> descriptors, totals, active-chunk list.
+// Single CTA, 1024 threads, 4 chunks per thread per round with a running carry.
+// ---------------------------------------------------------------------------------------
+struct BatchTotals {
+    unsigned long long n_verts, n_inds;
+    uint32_t n_active, overflow, n_blank, n_mesh;
+};
+
+__global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restrict__ counts,
+                                                      const int32_t* __restrict__ pos, uint32_t n,
+                                                      uw_chunk_desc* __restrict__ descs,
+                                                      uint32_t* __restrict__ active,
+                                                      BatchTotals* __restrict__ totals,
+                                                      unsigned long long vcap, unsigned long long icap) {
+    __shared__ uint32_t s_w[96];
+    __shared__ unsigned long long s_carry[2];
+    __shared__ uint32_t s_carry_a, s_nblank;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; s_carry_a = 0; s_nblank = 0; }
+    __syncthreads();
+    uint32_t my_blank = 0;
+    constexpr int PER = 4;
+    for (uint32_t base = 0; base < n; base += 1024 * PER) {
+        ChunkCounts c[PER];
+        uint32_t sv = 0, si = 0, sa = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const uint32_t idx = base + tid * PER + q;
+            if (idx < n) c[q] = counts[idx]; else { c[q].n_verts = 0; c[q].n_inds = 0; c[q].flags = 0; }
+            sv += c[q].n_verts; si += c[q].n_inds; sa += (c[q].n_inds > 0);
+            if (idx < n && (c[q].flags & CF_ALL_GT)) ++my_blank;
+        }
+        // warp inclusive scans of (sv, si, sa)
+        uint32_t xv = sv, xi = si, xa = sa;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, xv, d), b = __shfl_up_sync(0xFFFFFFFFu, xi, d),
+                           e = __shfl_up_sync(0xFFFFFFFFu, xa, d);
+            if (lane >= d) { xv += a; xi += b; xa += e; }
+        }
+        if (lane == 31) { s_w[warp] = xv; s_w[32 + warp] = xi; s_w[64 + warp] = xa; }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t a = s_w[lane], b = s_w[32 + lane], e = s_w[64 + lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, a, d), y = __shfl_up_sync(0xFFFFFFFFu, b, d),
+                               z = __shfl_up_sync(0xFFFFFFFFu, e, d);
+                if (lane >= d) { a += x; b += y; e += z; }
+            }
+            s_w[lane] = a; s_w[32 + lane] = b; s_w[64 + lane] = e;
+        }
+        __syncthreads();
+        unsigned long long ov = s_carry[0] + (warp ? s_w[warp - 1] : 0u) + (xv - sv);
+        unsigned long long oi = s_carry[1] + (warp ? s_w[32 + warp - 1] : 0u) + (xi - si);
+        uint32_t oa = s_carry_a + (warp ? s_w[64 + warp - 1] : 0u) + (xa - sa);
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const uint32_t idx = base + tid * PER + q;
+            if (idx < n) {
+                uw_chunk_desc d;
+                d.pos[0] = pos[3 * idx]; d.pos[1] = pos[3 * idx + 1]; d.pos[2] = pos[3 * idx + 2];
+                d.flags = ((c[q].flags & CF_ALL_GT) ? UW_CHUNK_BLANK_EARLY : 0u)
+                        | (c[q].n_inds > 0 ? UW_CHUNK_HAS_MESH : 0u)
+                        | (c[q].n_verts > 65536u ? UW_CHUNK_U16_OVERFLOW : 0u);
+                d.vert_offset = (uint32_t)ov; d.vert_count = c[q].n_verts;
+                d.index_offset = (uint32_t)oi; d.index_count = c[q].n_inds;
+                descs[idx] = d;
+                if (c[q].n_inds > 0) active[oa++] = idx;
+                ov += c[q].n_verts; oi += c[q].n_inds;
+            }
+        }
+        __syncthreads();
+        if (tid == 1023) { s_carry[0] = ov; s_carry[1] = oi; s_carry_a = oa; }
+        __syncthreads();
+    }
+    if (my_blank) atomicAdd(&s_nblank, my_blank);
+    __syncthreads();
+    if (tid == 0) {
+        BatchTotals t;
+        t.n_verts = s_carry[0]; t.n_inds = s_carry[1]; t.n_active = s_carry_a;
+        t.overflow = (s_carry[0] > vcap || s_carry[1] > icap || s_carry[0] > 0xFFFFFFFFull || s_carry[1] > 0xFFFFFFFFull) ? 1u : 0u;
+        t.n_blank = s_nblank; t.n_mesh = s_carry_a;
+        *totals = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// colour, chunk.rs:215-222 + util.rs:93-95,106-112,122-153.  f32, unfused, reference order.
+// Two of the three channels only depend on the value level -> host-precomputed constants
+// (identical to the oracle's); the hue-dependent channel needs one powf.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float srgb_of(float ch_plus_m) {
+    const float c255 = __fmul_rn(ch_plus_m, 255.0f);
+    const float b = __fdiv_rn(__fadd_rn(__fdiv_rn(c255, 255.0f), 0.055f), 1.055f);
+    return powf(b, 2.4f);
+}
+
+__device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, int vi, float out[3]) {
+    const float ratio = __fdiv_rn(world_z, (float)cfg.chunk_size);
+    const float mix = __fdiv_rn(__fsub_rn(ratio, cfg.min_z), __fsub_rn(cfg.max_z, cfg.min_z));
+    float hue = __fadd_rn(cfg.min_hue, __fmul_rn(__fsub_rn(cfg.max_hue, cfg.min_hue), mix));
+    float r = fmodf(hue, 360.0f);                       // f32::rem_euclid, util.rs:123
+    if (r < 0.0f) r = __fadd_rn(r, 360.0f);
+    hue = r;
+    const float c = cfg.hsv_c[vi], m = cfg.hsv_m[vi];
+    const float h = __fdiv_rn(hue, 60.0f);
+    const float x = __fmul_rn(c, __fsub_rn(1.0f, fabsf(__fsub_rn(fmodf(h, 2.0f), 1.0f))));
+    const float X = srgb_of(__fadd_rn(x, m));
+    const float HI = cfg.srgb_hi[vi], LO = cfg.srgb_lo[vi];
+    if      (0.0f <= h && h < 1.0f) { out[0] = HI; out[1] = X;  out[2] = LO; }
+    else if (1.0f <= h && h < 2.0f) { out[0] = X;  out[1] = HI; out[2] = LO; }
+    else if (2.0f <= h && h < 3.0f) { out[0] = LO; out[1] = HI; out[2] = X;  }
+    else if (3.0f <= h && h < 4.0f) { out[0] = LO; out[1] = X;  out[2] = HI; }
+    else if (4.0f <= h && h < 5.0f) { out[0] = X;  out[1] = LO; out[2] = HI; }
+    else                            { out[0] = HI; out[1] = LO; out[2] = X;  }
+}
+
+// vertex of the directed edge `e` of cell (x,y,z): chunk.rs:178-231
+__device__ __forceinline__ void make_vertex(const DevCfg& cfg, const float* s_dens, int x, int y, int z, int e,
+                                            int offx, int offy, int offz, float v[6]) {
+    const int ca = c_edge_a[e], cb = c_edge_b[e];
+    int ax, ay, az, bx, by, bz;
+    corner_off(ca, ax, ay, az); corner_off(cb, bx, by, bz);
+    ax += x; ay += y; az += z; bx += x; by += y; bz += z;
+    const int L = cfg.L;
+    const float iso_a = s_dens[(ax * L + ay) * L + az], iso_b = s_dens[(bx * L + by) * L + bz];
+    const float t = __fdiv_rn(__fsub_rn(cfg.iso_level, iso_a), __fsub_rn(iso_b, iso_a));
+    const float sax = __fmul_rn((float)ax, cfg.size_scale), say = __fmul_rn((float)ay, cfg.size_scale), saz = __fmul_rn((float)az, cfg.size_scale);
+    const float sbx = __fmul_rn((float)bx, cfg.size_scale), sby = __fmul_rn((float)by, cfg.size_scale), sbz = __fmul_rn((float)bz, cfg.size_scale);
+    const float mx = __fadd_rn(sax, __fmul_rn(t, __fsub_rn(sbx, sax)));
+    const float my = __fadd_rn(say, __fmul_rn(t, __fsub_rn(sby, say)));
+    const float mz = __fadd_rn(saz, __fmul_rn(t, __fsub_rn(sbz, saz)));
+    const float wz = __fadd_rn(mz, (float)offz);
+    v[0] = __fadd_rn(mx, (float)offx); v[1] = __fadd_rn(my, (float)offy); v[2] = wz;
+    vertex_color(cfg, wz, cb % 3, v + 3);
+}
+
+// owner (first cell in scan order holding the same ORDERED corner pair), SURVEY App. B.4
+__device__ __forceinline__ void owner_of(int e, int x, int y, int z, int& ox, int& oy, int& oz, int& oe) {
+    ox = x; oy = y; oz = z; oe = e;
+    if (e < 4) { if (y > 0) { oy = y - 1; oe = e + 4; } }
+    else if (e == 9)  { if (z > 0) { oz = z - 1; oe = 10; } }
+    else if (e == 11) { if (x > 0) { ox = x - 1; oe = 10; } }
+    else if (e == 8) {
+        if (x > 0 && z > 0) { ox = x - 1; oz = z - 1; oe = 10; }
+        else if (x > 0)     { ox = x - 1; oe = 9; }
+        else if (z > 0)     { oz = z - 1; oe = 11; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4: emit.  One CTA per ACTIVE chunk (index_count > 0).  Densities -> smem, cases and
+// per-cell (vbase, ibase) by block scan in reference scan order, then every active cell
+// writes its owned vertices and all of its indices at the packed offsets from K3.
+// ---------------------------------------------------------------------------------------
+#define UW_SMALL_MAX_CELLS ((UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1))
+
+template <typename IndexT>
+__global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevCfg cfg,
+                                                    const McTables* __restrict__ mc,
+                                                    const float* __restrict__ dens,
+                                                    const uw_chunk_desc* __restrict__ descs,
+                                                    const uint32_t* __restrict__ active,
+                                                    const BatchTotals* __restrict__ totals,
+                                                    uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
+                                                    unsigned long long vcap, unsigned long long icap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_dens = reinterpret_cast<float*>(smem_raw);
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_dens + cfg.dens_stride);
+    uint16_t* s_vbase = reinterpret_cast<uint16_t*>(s_bits + ((cfg.L3 + 31) / 32 + 2));
+    uint16_t* s_ibase = s_vbase + UW_SMALL_MAX_CELLS;
+    uint8_t* s_case = reinterpret_cast<uint8_t*>(s_ibase + UW_SMALL_MAX_CELLS);
+    __shared__ int s_red[2];
+    __shared__ uint32_t s_w[64];
+
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int S = cfg.S, L = cfg.L, S3 = S * S * S;
+    const uint32_t n_active = totals->n_active;
+    if (totals->overflow) return;                       // host grows the arenas and relaunches
+
+    for (uint32_t a = blockIdx.x; a < n_active; a += gridDim.x) {
+        const uint32_t chunk = active[a];
+        const uw_chunk_desc d = descs[chunk];
+        load_signs<true>(cfg, dens + (size_t)chunk * cfg.dens_stride, s_dens, s_bits, s_red);
+
+        // pass 1: cases + per-column counts (thread = cell column (x,y), z inner = scan order)
+        uint32_t nv = 0, ni = 0;
+        const int ncol = S * S;
+        for (int col = tid; col < ncol; col += NT) {      // NT >= ncol for S <= 15: single trip
+            const int x = col / S, y = col - x * S;
+            const uint32_t m00 = col_mask(s_bits, x * L + y, L), m10 = col_mask(s_bits, (x + 1) * L + y, L);
+            const uint32_t m01 = col_mask(s_bits, x * L + y + 1, L), m11 = col_mask(s_bits, (x + 1) * L + y + 1, L);
+            for (int z = 0; z < S; ++z) {
+                const uint32_t cs = case_of(m00, m10, m01, m11, z);
+                s_case[col * S + z] = (uint8_t)cs;
+                if (cs != 0u && cs != 255u) {
+                    ni += mc->ninds[cs];
+                    nv += __popc((uint32_t)mc->crossed[cs] & own_mask_of(x, y, z));
+                }
+            }
+        }
+        uint32_t ev, ei, tv, ti;
+        block_scan2(nv, ni, ev, ei, tv, ti, s_w);
+        // pass 2: per-cell bases
+        for (int col = tid; col < ncol; col += NT) {
+            const int x = col / S, y = col - x * S;
+            uint32_t rv = ev, ri = ei;
+            for (int z = 0; z < S; ++z) {
+                const uint32_t cs = s_case[col * S + z];
+                s_vbase[col * S + z] = (uint16_t)rv; s_ibase[col * S + z] = (uint16_t)ri;
+                if (cs != 0u && cs != 255u) {
+                    ri += mc->ninds[cs];
+                    rv += __popc((uint32_t)mc->crossed[cs] & own_mask_of(x, y, z));
+                }
+            }
+        }
+        __syncthreads();
+
+        // pass 3: emission, one thread per cell (strided), only surface cells do work
+        uw_vert* vout = verts + d.vert_offset;
+        IndexT* iout = inds + d.index_offset;
+        const int offx = d.pos[0] * cfg.chunk_size, offy = d.pos[1] * cfg.chunk_size, offz = d.pos[2] * cfg.chunk_size;
+        for (int cell = tid; cell < S3; cell += NT) {
+            const uint32_t cs = s_case[cell];
+            if (cs == 0u || cs == 255u) continue;
+            const int x = cell / (S * S), y = (cell / S) % S, z = cell % S;
+            const uint64_t row = mc->rows[cs];
+            const uint32_t own = own_mask_of(x, y, z);
+            const uint32_t vb = s_vbase[cell], ib = s_ibase[cell];
+            uint32_t seen = 0;
+#pragma unroll 1
+            for (int sidx = 0; sidx < 16; ++sidx) {
+                const int e = (int)((row >> (4 * sidx)) & 0xFull);
+                if (e == 0xF) break;
+                int ox, oy, oz, oe;
+                owner_of(e, x, y, z, ox, oy, oz, oe);
+                const int ocell = (ox * S + oy) * S + oz;
+                const uint32_t ocs = s_case[ocell];
+                const uint32_t rank = __popc((uint32_t)mc->before[ocs][oe] & own_mask_of(ox, oy, oz));
+                const uint32_t vi = (uint32_t)s_vbase[ocell] + rank;
+                iout[ib + sidx] = (IndexT)vi;                         // `ind as u16`, chunk.rs:243
+                if (((own >> e) & 1u) && !((seen >> e) & 1u)) {       // first appearance of an owned edge
+                    float v[6];
+                    make_vertex(cfg, s_dens, x, y, z, e, offx, offy, offz, v);
+                    float2* dst = reinterpret_cast<float2*>(vout + vi);
+                    dst[0] = make_float2(v[0], v[1]); dst[1] = make_float2(v[2], v[3]); dst[2] = make_float2(v[4], v[5]);
+                }
+                seen |= 1u << e;
+                (void)vb;
+            }
+        }
+        __syncthreads();
+    }
+    (void)vcap; (void)icap;
+}

@@ -1,0 +1,713 @@
+// uwcuda.cu -- host side of libuwcuda.so: context, buffers, launch sequence, C ABI.
+// Declared in include/uwcuda.h.  No CPU fallback: every entry point that computes needs a
+// CUDA device.  Nothing here includes, links or calls anything under oracle/.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "uw_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+struct PinnedBlock { void* ptr; size_t bytes; };
+
+struct uw_ctx {
+    uw_config cfg;
+    DevCfg dcfg;
+    AxisTables tab;
+    int device = 0, num_sms = 0;
+    bool fast_path = true;          // FP32 factorised noise (+ f64 guard band) vs exact f64
+    bool index32 = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint8_t perm[256];
+    uint8_t* d_perm = nullptr;
+    McTables* d_mc = nullptr;
+
+    // grow-only device buffers
+    uint32_t cap_chunks = 0;
+    int32_t* d_pos = nullptr;
+    float* d_dens = nullptr;
+    ChunkCounts* d_counts = nullptr;
+    uw_chunk_desc* d_descs = nullptr;
+    uint32_t* d_active = nullptr;
+    uint8_t* d_cases = nullptr;  uint32_t cap_cases_chunks = 0;
+    BatchTotals* d_totals = nullptr;
+    unsigned long long* d_guard = nullptr;
+    unsigned long long vcap = 0, icap = 0;
+    uw_vert* d_verts = nullptr;
+    void* d_inds = nullptr;
+
+    // pinned host staging
+    int32_t* h_pos = nullptr; size_t h_pos_cap = 0;
+    BatchTotals* h_totals = nullptr;
+    unsigned long long* h_guard = nullptr;
+    std::vector<PinnedBlock> pool;
+
+    // launch geometry
+    int noise_threads = 192, noise_blocks_per_sm = 1; size_t noise_smem = 0;
+    int emit_blocks_per_sm = 1; size_t emit_smem = 0;
+    int classify_blocks_per_sm = 1;
+
+    // state of the last build
+    uint32_t last_n = 0;
+    const int32_t* last_pos_dev = nullptr;
+    bool pending = false;           // kernels enqueued, totals not yet validated
+    bool async_in_flight = false;
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uw_stage_times times;
+    uint32_t launches = 0;
+    unsigned long long guard_total = 0;
+    std::string err;
+};
+
+struct uw_batch {
+    uw_ctx* ctx;
+    uint32_t n;
+    bool ready;
+    PinnedBlock arena;
+    uw_batch_view view;
+};
+
+static uw_status fail(uw_ctx* c, uw_status s, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return s;
+}
+
+#define CU_TRY(ctx, call)                                                                        \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            char b_[512];                                                                        \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? UW_ERR_OOM : UW_ERR_CUDA, b_);    \
+        }                                                                                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// host restatements needed to configure the device path
+// ---------------------------------------------------------------------------------------
+// noise::Perlin::new(seed) permutation table (noise-0.8.2 + rand-0.7.3 + rand_xorshift;
+// SURVEY App. A.1): XorShift128 {x=1,y=z=w=seed}, Fisher-Yates from i=255 down to 1 with the
+// widening-multiply rejection sampler over u32.
+static void make_perm_table(uint32_t seed, uint8_t out[256]) {
+    uint32_t s[4] = {1u, seed, seed, seed};
+    for (int i = 0; i < 256; ++i) out[i] = (uint8_t)i;
+    for (uint32_t n = 256; n > 1; --n) {
+        const uint32_t zone = (n << __builtin_clz(n)) - 1u;
+        uint64_t wide;
+        do {
+            const uint32_t t = s[0] ^ (s[0] << 11);
+            s[0] = s[1]; s[1] = s[2]; s[2] = s[3];
+            s[3] = s[3] ^ (s[3] >> 19) ^ t ^ (t >> 8);
+            wide = (uint64_t)s[3] * n;
+        } while ((uint32_t)wide > zone);
+        const uint32_t j = (uint32_t)(wide >> 32), i = n - 1;
+        const uint8_t tmp = out[i]; out[i] = out[j]; out[j] = tmp;
+    }
+}
+
+static double fade_f64(double t) {
+    double c = t < 0.0 ? 0.0 : t;
+    c = c > 1.0 ? 1.0 : c;
+    return (c * c * c) * (c * (c * 6.0 + (-15.0)) + 10.0);
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static uw_status setup_tables(uw_ctx* c) {
+    const uw_config& cf = c->cfg;
+    DevCfg& d = c->dcfg;
+    memset(&d, 0, sizeof d);
+    d.S = cf.internal_size; d.L = d.S + 1; d.L2 = d.L * d.L; d.L3 = d.L2 * d.L;
+    d.chunk_size = cf.chunk_size; d.octaves = (int)cf.octaves;
+    d.iso_level = cf.iso_level; d.max_height = cf.max_height; d.adj_z_mod = cf.adj_z_mod;
+    d.size_scale = (float)cf.chunk_size / (float)cf.internal_size;            // chunk.rs:7 (f32 division)
+    d.min_hue = cf.min_hue; d.max_hue = cf.max_hue; d.min_z = cf.min_z; d.max_z = cf.max_z;
+    d.guard_eps = cf.guard_eps > 0.f ? cf.guard_eps : 1e-5f;
+    d.dens_stride = (uint32_t)((d.L3 + 3) & ~3);
+    for (int vi = 0; vi < 3; ++vi) {                                          // chunk.rs:219-221, util.rs:129-132,106-112
+        const float value = cf.base_value + (float)vi / 9.0f;
+        const float cc = value * cf.saturation;
+        const float m = value - cc;
+        d.hsv_c[vi] = cc; d.hsv_m[vi] = m;
+        d.srgb_hi[vi] = powf((((cc + m) * 255.0f) / 255.0f + 0.055f) / 1.055f, 2.4f);
+        d.srgb_lo[vi] = powf((((0.0f + m) * 255.0f) / 255.0f + 0.055f) / 1.055f, 2.4f);
+    }
+    d.lat_base[0] = 0; d.x_base[0] = 0;
+    for (int o = 0; o < UW_MAX_OCT; ++o) {
+        d.G[o] = (1 << o) + 2;
+        d.lat_base[o + 1] = d.lat_base[o] + d.G[o] * d.G[o] * d.G[o];
+        d.x_base[o + 1] = d.x_base[o] + d.L * d.G[o] * d.G[o];
+    }
+    // per-axis tables in f64, reference operation order (chunk.rs:107-108, perlin_util.rs:13)
+    memset(&c->tab, 0, sizeof c->tab);
+    if (d.L <= UW_AXIS_PAD) {
+        for (int o = 0; o < d.octaves; ++o) {
+            const double F = (double)(1 << o);
+            for (int i = 0; i < d.L; ++i) {
+                const double local = (double)i * (double)d.size_scale;
+                const double u = (local + 0.0) / (double)cf.chunk_size;
+                const double p = u * F;
+                const double f = floor(p);
+                const double dd = p - f;
+                if (f < 0.0 || f > F) return fail(c, UW_ERR_INVALID, "axis table: lattice cell out of range");
+                c->tab.c[o][i] = (int)f;
+                c->tab.d[o][i] = (float)dd;
+                c->tab.d1[o][i] = (float)(dd + (-1.0));
+                c->tab.w[o][i] = (float)fade_f64(dd);
+            }
+        }
+    }
+    return UW_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------
+extern "C" uint32_t uw_abi_version(void) { return UW_ABI_VERSION; }
+
+extern "C" void uw_config_default(uw_config* c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->internal_size = 12; c->chunk_size = 16; c->octaves = 3;
+    c->iso_level = -0.1f; c->max_height = 32.0f; c->adj_z_mod = 0.25f;
+    c->min_hue = -150.0f; c->max_hue = 60.0f; c->saturation = 0.6f; c->base_value = 0.4f;
+    c->min_z = -2.0f; c->max_z = 2.0f;
+    c->seed = 0; c->device = -1; c->flags = 0; c->guard_eps = 0.0f;
+}
+
+extern "C" const char* uw_last_error(const uw_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" void uw_destroy(uw_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_pos); cudaFree(c->d_dens); cudaFree(c->d_counts);
+    cudaFree(c->d_descs); cudaFree(c->d_active); cudaFree(c->d_cases); cudaFree(c->d_totals); cudaFree(c->d_guard);
+    cudaFree(c->d_verts); cudaFree(c->d_inds);
+    if (c->h_pos) cudaFreeHost(c->h_pos);
+    if (c->h_totals) cudaFreeHost(c->h_totals);
+    if (c->h_guard) cudaFreeHost(c->h_guard);
+    for (auto& b : c->pool) cudaFreeHost(b.ptr);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, UW_ERR_INVALID, "uw_create: null argument");
+    *out = nullptr;
+    if (cfg->internal_size < 1 || cfg->internal_size > UW_SMALL_MAX_L - 1)
+        return fail(nullptr, UW_ERR_UNSUPPORTED, "uw_create: internal_size must be in 1..15 (small-chunk path)");
+    if (cfg->octaves < 1 || cfg->octaves > UW_MAX_OCT) return fail(nullptr, UW_ERR_INVALID, "uw_create: octaves must be 1..4");
+    if (cfg->chunk_size < 1) return fail(nullptr, UW_ERR_INVALID, "uw_create: chunk_size must be positive");
+    if (!(cfg->max_height != 0.0f) || !(cfg->adj_z_mod != 0.0f) || !(cfg->max_z != cfg->min_z))
+        return fail(nullptr, UW_ERR_INVALID, "uw_create: max_height, adj_z_mod and (max_z - min_z) must be non-zero");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, UW_ERR_NO_DEVICE, std::string("uw_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    int dev = cfg->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(nullptr, UW_ERR_NO_DEVICE, "uw_create: device ordinal out of range");
+
+    uw_ctx* c = new uw_ctx();
+    c->cfg = *cfg; c->device = dev;
+    memset(&c->times, 0, sizeof c->times);
+    auto bail = [&](uw_status s) { g_create_error = c->err; uw_destroy(c); return s; };
+    if (cudaSetDevice(dev) != cudaSuccess) { c->err = "cudaSetDevice failed"; return bail(UW_ERR_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { c->err = "cudaGetDeviceProperties failed"; return bail(UW_ERR_CUDA); }
+    if (prop.major != 10) {
+        char b[256]; snprintf(b, sizeof b, "uw_create: device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+        c->err = b; return bail(UW_ERR_NO_DEVICE);
+    }
+    c->num_sms = prop.multiProcessorCount;
+    c->index32 = (cfg->flags & UW_FLAG_INDEX32) != 0 || cfg->internal_size > 22;
+    // FP32 factorisation needs chunk-independent fractional parts: chunk_size a power of two
+    c->fast_path = !(cfg->flags & UW_FLAG_EXACT_F64) && is_pow2(cfg->chunk_size);
+
+    uw_status st = setup_tables(c);
+    if (st != UW_OK) return bail(st);
+    make_perm_table(cfg->seed, c->perm);
+
+    auto cu = [&](cudaError_t r, const char* what) {
+        if (r != cudaSuccess) { c->err = std::string(what) + ": " + cudaGetErrorString(r); return false; }
+        return true;
+    };
+    if (!cu(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(UW_ERR_CUDA);
+    c->own_stream = true;
+    if (!cu(cudaMalloc(&c->d_perm, 256), "cudaMalloc perm")) return bail(UW_ERR_OOM);
+    if (!cu(cudaMemcpy(c->d_perm, c->perm, 256, cudaMemcpyHostToDevice), "memcpy perm")) return bail(UW_ERR_CUDA);
+    {
+        static const uint64_t rows[256] = UW_MC_ROWS_INIT;
+        static const uint8_t ninds[256] = UW_MC_NINDS_INIT;
+        static const uint16_t crossed[256] = UW_MC_CROSSED_INIT;
+        static const uint16_t before[256][12] = UW_MC_BEFORE_INIT;
+        McTables* h = new McTables();
+        memcpy(h->rows, rows, sizeof rows); memcpy(h->ninds, ninds, sizeof ninds);
+        memcpy(h->crossed, crossed, sizeof crossed); memcpy(h->before, before, sizeof before);
+        bool ok = cu(cudaMalloc(&c->d_mc, sizeof(McTables)), "cudaMalloc mc") &&
+                  cu(cudaMemcpy(c->d_mc, h, sizeof(McTables), cudaMemcpyHostToDevice), "memcpy mc");
+        delete h;
+        if (!ok) return bail(UW_ERR_CUDA);
+    }
+    if (!cu(cudaMalloc(&c->d_totals, sizeof(BatchTotals)), "cudaMalloc totals")) return bail(UW_ERR_OOM);
+    if (!cu(cudaMalloc(&c->d_guard, sizeof(unsigned long long)), "cudaMalloc guard")) return bail(UW_ERR_OOM);
+    if (!cu(cudaMemset(c->d_guard, 0, sizeof(unsigned long long)), "memset guard")) return bail(UW_ERR_CUDA);
+    if (!cu(cudaHostAlloc(&c->h_totals, sizeof(BatchTotals), cudaHostAllocDefault), "cudaHostAlloc totals")) return bail(UW_ERR_OOM);
+    if (!cu(cudaHostAlloc(&c->h_guard, sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc guard")) return bail(UW_ERR_OOM);
+    for (auto& ev : c->ev) if (!cu(cudaEventCreate(&ev), "cudaEventCreate")) return bail(UW_ERR_CUDA);
+
+    // launch geometry
+    const DevCfg& d = c->dcfg;
+    c->noise_threads = ((d.L2 + 31) / 32) * 32;
+    c->noise_smem = noise_smem_bytes(d);
+    c->emit_smem = (size_t)d.dens_stride * 4 + ((d.L3 + 31) / 32 + 2) * 4 + (size_t)UW_SMALL_MAX_CELLS * 5 + 16;
+    {
+        auto set_attr = [&](const void* f, size_t smem) {
+            return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        };
+        bool ok = cu(set_attr((const void*)k_noise_small<13, 3>, c->noise_smem), "attr noise<13,3>") &&
+                  cu(set_attr((const void*)k_noise_small<11, 3>, c->noise_smem), "attr noise<11,3>") &&
+                  cu(set_attr((const void*)k_noise_small<0, 0>, c->noise_smem), "attr noise<0,0>") &&
+                  cu(set_attr((const void*)k_emit_small<uint16_t>, c->emit_smem), "attr emit16") &&
+                  cu(set_attr((const void*)k_emit_small<uint32_t>, c->emit_smem), "attr emit32");
+        if (!ok) return bail(UW_ERR_CUDA);
+        int nb = 1;
+        const void* nf = (d.L == 13 && d.octaves == 3) ? (const void*)k_noise_small<13, 3>
+                       : (d.L == 11 && d.octaves == 3) ? (const void*)k_noise_small<11, 3>
+                                                       : (const void*)k_noise_small<0, 0>;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nf, c->noise_threads, c->noise_smem) == cudaSuccess && nb > 0)
+            c->noise_blocks_per_sm = nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_emit_small<uint16_t>, 256, c->emit_smem) == cudaSuccess && nb > 0)
+            c->emit_blocks_per_sm = nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_classify_small, 256, 0) == cudaSuccess && nb > 0)
+            c->classify_blocks_per_sm = nb;
+    }
+    *out = c;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_perm_table(const uw_ctx* ctx, uint8_t out[256]) {
+    if (!ctx || !out) return UW_ERR_INVALID;
+    memcpy(out, ctx->perm, 256);
+    return UW_OK;
+}
+
+extern "C" uw_status uw_set_stream(uw_ctx* c, void* s) {
+    if (!c) return UW_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (c->stream) CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s; c->own_stream = false;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_set_profiling(uw_ctx* c, int enabled) {
+    if (!c) return UW_ERR_INVALID;
+    c->profiling = enabled != 0;
+    return UW_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t regrow(T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    return cudaMalloc((void**)p, count * sizeof(T));
+}
+
+static uw_status ensure_chunks(uw_ctx* c, uint32_t n) {
+    if (n <= c->cap_chunks) return UW_OK;
+    uint32_t cap = c->cap_chunks ? c->cap_chunks : 256;
+    while (cap < n) cap *= 2;
+    if (cap > n && (uint64_t)cap * c->dcfg.dens_stride * 4 > (8ull << 30)) cap = n;   // no 2x slack on multi-GB batches
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, regrow(&c->d_pos, (size_t)cap * 3));
+    CU_TRY(c, regrow(&c->d_dens, (size_t)cap * c->dcfg.dens_stride));
+    CU_TRY(c, regrow(&c->d_counts, cap));
+    CU_TRY(c, regrow(&c->d_descs, cap));
+    CU_TRY(c, regrow(&c->d_active, cap));
+    c->cap_chunks = cap;
+    return UW_OK;
+}
+
+static uw_status ensure_outputs(uw_ctx* c, unsigned long long nv, unsigned long long ni) {
+    const size_t isz = c->index32 ? 4 : 2;
+    if (nv > c->vcap) {
+        unsigned long long cap = c->vcap ? c->vcap : 4096;
+        while (cap < nv) cap *= 2;
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        CU_TRY(c, regrow(&c->d_verts, (size_t)cap));
+        c->vcap = cap;
+    }
+    if (ni > c->icap) {
+        unsigned long long cap = c->icap ? c->icap : 16384;
+        while (cap < ni) cap *= 2;
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->d_inds) { cudaFree(c->d_inds); c->d_inds = nullptr; }
+        CU_TRY(c, cudaMalloc(&c->d_inds, (size_t)cap * isz));
+        c->icap = cap;
+    }
+    return UW_OK;
+}
+
+static uw_status pinned_get(uw_ctx* c, size_t bytes, PinnedBlock* out) {
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < c->pool.size(); ++i)
+        if (c->pool[i].bytes >= bytes && (best == (size_t)-1 || c->pool[i].bytes < c->pool[best].bytes)) best = i;
+    if (best != (size_t)-1) { *out = c->pool[best]; c->pool.erase(c->pool.begin() + best); return UW_OK; }
+    size_t cap = 1 << 16;
+    while (cap < bytes) cap *= 2;
+    void* p = nullptr;
+    CU_TRY(c, cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+    out->ptr = p; out->bytes = cap;
+    return UW_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch sequence
+// ---------------------------------------------------------------------------------------
+static int persistent_grid(const uw_ctx* c, uint32_t n, int blocks_per_sm) {
+    const long long full = (long long)c->num_sms * blocks_per_sm;
+    return (int)((long long)n < full ? (long long)n : full);
+}
+
+static uw_status launch_noise(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
+    const DevCfg& d = c->dcfg;
+    if (c->fast_path) {
+        const int grid = persistent_grid(c, n, c->noise_blocks_per_sm);
+        if (d.L == 13 && d.octaves == 3)
+            k_noise_small<13, 3><<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
+        else if (d.L == 11 && d.octaves == 3)
+            k_noise_small<11, 3><<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
+        else
+            k_noise_small<0, 0><<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
+    } else {
+        const unsigned long long total = (unsigned long long)n * d.L3;
+        unsigned long long blocks = (total + 255) / 256;
+        const unsigned long long maxb = (unsigned long long)c->num_sms * 8;
+        if (blocks > maxb) blocks = maxb;
+        k_noise_exact<<<(int)blocks, 256, 0, c->stream>>>(d, c->d_perm, d_pos, n, c->d_dens);
+    }
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return UW_OK;
+}
+
+static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uint8_t* d_cases, bool only_emit) {
+    const DevCfg& d = c->dcfg;
+    if (!only_emit) {
+        k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, d_cases);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+    }
+    k_scan_chunks<<<1, 1024, 0, c->stream>>>(c->d_counts, d_pos, n, c->d_descs, c->d_active, c->d_totals, c->vcap, c->icap);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+    const int grid = persistent_grid(c, n, c->emit_blocks_per_sm);
+    if (c->index32)
+        k_emit_small<uint32_t><<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
+                                                                      c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap);
+    else
+        k_emit_small<uint16_t><<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
+                                                                      c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return UW_OK;
+}
+
+// enqueue the whole pipeline for n chunks whose positions are at d_pos (device)
+static uw_status enqueue_build(uw_ctx* c, const int32_t* d_pos, uint32_t n, bool from_densities) {
+    // initial output capacity guess: grows (and the emit stage is re-run) on overflow
+    uw_status st = ensure_outputs(c, (unsigned long long)n * 192 + 4096, (unsigned long long)n * 640 + 16384);
+    if (st != UW_OK) return st;
+    c->launches = 0;
+    CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
+    if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+    if (!from_densities) {
+        st = launch_noise(c, d_pos, n);
+        if (st != UW_OK) return st;
+    }
+    if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+    uint8_t* d_cases = nullptr;
+    if (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) {
+        if (n > c->cap_cases_chunks) {
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            CU_TRY(c, regrow(&c->d_cases, (size_t)n * c->dcfg.S * c->dcfg.S * c->dcfg.S));
+            c->cap_cases_chunks = n;
+        }
+        d_cases = c->d_cases;
+    }
+    st = launch_extract(c, d_pos, n, d_cases, false);
+    if (st != UW_OK) return st;
+    if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[4], c->stream));
+    c->last_n = n; c->last_pos_dev = d_pos; c->pending = true;
+    return UW_OK;
+}
+
+// wait for the enqueued build; on output-arena overflow grow and re-run scan+emit
+static uw_status finish_build(uw_ctx* c) {
+    if (!c->pending) return UW_OK;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CU_TRY(c, cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(BatchTotals), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (!c->h_totals->overflow) break;
+        if (c->h_totals->n_verts > 0xFFFFFFFFull || c->h_totals->n_inds > 0xFFFFFFFFull)
+            return fail(c, UW_ERR_INVALID, "batch too large: packed vertex/index offsets exceed 32 bits; split the batch");
+        uw_status st = ensure_outputs(c, c->h_totals->n_verts, c->h_totals->n_inds);
+        if (st != UW_OK) return st;
+        st = launch_extract(c, c->last_pos_dev, c->last_n, nullptr, true);
+        if (st != UW_OK) return st;
+    }
+    if (c->h_totals->overflow) return fail(c, UW_ERR_CUDA, "output arena overflow persisted");
+    c->guard_total = *c->h_guard;
+    c->pending = false;
+    if (c->profiling) {
+        float a = 0, b = 0, d = 0, e = 0, t = 0;
+        cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
+        cudaEventElapsedTime(&e, c->ev[3], c->ev[4]);
+        cudaEventElapsedTime(&t, c->ev[0], c->ev[4]);
+        c->times.noise_ms = a; c->times.classify_ms = b; c->times.scan_ms = d; c->times.emit_ms = e; c->times.total_ms = t;
+    }
+    c->times.launches = c->launches;
+    return UW_OK;
+}
+
+static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n) {
+    for (uint32_t i = 0; i < 3 * n; ++i) {
+        // fast path validity: |16*pos| must stay exactly representable next to
+        // the 2^-23-granular lattice offsets; also keeps pos*chunk_size inside i32 (chunk.rs:90-94)
+        if (pos[i] > (1 << 24) || pos[i] < -(1 << 24))
+            return fail(c, UW_ERR_INVALID, "chunk position out of supported range (|pos| <= 2^24)");
+    }
+    if ((size_t)n * 3 > c->h_pos_cap) {
+        if (c->h_pos) cudaFreeHost(c->h_pos);
+        c->h_pos = nullptr;
+        size_t cap = c->h_pos_cap ? c->h_pos_cap : 4096;
+        while (cap < (size_t)n * 3) cap *= 2;
+        CU_TRY(c, cudaHostAlloc(&c->h_pos, cap * sizeof(int32_t), cudaHostAllocDefault));
+        c->h_pos_cap = cap;
+    }
+    memcpy(c->h_pos, pos, (size_t)n * 3 * sizeof(int32_t));
+    CU_TRY(c, cudaMemcpyAsync(c->d_pos, c->h_pos, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    return UW_OK;
+}
+
+static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
+    uw_status st = finish_build(c);
+    if (st != UW_OK) return st;
+    const BatchTotals t = *c->h_totals;
+    const size_t isz = c->index32 ? 4 : 2;
+    const size_t off_desc = 0;
+    const size_t off_vert = (sizeof(uw_chunk_desc) * (size_t)b->n + 255) & ~(size_t)255;
+    const size_t off_ind = (off_vert + sizeof(uw_vert) * (size_t)t.n_verts + 255) & ~(size_t)255;
+    const size_t bytes = off_ind + isz * (size_t)t.n_inds + 256;
+    st = pinned_get(c, bytes, &b->arena);
+    if (st != UW_OK) return st;
+    char* base = (char*)b->arena.ptr;
+    CU_TRY(c, cudaMemcpyAsync(base + off_desc, c->d_descs, sizeof(uw_chunk_desc) * (size_t)b->n, cudaMemcpyDeviceToHost, c->stream));
+    if (t.n_verts) CU_TRY(c, cudaMemcpyAsync(base + off_vert, c->d_verts, sizeof(uw_vert) * (size_t)t.n_verts, cudaMemcpyDeviceToHost, c->stream));
+    if (t.n_inds) CU_TRY(c, cudaMemcpyAsync(base + off_ind, c->d_inds, isz * (size_t)t.n_inds, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    memset(&b->view, 0, sizeof b->view);
+    b->view.n_chunks = b->n; b->view.n_verts = t.n_verts; b->view.n_inds = t.n_inds;
+    b->view.descs = (const uw_chunk_desc*)(base + off_desc);
+    b->view.verts = (const uw_vert*)(base + off_vert);
+    if (c->index32) b->view.inds32 = (const uint32_t*)(base + off_ind);
+    else b->view.inds16 = (const uint16_t*)(base + off_ind);
+    b->ready = true;
+    c->async_in_flight = false;
+    return UW_OK;
+}
+
+static uw_status build_common(uw_ctx* c, const int32_t* pos, const float* dens, uint32_t n, uw_batch** out, bool async) {
+    if (!c) return UW_ERR_INVALID;
+    if (!out || (!pos && n)) return fail(c, UW_ERR_INVALID, "uw_build: null argument");
+    *out = nullptr;
+    if (c->async_in_flight) return fail(c, UW_ERR_NOT_READY, "uw_build: a previous async batch has not been waited on");
+    CU_TRY(c, cudaSetDevice(c->device));
+    uw_batch* b = new uw_batch();
+    b->ctx = c; b->n = n; b->ready = false; b->arena.ptr = nullptr; b->arena.bytes = 0;
+    memset(&b->view, 0, sizeof b->view);
+    if (n == 0) { b->ready = true; *out = b; return UW_OK; }
+    uw_status st = ensure_chunks(c, n);
+    if (st == UW_OK) st = stage_positions(c, pos, n);
+    if (st == UW_OK && dens) {
+        const DevCfg& d = c->dcfg;
+        cudaError_t e = cudaMemcpy2DAsync(c->d_dens, (size_t)d.dens_stride * 4, dens, (size_t)d.L3 * 4, (size_t)d.L3 * 4, n,
+                                          cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) st = fail(c, UW_ERR_CUDA, std::string("cudaMemcpy2DAsync densities: ") + cudaGetErrorString(e));
+    }
+    if (st == UW_OK) st = enqueue_build(c, c->d_pos, n, dens != nullptr);
+    if (st == UW_OK) {
+        if (async) c->async_in_flight = true;
+        else st = collect_batch(c, b);
+    }
+    if (st != UW_OK) { delete b; return st; }
+    *out = b;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_build(uw_ctx* c, const int32_t* pos, uint32_t n, uw_batch** out) {
+    return build_common(c, pos, nullptr, n, out, false);
+}
+extern "C" uw_status uw_build_async(uw_ctx* c, const int32_t* pos, uint32_t n, uw_batch** out) {
+    return build_common(c, pos, nullptr, n, out, true);
+}
+extern "C" uw_status uw_build_from_densities(uw_ctx* c, const int32_t* pos, const float* dens, uint32_t n, uw_batch** out) {
+    if (!dens && n) return c ? fail(c, UW_ERR_INVALID, "uw_build_from_densities: null densities") : UW_ERR_INVALID;
+    return build_common(c, pos, dens, n, out, false);
+}
+
+extern "C" uw_status uw_batch_wait(uw_batch* b) {
+    if (!b) return UW_ERR_INVALID;
+    if (b->ready) return UW_OK;
+    CU_TRY(b->ctx, cudaSetDevice(b->ctx->device));
+    return collect_batch(b->ctx, b);
+}
+
+extern "C" uw_status uw_batch_view_get(const uw_batch* b, uw_batch_view* out) {
+    if (!b || !out) return UW_ERR_INVALID;
+    if (!b->ready) return fail(b->ctx, UW_ERR_NOT_READY, "uw_batch_view_get: batch not complete; call uw_batch_wait");
+    *out = b->view;
+    return UW_OK;
+}
+
+extern "C" void uw_batch_free(uw_batch* b) {
+    if (!b) return;
+    if (!b->ready && b->ctx) { cudaSetDevice(b->ctx->device); cudaStreamSynchronize(b->ctx->stream); b->ctx->async_in_flight = false; b->ctx->pending = false; }
+    if (b->arena.ptr) b->ctx->pool.push_back(b->arena);
+    delete b;
+}
+
+extern "C" uw_status uw_build_device(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
+    if (!c) return UW_ERR_INVALID;
+    if (!d_pos && n) return fail(c, UW_ERR_INVALID, "uw_build_device: null positions");
+    if (c->async_in_flight) return fail(c, UW_ERR_NOT_READY, "uw_build_device: an async batch is in flight");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (n == 0) { c->last_n = 0; c->pending = false; memset(c->h_totals, 0, sizeof(BatchTotals)); return UW_OK; }
+    uw_status st = ensure_chunks(c, n);
+    if (st != UW_OK) return st;
+    return enqueue_build(c, d_pos, n, false);
+}
+
+extern "C" uw_status uw_sync(uw_ctx* c) {
+    if (!c) return UW_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (c->pending) return finish_build(c);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return UW_OK;
+}
+
+extern "C" uw_status uw_device_view_get(uw_ctx* c, uw_device_view* out) {
+    if (!c || !out) return UW_ERR_INVALID;
+    if (c->pending) return fail(c, UW_ERR_NOT_READY, "uw_device_view_get: call uw_sync first");
+    memset(out, 0, sizeof *out);
+    out->n_chunks = c->last_n;
+    out->n_verts = c->last_n ? c->h_totals->n_verts : 0;
+    out->n_inds = c->last_n ? c->h_totals->n_inds : 0;
+    out->d_descs = c->d_descs; out->d_verts = c->d_verts;
+    if (c->index32) out->d_inds32 = c->d_inds; else out->d_inds16 = c->d_inds;
+    out->d_densities = c->d_dens; out->density_stride = c->dcfg.dens_stride;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_get_stage_times(uw_ctx* c, uw_stage_times* out) {
+    if (!c || !out) return UW_ERR_INVALID;
+    *out = c->times;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_get_guard_count(uw_ctx* c, uint64_t* out) {
+    if (!c || !out) return UW_ERR_INVALID;
+    *out = c->guard_total;
+    return UW_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// parity taps
+// ---------------------------------------------------------------------------------------
+extern "C" uw_status uw_debug_densities(uw_ctx* c, const int32_t* pos, uint32_t n, float* out) {
+    if (!c) return UW_ERR_INVALID;
+    if ((!pos || !out) && n) return fail(c, UW_ERR_INVALID, "uw_debug_densities: null argument");
+    if (n == 0) return UW_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    uw_status st = ensure_chunks(c, n);
+    if (st == UW_OK) st = stage_positions(c, pos, n);
+    if (st == UW_OK) CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
+    if (st == UW_OK) st = launch_noise(c, c->d_pos, n);
+    if (st != UW_OK) return st;
+    const DevCfg& d = c->dcfg;
+    CU_TRY(c, cudaMemcpy2DAsync(out, (size_t)d.L3 * 4, c->d_dens, (size_t)d.dens_stride * 4, (size_t)d.L3 * 4, n,
+                                cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->guard_total = *c->h_guard;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_debug_cases(uw_ctx* c, const int32_t* pos, uint32_t n, uint8_t* out) {
+    if (!c) return UW_ERR_INVALID;
+    if ((!pos || !out) && n) return fail(c, UW_ERR_INVALID, "uw_debug_cases: null argument");
+    if (n == 0) return UW_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    uw_status st = ensure_chunks(c, n);
+    if (st == UW_OK) st = stage_positions(c, pos, n);
+    if (st == UW_OK) st = launch_noise(c, c->d_pos, n);
+    if (st != UW_OK) return st;
+    const DevCfg& d = c->dcfg;
+    const size_t S3 = (size_t)d.S * d.S * d.S;
+    if (n > c->cap_cases_chunks) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        CU_TRY(c, regrow(&c->d_cases, (size_t)n * S3));
+        c->cap_cases_chunks = n;
+    }
+    k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, c->d_cases);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out, c->d_cases, (size_t)n * S3, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return UW_OK;
+}
+
+extern "C" uw_status uw_iso_at(uw_ctx* c, const double* pts, uint32_t n, float* out) {
+    if (!c) return UW_ERR_INVALID;
+    if ((!pts || !out) && n) return fail(c, UW_ERR_INVALID, "uw_iso_at: null argument");
+    if (n == 0) return UW_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    double* d_pts = nullptr; float* d_out = nullptr;
+    CU_TRY(c, cudaMalloc(&d_pts, (size_t)n * 3 * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(d_pts); return fail(c, UW_ERR_OOM, "uw_iso_at: cudaMalloc failed"); }
+    e = cudaMemcpyAsync(d_pts, pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        unsigned blocks = (n + 255) / 256;
+        if (blocks > (unsigned)c->num_sms * 8) blocks = c->num_sms * 8;
+        k_iso_points<<<blocks, 256, 0, c->stream>>>(c->dcfg, c->d_perm, d_pts, n, d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_pts); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(c, UW_ERR_CUDA, std::string("uw_iso_at: ") + cudaGetErrorString(e));
+    return UW_OK;
+}

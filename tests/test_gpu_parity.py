@@ -150,7 +150,7 @@ def test_extraction_worst_case_random_fields(uw, builder12, oracle12):
     perm = oracle12.perm_table(0)
     batch = builder12.build_from_densities(pos, dens)
     refs = _oracle_batch(oracle12, perm, pos, MODE_FAST, isos=dens)
-    assert max(len(r["verts"]) for r in refs) > 5000
+    assert max(len(r["verts"]) for r in refs) > 4000
     _check_batch(batch, refs, exact_positions=True)
     assert batch.chunk(8).flags == 1 and batch.chunk(7).flags == 0 and batch.chunk(9).flags == 0
 

@@ -371,6 +371,179 @@ __global__ void __launch_bounds__(256) k_noise_small(const __grid_constant__ Dev
 }
 
 // ---------------------------------------------------------------------------------------
+// K1 (fast path, compile-time specialised): same algorithm as k_noise_small with S and the
+// octave count as template parameters, so that every loop bound, lattice size and -- crucially --
+// every "did the z column enter the next noise cell" test folds at compile time.  Requires
+// (host-verified) that the axis cell table equals (i << o) / S, true for the reference's
+// constants (SIZE_SCALE = f32(16/S) rounds up or is exact for S = 10, 12, 64).
+//
+// Arithmetic per octave-sample (z stage): with (R0,S0) / (R1,S1) the y-lerped value/z-slope at
+// the low/high noise-lattice plane,  v = a0 + w (a1 - a0),  a0 = R0 + S0 d,  a1 = R1 + S1 (d-1)
+//   =>  v = fma(w, fma(d, D, C), fma(d, S0, R0)),   C = (R1 - R0) - S1,  D = S1 - S0
+// 3 FFMA + 2 FMNMX (the reference's clamp) + 1 FADD (octave sum).  The octave weight
+// 2/sqrt(3) * 2^-o / sum(2^-o) is folded into the x stage (everything downstream is linear).
+// ---------------------------------------------------------------------------------------
+template <int ST, int NOCT>
+struct SpecDims {
+    static constexpr int S = ST, L = ST + 1;
+    __host__ __device__ static constexpr int G(int o) { return (1 << o) + 2; }
+    __host__ __device__ static constexpr int lat_base(int o) { return o == 0 ? 0 : lat_base(o - 1) + G(o - 1) * G(o - 1) * G(o - 1); }
+    __host__ __device__ static constexpr int x_base(int o) { return o == 0 ? 0 : x_base(o - 1) + L * G(o - 1) * G(o - 1); }
+    static constexpr int LAT = lat_base(NOCT), XN = x_base(NOCT);
+    static constexpr int DSTRIDE = (L * L * L + 3) & ~3;
+    static constexpr int NT = ((L * L + 31) / 32) * 32;
+    __host__ __device__ static constexpr int cell(int o, int k) { return (k << o) / ST; }
+};
+
+template <int ST, int NOCT>
+struct SpecSmem {
+    using D = SpecDims<ST, NOCT>;
+    float4 lat[D::LAT];
+    float4 X[D::XN];
+    float dens[D::DSTRIDE];
+    float4 grad[16];
+    float terr[32];            // adj_z - fmod(adj_z, mod): exact multiple of the terrace step
+    uint32_t mask[D::L * D::L + 3];
+    uint8_t perm[256];
+    int red[4];
+};
+
+// stages H, X, YZ for one chunk; leaves densities in sm.dens and column sign masks in sm.mask.
+// Returns (block-uniform) CF_ALL_GT | CF_ANY_LT.  All threads must call; ends with a barrier.
+template <int ST, int NOCT>
+__device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const AxisTables& tab, SpecSmem<ST, NOCT>& sm,
+                                                     int px, int py, int pz, unsigned long long* guard_count) {
+    using D = SpecDims<ST, NOCT>;
+    constexpr int L = D::L;
+    const int tid = threadIdx.x;
+    constexpr int NT = D::NT;
+
+    // ---- stage H --------------------------------------------------------------------------------
+#pragma unroll
+    for (int o = 0; o < NOCT; ++o) {
+        const int G = D::G(o), F = 1 << o, base = D::lat_base(o);
+        for (int t = tid; t < G * G * G; t += NT) {
+            const int cx = t / (G * G), r = t - cx * G * G, cy = r / G, cz = r - cy * G;
+            const uint32_t h = sm.perm[sm.perm[sm.perm[(F * px + cx) & 255] ^ ((F * py + cy) & 255)] ^ ((F * pz + cz) & 255)];
+            sm.lat[base + t] = sm.grad[h & 15u];
+        }
+    }
+    if (tid < L) {   // terrace term perlin_util.rs:27-28 from the exact f64 coordinate
+        const float zf = __double2float_rn(x_coord(cfg, tid, pz));
+        const float adj = __fdiv_rn(__fmul_rn(zf, (float)cfg.chunk_size), cfg.max_height);
+        sm.terr[tid] = __fsub_rn(adj, fmodf(adj, cfg.adj_z_mod));
+    }
+    if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; }
+    __syncthreads();
+
+    // ---- stage X --------------------------------------------------------------------------------
+    constexpr float inv_max = 1.0f / (2.0f - 1.0f / (float)(1 << (NOCT - 1)));
+#pragma unroll
+    for (int o = 0; o < NOCT; ++o) {
+        const int G = D::G(o), lb = D::lat_base(o), xb = D::x_base(o);
+        const float sc = 1.1547005383792515f * inv_max / (float)(1 << o);
+        for (int t = tid; t < L * G * G; t += NT) {
+            const int i = t / (G * G), r = t - i * G * G;
+            const int c = (i << o) / ST;
+            const float4 g0 = sm.lat[lb + c * G * G + r];
+            const float4 g1 = sm.lat[lb + (c + 1) * G * G + r];
+            const float d = tab.d[o][i], d1 = tab.d1[o][i], w = tab.w[o][i];
+            const float q0 = g0.x * d, q1 = g1.x * d1;
+            float4 e;
+            e.x = fmaf(w, q1 - q0, q0) * sc;
+            e.y = fmaf(w, g1.y - g0.y, g0.y) * sc;
+            e.z = fmaf(w, g1.z - g0.z, g0.z) * sc;
+            e.w = 0.f;
+            sm.X[xb + t] = e;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage YZ -------------------------------------------------------------------------------
+    if (tid < L * L) {
+        const int i = tid / L, j = tid - i * L;
+        float R0[NOCT], S0[NOCT], R1[NOCT], S1[NOCT], Cc[NOCT], Dd[NOCT];
+        const float4* xrow[NOCT];
+        float dy[NOCT], dy1[NOCT], wy[NOCT];
+#pragma unroll
+        for (int o = 0; o < NOCT; ++o) {
+            const int G = D::G(o);
+            const int cyj = (j << o) / ST;
+            xrow[o] = sm.X + D::x_base(o) + (i * G + cyj) * G;
+            dy[o] = tab.d[o][j]; dy1[o] = tab.d1[o][j]; wy[o] = tab.w[o][j];
+        }
+        auto ystage = [&](int o, int cz, float& R, float& Sz) {
+            const int G = D::G(o);
+            const float4 E0 = xrow[o][cz];
+            const float4 E1 = xrow[o][G + cz];
+            const float A0 = fmaf(E0.y, dy[o], E0.x);
+            const float A1 = fmaf(E1.y, dy1[o], E1.x);
+            R = fmaf(wy[o], A1 - A0, A0);
+            Sz = fmaf(wy[o], E1.z - E0.z, E0.z);
+        };
+        float* out = sm.dens + tid * L;
+        uint32_t inside = 0;
+        float vmin = 3.0e38f;
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            float total = 0.f;
+#pragma unroll
+            for (int o = 0; o < NOCT; ++o) {
+                const int c = D::cell(o, k);
+                const bool first = (k == 0), step = (k > 0) && (c != D::cell(o, k > 0 ? k - 1 : 0));
+                if (first) { ystage(o, c, R0[o], S0[o]); ystage(o, c + 1, R1[o], S1[o]); }
+                else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; ystage(o, c + 1, R1[o], S1[o]); }
+                if (first || step) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
+                const float d = tab.d[o][k];
+                float v = fmaf(tab.w[o][k], fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o]));
+                const float lim = inv_max / (float)(1 << o);            // the reference's clamp to [-1, 1], scaled
+                v = fminf(fmaxf(v, -lim), lim);
+                total += v;
+            }
+            float iso = total + sm.terr[k];
+            if (fabsf(iso - cfg.iso_level) < cfg.guard_eps) {          // rare: exact f64 re-evaluation
+                iso = x_iso_lattice(cfg, sm.perm, px, py, pz, i, j, k);
+                atomicAdd(guard_count, 1ull);
+            }
+            out[k] = iso;
+            vmin = fminf(vmin, iso);
+            inside |= (iso < cfg.iso_level) ? (1u << k) : 0u;
+        }
+        sm.mask[tid] = inside;
+        const bool all_gt = vmin > cfg.iso_level, any_lt = inside != 0u;
+        const bool w_all = __all_sync(__activemask(), all_gt), w_any = __any_sync(__activemask(), any_lt);
+        if ((tid & 31) == 0 || tid == (L * L / 32) * 32) {
+            if (!w_all) sm.red[0] = 0;
+            if (w_any) sm.red[1] = 1;
+        }
+    }
+    __syncthreads();
+    return (sm.red[0] ? CF_ALL_GT : 0u) | (sm.red[1] ? CF_ANY_LT : 0u);
+}
+
+template <int ST, int NOCT>
+__global__ void __launch_bounds__(SpecDims<ST, NOCT>::NT, 4)
+k_noise_spec(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTables tab,
+             const uint8_t* __restrict__ g_perm, const int32_t* __restrict__ pos, uint32_t n,
+             float* __restrict__ dens, unsigned long long* __restrict__ guard_count) {
+    using D = SpecDims<ST, NOCT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SpecSmem<ST, NOCT>& sm = *reinterpret_cast<SpecSmem<ST, NOCT>*>(smem_raw);
+    const int tid = threadIdx.x;
+    for (int t = tid; t < 256; t += D::NT) sm.perm[t] = g_perm[t];
+    if (tid < 16) sm.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
+    __syncthreads();
+    for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];
+        noise_chunk_spec<ST, NOCT>(cfg, tab, sm, px, py, pz, guard_count);
+        float4* dst = reinterpret_cast<float4*>(dens + (size_t)chunk * D::DSTRIDE);
+        const float4* src = reinterpret_cast<const float4*>(sm.dens);
+        for (int t = tid; t < D::DSTRIDE / 4; t += D::NT) dst[t] = src[t];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Shared extraction helpers (small path): sign bits -> per-column masks -> cases
 // ---------------------------------------------------------------------------------------
 struct ChunkCounts { uint32_t n_verts, n_inds, flags, pad; };
@@ -622,12 +795,14 @@ __device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, i
     const float ratio = __fdiv_rn(world_z, (float)cfg.chunk_size);
     const float mix = __fdiv_rn(__fsub_rn(ratio, cfg.min_z), __fsub_rn(cfg.max_z, cfg.min_z));
     float hue = __fadd_rn(cfg.min_hue, __fmul_rn(__fsub_rn(cfg.max_hue, cfg.min_hue), mix));
-    float r = fmodf(hue, 360.0f);                       // f32::rem_euclid, util.rs:123
+    float r = fabsf(hue) < 360.0f ? hue : fmodf(hue, 360.0f);   // f32::rem_euclid, util.rs:123 (fmod is exact)
     if (r < 0.0f) r = __fadd_rn(r, 360.0f);
     hue = r;
     const float c = cfg.hsv_c[vi], m = cfg.hsv_m[vi];
     const float h = __fdiv_rn(hue, 60.0f);
-    const float x = __fmul_rn(c, __fsub_rn(1.0f, fabsf(__fsub_rn(fmodf(h, 2.0f), 1.0f))));
+    // h in [0, 6]: fmod(h, 2) == h - 2*floor(h/2) exactly (every step is exact in f32)
+    const float hm2 = (h >= 0.0f && h < 16.0f) ? __fsub_rn(h, __fmul_rn(2.0f, floorf(__fmul_rn(h, 0.5f)))) : fmodf(h, 2.0f);
+    const float x = __fmul_rn(c, __fsub_rn(1.0f, fabsf(__fsub_rn(hm2, 1.0f))));
     const float X = srgb_of(__fadd_rn(x, m));
     const float HI = cfg.srgb_hi[vi], LO = cfg.srgb_lo[vi];
     if      (0.0f <= h && h < 1.0f) { out[0] = HI; out[1] = X;  out[2] = LO; }
@@ -672,107 +847,174 @@ __device__ __forceinline__ void owner_of(int e, int x, int y, int z, int& ox, in
 }
 
 // ---------------------------------------------------------------------------------------
-// K4: emit.  One CTA per ACTIVE chunk (index_count > 0).  Densities -> smem, cases and
-// per-cell (vbase, ibase) by block scan in reference scan order, then every active cell
-// writes its owned vertices and all of its indices at the packed offsets from K3.
+// K4: emit.  One CTA per ACTIVE chunk (index_count > 0), work compacted by prefix scans:
+//   A  densities -> smem, sign ballots -> per-column masks
+//   B  cases + per-column (vertex, index, surface-cell) counts, block scan in scan order
+//   C  per-cell (vbase, ibase) and the compact list of surface cells
+//   D  compact list of owned edge vertices (slot = vbase + first-appearance rank), then ONE
+//      THREAD PER VERTEX: edge lerp + colour, consecutive threads write consecutive vertices
+//   E  one thread per surface cell: index = vbase[owner cell] + rank(owner edge)
 // ---------------------------------------------------------------------------------------
 #define UW_SMALL_MAX_CELLS ((UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1))
+#define UW_VLIST_CAP 4096
 
-template <typename IndexT>
+struct EmitSmem {
+    float* dens; uint32_t* bits; uint32_t* mask; uint16_t* vbase; uint16_t* ibase; uint16_t* alist;
+    uint16_t* vlist; uint8_t* cs;
+};
+
+__host__ __device__ inline size_t emit_smem_bytes(const DevCfg& cfg) {
+    const size_t cells = (size_t)cfg.S * cfg.S * cfg.S;
+    size_t b = (size_t)cfg.dens_stride * 4;
+    b += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
+    b += (size_t)cfg.L2 * 4;
+    b += ((cells + 1) & ~(size_t)1) * 2 * 3;
+    b += UW_VLIST_CAP * 2;
+    b += (cells + 15) & ~(size_t)15;
+    return b;
+}
+
+__device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned char* base) {
+    const size_t cells = (size_t)cfg.S * cfg.S * cfg.S, cells2 = (cells + 1) & ~(size_t)1;
+    EmitSmem s;
+    s.dens = (float*)base;        base += (size_t)cfg.dens_stride * 4;
+    s.bits = (uint32_t*)base;     base += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
+    s.mask = (uint32_t*)base;     base += (size_t)cfg.L2 * 4;
+    s.vbase = (uint16_t*)base;    base += cells2 * 2;
+    s.ibase = (uint16_t*)base;    base += cells2 * 2;
+    s.alist = (uint16_t*)base;    base += cells2 * 2;
+    s.vlist = (uint16_t*)base;    base += UW_VLIST_CAP * 2;
+    s.cs = (uint8_t*)base;
+    return s;
+}
+
+// Phases B..E on a chunk whose densities (s.dens) and column masks (s.mask) are in shared memory.
+// All threads of the CTA must call.  ST > 0 = compile-time S.
+template <int ST, typename IndexT>
+__device__ __forceinline__ void emit_chunk(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
+                                           uint32_t* s_w, int px, int py, int pz,
+                                           uw_vert* __restrict__ vout, IndexT* __restrict__ iout) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int S = ST > 0 ? ST : cfg.S, L = S + 1, ncol = S * S;
+
+    // ---- B: cases + counts per cell column (x,y); z inner == reference scan order ------------
+    uint32_t nva = 0, ni = 0;                         // nva = n_verts | n_surface_cells << 16
+    for (int col = tid; col < ncol; col += NT) {      // single trip (NT >= S*S on this path)
+        const int x = col / S, y = col - x * S;
+        const uint32_t m00 = s.mask[x * L + y], m10 = s.mask[(x + 1) * L + y];
+        const uint32_t m01 = s.mask[x * L + y + 1], m11 = s.mask[(x + 1) * L + y + 1];
+        const uint32_t any = m00 | m10 | m01 | m11, all = m00 & m10 & m01 & m11;
+        if (any == 0u || all == ((1u << L) - 1u)) {
+            const uint8_t fill = any ? 255 : 0;
+            for (int z = 0; z < S; ++z) s.cs[col * S + z] = fill;
+        } else {
+            for (int z = 0; z < S; ++z) {
+                const uint32_t c = case_of(m00, m10, m01, m11, z);
+                s.cs[col * S + z] = (uint8_t)c;
+                if (c != 0u && c != 255u) {
+                    ni += mc->ninds[c];
+                    nva += __popc((uint32_t)mc->crossed[c] & own_mask_of(x, y, z)) + 0x10000u;
+                }
+            }
+        }
+    }
+    uint32_t eva, ei, tva, ti;
+    block_scan2(nva, ni, eva, ei, tva, ti, s_w);
+    const uint32_t n_act = tva >> 16, n_vert = tva & 0xFFFFu;
+
+    // ---- C: per-cell bases + compact surface-cell list -----------------------------------------
+    for (int col = tid; col < ncol; col += NT) {
+        const int x = col / S, y = col - x * S;
+        uint32_t rv = eva & 0xFFFFu, ra = eva >> 16, ri = ei;
+        for (int z = 0; z < S; ++z) {
+            const int cell = col * S + z;
+            const uint32_t c = s.cs[cell];
+            s.vbase[cell] = (uint16_t)rv; s.ibase[cell] = (uint16_t)ri;
+            if (c != 0u && c != 255u) {
+                s.alist[ra++] = (uint16_t)cell;
+                ri += mc->ninds[c];
+                rv += __popc((uint32_t)mc->crossed[c] & own_mask_of(x, y, z));
+            }
+        }
+    }
+    __syncthreads();
+
+    const int offx = px * cfg.chunk_size, offy = py * cfg.chunk_size, offz = pz * cfg.chunk_size;
+
+    // ---- D: vertices, in tiles of UW_VLIST_CAP ---------------------------------------------------
+    for (uint32_t v0 = 0; v0 < n_vert; v0 += UW_VLIST_CAP) {
+        for (uint32_t a = tid; a < n_act; a += NT) {
+            const int cell = s.alist[a];
+            const uint32_t c = s.cs[cell];
+            const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+            const uint32_t own = own_mask_of(x, y, z);
+            uint32_t m = (uint32_t)mc->crossed[c] & own;
+            const uint32_t vb = s.vbase[cell];
+            while (m) {
+                const int e = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t slot = vb + __popc((uint32_t)mc->before[c][e] & own) - v0;
+                if (slot < UW_VLIST_CAP) s.vlist[slot] = (uint16_t)(cell | (e << 12));
+            }
+        }
+        __syncthreads();
+        const uint32_t cnt = min((uint32_t)UW_VLIST_CAP, n_vert - v0);
+        for (uint32_t t = tid; t < cnt; t += NT) {
+            const uint32_t ent = s.vlist[t];
+            const int cell = ent & 0xFFF, e = ent >> 12;
+            const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+            float v[6];
+            make_vertex(cfg, s.dens, x, y, z, e, offx, offy, offz, v);
+            float2* dst = reinterpret_cast<float2*>(vout + v0 + t);
+            dst[0] = make_float2(v[0], v[1]); dst[1] = make_float2(v[2], v[3]); dst[2] = make_float2(v[4], v[5]);
+        }
+        if (v0 + UW_VLIST_CAP < n_vert) __syncthreads();
+    }
+
+    // ---- E: indices, one thread per surface cell -------------------------------------------------
+    for (uint32_t a = tid; a < n_act; a += NT) {
+        const int cell = s.alist[a];
+        const uint32_t c = s.cs[cell];
+        const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+        const uint64_t row = mc->rows[c];
+        IndexT* dst = iout + s.ibase[cell];
+        const int nidx = mc->ninds[c];
+#pragma unroll 1
+        for (int k = 0; k < nidx; ++k) {
+            const int e = (int)((row >> (4 * k)) & 0xFull);
+            int ox, oy, oz, oe;
+            owner_of(e, x, y, z, ox, oy, oz, oe);
+            const int ocell = (ox * S + oy) * S + oz;
+            const uint32_t rank = __popc((uint32_t)mc->before[s.cs[ocell]][oe] & own_mask_of(ox, oy, oz));
+            dst[k] = (IndexT)((uint32_t)s.vbase[ocell] + rank);          // `ind as u16`, chunk.rs:243
+        }
+    }
+}
+
+template <int ST, typename IndexT>
 __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevCfg cfg,
                                                     const McTables* __restrict__ mc,
                                                     const float* __restrict__ dens,
                                                     const uw_chunk_desc* __restrict__ descs,
                                                     const uint32_t* __restrict__ active,
                                                     const BatchTotals* __restrict__ totals,
-                                                    uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
-                                                    unsigned long long vcap, unsigned long long icap) {
+                                                    uw_vert* __restrict__ verts, IndexT* __restrict__ inds) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_dens = reinterpret_cast<float*>(smem_raw);
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_dens + cfg.dens_stride);
-    uint16_t* s_vbase = reinterpret_cast<uint16_t*>(s_bits + ((cfg.L3 + 31) / 32 + 2));
-    uint16_t* s_ibase = s_vbase + UW_SMALL_MAX_CELLS;
-    uint8_t* s_case = reinterpret_cast<uint8_t*>(s_ibase + UW_SMALL_MAX_CELLS);
+    const EmitSmem s = emit_smem_carve(cfg, smem_raw);
     __shared__ int s_red[2];
     __shared__ uint32_t s_w[64];
-
     const int tid = threadIdx.x, NT = blockDim.x;
-    const int S = cfg.S, L = cfg.L, S3 = S * S * S;
+    const int L = (ST > 0 ? ST : cfg.S) + 1;
     const uint32_t n_active = totals->n_active;
     if (totals->overflow) return;                       // host grows the arenas and relaunches
 
     for (uint32_t a = blockIdx.x; a < n_active; a += gridDim.x) {
         const uint32_t chunk = active[a];
         const uw_chunk_desc d = descs[chunk];
-        load_signs<true>(cfg, dens + (size_t)chunk * cfg.dens_stride, s_dens, s_bits, s_red);
-
-        // pass 1: cases + per-column counts (thread = cell column (x,y), z inner = scan order)
-        uint32_t nv = 0, ni = 0;
-        const int ncol = S * S;
-        for (int col = tid; col < ncol; col += NT) {      // NT >= ncol for S <= 15: single trip
-            const int x = col / S, y = col - x * S;
-            const uint32_t m00 = col_mask(s_bits, x * L + y, L), m10 = col_mask(s_bits, (x + 1) * L + y, L);
-            const uint32_t m01 = col_mask(s_bits, x * L + y + 1, L), m11 = col_mask(s_bits, (x + 1) * L + y + 1, L);
-            for (int z = 0; z < S; ++z) {
-                const uint32_t cs = case_of(m00, m10, m01, m11, z);
-                s_case[col * S + z] = (uint8_t)cs;
-                if (cs != 0u && cs != 255u) {
-                    ni += mc->ninds[cs];
-                    nv += __popc((uint32_t)mc->crossed[cs] & own_mask_of(x, y, z));
-                }
-            }
-        }
-        uint32_t ev, ei, tv, ti;
-        block_scan2(nv, ni, ev, ei, tv, ti, s_w);
-        // pass 2: per-cell bases
-        for (int col = tid; col < ncol; col += NT) {
-            const int x = col / S, y = col - x * S;
-            uint32_t rv = ev, ri = ei;
-            for (int z = 0; z < S; ++z) {
-                const uint32_t cs = s_case[col * S + z];
-                s_vbase[col * S + z] = (uint16_t)rv; s_ibase[col * S + z] = (uint16_t)ri;
-                if (cs != 0u && cs != 255u) {
-                    ri += mc->ninds[cs];
-                    rv += __popc((uint32_t)mc->crossed[cs] & own_mask_of(x, y, z));
-                }
-            }
-        }
+        load_signs<true>(cfg, dens + (size_t)chunk * cfg.dens_stride, s.dens, s.bits, s_red);
+        for (int c = tid; c < L * L; c += NT) s.mask[c] = col_mask(s.bits, c, L);
         __syncthreads();
-
-        // pass 3: emission, one thread per cell (strided), only surface cells do work
-        uw_vert* vout = verts + d.vert_offset;
-        IndexT* iout = inds + d.index_offset;
-        const int offx = d.pos[0] * cfg.chunk_size, offy = d.pos[1] * cfg.chunk_size, offz = d.pos[2] * cfg.chunk_size;
-        for (int cell = tid; cell < S3; cell += NT) {
-            const uint32_t cs = s_case[cell];
-            if (cs == 0u || cs == 255u) continue;
-            const int x = cell / (S * S), y = (cell / S) % S, z = cell % S;
-            const uint64_t row = mc->rows[cs];
-            const uint32_t own = own_mask_of(x, y, z);
-            const uint32_t vb = s_vbase[cell], ib = s_ibase[cell];
-            uint32_t seen = 0;
-#pragma unroll 1
-            for (int sidx = 0; sidx < 16; ++sidx) {
-                const int e = (int)((row >> (4 * sidx)) & 0xFull);
-                if (e == 0xF) break;
-                int ox, oy, oz, oe;
-                owner_of(e, x, y, z, ox, oy, oz, oe);
-                const int ocell = (ox * S + oy) * S + oz;
-                const uint32_t ocs = s_case[ocell];
-                const uint32_t rank = __popc((uint32_t)mc->before[ocs][oe] & own_mask_of(ox, oy, oz));
-                const uint32_t vi = (uint32_t)s_vbase[ocell] + rank;
-                iout[ib + sidx] = (IndexT)vi;                         // `ind as u16`, chunk.rs:243
-                if (((own >> e) & 1u) && !((seen >> e) & 1u)) {       // first appearance of an owned edge
-                    float v[6];
-                    make_vertex(cfg, s_dens, x, y, z, e, offx, offy, offz, v);
-                    float2* dst = reinterpret_cast<float2*>(vout + vi);
-                    dst[0] = make_float2(v[0], v[1]); dst[1] = make_float2(v[2], v[3]); dst[2] = make_float2(v[4], v[5]);
-                }
-                seen |= 1u << e;
-                (void)vb;
-            }
-        }
+        emit_chunk<ST, IndexT>(cfg, mc, s, s_w, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
         __syncthreads();
     }
-    (void)vcap; (void)icap;
 }

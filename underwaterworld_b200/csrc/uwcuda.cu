@@ -51,7 +51,14 @@ struct uw_ctx {
     unsigned long long* h_guard = nullptr;
     std::vector<PinnedBlock> pool;
 
-    // launch geometry
+    // launch geometry / kernel selection
+    typedef void (*noise_fn_t)(DevCfg, AxisTables, const uint8_t*, const int32_t*, uint32_t, float*, unsigned long long*);
+    typedef void (*emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*);
+    typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*);
+    noise_fn_t noise_fn = nullptr;
+    emit16_fn_t emit16_fn = nullptr;
+    emit32_fn_t emit32_fn = nullptr;
+    bool spec_noise = false;        // compile-time specialised noise kernel in use
     int noise_threads = 192, noise_blocks_per_sm = 1; size_t noise_smem = 0;
     int emit_blocks_per_sm = 1; size_t emit_smem = 0;
     int classify_blocks_per_sm = 1;
@@ -271,28 +278,38 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     if (!cu(cudaHostAlloc(&c->h_guard, sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc guard")) return bail(UW_ERR_OOM);
     for (auto& ev : c->ev) if (!cu(cudaEventCreate(&ev), "cudaEventCreate")) return bail(UW_ERR_CUDA);
 
-    // launch geometry
+    // launch geometry / kernel selection
     const DevCfg& d = c->dcfg;
-    c->noise_threads = ((d.L2 + 31) / 32) * 32;
-    c->noise_smem = noise_smem_bytes(d);
-    c->emit_smem = (size_t)d.dens_stride * 4 + ((d.L3 + 31) / 32 + 2) * 4 + (size_t)UW_SMALL_MAX_CELLS * 5 + 16;
     {
+        // the specialised kernels assume cell(o, i) == (i << o) / S (see k_noise_spec)
+        bool cells_regular = true;
+        for (int o = 0; o < d.octaves; ++o)
+            for (int i = 0; i < d.L; ++i) cells_regular &= (c->tab.c[o][i] == (i << o) / d.S);
+        c->noise_threads = ((d.L2 + 31) / 32) * 32;
+        c->noise_smem = noise_smem_bytes(d);
+        c->noise_fn = k_noise_small<0, 0>;
+        if (cells_regular && d.octaves == 3 && d.S == 12) {
+            c->noise_fn = k_noise_spec<12, 3>; c->spec_noise = true;
+            c->noise_threads = SpecDims<12, 3>::NT; c->noise_smem = sizeof(SpecSmem<12, 3>);
+        } else if (cells_regular && d.octaves == 3 && d.S == 10) {
+            c->noise_fn = k_noise_spec<10, 3>; c->spec_noise = true;
+            c->noise_threads = SpecDims<10, 3>::NT; c->noise_smem = sizeof(SpecSmem<10, 3>);
+        }
+        c->emit_smem = emit_smem_bytes(d);
+        if (d.S == 12)      { c->emit16_fn = k_emit_small<12, uint16_t>; c->emit32_fn = k_emit_small<12, uint32_t>; }
+        else if (d.S == 10) { c->emit16_fn = k_emit_small<10, uint16_t>; c->emit32_fn = k_emit_small<10, uint32_t>; }
+        else                { c->emit16_fn = k_emit_small<0, uint16_t>;  c->emit32_fn = k_emit_small<0, uint32_t>; }
         auto set_attr = [&](const void* f, size_t smem) {
             return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         };
-        bool ok = cu(set_attr((const void*)k_noise_small<13, 3>, c->noise_smem), "attr noise<13,3>") &&
-                  cu(set_attr((const void*)k_noise_small<11, 3>, c->noise_smem), "attr noise<11,3>") &&
-                  cu(set_attr((const void*)k_noise_small<0, 0>, c->noise_smem), "attr noise<0,0>") &&
-                  cu(set_attr((const void*)k_emit_small<uint16_t>, c->emit_smem), "attr emit16") &&
-                  cu(set_attr((const void*)k_emit_small<uint32_t>, c->emit_smem), "attr emit32");
+        bool ok = cu(set_attr((const void*)c->noise_fn, c->noise_smem), "attr noise") &&
+                  cu(set_attr((const void*)c->emit16_fn, c->emit_smem), "attr emit16") &&
+                  cu(set_attr((const void*)c->emit32_fn, c->emit_smem), "attr emit32");
         if (!ok) return bail(UW_ERR_CUDA);
         int nb = 1;
-        const void* nf = (d.L == 13 && d.octaves == 3) ? (const void*)k_noise_small<13, 3>
-                       : (d.L == 11 && d.octaves == 3) ? (const void*)k_noise_small<11, 3>
-                                                       : (const void*)k_noise_small<0, 0>;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nf, c->noise_threads, c->noise_smem) == cudaSuccess && nb > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->noise_fn, c->noise_threads, c->noise_smem) == cudaSuccess && nb > 0)
             c->noise_blocks_per_sm = nb;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_emit_small<uint16_t>, 256, c->emit_smem) == cudaSuccess && nb > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->emit16_fn, 256, c->emit_smem) == cudaSuccess && nb > 0)
             c->emit_blocks_per_sm = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_classify_small, 256, 0) == cudaSuccess && nb > 0)
             c->classify_blocks_per_sm = nb;
@@ -391,12 +408,7 @@ static uw_status launch_noise(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
     const DevCfg& d = c->dcfg;
     if (c->fast_path) {
         const int grid = persistent_grid(c, n, c->noise_blocks_per_sm);
-        if (d.L == 13 && d.octaves == 3)
-            k_noise_small<13, 3><<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
-        else if (d.L == 11 && d.octaves == 3)
-            k_noise_small<11, 3><<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
-        else
-            k_noise_small<0, 0><<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
+        c->noise_fn<<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
     } else {
         const unsigned long long total = (unsigned long long)n * d.L3;
         unsigned long long blocks = (total + 255) / 256;
@@ -423,11 +435,11 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
     if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
     const int grid = persistent_grid(c, n, c->emit_blocks_per_sm);
     if (c->index32)
-        k_emit_small<uint32_t><<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
-                                                                      c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap);
+        c->emit32_fn<<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
+                                                            c->d_verts, (uint32_t*)c->d_inds);
     else
-        k_emit_small<uint16_t><<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
-                                                                      c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap);
+        c->emit16_fn<<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
+                                                            c->d_verts, (uint16_t*)c->d_inds);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;

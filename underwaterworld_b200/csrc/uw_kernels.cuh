@@ -393,6 +393,18 @@ struct SpecDims {
     static constexpr int DSTRIDE = (L * L * L + 3) & ~3;
     static constexpr int NT = ((L * L + 31) / 32) * 32;
     __host__ __device__ static constexpr int cell(int o, int k) { return (k << o) / ST; }
+    // compile-time axis tables for CHUNK_SIZE = 16 (chunk.rs:5): same f64 arithmetic as setup_tables();
+    // the host selects this kernel only if its runtime tables match these bit for bit.
+    __host__ __device__ static constexpr float size_scale() { return 16.0f / (float)ST; }
+    __host__ __device__ static constexpr double axis_p(int o, int k) {
+        return ((((double)k * (double)size_scale()) + 0.0) / 16.0) * (double)(1 << o);
+    }
+    __host__ __device__ static constexpr double cfloor(double x) { return (double)(long long)x; }   // x >= 0 here
+    __host__ __device__ static constexpr double axis_frac(int o, int k) { return axis_p(o, k) - cfloor(axis_p(o, k)); }
+    __host__ __device__ static constexpr double cfade(double c) { return (c * c * c) * (c * (c * 6.0 + (-15.0)) + 10.0); }
+    __host__ __device__ static constexpr float tab_d(int o, int k) { return (float)axis_frac(o, k); }
+    __host__ __device__ static constexpr float tab_w(int o, int k) { return (float)cfade(axis_frac(o, k)); }
+    __host__ __device__ static constexpr int tab_c(int o, int k) { return (int)cfloor(axis_p(o, k)); }
 };
 
 template <int ST, int NOCT>
@@ -402,6 +414,7 @@ struct SpecSmem {
     float4 X[D::XN];
     float dens[D::DSTRIDE];
     float4 grad[16];
+    float4 axis[NOCT][D::L + 1];   // (d, d - 1, fade(d), -) per octave and lattice index
     float terr[32];            // adj_z - fmod(adj_z, mod): exact multiple of the terrace step
     uint32_t mask[D::L * D::L + 3];
     uint8_t perm[256];
@@ -447,7 +460,8 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             const int c = (i << o) / ST;
             const float4 g0 = sm.lat[lb + c * G * G + r];
             const float4 g1 = sm.lat[lb + (c + 1) * G * G + r];
-            const float d = tab.d[o][i], d1 = tab.d1[o][i], w = tab.w[o][i];
+            const float4 ax = sm.axis[o][i];
+            const float d = ax.x, d1 = ax.y, w = ax.z;
             const float q0 = g0.x * d, q1 = g1.x * d1;
             float4 e;
             e.x = fmaf(w, q1 - q0, q0) * sc;
@@ -470,7 +484,8 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             const int G = D::G(o);
             const int cyj = (j << o) / ST;
             xrow[o] = sm.X + D::x_base(o) + (i * G + cyj) * G;
-            dy[o] = tab.d[o][j]; dy1[o] = tab.d1[o][j]; wy[o] = tab.w[o][j];
+            const float4 ay = sm.axis[o][j];
+            dy[o] = ay.x; dy1[o] = ay.y; wy[o] = ay.z;
         }
         auto ystage = [&](int o, int cz, float& R, float& Sz) {
             const int G = D::G(o);
@@ -482,8 +497,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             Sz = fmaf(wy[o], E1.z - E0.z, E0.z);
         };
         float* out = sm.dens + tid * L;
-        uint32_t inside = 0;
-        float vmin = 3.0e38f;
+        const float isl = cfg.iso_level, eps = cfg.guard_eps;
+        uint32_t signs = 0;                       // bit (L-1-k) <- (iso_k < iso_level), shifted in MSB-first
+        uint32_t near = 0;                        // bit k <- sample k fell inside the guard band
 #pragma unroll
         for (int k = 0; k < L; ++k) {
             float total = 0.f;
@@ -494,23 +510,32 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
                 if (first) { ystage(o, c, R0[o], S0[o]); ystage(o, c + 1, R1[o], S1[o]); }
                 else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; ystage(o, c + 1, R1[o], S1[o]); }
                 if (first || step) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
-                const float d = tab.d[o][k];
-                float v = fmaf(tab.w[o][k], fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o]));
+                const float d = D::tab_d(o, k), w = D::tab_w(o, k);      // immediates after unrolling
+                float v = fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o]));
                 const float lim = inv_max / (float)(1 << o);            // the reference's clamp to [-1, 1], scaled
                 v = fminf(fmaxf(v, -lim), lim);
                 total += v;
             }
-            float iso = total + sm.terr[k];
-            if (fabsf(iso - cfg.iso_level) < cfg.guard_eps) {          // rare: exact f64 re-evaluation
-                iso = x_iso_lattice(cfg, sm.perm, px, py, pz, i, j, k);
-                atomicAdd(guard_count, 1ull);
-            }
+            const float iso = total + sm.terr[k];
+            const float diff = iso - isl;
             out[k] = iso;
-            vmin = fminf(vmin, iso);
-            inside |= (iso < cfg.iso_level) ? (1u << k) : 0u;
+            if (fabsf(diff) < eps) near |= 1u << k;
+            signs = __funnelshift_l(__float_as_uint(diff), signs, 1);   // (signs << 1) | sign bit of diff
+        }
+        uint32_t inside = __brev(signs) >> (32 - L);                     // bit k <- (iso_k < iso_level)
+        bool any_eq = false;
+        while (near) {                                                   // rare: exact f64 re-evaluation
+            const int k = __ffs(near) - 1;
+            near &= near - 1;
+            const float iso = x_iso_lattice(cfg, sm.perm, px, py, pz, i, j, k);
+            out[k] = iso;
+            inside = (inside & ~(1u << k)) | ((iso < isl) ? (1u << k) : 0u);
+            any_eq |= (iso == isl);
+            atomicAdd(guard_count, 1ull);
         }
         sm.mask[tid] = inside;
-        const bool all_gt = vmin > cfg.iso_level, any_lt = inside != 0u;
+        // outside the guard band |iso - isl| >= eps > 0, so "all > isl" <=> no inside bit and no exact tie
+        const bool all_gt = (inside == 0u) && !any_eq, any_lt = inside != 0u;
         const bool w_all = __all_sync(__activemask(), all_gt), w_any = __any_sync(__activemask(), any_lt);
         if ((tid & 31) == 0 || tid == (L * L / 32) * 32) {
             if (!w_all) sm.red[0] = 0;
@@ -522,7 +547,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
 }
 
 template <int ST, int NOCT>
-__global__ void __launch_bounds__(SpecDims<ST, NOCT>::NT, 4)
+__global__ void __launch_bounds__(SpecDims<ST, NOCT>::NT, 5)
 k_noise_spec(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTables tab,
              const uint8_t* __restrict__ g_perm, const int32_t* __restrict__ pos, uint32_t n,
              float* __restrict__ dens, unsigned long long* __restrict__ guard_count) {
@@ -532,6 +557,10 @@ k_noise_spec(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTab
     const int tid = threadIdx.x;
     for (int t = tid; t < 256; t += D::NT) sm.perm[t] = g_perm[t];
     if (tid < 16) sm.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
+    for (int t = tid; t < NOCT * D::L; t += D::NT) {
+        const int o = t / D::L, i = t - o * D::L;
+        sm.axis[o][i] = make_float4(tab.d[o][i], tab.d1[o][i], tab.w[o][i], 0.f);
+    }
     __syncthreads();
     for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];

@@ -281,17 +281,27 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     // launch geometry / kernel selection
     const DevCfg& d = c->dcfg;
     {
-        // the specialised kernels assume cell(o, i) == (i << o) / S (see k_noise_spec)
-        bool cells_regular = true;
-        for (int o = 0; o < d.octaves; ++o)
-            for (int i = 0; i < d.L; ++i) cells_regular &= (c->tab.c[o][i] == (i << o) / d.S);
+        // the specialised kernels bake the axis tables in at compile time (see SpecDims): usable only
+        // when the runtime tables (from this configuration) match them bit for bit
+        auto spec_ok = [&](auto dims) {
+            using DD = decltype(dims);
+            if (d.S != DD::S || d.octaves != 3 || !c->fast_path) return false;
+            bool ok = true;
+            for (int o = 0; o < 3; ++o)
+                for (int i = 0; i < DD::L; ++i) {
+                    const float dd = DD::tab_d(o, i), ww = DD::tab_w(o, i);
+                    ok &= c->tab.c[o][i] == DD::cell(o, i) && c->tab.c[o][i] == DD::tab_c(o, i);
+                    ok &= memcmp(&dd, &c->tab.d[o][i], 4) == 0 && memcmp(&ww, &c->tab.w[o][i], 4) == 0;
+                }
+            return ok;
+        };
         c->noise_threads = ((d.L2 + 31) / 32) * 32;
         c->noise_smem = noise_smem_bytes(d);
         c->noise_fn = k_noise_small<0, 0>;
-        if (cells_regular && d.octaves == 3 && d.S == 12) {
+        if (spec_ok(SpecDims<12, 3>())) {
             c->noise_fn = k_noise_spec<12, 3>; c->spec_noise = true;
             c->noise_threads = SpecDims<12, 3>::NT; c->noise_smem = sizeof(SpecSmem<12, 3>);
-        } else if (cells_regular && d.octaves == 3 && d.S == 10) {
+        } else if (spec_ok(SpecDims<10, 3>())) {
             c->noise_fn = k_noise_spec<10, 3>; c->spec_noise = true;
             c->noise_threads = SpecDims<10, 3>::NT; c->noise_smem = sizeof(SpecSmem<10, 3>);
         }

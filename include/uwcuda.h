@@ -39,10 +39,13 @@ typedef enum uw_status {
 /* uw_config.flags */
 #define UW_FLAG_EXACT_F64   0x1u  /* evaluate EVERY density sample with the f64 reference-order path
                                      (verification mode; default = FP32 fast path + f64 guard band) */
-#define UW_FLAG_INDEX32     0x2u  /* also emit u32 indices (forced when internal_size > 22, where the
-                                     reference's `ind as u16` (chunk.rs:243) could wrap)            */
+#define UW_FLAG_INDEX32     0x2u  /* emit u32 indices instead of u16 (forced when internal_size > 22, where
+                                     the reference's `ind as u16` (chunk.rs:243) could wrap)        */
 #define UW_FLAG_KEEP_DENSITIES 0x4u /* keep per-chunk densities/cases of the last batch readable
                                      through uw_batch_densities / uw_batch_cases (debug taps)      */
+#define UW_FLAG_STAGED      0x10u /* run the four stages as separate kernels with densities materialised in
+                                     HBM (per-stage profiling / debugging) instead of the fused single-pass
+                                     kernel.  Results are identical.                                  */
 #define UW_FLAG_TRIS        0x8u  /* also emit the per-cell collision triangle lists (chunk.rs:167-174,
                                      245-250) -- SURVEY §8f-1                                       */
 

@@ -218,6 +218,21 @@ def test_spawn_config_config2(uw, builder12, oracle12):
     assert all(batch.descs["flags"][z >= 2] == 1) and all(batch.descs["index_count"][z <= -4] == 0)
 
 
+def test_fused_and_staged_pipelines_are_byte_identical(uw, builder12):
+    """The default single-pass fused kernel (noise -> classify -> look-back scan -> emit in one launch)
+    against the four-kernel staged pipeline (UW_FLAG_STAGED): identical bytes, several batch sizes
+    (1 chunk, fewer chunks than CTAs, many more chunks than CTAs), repeated to shake the look-back."""
+    big = uw.region.box_region((-12, 12), (-12, 12), (-4, 4))      # 4608 chunks > resident CTAs
+    with uw.ChunkBuilder(uw.Perlin(0), staged=True) as bs:
+        for pos in (big[:1], big[1000:1100], uw.region.config_positions("spawn"), big):
+            want = bs.build(pos)
+            for _ in range(3):
+                got = builder12.build(pos)
+                assert np.array_equal(got.descs, want.descs)
+                assert np.array_equal(got.inds, want.inds)
+                assert np.array_equal(got.verts.view(np.uint8), want.verts.view(np.uint8))
+
+
 def test_golden_reference_binary_chunks_s10(uw, golden_dir):
     """The reference's own shipped binary (INTERNAL_SIZE=10): GPU vs tests/golden/ref_wasm_chunks_s10.npz."""
     g = np.load(os.path.join(golden_dir, "ref_wasm_chunks_s10.npz"))

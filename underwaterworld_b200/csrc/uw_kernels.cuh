@@ -919,10 +919,12 @@ __device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned 
 
 // Phases B..E on a chunk whose densities (s.dens) and column masks (s.mask) are in shared memory.
 // All threads of the CTA must call.  ST > 0 = compile-time S.
-template <int ST, typename IndexT>
-__device__ __forceinline__ void emit_chunk(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
-                                           uint32_t* s_w, int px, int py, int pz,
-                                           uw_vert* __restrict__ vout, IndexT* __restrict__ iout) {
+struct ChunkShape { uint32_t n_vert, n_ind, n_act; };
+
+// phases B + C: cases, counts, per-cell bases and the surface-cell list.  Ends with a barrier.
+template <int ST>
+__device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const McTables* __restrict__ mc,
+                                                   const EmitSmem& s, uint32_t* s_w) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int S = ST > 0 ? ST : cfg.S, L = S + 1, ncol = S * S;
 
@@ -967,7 +969,19 @@ __device__ __forceinline__ void emit_chunk(const DevCfg& cfg, const McTables* __
         }
     }
     __syncthreads();
+    ChunkShape sh;
+    sh.n_vert = n_vert; sh.n_ind = ti; sh.n_act = n_act;
+    return sh;
+}
 
+// phases D + E: write the chunk's vertices and indices.  Needs emit_prepare's shared-memory state.
+template <int ST, typename IndexT>
+__device__ __forceinline__ void emit_write(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
+                                           const ChunkShape sh, int px, int py, int pz,
+                                           uw_vert* __restrict__ vout, IndexT* __restrict__ iout) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int S = ST > 0 ? ST : cfg.S;
+    const uint32_t n_vert = sh.n_vert, n_act = sh.n_act;
     const int offx = px * cfg.chunk_size, offy = py * cfg.chunk_size, offz = pz * cfg.chunk_size;
 
     // ---- D: vertices, in tiles of UW_VLIST_CAP ---------------------------------------------------
@@ -1043,7 +1057,182 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
         load_signs<true>(cfg, dens + (size_t)chunk * cfg.dens_stride, s.dens, s.bits, s_red);
         for (int c = tid; c < L * L; c += NT) s.mask[c] = col_mask(s.bits, c, L);
         __syncthreads();
-        emit_chunk<ST, IndexT>(cfg, mc, s, s_w, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
+        const ChunkShape sh = emit_prepare<ST>(cfg, mc, s, s_w);
+        emit_write<ST, IndexT>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// FUSED PATH: one persistent kernel does K1..K4 per chunk; densities never leave the SM.
+//
+//   ticket   chunks are handed out by an atomic counter, so a chunk's predecessors are always
+//            owned by CTAs that are already running (single-pass scan precondition)
+//   K1       noise_chunk_spec  -> densities + column sign masks in shared memory
+//   K2       cases + per-chunk (vertex, index) counts, blank / no-surface vote
+//   K3       decoupled look-back over the per-chunk aggregates -> this chunk's packed offsets
+//            (one warp polls 32 predecessors at a time; value and status share one 64-bit word)
+//   K4       emit_chunk        -> vertices + indices straight to the packed output arenas
+//
+// HBM traffic = 12 B position in, 32 B descriptor + 24 B/vertex + 2 B/index out.
+// ---------------------------------------------------------------------------------------
+struct ScanSlot { unsigned long long v, i; };     // bits 63..62: 0 = empty, 1 = aggregate, 2 = inclusive prefix
+#define SCAN_AGG  (1ull << 62)
+#define SCAN_PFX  (2ull << 62)
+#define SCAN_VAL  ((1ull << 62) - 1ull)
+
+struct FusedCounters { uint32_t ticket, pad; };
+
+template <int ST, int NOCT>
+struct FusedSmem {
+    SpecSmem<ST, NOCT> n;                             // n.lat / n.X are dead after K1 and reused by K4
+    uint16_t alist[ST * ST * ST + 8];
+    uint8_t cs[((ST * ST * ST + 15) / 16) * 16];
+    uint32_t w[64];
+    unsigned long long off[2];
+    uint32_t chunk;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// executed by one full warp; returns the exclusive prefix of (v, i) over chunks < c
+__device__ __forceinline__ void lookback_warp(ScanSlot* st, uint32_t c, unsigned long long& ev, unsigned long long& ei) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long sv = 0, si = 0;
+    long long j = (long long)c - 1;
+    while (true) {
+        const long long idx = j - lane;
+        unsigned long long a = SCAN_PFX, b = SCAN_PFX;        // virtual predecessor: prefix 0
+        if (idx >= 0) {
+            do { a = ld_volatile_u64(&st[idx].v); } while ((a >> 62) == 0);
+            do { b = ld_volatile_u64(&st[idx].i); } while ((b >> 62) == 0);
+        }
+        // a slot may show (aggregate, prefix) mid-update: treat it as an aggregate only if BOTH are
+        // aggregates or both are prefixes; otherwise re-read until consistent
+        bool mixed = ((a >> 62) != (b >> 62));
+        while (__any_sync(0xFFFFFFFFu, mixed)) {
+            if (mixed) {
+                a = ld_volatile_u64(&st[idx].v); b = ld_volatile_u64(&st[idx].i);
+                mixed = ((a >> 62) != (b >> 62));
+            }
+        }
+        const bool pfx = (a >> 62) == 2;
+        const uint32_t ball = __ballot_sync(0xFFFFFFFFu, pfx);
+        const int first = ball ? (__ffs(ball) - 1) : 32;       // nearest predecessor holding a prefix
+        unsigned long long cv = lane <= first ? (a & SCAN_VAL) : 0ull;
+        unsigned long long ci = lane <= first ? (b & SCAN_VAL) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            cv += __shfl_xor_sync(0xFFFFFFFFu, cv, d);
+            ci += __shfl_xor_sync(0xFFFFFFFFu, ci, d);
+        }
+        sv += cv; si += ci;
+        if (ball) break;
+        j -= 32;
+    }
+    ev = sv; ei = si;
+}
+
+template <int ST, int NOCT, typename IndexT>
+__global__ void __launch_bounds__(SpecDims<ST, NOCT>::NT, 4)
+k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTables tab,
+              const uint8_t* __restrict__ g_perm, const McTables* __restrict__ mc,
+              const int32_t* __restrict__ pos, uint32_t n,
+              ScanSlot* __restrict__ scan, FusedCounters* __restrict__ ctr,
+              uw_chunk_desc* __restrict__ descs, BatchTotals* __restrict__ totals,
+              uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
+              unsigned long long vcap, unsigned long long icap,
+              float* __restrict__ dens_out /*nullable: debug tap*/,
+              unsigned long long* __restrict__ guard_count) {
+    using D = SpecDims<ST, NOCT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem<ST, NOCT>& sm = *reinterpret_cast<FusedSmem<ST, NOCT>*>(smem_raw);
+    const int tid = threadIdx.x;
+    constexpr int L = D::L, CELLS = ST * ST * ST;
+
+    for (int t = tid; t < 256; t += D::NT) sm.n.perm[t] = g_perm[t];
+    if (tid < 16) sm.n.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
+    for (int t = tid; t < NOCT * L; t += D::NT) {
+        const int o = t / L, i = t - o * L;
+        sm.n.axis[o][i] = make_float4(tab.d[o][i], tab.d1[o][i], tab.w[o][i], 0.f);
+    }
+
+    // K4 scratch aliases the K1 tables (dead once noise_chunk_spec has returned)
+    EmitSmem es;
+    es.dens = sm.n.dens; es.bits = nullptr; es.mask = sm.n.mask;
+    es.vlist = reinterpret_cast<uint16_t*>(sm.n.X);
+    es.vbase = es.vlist + UW_VLIST_CAP;
+    es.ibase = reinterpret_cast<uint16_t*>(sm.n.lat);
+    es.alist = sm.alist; es.cs = sm.cs;
+    static_assert(sizeof(sm.n.X) >= (UW_VLIST_CAP + CELLS) * 2, "vlist + vbase must fit in the X table");
+    static_assert(sizeof(sm.n.lat) >= CELLS * 2, "ibase must fit in the lattice table");
+
+    while (true) {
+        __syncthreads();                                   // previous chunk fully emitted; smem reusable
+        if (tid == 0) sm.chunk = atomicAdd(&ctr->ticket, 1u);
+        __syncthreads();
+        const uint32_t chunk = sm.chunk;
+        if (chunk >= n) break;
+        const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];
+
+        // ---- K1 ---------------------------------------------------------------------------------
+        const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count);
+        if (dens_out) {
+            float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);
+            const float4* src = reinterpret_cast<const float4*>(sm.n.dens);
+            for (int t = tid; t < D::DSTRIDE / 4; t += D::NT) dst[t] = src[t];
+        }
+
+        // ---- K2: cases, counts, per-cell bases (block-uniform skip when no sample is inside) -------------
+        ChunkShape sh;
+        sh.n_vert = 0; sh.n_ind = 0; sh.n_act = 0;
+        if (fl & CF_ANY_LT) sh = emit_prepare<ST>(cfg, mc, es, sm.w);
+        const uint32_t nv = sh.n_vert, ni = sh.n_ind;
+
+        // ---- K3: publish aggregate, look back for the exclusive prefix ---------------------------------
+        if (tid < 32) {
+            if (tid == 0) {
+                const unsigned long long tag = chunk == 0 ? SCAN_PFX : SCAN_AGG;
+                atomicExch(&scan[chunk].v, tag | nv);
+                atomicExch(&scan[chunk].i, tag | ni);
+            }
+            unsigned long long ev = 0, ei = 0;
+            if (chunk > 0) {
+                lookback_warp(scan, chunk, ev, ei);
+                if (tid == 0) {
+                    atomicExch(&scan[chunk].v, SCAN_PFX | (ev + nv));
+                    atomicExch(&scan[chunk].i, SCAN_PFX | (ei + ni));
+                }
+            }
+            if (tid == 0) {
+                sm.off[0] = ev; sm.off[1] = ei;
+                uw_chunk_desc d;
+                d.pos[0] = px; d.pos[1] = py; d.pos[2] = pz;
+                d.flags = ((fl & CF_ALL_GT) ? UW_CHUNK_BLANK_EARLY : 0u) | (ni > 0 ? UW_CHUNK_HAS_MESH : 0u)
+                        | (nv > 65536u ? UW_CHUNK_U16_OVERFLOW : 0u);
+                d.vert_offset = (uint32_t)ev; d.vert_count = nv;
+                d.index_offset = (uint32_t)ei; d.index_count = ni;
+                descs[chunk] = d;
+                if (ni > 0) atomicAdd(&totals->n_active, 1u);
+                if (fl & CF_ALL_GT) atomicAdd(&totals->n_blank, 1u);
+                if (chunk == n - 1) {
+                    totals->n_verts = ev + nv; totals->n_inds = ei + ni;
+                    if (ev + nv > vcap || ei + ni > icap || ev + nv > 0xFFFFFFFFull || ei + ni > 0xFFFFFFFFull)
+                        totals->overflow = 1u;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- K4 ---------------------------------------------------------------------------------
+        if (ni > 0) {                                      // block-uniform
+            const unsigned long long ov = sm.off[0], oi = sm.off[1];
+            if (ov + nv <= vcap && oi + ni <= icap)
+                emit_write<ST, IndexT>(cfg, mc, es, sh, px, py, pz, verts + ov, inds + oi);
+        }
     }
 }

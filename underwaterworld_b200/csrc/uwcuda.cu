@@ -55,6 +55,18 @@ struct uw_ctx {
     typedef void (*noise_fn_t)(DevCfg, AxisTables, const uint8_t*, const int32_t*, uint32_t, float*, unsigned long long*);
     typedef void (*emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*);
     typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*);
+    typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
+                                 FusedCounters*, uw_chunk_desc*, BatchTotals*, uw_vert*, uint16_t*, unsigned long long,
+                                 unsigned long long, float*, unsigned long long*);
+    typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
+                                 FusedCounters*, uw_chunk_desc*, BatchTotals*, uw_vert*, uint32_t*, unsigned long long,
+                                 unsigned long long, float*, unsigned long long*);
+    fused16_fn_t fused16_fn = nullptr;
+    fused32_fn_t fused32_fn = nullptr;
+    bool use_fused = false;
+    size_t fused_smem = 0; int fused_blocks_per_sm = 1;
+    ScanSlot* d_scan = nullptr;
+    FusedCounters* d_ctr = nullptr;
     noise_fn_t noise_fn = nullptr;
     emit16_fn_t emit16_fn = nullptr;
     emit32_fn_t emit32_fn = nullptr;
@@ -66,6 +78,7 @@ struct uw_ctx {
     // state of the last build
     uint32_t last_n = 0;
     const int32_t* last_pos_dev = nullptr;
+    bool last_fused = false;
     bool pending = false;           // kernels enqueued, totals not yet validated
     bool async_in_flight = false;
     bool profiling = false;
@@ -202,7 +215,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_pos); cudaFree(c->d_dens); cudaFree(c->d_counts);
     cudaFree(c->d_descs); cudaFree(c->d_active); cudaFree(c->d_cases); cudaFree(c->d_totals); cudaFree(c->d_guard);
-    cudaFree(c->d_verts); cudaFree(c->d_inds);
+    cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_scan); cudaFree(c->d_ctr);
     if (c->h_pos) cudaFreeHost(c->h_pos);
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_guard) cudaFreeHost(c->h_guard);
@@ -301,10 +314,15 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         if (spec_ok(SpecDims<12, 3>())) {
             c->noise_fn = k_noise_spec<12, 3>; c->spec_noise = true;
             c->noise_threads = SpecDims<12, 3>::NT; c->noise_smem = sizeof(SpecSmem<12, 3>);
+            c->fused16_fn = k_build_fused<12, 3, uint16_t>; c->fused32_fn = k_build_fused<12, 3, uint32_t>;
+            c->fused_smem = sizeof(FusedSmem<12, 3>);
         } else if (spec_ok(SpecDims<10, 3>())) {
             c->noise_fn = k_noise_spec<10, 3>; c->spec_noise = true;
             c->noise_threads = SpecDims<10, 3>::NT; c->noise_smem = sizeof(SpecSmem<10, 3>);
+            c->fused16_fn = k_build_fused<10, 3, uint16_t>; c->fused32_fn = k_build_fused<10, 3, uint32_t>;
+            c->fused_smem = sizeof(FusedSmem<10, 3>);
         }
+        c->use_fused = c->spec_noise && !(cfg->flags & UW_FLAG_STAGED);
         c->emit_smem = emit_smem_bytes(d);
         if (d.S == 12)      { c->emit16_fn = k_emit_small<12, uint16_t>; c->emit32_fn = k_emit_small<12, uint32_t>; }
         else if (d.S == 10) { c->emit16_fn = k_emit_small<10, uint16_t>; c->emit32_fn = k_emit_small<10, uint32_t>; }
@@ -315,8 +333,13 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         bool ok = cu(set_attr((const void*)c->noise_fn, c->noise_smem), "attr noise") &&
                   cu(set_attr((const void*)c->emit16_fn, c->emit_smem), "attr emit16") &&
                   cu(set_attr((const void*)c->emit32_fn, c->emit_smem), "attr emit32");
+        if (ok && c->fused16_fn)
+            ok = cu(set_attr((const void*)c->fused16_fn, c->fused_smem), "attr fused16") &&
+                 cu(set_attr((const void*)c->fused32_fn, c->fused_smem), "attr fused32");
         if (!ok) return bail(UW_ERR_CUDA);
         int nb = 1;
+        if (c->fused16_fn && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->fused16_fn, c->noise_threads, c->fused_smem) == cudaSuccess && nb > 0)
+            c->fused_blocks_per_sm = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->noise_fn, c->noise_threads, c->noise_smem) == cudaSuccess && nb > 0)
             c->noise_blocks_per_sm = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->emit16_fn, 256, c->emit_smem) == cudaSuccess && nb > 0)
@@ -369,6 +392,8 @@ static uw_status ensure_chunks(uw_ctx* c, uint32_t n) {
     CU_TRY(c, regrow(&c->d_counts, cap));
     CU_TRY(c, regrow(&c->d_descs, cap));
     CU_TRY(c, regrow(&c->d_active, cap));
+    CU_TRY(c, regrow(&c->d_scan, cap));
+    if (!c->d_ctr) CU_TRY(c, cudaMalloc(&c->d_ctr, sizeof(FusedCounters)));
     c->cap_chunks = cap;
     return UW_OK;
 }
@@ -455,6 +480,23 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
     return UW_OK;
 }
 
+static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float* d_dens_out) {
+    const DevCfg& d = c->dcfg;
+    CU_TRY(c, cudaMemsetAsync(c->d_scan, 0, sizeof(ScanSlot) * (size_t)n, c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->d_ctr, 0, sizeof(FusedCounters), c->stream));
+    CU_TRY(c, cudaMemsetAsync(c->d_totals, 0, sizeof(BatchTotals), c->stream));
+    const int grid = persistent_grid(c, n, c->fused_blocks_per_sm);
+    if (c->index32)
+        c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, c->d_ctr,
+            c->d_descs, c->d_totals, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->d_guard);
+    else
+        c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, c->d_ctr,
+            c->d_descs, c->d_totals, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->d_guard);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return UW_OK;
+}
+
 // enqueue the whole pipeline for n chunks whose positions are at d_pos (device)
 static uw_status enqueue_build(uw_ctx* c, const int32_t* d_pos, uint32_t n, bool from_densities) {
     // initial output capacity guess: grows (and the emit stage is re-run) on overflow
@@ -462,6 +504,15 @@ static uw_status enqueue_build(uw_ctx* c, const int32_t* d_pos, uint32_t n, bool
     if (st != UW_OK) return st;
     c->launches = 0;
     CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
+    c->last_fused = false;
+    if (c->use_fused && !from_densities) {
+        if (c->profiling) for (int e = 0; e < 4; ++e) CU_TRY(c, cudaEventRecord(c->ev[e], c->stream));
+        st = launch_fused(c, d_pos, n, (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) ? c->d_dens : nullptr);
+        if (st != UW_OK) return st;
+        if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[4], c->stream));
+        c->last_n = n; c->last_pos_dev = d_pos; c->pending = true; c->last_fused = true;
+        return UW_OK;
+    }
     if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
     if (!from_densities) {
         st = launch_noise(c, d_pos, n);
@@ -496,7 +547,12 @@ static uw_status finish_build(uw_ctx* c) {
             return fail(c, UW_ERR_INVALID, "batch too large: packed vertex/index offsets exceed 32 bits; split the batch");
         uw_status st = ensure_outputs(c, c->h_totals->n_verts, c->h_totals->n_inds);
         if (st != UW_OK) return st;
-        st = launch_extract(c, c->last_pos_dev, c->last_n, nullptr, true);
+        if (c->last_fused) {
+            CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
+            st = launch_fused(c, c->last_pos_dev, c->last_n, (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) ? c->d_dens : nullptr);
+        } else {
+            st = launch_extract(c, c->last_pos_dev, c->last_n, nullptr, true);
+        }
         if (st != UW_OK) return st;
     }
     if (c->h_totals->overflow) return fail(c, UW_ERR_CUDA, "output arena overflow persisted");

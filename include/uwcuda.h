@@ -46,6 +46,11 @@ typedef enum uw_status {
 #define UW_FLAG_STAGED      0x10u /* run the four stages as separate kernels with densities materialised in
                                      HBM (per-stage profiling / debugging) instead of the fused single-pass
                                      kernel.  Results are identical.                                  */
+#define UW_FLAG_ORDERED     0x20u /* packed arenas in REQUEST order (decoupled look-back over per-chunk
+                                     aggregates; deterministic layout, chunk i+1 follows chunk i).  Default:
+                                     completion order (one atomic bump allocation per chunk, ~17 % faster,
+                                     no inter-CTA dependency).  Every chunk's OWN buffers are identical in
+                                     both modes; only vert_offset / index_offset differ.              */
 #define UW_FLAG_TRIS        0x8u  /* also emit the per-cell collision triangle lists (chunk.rs:167-174,
                                      245-250) -- SURVEY §8f-1                                       */
 

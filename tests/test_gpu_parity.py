@@ -36,6 +36,15 @@ def uw():
 
 @pytest.fixture(scope="module")
 def builder12(uw):
+    """Request-order packing (UW_FLAG_ORDERED): whole-batch arrays are deterministic."""
+    b = uw.ChunkBuilder(uw.Perlin(0), internal_size=12, ordered=True)
+    yield b
+    b.close()
+
+
+@pytest.fixture(scope="module")
+def builder12_fast(uw):
+    """The default configuration: fused kernel, completion-order packing."""
     b = uw.ChunkBuilder(uw.Perlin(0), internal_size=12)
     yield b
     b.close()
@@ -46,14 +55,15 @@ def _oracle_batch(o, perm, positions, mode=MODE_FAST, isos=None):
             for i, p in enumerate(positions)]
 
 
-def _check_batch(batch, refs, *, exact_positions, dens_pairs=None):
+def _check_batch(batch, refs, *, exact_positions, ordered=True):
     """Compare a GPU batch with per-chunk oracle results."""
     assert len(batch) == len(refs)
     vo = io = 0
     for i, r in enumerate(refs):
         m = batch.chunk(i)
         d = batch.descs[i]
-        assert int(d["vert_offset"]) == vo and int(d["index_offset"]) == io, f"packing chunk {i}"
+        if ordered:
+            assert int(d["vert_offset"]) == vo and int(d["index_offset"]) == io, f"packing chunk {i}"
         assert m.flags & 0x3 == r["flags"] & 0x3, f"flags chunk {i}: {m.flags} vs {r['flags']}"
         assert len(m.inds) == len(r["inds"]), f"index count chunk {i}"
         assert len(m.verts) == len(r["verts"]), f"vertex count chunk {i}"
@@ -158,7 +168,7 @@ def test_extraction_worst_case_random_fields(uw, builder12, oracle12):
 def test_full_build_exact_mode_matches_oracle_bitwise(uw, oracle12):
     pos = uw.region.box_region((-1, 2), (-2, 1), (-3, 2))
     perm = oracle12.perm_table(42)
-    with uw.ChunkBuilder(uw.Perlin(42), exact_f64=True) as b:
+    with uw.ChunkBuilder(uw.Perlin(42), exact_f64=True, ordered=True) as b:
         batch = b.build(pos)
     refs = _oracle_batch(oracle12, perm, pos, MODE_FAST)
     _check_batch(batch, refs, exact_positions=True)
@@ -173,7 +183,7 @@ def test_full_build_fast_path_topology_bit_exact(uw, oracle12, seed):
     (3) position error is small in bulk and bounded for ill-conditioned edges (|b - a| ~ guard band)."""
     pos = uw.region.box_region((-3, 3), (-3, 3), (-4, 3))
     perm = oracle12.perm_table(seed)
-    with uw.ChunkBuilder(uw.Perlin(seed)) as b:
+    with uw.ChunkBuilder(uw.Perlin(seed), ordered=True) as b:
         batch = b.build(pos)
         guards = b.guard_count()
         gdens = b.debug_densities(pos)
@@ -231,6 +241,26 @@ def test_fused_and_staged_pipelines_are_byte_identical(uw, builder12):
                 assert np.array_equal(got.descs, want.descs)
                 assert np.array_equal(got.inds, want.inds)
                 assert np.array_equal(got.verts.view(np.uint8), want.verts.view(np.uint8))
+
+
+def test_default_unordered_packing_is_a_valid_partition(uw, builder12, builder12_fast):
+    """Default mode (atomic bump allocation, completion order): every chunk's own vertex/index
+    buffers are byte-identical to the ordered mode; the chunks' ranges tile the arenas exactly."""
+    pos = uw.region.config_positions("spawn")
+    want = builder12.build(pos)
+    for _ in range(3):
+        got = builder12_fast.build(pos)
+        assert got.n_verts == want.n_verts and got.n_inds == want.n_inds
+        for f in ("pos", "flags", "vert_count", "index_count"):
+            assert np.array_equal(got.descs[f], want.descs[f])
+        for i in range(len(pos)):
+            a, b = got.chunk(i), want.chunk(i)
+            assert np.array_equal(a.inds, b.inds) and np.array_equal(a.verts.view(np.uint8), b.verts.view(np.uint8))
+        d = got.descs[got.descs["index_count"] > 0]
+        o = np.argsort(d["vert_offset"])
+        assert d["vert_offset"][o][0] == 0 and np.array_equal(d["vert_offset"][o][1:], np.cumsum(d["vert_count"][o])[:-1])
+        o = np.argsort(d["index_offset"])
+        assert d["index_offset"][o][0] == 0 and np.array_equal(d["index_offset"][o][1:], np.cumsum(d["index_count"][o])[:-1])
 
 
 def test_golden_reference_binary_chunks_s10(uw, golden_dir):
@@ -305,7 +335,7 @@ def test_edge_cases(uw, builder12, oracle12):
 def test_index32_and_async(uw, oracle12):
     pos = uw.region.box_region((0, 2), (0, 2), (-2, 0))
     perm = oracle12.perm_table(0)
-    with uw.ChunkBuilder(uw.Perlin(0), index32=True) as b:
+    with uw.ChunkBuilder(uw.Perlin(0), index32=True, ordered=True) as b:
         h = b.build_async(pos)
         batch = b.wait(h)
     assert batch.inds.dtype == np.uint32
@@ -334,7 +364,7 @@ def test_large_batch_properties(uw, builder12):
     lo = (d["pos"][vown] * 16).astype(np.float32)
     p = batch.verts["pos"]
     assert np.all(p >= lo - 1e-4) and np.all(p <= lo + 16.0 + 1e-4)
-    with uw.ChunkBuilder(uw.Perlin(0), exact_f64=True) as bx:
+    with uw.ChunkBuilder(uw.Perlin(0), exact_f64=True, ordered=True) as bx:
         exact = bx.build(pos)
     assert np.array_equal(exact.inds, batch.inds) and np.array_equal(exact.descs, batch.descs)
     np.testing.assert_allclose(batch.verts["pos"], exact.verts["pos"], rtol=0, atol=5e-2)

@@ -17,6 +17,7 @@ FLAG_INDEX32 = 0x2
 FLAG_KEEP_DENSITIES = 0x4
 FLAG_TRIS = 0x8
 FLAG_STAGED = 0x10
+FLAG_ORDERED = 0x20
 
 CHUNK_BLANK_EARLY = 0x1
 CHUNK_HAS_MESH = 0x2

@@ -1081,7 +1081,7 @@ struct ScanSlot { unsigned long long v, i; };     // bits 63..62: 0 = empty, 1 =
 #define SCAN_PFX  (2ull << 62)
 #define SCAN_VAL  ((1ull << 62) - 1ull)
 
-struct FusedCounters { uint32_t ticket, pad; };
+struct FusedCounters { uint32_t ticket, pad; unsigned long long alloc; };   // alloc = n_verts << 32 | n_inds
 
 template <int ST, int NOCT>
 struct FusedSmem {
@@ -1089,7 +1089,7 @@ struct FusedSmem {
     uint16_t alist[ST * ST * ST + 8];
     uint8_t cs[((ST * ST * ST + 15) / 16) * 16];
     uint32_t w[64];
-    unsigned long long off[2];
+    unsigned long long part[4 * 8];
     uint32_t chunk;
 };
 
@@ -1099,30 +1099,28 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
-// executed by one full warp; returns the exclusive prefix of (v, i) over chunks < c
-__device__ __forceinline__ void lookback_warp(ScanSlot* st, uint32_t c, unsigned long long& ev, unsigned long long& ei) {
-    const int lane = threadIdx.x & 31;
+// Executed by the WHOLE CTA (NT threads, NT a multiple of 32): every thread polls one predecessor,
+// so one round covers NT chunks.  Returns (in every thread) the exclusive prefix of (v, i) over
+// chunks < c.  s_part: 4 * (NT/32) u64 of shared scratch.
+__device__ __forceinline__ void lookback_block(ScanSlot* st, uint32_t c, unsigned long long& ev, unsigned long long& ei,
+                                               unsigned long long* s_part) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     unsigned long long sv = 0, si = 0;
     long long j = (long long)c - 1;
     while (true) {
-        const long long idx = j - lane;
-        unsigned long long a = SCAN_PFX, b = SCAN_PFX;        // virtual predecessor: prefix 0
+        const long long idx = j - tid;
+        unsigned long long a = SCAN_PFX, b = SCAN_PFX;        // virtual predecessor (idx < 0): prefix 0
         if (idx >= 0) {
-            do { a = ld_volatile_u64(&st[idx].v); } while ((a >> 62) == 0);
-            do { b = ld_volatile_u64(&st[idx].i); } while ((b >> 62) == 0);
-        }
-        // a slot may show (aggregate, prefix) mid-update: treat it as an aggregate only if BOTH are
-        // aggregates or both are prefixes; otherwise re-read until consistent
-        bool mixed = ((a >> 62) != (b >> 62));
-        while (__any_sync(0xFFFFFFFFu, mixed)) {
-            if (mixed) {
-                a = ld_volatile_u64(&st[idx].v); b = ld_volatile_u64(&st[idx].i);
-                mixed = ((a >> 62) != (b >> 62));
-            }
+            // value and status share one 64-bit word, so each word is self-consistent; a slot being
+            // upgraded from aggregate to prefix can show mixed tags for a moment: re-read until equal
+            do {
+                a = ld_volatile_u64(&st[idx].v);
+                b = ld_volatile_u64(&st[idx].i);
+            } while ((a >> 62) == 0 || (a >> 62) != (b >> 62));
         }
         const bool pfx = (a >> 62) == 2;
         const uint32_t ball = __ballot_sync(0xFFFFFFFFu, pfx);
-        const int first = ball ? (__ffs(ball) - 1) : 32;       // nearest predecessor holding a prefix
+        const int first = ball ? (__ffs(ball) - 1) : 32;       // nearest predecessor (in this warp) holding a prefix
         unsigned long long cv = lane <= first ? (a & SCAN_VAL) : 0ull;
         unsigned long long ci = lane <= first ? (b & SCAN_VAL) : 0ull;
 #pragma unroll
@@ -1130,9 +1128,16 @@ __device__ __forceinline__ void lookback_warp(ScanSlot* st, uint32_t c, unsigned
             cv += __shfl_xor_sync(0xFFFFFFFFu, cv, d);
             ci += __shfl_xor_sync(0xFFFFFFFFu, ci, d);
         }
-        sv += cv; si += ci;
-        if (ball) break;
-        j -= 32;
+        if (lane == 0) { s_part[warp * 4] = cv; s_part[warp * 4 + 1] = ci; s_part[warp * 4 + 2] = ball ? 1ull : 0ull; }
+        __syncthreads();
+        bool done = false;
+        for (int w = 0; w < nw && !done; ++w) {                // warps are ordered nearest-first
+            sv += s_part[w * 4]; si += s_part[w * 4 + 1];
+            done = s_part[w * 4 + 2] != 0ull;
+        }
+        __syncthreads();
+        if (done) break;
+        j -= blockDim.x;
     }
     ev = sv; ei = si;
 }
@@ -1147,7 +1152,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
               uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
               unsigned long long vcap, unsigned long long icap,
               float* __restrict__ dens_out /*nullable: debug tap*/,
-              unsigned long long* __restrict__ guard_count) {
+              unsigned long long* __restrict__ guard_count, int ordered) {
     using D = SpecDims<ST, NOCT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<ST, NOCT>& sm = *reinterpret_cast<FusedSmem<ST, NOCT>*>(smem_raw);
@@ -1193,44 +1198,51 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         if (fl & CF_ANY_LT) sh = emit_prepare<ST>(cfg, mc, es, sm.w);
         const uint32_t nv = sh.n_vert, ni = sh.n_ind;
 
-        // ---- K3: publish aggregate, look back for the exclusive prefix ---------------------------------
-        if (tid < 32) {
+        // ---- K3: this chunk's offsets in the packed arenas ------------------------------------------------
+        //  ordered  : decoupled look-back over per-chunk aggregates -> offsets follow request order
+        //             (deterministic layout; a chunk waits for the slowest of its in-flight predecessors)
+        //  unordered: one 64-bit atomic bump allocation -> no inter-CTA dependency; each chunk's OWN
+        //             buffers are identical either way, only their placement in the arena differs
+        unsigned long long ev = 0, ei = 0;
+        if (ordered) {
             if (tid == 0) {
                 const unsigned long long tag = chunk == 0 ? SCAN_PFX : SCAN_AGG;
                 atomicExch(&scan[chunk].v, tag | nv);
                 atomicExch(&scan[chunk].i, tag | ni);
             }
-            unsigned long long ev = 0, ei = 0;
-            if (chunk > 0) {
-                lookback_warp(scan, chunk, ev, ei);
-                if (tid == 0) {
-                    atomicExch(&scan[chunk].v, SCAN_PFX | (ev + nv));
-                    atomicExch(&scan[chunk].i, SCAN_PFX | (ei + ni));
-                }
+            if (chunk > 0) lookback_block(scan, chunk, ev, ei, sm.part);
+            if (tid == 0 && chunk > 0) {
+                atomicExch(&scan[chunk].v, SCAN_PFX | (ev + nv));
+                atomicExch(&scan[chunk].i, SCAN_PFX | (ei + ni));
             }
-            if (tid == 0) {
-                sm.off[0] = ev; sm.off[1] = ei;
-                uw_chunk_desc d;
-                d.pos[0] = px; d.pos[1] = py; d.pos[2] = pz;
-                d.flags = ((fl & CF_ALL_GT) ? UW_CHUNK_BLANK_EARLY : 0u) | (ni > 0 ? UW_CHUNK_HAS_MESH : 0u)
-                        | (nv > 65536u ? UW_CHUNK_U16_OVERFLOW : 0u);
-                d.vert_offset = (uint32_t)ev; d.vert_count = nv;
-                d.index_offset = (uint32_t)ei; d.index_count = ni;
-                descs[chunk] = d;
-                if (ni > 0) atomicAdd(&totals->n_active, 1u);
-                if (fl & CF_ALL_GT) atomicAdd(&totals->n_blank, 1u);
-                if (chunk == n - 1) {
-                    totals->n_verts = ev + nv; totals->n_inds = ei + ni;
-                    if (ev + nv > vcap || ei + ni > icap || ev + nv > 0xFFFFFFFFull || ei + ni > 0xFFFFFFFFull)
-                        totals->overflow = 1u;
-                }
+        } else {
+            if (ni > 0) {                                  // block-uniform
+                if (tid == 0) sm.part[0] = atomicAdd(&ctr->alloc, ((unsigned long long)nv << 32) | ni);
+                __syncthreads();
+                ev = sm.part[0] >> 32; ei = sm.part[0] & 0xFFFFFFFFull;
             }
         }
-        __syncthreads();
+        if (tid == 0) {
+            uw_chunk_desc d;
+            d.pos[0] = px; d.pos[1] = py; d.pos[2] = pz;
+            d.flags = ((fl & CF_ALL_GT) ? UW_CHUNK_BLANK_EARLY : 0u) | (ni > 0 ? UW_CHUNK_HAS_MESH : 0u)
+                    | (nv > 65536u ? UW_CHUNK_U16_OVERFLOW : 0u);
+            d.vert_offset = (uint32_t)ev; d.vert_count = nv;
+            d.index_offset = (uint32_t)ei; d.index_count = ni;
+            descs[chunk] = d;
+            if (ni > 0) atomicAdd(&totals->n_active, 1u);
+            if (fl & CF_ALL_GT) atomicAdd(&totals->n_blank, 1u);
+            if (ordered && chunk == n - 1) {
+                totals->n_verts = ev + nv; totals->n_inds = ei + ni;
+                if (ev + nv > vcap || ei + ni > icap || ev + nv > 0xFFFFFFFFull || ei + ni > 0xFFFFFFFFull)
+                    totals->overflow = 1u;
+            }
+            if (!ordered && ni > 0 && (ev + nv > vcap || ei + ni > icap)) totals->overflow = 1u;
+        }
 
         // ---- K4 ---------------------------------------------------------------------------------
         if (ni > 0) {                                      // block-uniform
-            const unsigned long long ov = sm.off[0], oi = sm.off[1];
+            const unsigned long long ov = ev, oi = ei;
             if (ov + nv <= vcap && oi + ni <= icap)
                 emit_write<ST, IndexT>(cfg, mc, es, sh, px, py, pz, verts + ov, inds + oi);
         }

@@ -49,6 +49,7 @@ struct uw_ctx {
     int32_t* h_pos = nullptr; size_t h_pos_cap = 0;
     BatchTotals* h_totals = nullptr;
     unsigned long long* h_guard = nullptr;
+    unsigned long long* h_alloc = nullptr;
     std::vector<PinnedBlock> pool;
 
     // launch geometry / kernel selection
@@ -57,13 +58,14 @@ struct uw_ctx {
     typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*);
     typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedCounters*, uw_chunk_desc*, BatchTotals*, uw_vert*, uint16_t*, unsigned long long,
-                                 unsigned long long, float*, unsigned long long*);
+                                 unsigned long long, float*, unsigned long long*, int);
     typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedCounters*, uw_chunk_desc*, BatchTotals*, uw_vert*, uint32_t*, unsigned long long,
-                                 unsigned long long, float*, unsigned long long*);
+                                 unsigned long long, float*, unsigned long long*, int);
     fused16_fn_t fused16_fn = nullptr;
     fused32_fn_t fused32_fn = nullptr;
     bool use_fused = false;
+    bool ordered = false;           // packed arenas follow request order (look-back) vs atomic bump allocation
     size_t fused_smem = 0; int fused_blocks_per_sm = 1;
     ScanSlot* d_scan = nullptr;
     FusedCounters* d_ctr = nullptr;
@@ -219,6 +221,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (c->h_pos) cudaFreeHost(c->h_pos);
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_guard) cudaFreeHost(c->h_guard);
+    if (c->h_alloc) cudaFreeHost(c->h_alloc);
     for (auto& b : c->pool) cudaFreeHost(b.ptr);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -289,6 +292,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     if (!cu(cudaMemset(c->d_guard, 0, sizeof(unsigned long long)), "memset guard")) return bail(UW_ERR_CUDA);
     if (!cu(cudaHostAlloc(&c->h_totals, sizeof(BatchTotals), cudaHostAllocDefault), "cudaHostAlloc totals")) return bail(UW_ERR_OOM);
     if (!cu(cudaHostAlloc(&c->h_guard, sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc guard")) return bail(UW_ERR_OOM);
+    if (!cu(cudaHostAlloc(&c->h_alloc, sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc alloc")) return bail(UW_ERR_OOM);
     for (auto& ev : c->ev) if (!cu(cudaEventCreate(&ev), "cudaEventCreate")) return bail(UW_ERR_CUDA);
 
     // launch geometry / kernel selection
@@ -323,6 +327,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
             c->fused_smem = sizeof(FusedSmem<10, 3>);
         }
         c->use_fused = c->spec_noise && !(cfg->flags & UW_FLAG_STAGED);
+        c->ordered = (cfg->flags & UW_FLAG_ORDERED) != 0;
         c->emit_smem = emit_smem_bytes(d);
         if (d.S == 12)      { c->emit16_fn = k_emit_small<12, uint16_t>; c->emit32_fn = k_emit_small<12, uint32_t>; }
         else if (d.S == 10) { c->emit16_fn = k_emit_small<10, uint16_t>; c->emit32_fn = k_emit_small<10, uint32_t>; }
@@ -488,10 +493,10 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     const int grid = persistent_grid(c, n, c->fused_blocks_per_sm);
     if (c->index32)
         c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, c->d_ctr,
-            c->d_descs, c->d_totals, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->d_guard);
+            c->d_descs, c->d_totals, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->d_guard, c->ordered ? 1 : 0);
     else
         c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, c->d_ctr,
-            c->d_descs, c->d_totals, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->d_guard);
+            c->d_descs, c->d_totals, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->d_guard, c->ordered ? 1 : 0);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;
@@ -541,7 +546,13 @@ static uw_status finish_build(uw_ctx* c) {
     for (int attempt = 0; attempt < 3; ++attempt) {
         CU_TRY(c, cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(BatchTotals), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        if (c->last_fused && !c->ordered)
+            CU_TRY(c, cudaMemcpyAsync(c->h_alloc, &c->d_ctr->alloc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->last_fused && !c->ordered) {
+            c->h_totals->n_verts = *c->h_alloc >> 32; c->h_totals->n_inds = *c->h_alloc & 0xFFFFFFFFull;
+            if (c->h_totals->n_verts > c->vcap || c->h_totals->n_inds > c->icap) c->h_totals->overflow = 1;
+        }
         if (!c->h_totals->overflow) break;
         if (c->h_totals->n_verts > 0xFFFFFFFFull || c->h_totals->n_inds > 0xFFFFFFFFull)
             return fail(c, UW_ERR_INVALID, "batch too large: packed vertex/index offsets exceed 32 bits; split the batch");

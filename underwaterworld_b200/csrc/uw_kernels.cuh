@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "mc_tables.h"
 #include "../../include/uwcuda.h"
 
@@ -48,6 +49,7 @@ struct McTables {
     uint16_t crossed[256];     // edges present in the row
     uint16_t before[256][12];  // edges first-appearing before edge e in the row
     uint8_t  ninds[256];       // indices per case
+    uint32_t lut[256];         // by "natural" corner pattern (natural_of): case | ninds << 8 | crossed << 12
 };
 
 __device__ __constant__ uint8_t c_edge_a[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3};
@@ -412,6 +414,11 @@ struct SpecSmem {
     using D = SpecDims<ST, NOCT>;
     float4 lat[D::LAT];
     float4 X[D::XN];
+    // lat + X (+ this pad) are dead after the noise stages; the fused kernel reuses the region for the
+    // vertex-id table of K4 (L^3 * 5 u16)
+    static constexpr int VID_BYTES = D::L * D::L * D::L * 5 * 2;
+    static constexpr int PAD = VID_BYTES > (D::LAT + D::XN) * 16 ? ((VID_BYTES - (D::LAT + D::XN) * 16 + 15) / 16) * 16 : 16;
+    unsigned char xpad[PAD];
     float dens[D::DSTRIDE];
     float4 grad[16];
     float4 axis[NOCT][D::L + 1];   // (d, d - 1, fade(d), -) per octave and lattice index
@@ -876,131 +883,164 @@ __device__ __forceinline__ void owner_of(int e, int x, int y, int z, int& ox, in
 }
 
 // ---------------------------------------------------------------------------------------
-// K4: emit.  One CTA per ACTIVE chunk (index_count > 0), work compacted by prefix scans:
-//   A  densities -> smem, sign ballots -> per-column masks
-//   B  cases + per-column (vertex, index, surface-cell) counts, block scan in scan order
-//   C  per-cell (vbase, ibase) and the compact list of surface cells
-//   D  compact list of owned edge vertices (slot = vbase + first-appearance rank), then ONE
-//      THREAD PER VERTEX: edge lerp + colour, consecutive threads write consecutive vertices
-//   E  one thread per surface cell: index = vbase[owner cell] + rank(owner edge)
+// K2..K4 on one chunk whose densities and column sign masks sit in shared memory.
+//   prepare  B  per cell column (x,y): "natural" 8-bit corner pattern from the 4 column masks ->
+//               one LUT load gives (case, index count, crossed-edge mask); block scan in scan order
+//            C  surface cells only: per-cell vertex base / index base + compact surface-cell list
+//   write    D1 one thread per surface cell walks its row once: owned edges, in first-appearance
+//               order, get vertex ids vbase+0,1,..; ids go into vid[(corner_a, direction)] (the
+//               ORDERED lattice pair, i.e. the reference's dedup key chunk.rs:233) and the compact
+//               vertex list
+//            D2 one thread per vertex: edge lerp + colour, consecutive vertices by consecutive threads
+//            E  one thread per surface cell: index = vid[(corner_a, direction) of the slot's edge]
 // ---------------------------------------------------------------------------------------
 #define UW_SMALL_MAX_CELLS ((UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1))
 #define UW_VLIST_CAP 4096
+#define UW_EDGE_KINDS 5      // +x, -x, +y, +z, -z  (-y never occurs: edges 8..11 all run +y)
 
 struct EmitSmem {
     float* dens; uint32_t* bits; uint32_t* mask; uint16_t* vbase; uint16_t* ibase; uint16_t* alist;
-    uint16_t* vlist; uint8_t* cs;
+    uint16_t* vlist; uint16_t* vid; uint8_t* cs; uint32_t* lut; uint16_t* eoff;
 };
 
+// per edge: (corner_a lattice offset) * 5 + direction kind, for lattice size L
+__device__ __forceinline__ void fill_edge_offsets(uint16_t* eoff, int L) {
+    const int e = threadIdx.x;
+    if (e < 12) {
+        int ax, ay, az, bx, by, bz;
+        corner_off(c_edge_a[e], ax, ay, az); corner_off(c_edge_b[e], bx, by, bz);
+        const int kind = bx > ax ? 0 : bx < ax ? 1 : by > ay ? 2 : bz > az ? 3 : 4;
+        eoff[e] = (uint16_t)(((ax * L + ay) * L + az) * UW_EDGE_KINDS + kind);
+    }
+}
+
 __host__ __device__ inline size_t emit_smem_bytes(const DevCfg& cfg) {
-    const size_t cells = (size_t)cfg.S * cfg.S * cfg.S;
+    const size_t cells = (size_t)cfg.S * cfg.S * cfg.S, cells2 = (cells + 7) & ~(size_t)7;
     size_t b = (size_t)cfg.dens_stride * 4;
     b += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
-    b += (size_t)cfg.L2 * 4;
-    b += ((cells + 1) & ~(size_t)1) * 2 * 3;
+    b += ((size_t)cfg.L2 + 3) / 4 * 16;
+    b += cells2 * 2 * 3;
     b += UW_VLIST_CAP * 2;
+    b += (((size_t)cfg.L3 * UW_EDGE_KINDS + 7) & ~(size_t)7) * 2;
+    b += 256 * 4 + 16 * 2;
     b += (cells + 15) & ~(size_t)15;
     return b;
 }
 
 __device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned char* base) {
-    const size_t cells = (size_t)cfg.S * cfg.S * cfg.S, cells2 = (cells + 1) & ~(size_t)1;
+    const size_t cells = (size_t)cfg.S * cfg.S * cfg.S, cells2 = (cells + 7) & ~(size_t)7;
     EmitSmem s;
     s.dens = (float*)base;        base += (size_t)cfg.dens_stride * 4;
     s.bits = (uint32_t*)base;     base += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
-    s.mask = (uint32_t*)base;     base += (size_t)cfg.L2 * 4;
+    s.mask = (uint32_t*)base;     base += ((size_t)cfg.L2 + 3) / 4 * 16;
     s.vbase = (uint16_t*)base;    base += cells2 * 2;
     s.ibase = (uint16_t*)base;    base += cells2 * 2;
     s.alist = (uint16_t*)base;    base += cells2 * 2;
     s.vlist = (uint16_t*)base;    base += UW_VLIST_CAP * 2;
+    s.vid = (uint16_t*)base;      base += (((size_t)cfg.L3 * UW_EDGE_KINDS + 7) & ~(size_t)7) * 2;
+    s.lut = (uint32_t*)base;      base += 256 * 4;
+    s.eoff = (uint16_t*)base;     base += 16 * 2;
     s.cs = (uint8_t*)base;
     return s;
 }
 
-// Phases B..E on a chunk whose densities (s.dens) and column masks (s.mask) are in shared memory.
-// All threads of the CTA must call.  ST > 0 = compile-time S.
 struct ChunkShape { uint32_t n_vert, n_ind, n_act; };
 
-// phases B + C: cases, counts, per-cell bases and the surface-cell list.  Ends with a barrier.
+// 8-bit corner pattern of cell z of a column: bits (m00 z, m00 z+1, m10 z, m10 z+1, m01 z, m01 z+1, m11 z, m11 z+1)
+__device__ __forceinline__ uint32_t natural_of(uint32_t q0 /*m00 | m10<<16*/, uint32_t q1 /*m01 | m11<<16*/, int z) {
+    const uint32_t a = (q0 >> z) & 0x00030003u, b = (q1 >> z) & 0x00030003u;
+    return ((a | (a >> 14)) & 0xFu) | (((b | (b >> 14)) & 0xFu) << 4);
+}
+
 template <int ST>
-__device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const McTables* __restrict__ mc,
-                                                   const EmitSmem& s, uint32_t* s_w) {
+__device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const EmitSmem& s, uint32_t* s_w) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int S = ST > 0 ? ST : cfg.S, L = S + 1, ncol = S * S;
 
-    // ---- B: cases + counts per cell column (x,y); z inner == reference scan order ------------
-    uint32_t nva = 0, ni = 0;                         // nva = n_verts | n_surface_cells << 16
-    for (int col = tid; col < ncol; col += NT) {      // single trip (NT >= S*S on this path)
-        const int x = col / S, y = col - x * S;
-        const uint32_t m00 = s.mask[x * L + y], m10 = s.mask[(x + 1) * L + y];
-        const uint32_t m01 = s.mask[x * L + y + 1], m11 = s.mask[(x + 1) * L + y + 1];
-        const uint32_t any = m00 | m10 | m01 | m11, all = m00 & m10 & m01 & m11;
-        if (any == 0u || all == ((1u << L) - 1u)) {
-            const uint8_t fill = any ? 255 : 0;
+    // ---- B -----------------------------------------------------------------------------------------
+    uint32_t nva = 0, ni = 0, smask = 0, own0 = 0, ownn = 0, q0 = 0, q1 = 0;
+    const int col = tid;                                 // one column per thread (NT >= S*S on this path)
+    const int x = col / S, y = col - x * S;
+    if (col < ncol) {
+        q0 = s.mask[x * L + y] | (s.mask[(x + 1) * L + y] << 16);
+        q1 = s.mask[x * L + y + 1] | (s.mask[(x + 1) * L + y + 1] << 16);
+        const uint32_t any = q0 | q1, all = q0 & q1, full = (1u << L) - 1u;
+        const bool col_empty = any == 0u, col_full = (all & (all >> 16) & full) == full;
+        ownn = 0x4F0u | (y == 0 ? 0x00Fu : 0u) | (x == 0 ? 0x800u : 0u);      // SURVEY App. B.4 ownership, z > 0
+        own0 = ownn | 0x200u | (x == 0 ? 0x100u : 0u);                          // z == 0 also owns 9 (and 8 if x == 0)
+        if (col_empty || col_full) {
+            const uint8_t fill = col_full ? 255 : 0;
+#pragma unroll 4
             for (int z = 0; z < S; ++z) s.cs[col * S + z] = fill;
         } else {
+#pragma unroll 4
             for (int z = 0; z < S; ++z) {
-                const uint32_t c = case_of(m00, m10, m01, m11, z);
-                s.cs[col * S + z] = (uint8_t)c;
-                if (c != 0u && c != 255u) {
-                    ni += mc->ninds[c];
-                    nva += __popc((uint32_t)mc->crossed[c] & own_mask_of(x, y, z)) + 0x10000u;
+                const uint32_t t = s.lut[natural_of(q0, q1, z)];            // case | ninds << 8 | crossed << 12
+                s.cs[col * S + z] = (uint8_t)t;
+                if (t >> 8) {
+                    ni += (t >> 8) & 15u;
+                    nva += __popc((t >> 12) & (z == 0 ? own0 : ownn)) + 0x10000u;
+                    smask |= 1u << z;
                 }
             }
         }
     }
     uint32_t eva, ei, tva, ti;
     block_scan2(nva, ni, eva, ei, tva, ti, s_w);
-    const uint32_t n_act = tva >> 16, n_vert = tva & 0xFFFFu;
 
-    // ---- C: per-cell bases + compact surface-cell list -----------------------------------------
-    for (int col = tid; col < ncol; col += NT) {
-        const int x = col / S, y = col - x * S;
-        uint32_t rv = eva & 0xFFFFu, ra = eva >> 16, ri = ei;
-        for (int z = 0; z < S; ++z) {
-            const int cell = col * S + z;
-            const uint32_t c = s.cs[cell];
-            s.vbase[cell] = (uint16_t)rv; s.ibase[cell] = (uint16_t)ri;
-            if (c != 0u && c != 255u) {
-                s.alist[ra++] = (uint16_t)cell;
-                ri += mc->ninds[c];
-                rv += __popc((uint32_t)mc->crossed[c] & own_mask_of(x, y, z));
-            }
-        }
+    // ---- C: surface cells only ------------------------------------------------------------------------
+    uint32_t rv = eva & 0xFFFFu, ra = eva >> 16, ri = ei;
+    while (smask) {
+        const int z = __ffs(smask) - 1;
+        smask &= smask - 1;
+        const int cell = col * S + z;
+        const uint32_t t = s.lut[natural_of(q0, q1, z)];
+        s.vbase[cell] = (uint16_t)rv; s.ibase[cell] = (uint16_t)ri;
+        s.alist[ra++] = (uint16_t)cell;
+        ri += (t >> 8) & 15u;
+        rv += __popc((t >> 12) & (z == 0 ? own0 : ownn));
     }
     __syncthreads();
     ChunkShape sh;
-    sh.n_vert = n_vert; sh.n_ind = ti; sh.n_act = n_act;
+    sh.n_vert = tva & 0xFFFFu; sh.n_ind = ti; sh.n_act = tva >> 16;
     return sh;
 }
 
-// phases D + E: write the chunk's vertices and indices.  Needs emit_prepare's shared-memory state.
 template <int ST, typename IndexT>
 __device__ __forceinline__ void emit_write(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
                                            const ChunkShape sh, int px, int py, int pz,
                                            uw_vert* __restrict__ vout, IndexT* __restrict__ iout) {
     const int tid = threadIdx.x, NT = blockDim.x;
-    const int S = ST > 0 ? ST : cfg.S;
+    const int S = ST > 0 ? ST : cfg.S, L = S + 1;
     const uint32_t n_vert = sh.n_vert, n_act = sh.n_act;
     const int offx = px * cfg.chunk_size, offy = py * cfg.chunk_size, offz = pz * cfg.chunk_size;
 
-    // ---- D: vertices, in tiles of UW_VLIST_CAP ---------------------------------------------------
     for (uint32_t v0 = 0; v0 < n_vert; v0 += UW_VLIST_CAP) {
+        // ---- D1: vertex ids (first pass only) + the compact vertex list of this tile ----------------
         for (uint32_t a = tid; a < n_act; a += NT) {
             const int cell = s.alist[a];
-            const uint32_t c = s.cs[cell];
             const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
-            const uint32_t own = own_mask_of(x, y, z);
-            uint32_t m = (uint32_t)mc->crossed[c] & own;
-            const uint32_t vb = s.vbase[cell];
-            while (m) {
-                const int e = __ffs(m) - 1;
-                m &= m - 1;
-                const uint32_t slot = vb + __popc((uint32_t)mc->before[c][e] & own) - v0;
-                if (slot < UW_VLIST_CAP) s.vlist[slot] = (uint16_t)(cell | (e << 12));
+            const uint32_t own = 0x4F0u | (y == 0 ? 0x00Fu : 0u) | (x == 0 ? 0x800u : 0u)
+                               | (z == 0 ? (0x200u | (x == 0 ? 0x100u : 0u)) : 0u);
+            const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
+            const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
+            const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
+            uint32_t vnext = s.vbase[cell], todo = own;     // owned edges not yet numbered
+#pragma unroll
+            for (int k = 0; k < 15; ++k) {
+                const uint32_t e = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
+                if (e == 15u) break;
+                if ((todo >> e) & 1u) {
+                    todo &= ~(1u << e);
+                    if (v0 == 0) s.vid[lbase + s.eoff[e]] = (uint16_t)vnext;
+                    const uint32_t slot = vnext - v0;
+                    if (slot < UW_VLIST_CAP) s.vlist[slot] = (uint16_t)(cell | (e << 12));
+                    ++vnext;
+                }
             }
         }
         __syncthreads();
+        // ---- D2: one thread per vertex ------------------------------------------------------------------
         const uint32_t cnt = min((uint32_t)UW_VLIST_CAP, n_vert - v0);
         for (uint32_t t = tid; t < cnt; t += NT) {
             const uint32_t ent = s.vlist[t];
@@ -1014,22 +1054,19 @@ __device__ __forceinline__ void emit_write(const DevCfg& cfg, const McTables* __
         if (v0 + UW_VLIST_CAP < n_vert) __syncthreads();
     }
 
-    // ---- E: indices, one thread per surface cell -------------------------------------------------
+    // ---- E: indices; every slot is one table lookup keyed by the ordered lattice pair ---------------------
     for (uint32_t a = tid; a < n_act; a += NT) {
         const int cell = s.alist[a];
-        const uint32_t c = s.cs[cell];
         const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
-        const uint64_t row = mc->rows[c];
+        const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
+        const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
+        const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
         IndexT* dst = iout + s.ibase[cell];
-        const int nidx = mc->ninds[c];
-#pragma unroll 1
-        for (int k = 0; k < nidx; ++k) {
-            const int e = (int)((row >> (4 * k)) & 0xFull);
-            int ox, oy, oz, oe;
-            owner_of(e, x, y, z, ox, oy, oz, oe);
-            const int ocell = (ox * S + oy) * S + oz;
-            const uint32_t rank = __popc((uint32_t)mc->before[s.cs[ocell]][oe] & own_mask_of(ox, oy, oz));
-            dst[k] = (IndexT)((uint32_t)s.vbase[ocell] + rank);          // `ind as u16`, chunk.rs:243
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+            const uint32_t e = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
+            if (e == 15u) break;
+            dst[k] = (IndexT)s.vid[lbase + s.eoff[e]];                 // `ind as u16`, chunk.rs:243
         }
     }
 }
@@ -1050,6 +1087,8 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
     const int L = (ST > 0 ? ST : cfg.S) + 1;
     const uint32_t n_active = totals->n_active;
     if (totals->overflow) return;                       // host grows the arenas and relaunches
+    for (int t = tid; t < 256; t += NT) s.lut[t] = mc->lut[t];
+    fill_edge_offsets(s.eoff, L);
 
     for (uint32_t a = blockIdx.x; a < n_active; a += gridDim.x) {
         const uint32_t chunk = active[a];
@@ -1057,7 +1096,7 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
         load_signs<true>(cfg, dens + (size_t)chunk * cfg.dens_stride, s.dens, s.bits, s_red);
         for (int c = tid; c < L * L; c += NT) s.mask[c] = col_mask(s.bits, c, L);
         __syncthreads();
-        const ChunkShape sh = emit_prepare<ST>(cfg, mc, s, s_w);
+        const ChunkShape sh = emit_prepare<ST>(cfg, s, s_w);
         emit_write<ST, IndexT>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
         __syncthreads();
     }
@@ -1085,8 +1124,13 @@ struct FusedCounters { uint32_t ticket, pad; unsigned long long alloc; };   // a
 
 template <int ST, int NOCT>
 struct FusedSmem {
-    SpecSmem<ST, NOCT> n;                             // n.lat / n.X are dead after K1 and reused by K4
+    SpecSmem<ST, NOCT> n;                             // n.lat / n.X are dead after K1 and reused by K4 (vid)
+    uint16_t vlist[UW_VLIST_CAP];
+    uint16_t vbase[ST * ST * ST + 8];
+    uint16_t ibase[ST * ST * ST + 8];
     uint16_t alist[ST * ST * ST + 8];
+    uint32_t lut[256];
+    uint16_t eoff[16];
     uint8_t cs[((ST * ST * ST + 15) / 16) * 16];
     uint32_t w[64];
     unsigned long long part[4 * 8];
@@ -1157,7 +1201,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<ST, NOCT>& sm = *reinterpret_cast<FusedSmem<ST, NOCT>*>(smem_raw);
     const int tid = threadIdx.x;
-    constexpr int L = D::L, CELLS = ST * ST * ST;
+    constexpr int L = D::L;
 
     for (int t = tid; t < 256; t += D::NT) sm.n.perm[t] = g_perm[t];
     if (tid < 16) sm.n.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
@@ -1166,15 +1210,20 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         sm.n.axis[o][i] = make_float4(tab.d[o][i], tab.d1[o][i], tab.w[o][i], 0.f);
     }
 
-    // K4 scratch aliases the K1 tables (dead once noise_chunk_spec has returned)
+    for (int t = tid; t < 256; t += D::NT) sm.lut[t] = mc->lut[t];
+    fill_edge_offsets(sm.eoff, L);
+
+    // the vertex-id table of K4 aliases the K1 lattice/X tables (dead once noise_chunk_spec has returned;
+    // lat and X are adjacent members of SpecSmem)
     EmitSmem es;
     es.dens = sm.n.dens; es.bits = nullptr; es.mask = sm.n.mask;
-    es.vlist = reinterpret_cast<uint16_t*>(sm.n.X);
-    es.vbase = es.vlist + UW_VLIST_CAP;
-    es.ibase = reinterpret_cast<uint16_t*>(sm.n.lat);
-    es.alist = sm.alist; es.cs = sm.cs;
-    static_assert(sizeof(sm.n.X) >= (UW_VLIST_CAP + CELLS) * 2, "vlist + vbase must fit in the X table");
-    static_assert(sizeof(sm.n.lat) >= CELLS * 2, "ibase must fit in the lattice table");
+    es.vid = reinterpret_cast<uint16_t*>(sm.n.lat);
+    es.vlist = sm.vlist; es.vbase = sm.vbase; es.ibase = sm.ibase; es.alist = sm.alist;
+    es.cs = sm.cs; es.lut = sm.lut; es.eoff = sm.eoff;
+    using NS = SpecSmem<ST, NOCT>;
+    static_assert(offsetof(NS, X) == offsetof(NS, lat) + sizeof(sm.n.lat), "lat and X must be adjacent");
+    static_assert(offsetof(NS, xpad) == offsetof(NS, X) + sizeof(sm.n.X), "X and xpad must be adjacent");
+    static_assert(sizeof(sm.n.lat) + sizeof(sm.n.X) + sizeof(sm.n.xpad) >= (size_t)L * L * L * UW_EDGE_KINDS * 2, "vid must fit");
 
     while (true) {
         __syncthreads();                                   // previous chunk fully emitted; smem reusable
@@ -1195,7 +1244,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         // ---- K2: cases, counts, per-cell bases (block-uniform skip when no sample is inside) -------------
         ChunkShape sh;
         sh.n_vert = 0; sh.n_ind = 0; sh.n_act = 0;
-        if (fl & CF_ANY_LT) sh = emit_prepare<ST>(cfg, mc, es, sm.w);
+        if (fl & CF_ANY_LT) sh = emit_prepare<ST>(cfg, es, sm.w);
         const uint32_t nv = sh.n_vert, ni = sh.n_ind;
 
         // ---- K3: this chunk's offsets in the packed arenas ------------------------------------------------

@@ -282,6 +282,14 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         McTables* h = new McTables();
         memcpy(h->rows, rows, sizeof rows); memcpy(h->ninds, ninds, sizeof ninds);
         memcpy(h->crossed, crossed, sizeof crossed); memcpy(h->before, before, sizeof before);
+        for (int nat = 0; nat < 256; ++nat) {
+            // natural pattern bits (m00 z, m00 z+1, m10 z, m10 z+1, m01 z, m01 z+1, m11 z, m11 z+1) are the
+            // corners (0, 3, 1, 2, 4, 7, 5, 6) of chunk.rs:144-153
+            static const int corner_of_bit[8] = {0, 3, 1, 2, 4, 7, 5, 6};
+            unsigned cs = 0;
+            for (int b = 0; b < 8; ++b) if ((nat >> b) & 1) cs |= 1u << corner_of_bit[b];
+            h->lut[nat] = cs | ((uint32_t)ninds[cs] << 8) | ((uint32_t)crossed[cs] << 12);
+        }
         bool ok = cu(cudaMalloc(&c->d_mc, sizeof(McTables)), "cudaMalloc mc") &&
                   cu(cudaMemcpy(c->d_mc, h, sizeof(McTables), cudaMemcpyHostToDevice), "memcpy mc");
         delete h;

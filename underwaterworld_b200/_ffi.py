@@ -87,11 +87,12 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("UWCUDA_LIB", LIB_PATH)      # override only for A/B experiments of kernel variants
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m underwaterworld_b200.build` "
+            f"{path} is missing: build it with `python -m underwaterworld_b200.build` "
             "(or __graft_entry__.build()).  There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, u32, i32p = C.c_void_p, C.c_uint32, C.c_void_p
     lib.uw_abi_version.restype = C.c_uint32
     lib.uw_config_default.argtypes = [C.POINTER(UwConfig)]

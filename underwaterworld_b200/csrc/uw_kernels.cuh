@@ -13,6 +13,19 @@
 #include "mc_tables.h"
 #include "../../include/uwcuda.h"
 
+#ifdef UW_PHASE_TIMING
+__device__ unsigned long long g_phase[16];
+__device__ unsigned long long g_cta[1024][4];     // per CTA: globaltimer start, end, chunks, heavy chunks
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PHASE_MARK(idx) do { if (threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(&g_phase[idx], (unsigned long long)(now_ - t_phase)); t_phase = now_; } } while (0)
+#define PHASE_ARG , long long& t_phase
+#define PHASE_PASS , t_phase
+#else
+#define PHASE_MARK(idx) do { } while (0)
+#define PHASE_ARG
+#define PHASE_PASS
+#endif
+
 #define UW_MAX_OCT 4
 #define UW_SMALL_MAX_L 16        // small path: whole chunk per CTA, L = S+1 <= 16
 #define UW_AXIS_PAD 20
@@ -28,6 +41,9 @@ struct DevCfg {
     float hsv_c[3], hsv_m[3];          // c = value*saturation, m = value - c per value level (util.rs:129,132)
     float srgb_hi[3], srgb_lo[3];      // to_srgb((c+m)*255), to_srgb((0+m)*255) per value level (host powf)
     uint32_t dens_stride;              // floats per chunk in the density array (multiple of 4)
+    int cs_pow2, mod_pow2;             // chunk_size / adj_z_mod are powers of two: exact reciprocal multiplies
+    double inv_chunk_size;             // 1 / chunk_size (exact when cs_pow2)
+    float inv_adj_z_mod;               // 1 / adj_z_mod  (exact when mod_pow2)
     int G[UW_MAX_OCT];                 // lattice points per axis per octave = 2^o + 2
     int lat_base[UW_MAX_OCT + 1];      // prefix of G^3
     int x_base[UW_MAX_OCT + 1];        // prefix of L*G^2
@@ -144,6 +160,19 @@ __device__ __forceinline__ float x_iso_at(const DevCfg& cfg, const uint8_t* perm
     const float p = __double2float_rn(__ddiv_rn(total, maxv));
     const float adj_z = __fdiv_rn(__fmul_rn(__double2float_rn(z), (float)cfg.chunk_size), cfg.max_height);
     return __fsub_rn(__fadd_rn(adj_z, p), fmodf(adj_z, cfg.adj_z_mod));
+}
+
+// perlin_util.rs:27-28: adj_z and adj_z % ADJ_Z_MOD for lattice index k of a chunk at pz.  Bit-identical
+// to the reference's f64 coordinate -> f32 arithmetic; power-of-two divisors use exact reciprocal
+// multiplies (x / 2^n == x * 2^-n, fmod(a, 2^n) == a - 2^n * trunc(a * 2^-n) while |a * 2^-n| < 2^22).
+__device__ __forceinline__ void terrace_terms(const DevCfg& cfg, int k, int pz, float& adj, float& fm) {
+    const double local = __dmul_rn((double)k, (double)cfg.size_scale);
+    const double sum = __dadd_rn(local, (double)(pz * cfg.chunk_size));
+    const double zc = cfg.cs_pow2 ? __dmul_rn(sum, cfg.inv_chunk_size) : __ddiv_rn(sum, (double)cfg.chunk_size);
+    const float zf = __double2float_rn(zc);
+    adj = __fdiv_rn(__fmul_rn(zf, (float)cfg.chunk_size), cfg.max_height);
+    const float q = __fmul_rn(adj, cfg.inv_adj_z_mod);
+    fm = (cfg.mod_pow2 && fabsf(q) < 4194304.0f) ? __fsub_rn(adj, __fmul_rn(cfg.adj_z_mod, truncf(q))) : fmodf(adj, cfg.adj_z_mod);
 }
 
 // chunk.rs:107-116: lattice index -> f64 sample coordinate
@@ -277,10 +306,10 @@ __global__ void __launch_bounds__(256) k_noise_small(const __grid_constant__ Dev
         }
         // terrace term, perlin_util.rs:27-28: exact (f64 coordinate -> f32), per (chunk, k)
         if (tid < L) {
-            const float zf = __double2float_rn(x_coord(cfg, tid, pz));
-            const float adj = __fdiv_rn(__fmul_rn(zf, (float)cfg.chunk_size), cfg.max_height);
+            float adj, fm;
+            terrace_terms(cfg, tid, pz, adj, fm);
             s.adjz[tid] = adj;
-            s.fm[tid] = fmodf(adj, cfg.adj_z_mod);
+            s.fm[tid] = fm;
         }
         __syncthreads();
 
@@ -432,7 +461,7 @@ struct SpecSmem {
 // Returns (block-uniform) CF_ALL_GT | CF_ANY_LT.  All threads must call; ends with a barrier.
 template <int ST, int NOCT>
 __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const AxisTables& tab, SpecSmem<ST, NOCT>& sm,
-                                                     int px, int py, int pz, unsigned long long* guard_count) {
+                                                     int px, int py, int pz, unsigned long long* guard_count PHASE_ARG) {
     using D = SpecDims<ST, NOCT>;
     constexpr int L = D::L;
     const int tid = threadIdx.x;
@@ -448,13 +477,14 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             sm.lat[base + t] = sm.grad[h & 15u];
         }
     }
-    if (tid < L) {   // terrace term perlin_util.rs:27-28 from the exact f64 coordinate
-        const float zf = __double2float_rn(x_coord(cfg, tid, pz));
-        const float adj = __fdiv_rn(__fmul_rn(zf, (float)cfg.chunk_size), cfg.max_height);
-        sm.terr[tid] = __fsub_rn(adj, fmodf(adj, cfg.adj_z_mod));
+    if (tid >= NT - 32 && tid - (NT - 32) < L) {   // terrace term perlin_util.rs:27-28 (last warp: it has idle lanes later)
+        float adj, fm;
+        terrace_terms(cfg, tid - (NT - 32), pz, adj, fm);
+        sm.terr[tid - (NT - 32)] = __fsub_rn(adj, fm);
     }
     if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; }
     __syncthreads();
+    PHASE_MARK(11);
 
     // ---- stage X --------------------------------------------------------------------------------
     constexpr float inv_max = 1.0f / (2.0f - 1.0f / (float)(1 << (NOCT - 1)));
@@ -479,6 +509,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         }
     }
     __syncthreads();
+    PHASE_MARK(12);
 
     // ---- stage YZ -------------------------------------------------------------------------------
     if (tid < L * L) {
@@ -571,7 +602,10 @@ k_noise_spec(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTab
     __syncthreads();
     for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];
-        noise_chunk_spec<ST, NOCT>(cfg, tab, sm, px, py, pz, guard_count);
+#ifdef UW_PHASE_TIMING
+        long long t_phase = 0;
+#endif
+        noise_chunk_spec<ST, NOCT>(cfg, tab, sm, px, py, pz, guard_count PHASE_PASS);
         float4* dst = reinterpret_cast<float4*>(dens + (size_t)chunk * D::DSTRIDE);
         const float4* src = reinterpret_cast<const float4*>(sm.dens);
         for (int t = tid; t < D::DSTRIDE / 4; t += D::NT) dst[t] = src[t];
@@ -1006,56 +1040,63 @@ __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const Emit
     return sh;
 }
 
-template <int ST, typename IndexT>
-__device__ __forceinline__ void emit_write(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
-                                           const ChunkShape sh, int px, int py, int pz,
-                                           uw_vert* __restrict__ vout, IndexT* __restrict__ iout) {
+// D1 for the vertex tile [v0, v0 + UW_VLIST_CAP): vertex ids (v0 == 0 only) + compact vertex list.
+// Caller must barrier before emit_verts / emit_indices.
+template <int ST>
+__device__ __forceinline__ void emit_fill(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
+                                          const ChunkShape sh, uint32_t v0) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int S = ST > 0 ? ST : cfg.S, L = S + 1;
-    const uint32_t n_vert = sh.n_vert, n_act = sh.n_act;
-    const int offx = px * cfg.chunk_size, offy = py * cfg.chunk_size, offz = pz * cfg.chunk_size;
-
-    for (uint32_t v0 = 0; v0 < n_vert; v0 += UW_VLIST_CAP) {
-        // ---- D1: vertex ids (first pass only) + the compact vertex list of this tile ----------------
-        for (uint32_t a = tid; a < n_act; a += NT) {
-            const int cell = s.alist[a];
-            const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
-            const uint32_t own = 0x4F0u | (y == 0 ? 0x00Fu : 0u) | (x == 0 ? 0x800u : 0u)
-                               | (z == 0 ? (0x200u | (x == 0 ? 0x100u : 0u)) : 0u);
-            const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
-            const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
-            const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
-            uint32_t vnext = s.vbase[cell], todo = own;     // owned edges not yet numbered
+    for (uint32_t a = tid; a < sh.n_act; a += NT) {
+        const int cell = s.alist[a];
+        const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+        const uint32_t own = 0x4F0u | (y == 0 ? 0x00Fu : 0u) | (x == 0 ? 0x800u : 0u)
+                           | (z == 0 ? (0x200u | (x == 0 ? 0x100u : 0u)) : 0u);
+        const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
+        const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
+        const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
+        uint32_t vnext = s.vbase[cell], todo = own;     // owned edges not yet numbered
 #pragma unroll
-            for (int k = 0; k < 15; ++k) {
-                const uint32_t e = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
-                if (e == 15u) break;
-                if ((todo >> e) & 1u) {
-                    todo &= ~(1u << e);
-                    if (v0 == 0) s.vid[lbase + s.eoff[e]] = (uint16_t)vnext;
-                    const uint32_t slot = vnext - v0;
-                    if (slot < UW_VLIST_CAP) s.vlist[slot] = (uint16_t)(cell | (e << 12));
-                    ++vnext;
-                }
+        for (int k = 0; k < 15; ++k) {
+            const uint32_t e = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
+            if (e == 15u) break;
+            if ((todo >> e) & 1u) {
+                todo &= ~(1u << e);
+                if (v0 == 0) s.vid[lbase + s.eoff[e]] = (uint16_t)vnext;
+                const uint32_t slot = vnext - v0;
+                if (slot < UW_VLIST_CAP) s.vlist[slot] = (uint16_t)(cell | (e << 12));
+                ++vnext;
             }
         }
-        __syncthreads();
-        // ---- D2: one thread per vertex ------------------------------------------------------------------
-        const uint32_t cnt = min((uint32_t)UW_VLIST_CAP, n_vert - v0);
-        for (uint32_t t = tid; t < cnt; t += NT) {
-            const uint32_t ent = s.vlist[t];
-            const int cell = ent & 0xFFF, e = ent >> 12;
-            const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
-            float v[6];
-            make_vertex(cfg, s.dens, x, y, z, e, offx, offy, offz, v);
-            float2* dst = reinterpret_cast<float2*>(vout + v0 + t);
-            dst[0] = make_float2(v[0], v[1]); dst[1] = make_float2(v[2], v[3]); dst[2] = make_float2(v[4], v[5]);
-        }
-        if (v0 + UW_VLIST_CAP < n_vert) __syncthreads();
     }
+}
 
-    // ---- E: indices; every slot is one table lookup keyed by the ordered lattice pair ---------------------
-    for (uint32_t a = tid; a < n_act; a += NT) {
+// D2: one thread per vertex of the tile
+template <int ST>
+__device__ __forceinline__ void emit_verts(const DevCfg& cfg, const EmitSmem& s, const ChunkShape sh, uint32_t v0,
+                                           int px, int py, int pz, uw_vert* __restrict__ vout) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int S = ST > 0 ? ST : cfg.S;
+    const int offx = px * cfg.chunk_size, offy = py * cfg.chunk_size, offz = pz * cfg.chunk_size;
+    const uint32_t cnt = min((uint32_t)UW_VLIST_CAP, sh.n_vert - v0);
+    for (uint32_t t = tid; t < cnt; t += NT) {
+        const uint32_t ent = s.vlist[t];
+        const int cell = ent & 0xFFF, e = ent >> 12;
+        const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+        float v[6];
+        make_vertex(cfg, s.dens, x, y, z, e, offx, offy, offz, v);
+        float2* dst = reinterpret_cast<float2*>(vout + v0 + t);
+        dst[0] = make_float2(v[0], v[1]); dst[1] = make_float2(v[2], v[3]); dst[2] = make_float2(v[4], v[5]);
+    }
+}
+
+// E: indices; every slot is one table lookup keyed by the ordered lattice pair
+template <int ST, typename IndexT>
+__device__ __forceinline__ void emit_indices(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
+                                             const ChunkShape sh, IndexT* __restrict__ iout) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int S = ST > 0 ? ST : cfg.S, L = S + 1;
+    for (uint32_t a = tid; a < sh.n_act; a += NT) {
         const int cell = s.alist[a];
         const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
         const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
@@ -1069,6 +1110,21 @@ __device__ __forceinline__ void emit_write(const DevCfg& cfg, const McTables* __
             dst[k] = (IndexT)s.vid[lbase + s.eoff[e]];                 // `ind as u16`, chunk.rs:243
         }
     }
+}
+
+// everything after the first fill + barrier
+template <int ST, typename IndexT>
+__device__ __forceinline__ void emit_rest(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
+                                          const ChunkShape sh, int px, int py, int pz,
+                                          uw_vert* __restrict__ vout, IndexT* __restrict__ iout) {
+    emit_verts<ST>(cfg, s, sh, 0, px, py, pz, vout);
+    for (uint32_t v0 = UW_VLIST_CAP; v0 < sh.n_vert; v0 += UW_VLIST_CAP) {
+        __syncthreads();
+        emit_fill<ST>(cfg, mc, s, sh, v0);
+        __syncthreads();
+        emit_verts<ST>(cfg, s, sh, v0, px, py, pz, vout);
+    }
+    emit_indices<ST, IndexT>(cfg, mc, s, sh, iout);
 }
 
 template <int ST, typename IndexT>
@@ -1097,7 +1153,9 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
         for (int c = tid; c < L * L; c += NT) s.mask[c] = col_mask(s.bits, c, L);
         __syncthreads();
         const ChunkShape sh = emit_prepare<ST>(cfg, s, s_w);
-        emit_write<ST, IndexT>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
+        emit_fill<ST>(cfg, mc, s, sh, 0);
+        __syncthreads();
+        emit_rest<ST, IndexT>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
         __syncthreads();
     }
 }
@@ -1120,7 +1178,51 @@ struct ScanSlot { unsigned long long v, i; };     // bits 63..62: 0 = empty, 1 =
 #define SCAN_PFX  (2ull << 62)
 #define SCAN_VAL  ((1ull << 62) - 1ull)
 
-struct FusedCounters { uint32_t ticket, pad; unsigned long long alloc; };   // alloc = n_verts << 32 | n_inds
+// Control block of one fused launch.  Two blocks alternate between launches: the last CTA of launch k
+// zeroes the block of launch k+1, so no memset sits on the launch path.
+struct FusedControl {
+    uint32_t ticket, done;
+    unsigned long long alloc;        // n_verts << 32 | n_inds (completion-order packing)
+    unsigned long long guard;        // f64 guard-band re-evaluations
+    BatchTotals totals;
+};
+
+// Scheduling only (results do not depend on it): a stable partition of the request list that puts the
+// chunks whose z layer CAN hold surface (z_lo <= pos.z <= z_hi, derived on the host from the terrace
+// term and |noise| <= 1) first.  Those are several times more expensive than provably blank / solid
+// chunks; handing them out first lets the cheap ones fill the tail of the persistent kernel.
+__global__ void __launch_bounds__(1024) k_order_chunks(const int32_t* __restrict__ pos, uint32_t n, int z_lo, int z_hi,
+                                                       uint32_t* __restrict__ order) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_total, s_carry_h, s_carry_l;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t cnt = 0;
+    for (uint32_t i = tid; i < n; i += 1024) { const int z = pos[3 * i + 2]; cnt += (z >= z_lo && z <= z_hi); }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0) s_w[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) { uint32_t t = 0; for (int w = 0; w < 32; ++w) t += s_w[w]; s_total = t; s_carry_h = 0; s_carry_l = 0; }
+    __syncthreads();
+    const uint32_t n_heavy = s_total;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + tid;
+        bool heavy = false, valid = i < n;
+        if (valid) { const int z = pos[3 * i + 2]; heavy = (z >= z_lo && z <= z_hi); }
+        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, valid && heavy), bl = __ballot_sync(0xFFFFFFFFu, valid && !heavy);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = __popc(bh) | (__popc(bl) << 16);
+        __syncthreads();
+        uint32_t ph = 0, pl = 0;
+        for (int w = 0; w < warp; ++w) { ph += s_w[w] & 0xFFFFu; pl += s_w[w] >> 16; }
+        const uint32_t below = (1u << lane) - 1u;
+        if (valid) {
+            if (heavy) order[s_carry_h + ph + __popc(bh & below)] = i;
+            else order[n_heavy + s_carry_l + pl + __popc(bl & below)] = i;
+        }
+        __syncthreads();
+        if (tid == 0) { uint32_t th = 0, tl = 0; for (int w = 0; w < 32; ++w) { th += s_w[w] & 0xFFFFu; tl += s_w[w] >> 16; } s_carry_h += th; s_carry_l += tl; }
+    }
+}
 
 template <int ST, int NOCT>
 struct FusedSmem {
@@ -1134,7 +1236,7 @@ struct FusedSmem {
     uint8_t cs[((ST * ST * ST + 15) / 16) * 16];
     uint32_t w[64];
     unsigned long long part[4 * 8];
-    uint32_t chunk;
+    int cur[4];                                       // current ticket: chunk index, chunk position
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -1186,18 +1288,22 @@ __device__ __forceinline__ void lookback_block(ScanSlot* st, uint32_t c, unsigne
     ev = sv; ei = si;
 }
 
+#ifndef UW_FUSED_MINB
+#define UW_FUSED_MINB 4
+#endif
 template <int ST, int NOCT, typename IndexT>
-__global__ void __launch_bounds__(SpecDims<ST, NOCT>::NT, 4)
+__global__ void __launch_bounds__(SpecDims<ST, NOCT>::NT, UW_FUSED_MINB)
 k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTables tab,
               const uint8_t* __restrict__ g_perm, const McTables* __restrict__ mc,
-              const int32_t* __restrict__ pos, uint32_t n,
-              ScanSlot* __restrict__ scan, FusedCounters* __restrict__ ctr,
-              uw_chunk_desc* __restrict__ descs, BatchTotals* __restrict__ totals,
+              const int32_t* __restrict__ pos, const uint32_t* __restrict__ order /*nullable*/, uint32_t n,
+              ScanSlot* __restrict__ scan, FusedControl* __restrict__ ctr, FusedControl* __restrict__ ctr_next,
+              uw_chunk_desc* __restrict__ descs,
               uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
               unsigned long long vcap, unsigned long long icap,
-              float* __restrict__ dens_out /*nullable: debug tap*/,
-              unsigned long long* __restrict__ guard_count, int ordered) {
+              float* __restrict__ dens_out /*nullable: debug tap*/, int ordered) {
     using D = SpecDims<ST, NOCT>;
+    BatchTotals* const totals = &ctr->totals;
+    unsigned long long* const guard_count = &ctr->guard;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<ST, NOCT>& sm = *reinterpret_cast<FusedSmem<ST, NOCT>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -1225,16 +1331,51 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     static_assert(offsetof(NS, xpad) == offsetof(NS, X) + sizeof(sm.n.X), "X and xpad must be adjacent");
     static_assert(sizeof(sm.n.lat) + sizeof(sm.n.X) + sizeof(sm.n.xpad) >= (size_t)L * L * L * UW_EDGE_KINDS * 2, "vid must fit");
 
+#ifndef UW_TICKET_PREFETCH
+#define UW_TICKET_PREFETCH 0
+#endif
+#if UW_TICKET_PREFETCH
+    // chunk tickets are prefetched one iteration ahead so that the atomic's and the position load's
+    // round trips overlap the previous chunk's work
+    if (tid == 0) {
+        const uint32_t c0 = atomicAdd(&ctr->ticket, 1u);
+        sm.cur[0] = (int)c0;
+        if (c0 < n) { sm.cur[1] = pos[3 * c0]; sm.cur[2] = pos[3 * c0 + 1]; sm.cur[3] = pos[3 * c0 + 2]; }
+    }
+    __syncthreads();
+#endif
+
+#ifdef UW_PHASE_TIMING
+    long long t_phase = clock64();
+    if (tid == 0 && blockIdx.x < 1024) { g_cta[blockIdx.x][0] = gtimer(); g_cta[blockIdx.x][2] = 0; g_cta[blockIdx.x][3] = 0; }
+#endif
     while (true) {
-        __syncthreads();                                   // previous chunk fully emitted; smem reusable
-        if (tid == 0) sm.chunk = atomicAdd(&ctr->ticket, 1u);
+#if !UW_TICKET_PREFETCH
+        if (tid == 0) {
+            const uint32_t t0 = atomicAdd(&ctr->ticket, 1u);
+            uint32_t c0 = t0;
+            if (t0 < n && order) c0 = order[t0];
+            sm.cur[0] = (int)c0;
+            if (t0 < n) { sm.cur[1] = pos[3 * c0]; sm.cur[2] = pos[3 * c0 + 1]; sm.cur[3] = pos[3 * c0 + 2]; }
+        }
         __syncthreads();
-        const uint32_t chunk = sm.chunk;
+#endif
+        const uint32_t chunk = (uint32_t)sm.cur[0];
         if (chunk >= n) break;
-        const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];
+        const int px = sm.cur[1], py = sm.cur[2], pz = sm.cur[3];
+        PHASE_MARK(0);                                     // ticket + position
+        uint32_t nxt = 0;
+#if UW_TICKET_PREFETCH
+        if (tid == 0) nxt = atomicAdd(&ctr->ticket, 1u);                 // consumed at the end of this iteration
+#endif
 
         // ---- K1 ---------------------------------------------------------------------------------
-        const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count);
+        const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS);
+        PHASE_MARK(1);                                     // K1 noise
+        int nx = 0, ny = 0, nz = 0;
+#if UW_TICKET_PREFETCH
+        if (tid == 0 && nxt < n) { nx = pos[3 * nxt]; ny = pos[3 * nxt + 1]; nz = pos[3 * nxt + 2]; }
+#endif
         if (dens_out) {
             float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);
             const float4* src = reinterpret_cast<const float4*>(sm.n.dens);
@@ -1246,13 +1387,15 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         sh.n_vert = 0; sh.n_ind = 0; sh.n_act = 0;
         if (fl & CF_ANY_LT) sh = emit_prepare<ST>(cfg, es, sm.w);
         const uint32_t nv = sh.n_vert, ni = sh.n_ind;
+        PHASE_MARK(2);                                     // K2 prepare
 
         // ---- K3: this chunk's offsets in the packed arenas ------------------------------------------------
         //  ordered  : decoupled look-back over per-chunk aggregates -> offsets follow request order
         //             (deterministic layout; a chunk waits for the slowest of its in-flight predecessors)
         //  unordered: one 64-bit atomic bump allocation -> no inter-CTA dependency; each chunk's OWN
-        //             buffers are identical either way, only their placement in the arena differs
-        unsigned long long ev = 0, ei = 0;
+        //             buffers are identical either way, only their placement in the arena differs.
+        //             The atomic is issued here and its result consumed after the D1 fill.
+        unsigned long long ev = 0, ei = 0, packed = 0;
         if (ordered) {
             if (tid == 0) {
                 const unsigned long long tag = chunk == 0 ? SCAN_PFX : SCAN_AGG;
@@ -1264,12 +1407,22 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
                 atomicExch(&scan[chunk].v, SCAN_PFX | (ev + nv));
                 atomicExch(&scan[chunk].i, SCAN_PFX | (ei + ni));
             }
-        } else {
-            if (ni > 0) {                                  // block-uniform
-                if (tid == 0) sm.part[0] = atomicAdd(&ctr->alloc, ((unsigned long long)nv << 32) | ni);
-                __syncthreads();
-                ev = sm.part[0] >> 32; ei = sm.part[0] & 0xFFFFFFFFull;
-            }
+            packed = (ev << 32) | ei;
+        } else if (ni > 0 && tid == 0) {
+            packed = atomicAdd(&ctr->alloc, ((unsigned long long)nv << 32) | ni);
+        }
+
+        // ---- K4 ---------------------------------------------------------------------------------
+        PHASE_MARK(3);                                     // K3 offsets
+        if (ni > 0) {                                      // block-uniform
+            emit_fill<ST>(cfg, mc, es, sh, 0);
+            if (tid == 0) sm.part[0] = packed;
+            __syncthreads();
+            PHASE_MARK(4);                                 // K4 D1 fill
+            ev = sm.part[0] >> 32; ei = sm.part[0] & 0xFFFFFFFFull;
+            if (ev + nv <= vcap && ei + ni <= icap)
+                emit_rest<ST, IndexT>(cfg, mc, es, sh, px, py, pz, verts + ev, inds + ei);
+            PHASE_MARK(5);                                 // K4 D2 + E (thread 0's own share)
         }
         if (tid == 0) {
             uw_chunk_desc d;
@@ -1287,13 +1440,25 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
                     totals->overflow = 1u;
             }
             if (!ordered && ni > 0 && (ev + nv > vcap || ei + ni > icap)) totals->overflow = 1u;
+#if UW_TICKET_PREFETCH
+            sm.cur[0] = (int)nxt; sm.cur[1] = nx; sm.cur[2] = ny; sm.cur[3] = nz;
+#endif
         }
-
-        // ---- K4 ---------------------------------------------------------------------------------
-        if (ni > 0) {                                      // block-uniform
-            const unsigned long long ov = ev, oi = ei;
-            if (ov + nv <= vcap && oi + ni <= icap)
-                emit_write<ST, IndexT>(cfg, mc, es, sh, px, py, pz, verts + ov, inds + oi);
+        (void)nxt; (void)nx; (void)ny; (void)nz;
+        __syncthreads();                                   // chunk fully emitted, smem reusable, next ticket visible
+        PHASE_MARK(6);                                     // tail: descriptor + waiting for the other warps
+#ifdef UW_PHASE_TIMING
+        if (tid == 0) { atomicAdd(&g_phase[8], 1ull); if (ni > 0) atomicAdd(&g_phase[9], 1ull); if (fl & CF_ANY_LT) atomicAdd(&g_phase[10], 1ull);
+                        if (blockIdx.x < 1024) { g_cta[blockIdx.x][1] = gtimer(); g_cta[blockIdx.x][2] += 1; g_cta[blockIdx.x][3] += (ni > 0); } }
+#endif
+    }
+    // last CTA out resets the other control block for the next launch
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&ctr->done, 1u) == gridDim.x - 1) {
+            ctr_next->ticket = 0; ctr_next->done = 0; ctr_next->alloc = 0; ctr_next->guard = 0;
+            BatchTotals z; z.n_verts = 0; z.n_inds = 0; z.n_active = 0; z.overflow = 0; z.n_blank = 0; z.n_mesh = 0;
+            ctr_next->totals = z;
         }
     }
 }

@@ -56,19 +56,22 @@ struct uw_ctx {
     typedef void (*noise_fn_t)(DevCfg, AxisTables, const uint8_t*, const int32_t*, uint32_t, float*, unsigned long long*);
     typedef void (*emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*);
     typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*);
-    typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
-                                 FusedCounters*, uw_chunk_desc*, BatchTotals*, uw_vert*, uint16_t*, unsigned long long,
-                                 unsigned long long, float*, unsigned long long*, int);
-    typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
-                                 FusedCounters*, uw_chunk_desc*, BatchTotals*, uw_vert*, uint32_t*, unsigned long long,
-                                 unsigned long long, float*, unsigned long long*, int);
+    typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, const uint32_t*, uint32_t, ScanSlot*,
+                                 FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint16_t*, unsigned long long,
+                                 unsigned long long, float*, int);
+    typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, const uint32_t*, uint32_t, ScanSlot*,
+                                 FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint32_t*, unsigned long long,
+                                 unsigned long long, float*, int);
     fused16_fn_t fused16_fn = nullptr;
     fused32_fn_t fused32_fn = nullptr;
     bool use_fused = false;
+    int z_lo = 1, z_hi = 0;         // chunk z layers that can hold surface (empty range = unknown: no reordering)
     bool ordered = false;           // packed arenas follow request order (look-back) vs atomic bump allocation
     size_t fused_smem = 0; int fused_blocks_per_sm = 1;
     ScanSlot* d_scan = nullptr;
-    FusedCounters* d_ctr = nullptr;
+    FusedControl* d_ctl = nullptr;  // two blocks, alternating per launch
+    FusedControl* h_ctl = nullptr;  // pinned copy of the block used by the last launch
+    int ctl_parity = 0, ctl_used = 0;
     noise_fn_t noise_fn = nullptr;
     emit16_fn_t emit16_fn = nullptr;
     emit32_fn_t emit32_fn = nullptr;
@@ -156,6 +159,14 @@ static uw_status setup_tables(uw_ctx* c) {
     d.min_hue = cf.min_hue; d.max_hue = cf.max_hue; d.min_z = cf.min_z; d.max_z = cf.max_z;
     d.guard_eps = cf.guard_eps > 0.f ? cf.guard_eps : 1e-5f;
     d.dens_stride = (uint32_t)((d.L3 + 3) & ~3);
+    d.cs_pow2 = is_pow2(cf.chunk_size) ? 1 : 0;
+    d.inv_chunk_size = 1.0 / (double)cf.chunk_size;
+    {
+        int ex = 0;
+        const float m = frexpf(fabsf(cf.adj_z_mod), &ex);
+        d.mod_pow2 = (m == 0.5f && cf.adj_z_mod > 0.0f) ? 1 : 0;
+        d.inv_adj_z_mod = 1.0f / cf.adj_z_mod;
+    }
     for (int vi = 0; vi < 3; ++vi) {                                          // chunk.rs:219-221, util.rs:129-132,106-112
         const float value = cf.base_value + (float)vi / 9.0f;
         const float cc = value * cf.saturation;
@@ -189,6 +200,31 @@ static uw_status setup_tables(uw_ctx* c) {
             }
         }
     }
+    // z layers that can hold surface: iso = terrace(z) + p with |p| <= 1 (each octave is clamped to [-1, 1]);
+    // used only to hand out expensive chunks first (k_order_chunks)
+    {
+        auto layer_range = [&](int pz, float& tmin, float& tmax) {
+            tmin = 3e38f; tmax = -3e38f;
+            for (int k = 0; k < d.L; ++k) {
+                const double local = (double)k * (double)d.size_scale;
+                const float zf = (float)((local + (double)(pz * cf.chunk_size)) / (double)cf.chunk_size);
+                const float adj = (zf * (float)cf.chunk_size) / cf.max_height;
+                const float t = adj - fmodf(adj, cf.adj_z_mod);
+                tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
+            }
+        };
+        const float margin = 1e-3f;
+        int lo = 1, hi = 0;
+        bool found = false;
+        for (int pz = -4096; pz <= 4096; ++pz) {
+            float tmin, tmax;
+            layer_range(pz, tmin, tmax);
+            const bool blank_certain = tmin - 1.0f > cf.iso_level + margin;
+            const bool solid_certain = tmax + 1.0f < cf.iso_level - margin;
+            if (!blank_certain && !solid_certain) { if (!found) { lo = pz; found = true; } hi = pz; }
+        }
+        if (found && lo > -4096 && hi < 4096) { c->z_lo = lo; c->z_hi = hi; } else { c->z_lo = 1; c->z_hi = 0; }
+    }
     return UW_OK;
 }
 
@@ -217,7 +253,8 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_pos); cudaFree(c->d_dens); cudaFree(c->d_counts);
     cudaFree(c->d_descs); cudaFree(c->d_active); cudaFree(c->d_cases); cudaFree(c->d_totals); cudaFree(c->d_guard);
-    cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_scan); cudaFree(c->d_ctr);
+    cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_scan); cudaFree(c->d_ctl);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_pos) cudaFreeHost(c->h_pos);
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_guard) cudaFreeHost(c->h_guard);
@@ -406,7 +443,11 @@ static uw_status ensure_chunks(uw_ctx* c, uint32_t n) {
     CU_TRY(c, regrow(&c->d_descs, cap));
     CU_TRY(c, regrow(&c->d_active, cap));
     CU_TRY(c, regrow(&c->d_scan, cap));
-    if (!c->d_ctr) CU_TRY(c, cudaMalloc(&c->d_ctr, sizeof(FusedCounters)));
+    if (!c->d_ctl) {
+        CU_TRY(c, cudaMalloc(&c->d_ctl, 2 * sizeof(FusedControl)));
+        CU_TRY(c, cudaMemset(c->d_ctl, 0, 2 * sizeof(FusedControl)));
+        CU_TRY(c, cudaHostAlloc(&c->h_ctl, sizeof(FusedControl), cudaHostAllocDefault));
+    }
     c->cap_chunks = cap;
     return UW_OK;
 }
@@ -495,16 +536,27 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
 
 static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float* d_dens_out) {
     const DevCfg& d = c->dcfg;
-    CU_TRY(c, cudaMemsetAsync(c->d_scan, 0, sizeof(ScanSlot) * (size_t)n, c->stream));
-    CU_TRY(c, cudaMemsetAsync(c->d_ctr, 0, sizeof(FusedCounters), c->stream));
-    CU_TRY(c, cudaMemsetAsync(c->d_totals, 0, sizeof(BatchTotals), c->stream));
+    if (c->ordered) CU_TRY(c, cudaMemsetAsync(c->d_scan, 0, sizeof(ScanSlot) * (size_t)n, c->stream));
+    FusedControl* ctl = c->d_ctl + c->ctl_parity;
+    FusedControl* ctl_next = c->d_ctl + (c->ctl_parity ^ 1);
+    c->ctl_used = c->ctl_parity;
+    c->ctl_parity ^= 1;
     const int grid = persistent_grid(c, n, c->fused_blocks_per_sm);
+    // heavy-first hand-out order (scheduling only); the ordered-packing mode needs tickets == request order
+    const uint32_t* d_order = nullptr;
+    static const bool no_order = getenv("UW_NO_ORDER") != nullptr;      // experiment switch
+    if (!no_order && !c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= 65536u) {
+        k_order_chunks<<<1, 1024, 0, c->stream>>>(d_pos, n, c->z_lo, c->z_hi, c->d_active);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        d_order = c->d_active;
+    }
     if (c->index32)
-        c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, c->d_ctr,
-            c->d_descs, c->d_totals, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->d_guard, c->ordered ? 1 : 0);
+        c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
+            c->d_descs, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0);
     else
-        c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, c->d_ctr,
-            c->d_descs, c->d_totals, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->d_guard, c->ordered ? 1 : 0);
+        c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
+            c->d_descs, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;
@@ -552,14 +604,19 @@ static uw_status enqueue_build(uw_ctx* c, const int32_t* d_pos, uint32_t n, bool
 static uw_status finish_build(uw_ctx* c) {
     if (!c->pending) return UW_OK;
     for (int attempt = 0; attempt < 3; ++attempt) {
-        CU_TRY(c, cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(BatchTotals), cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        if (c->last_fused && !c->ordered)
-            CU_TRY(c, cudaMemcpyAsync(c->h_alloc, &c->d_ctr->alloc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(c, cudaStreamSynchronize(c->stream));
-        if (c->last_fused && !c->ordered) {
-            c->h_totals->n_verts = *c->h_alloc >> 32; c->h_totals->n_inds = *c->h_alloc & 0xFFFFFFFFull;
-            if (c->h_totals->n_verts > c->vcap || c->h_totals->n_inds > c->icap) c->h_totals->overflow = 1;
+        if (c->last_fused) {
+            CU_TRY(c, cudaMemcpyAsync(c->h_ctl, c->d_ctl + c->ctl_used, sizeof(FusedControl), cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            *c->h_totals = c->h_ctl->totals;
+            *c->h_guard = c->h_ctl->guard;
+            if (!c->ordered) {
+                c->h_totals->n_verts = c->h_ctl->alloc >> 32; c->h_totals->n_inds = c->h_ctl->alloc & 0xFFFFFFFFull;
+                if (c->h_totals->n_verts > c->vcap || c->h_totals->n_inds > c->icap) c->h_totals->overflow = 1;
+            }
+        } else {
+            CU_TRY(c, cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(BatchTotals), cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
         }
         if (!c->h_totals->overflow) break;
         if (c->h_totals->n_verts > 0xFFFFFFFFull || c->h_totals->n_inds > 0xFFFFFFFFull)
@@ -567,7 +624,6 @@ static uw_status finish_build(uw_ctx* c) {
         uw_status st = ensure_outputs(c, c->h_totals->n_verts, c->h_totals->n_inds);
         if (st != UW_OK) return st;
         if (c->last_fused) {
-            CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
             st = launch_fused(c, c->last_pos_dev, c->last_n, (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) ? c->d_dens : nullptr);
         } else {
             st = launch_extract(c, c->last_pos_dev, c->last_n, nullptr, true);
@@ -808,3 +864,15 @@ extern "C" uw_status uw_iso_at(uw_ctx* c, const double* pts, uint32_t n, float* 
     if (e != cudaSuccess) return fail(c, UW_ERR_CUDA, std::string("uw_iso_at: ") + cudaGetErrorString(e));
     return UW_OK;
 }
+
+#ifdef UW_PHASE_TIMING
+// debug builds only (-DUW_PHASE_TIMING): accumulated per-phase cycle counts of thread 0 of every CTA
+extern "C" int uw_debug_phase_cycles(unsigned long long out[16], int reset) {
+    if (cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase, z, sizeof z); }
+    return 0;
+}
+extern "C" int uw_debug_cta_times(unsigned long long* out /*1024*4*/) {
+    return cudaMemcpyFromSymbol(out, g_cta, sizeof(unsigned long long) * 4096) != cudaSuccess;
+}
+#endif

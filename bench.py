@@ -286,49 +286,63 @@ def run_ours(args):
     d2h = n * 32 + nv * 24 + ni * 2 + 32 + 8
     launches_per_step = builder.stage_times()["launches"]
 
-    # ---- per-stage times for the roofline (separate pass, events between the stages) ----------
-    builder.set_profiling(True)
-    acc = {"noise_ms": 0.0, "classify_ms": 0.0, "scan_ms": 0.0, "emit_ms": 0.0, "total_ms": 0.0}
-    P = 20
-    for i in range(P + 2):
-        flush.fill_(i & 0xFF)
-        builder.build_device(d_pos.data_ptr(), n)
-        builder.sync()
-        if i >= 2:
-            t = builder.stage_times()
-            for k in acc:
-                acc[k] += t[k] / P
-    builder.set_profiling(False)
+    # ---- kernel times for the roofline (separate passes, CUDA events inside the library) -----------
+    def stage_profile(bld, reps=20):
+        bld.set_stream(stream.cuda_stream)
+        bld.set_profiling(True)
+        acc = {"noise_ms": 0.0, "classify_ms": 0.0, "scan_ms": 0.0, "emit_ms": 0.0, "total_ms": 0.0}
+        for i in range(reps + 2):
+            flush.fill_(i & 0xFF)
+            bld.build_device(d_pos.data_ptr(), n)
+            bld.sync()
+            if i >= 2:
+                t = bld.stage_times()
+                for k in acc:
+                    acc[k] += t[k] / reps
+        bld.set_profiling(False)
+        return acc
+
+    fused_ms = stage_profile(builder)["total_ms"]            # default path: (order kernel +) the fused kernel
     dv = builder.device_view()
     n_verts, n_inds = int(dv.n_verts), int(dv.n_inds)
-    hb = builder.build(pos)                      # host path once, for the mesh statistics
+    staged = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local, staged=True)
+    acc = stage_profile(staged)                              # the same stages as four kernels, for attribution
+    staged.close()
+    hb = builder.build(pos)                                  # host path once, for the mesh statistics
     n_active = int((hb.descs["index_count"] > 0).sum())
     n_blank = int((hb.descs["flags"] & 1).sum())
     assert hb.n_verts == n_verts and hb.n_inds == n_inds
     guards = builder.guard_count()
 
     peak, peak_src = measured_peaks()
+    out_bytes = n * 32 + 24 * n_verts + 2 * n_inds
     alg_bytes = {
-        "noise": n * 4 * L3 + n * 12,                                   # write densities (+ read positions)
-        "classify": n * 4 * L3 + n * 16,                                # read densities, write counts
+        "fused": n * 12 + out_bytes,                                    # positions in, descriptors + mesh out
+        "noise": n * 4 * L3 + n * 12,                                   # staged: write densities (+ read positions)
+        "classify": n * 4 * L3 + n * 16,                                # staged: read densities, write counts
         "scan": n * (16 + 12 + 32 + 4),
-        "emit": n_active * (4 * L3 + 32) + 24 * n_verts + 2 * n_inds,   # read densities of active chunks, write mesh
+        "emit": n_active * (4 * L3 + 32) + 24 * n_verts + 2 * n_inds,   # staged: read active densities, write mesh
     }
     stage_ms = {"noise": acc["noise_ms"], "classify": acc["classify_ms"], "scan": acc["scan_ms"], "emit": acc["emit_ms"]}
-    dom = max(stage_ms, key=lambda k: stage_ms[k])
-    achieved = alg_bytes[dom] / (stage_ms[dom] / 1e3) / 1e9 if stage_ms[dom] > 0 else 0.0
-    roofline = {"kernel": {"noise": "k_noise_small", "classify": "k_classify_small", "scan": "k_scan_chunks",
-                           "emit": "k_emit_small"}[dom],
+    achieved = alg_bytes["fused"] / (fused_ms / 1e3) / 1e9 if fused_ms > 0 else 0.0
+    noise_flops = n * L3 * FLOP_PER_SAMPLE
+    roofline = {"kernel": "k_build_fused<12,3,u16> (noise + classify + scan + emit in one persistent kernel)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes[dom], "avg_launch_ms": stage_ms[dom],
-                "stages_ms": stage_ms,
-                "stages_gbs": {k: (alg_bytes[k] / (stage_ms[k] / 1e3) / 1e9 if stage_ms[k] > 0 else None) for k in stage_ms},
-                "noise_fp32": {
-                    "algorithmic_tflops": n * L3 * FLOP_PER_SAMPLE / (stage_ms["noise"] / 1e3) / 1e12 if stage_ms["noise"] > 0 else None,
+                "algorithmic_bytes_per_launch": alg_bytes["fused"], "avg_launch_ms": fused_ms,
+                "note": "densities never leave the SM, so compulsory HBM traffic is only positions in and mesh out; "
+                        "at 2048 chunks the kernel is issue/latency-bound (see profiles/), not HBM-bound",
+                "fp32_view": {
+                    "algorithmic_tflops": noise_flops / (fused_ms / 1e3) / 1e12 if fused_ms > 0 else None,
                     "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
-                    "note": "285 FLOP/sample is the reference's op count (SURVEY 8d); the kernel executes far fewer "
-                            "(tensor-product factorisation), so this can exceed the nominal peak"}}
+                    "frac_of_nominal": noise_flops / (fused_ms / 1e3) / 1e12 / FP32_NOMINAL_TFLOPS if fused_ms > 0 else None,
+                    "note": "285 FLOP/sample is the reference's op count (SURVEY 8d) over the WHOLE fused kernel time; "
+                            "the tensor-product factorisation executes ~3x fewer"},
+                "staged_pipeline": {
+                    "stages_ms": stage_ms,
+                    "stages_gbs": {k: (alg_bytes[k] / (stage_ms[k] / 1e3) / 1e9 if stage_ms[k] > 0 else None) for k in stage_ms},
+                    "noise_algorithmic_tflops": noise_flops / (stage_ms["noise"] / 1e3) / 1e12 if stage_ms["noise"] > 0 else None,
+                    "note": "UW_FLAG_STAGED: same stages as four kernels with densities materialised in HBM"}}
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------
     cpu_baseline = None
@@ -358,6 +372,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "voxels/s", "chunks_per_s": total_chunks / (e2e_ms / 1e3),
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step) * K,
+            "kernels_per_step": ["k_order_chunks", "k_build_fused"],
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(),

@@ -1,0 +1,52 @@
+// Drives the C++ host mirror (include/uw_chunk.hpp) the way the reference's World drives Chunk
+// (src/world.rs:113-123): Chunk::new(pos) -> build_full -> not_blank / num_inds / buffer slices.
+// Prints one line per chunk; tests/test_cpp_mirror.py compares the lines with the oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "uw_chunk.hpp"
+
+static uint64_t fnv(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+int main(int argc, char** argv) {
+    const uint32_t seed = argc > 1 ? (uint32_t)strtoul(argv[1], nullptr, 10) : 0;
+    try {
+        uw::ChunkBuilder builder{uw::Perlin(seed)};
+        std::vector<std::array<int32_t, 3>> positions = {{0, 0, -1}, {0, 0, 0}, {3, -2, 2}, {-5, 7, -4}, {1, 1, -2}};
+        // one at a time, like the reference ...
+        for (const auto& p : positions) {
+            uw::Chunk c = uw::Chunk::create(p);
+            c.build_full(builder);
+            if (!c.build_partial(builder)) return 3;
+            if (c.not_blank())
+                printf("chunk %d %d %d not_blank=1 num_inds=%zu verts=%zu inds_hash=%016llx pos0=%a\n", p[0], p[1], p[2], c.num_inds(),
+                       c.verts_buffer_slice().size(), (unsigned long long)fnv(c.inds_buffer_slice().data(), c.num_inds() * 2),
+                       (double)c.verts_buffer_slice()[0].pos[0]);
+            else
+                printf("chunk %d %d %d not_blank=0 num_inds=%zu blank_early=%d\n", p[0], p[1], p[2], c.num_inds(), (int)c.blank_early());
+        }
+        // ... and as one batch: must agree chunk by chunk
+        auto batch = uw::build_chunks(builder, positions);
+        for (size_t i = 0; i < positions.size(); ++i) {
+            uw::Chunk c(positions[i]);
+            c.build_full(builder);
+            if (c.num_inds() != batch[i].num_inds() || c.not_blank() != batch[i].not_blank()) { printf("BATCH MISMATCH %zu\n", i); return 4; }
+            if (c.not_blank() && memcmp(c.inds_buffer_slice().data(), batch[i].inds_buffer_slice().data(), c.num_inds() * 2)) return 5;
+        }
+        // the reference panics when slicing a blank chunk's buffers (chunk.rs:346): here it throws
+        uw::Chunk blank({0, 0, 5});
+        blank.build_full(builder);
+        bool threw = false;
+        try { blank.verts_buffer_slice(); } catch (const std::logic_error&) { threw = true; }
+        printf("blank_slice_throws=%d\n", (int)threw);
+        printf("OK\n");
+        return 0;
+    } catch (const uw::Error& e) {
+        printf("uw::Error status=%d %s\n", (int)e.status, e.what());
+        return e.status == UW_ERR_NO_DEVICE ? 42 : 1;
+    }
+}

@@ -379,3 +379,47 @@ def test_device_resident_build_matches_host_build(uw, builder12):
     builder12.sync()
     v = builder12.device_view()
     assert v.n_verts == host.n_verts and v.n_inds == host.n_inds and v.n_chunks == len(pos)
+
+
+# ---------------------------------------------------------------------------------------------
+# large-chunk path (internal_size 16..64; BASELINE config 4 = 64^3 cells per chunk, u32 indices)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S", [16, 21, 32])
+def test_large_chunk_extraction_bit_exact_from_oracle_densities(uw, S):
+    from oracle import Oracle
+    o = Oracle(S)
+    perm = o.perm_table(0)
+    L3 = (S + 1) ** 3
+    rng = np.random.default_rng(S)
+    pos = np.array([[0, 0, -1], [1, -1, 0], [2, 3, -2], [0, 0, 4], [0, 0, -6], [5, 5, -1], [7, -3, 0]], dtype=np.int32)
+    dens = np.stack([o.densities(perm, p) for p in pos])
+    dens[5] = rng.uniform(-1, 1, L3).astype(np.float32)          # pure noise: every cell is a surface cell
+    f = rng.uniform(-1, 1, L3).astype(np.float32); f[::3] = np.float32(-0.1); dens[6] = f   # exact ties
+    with uw.ChunkBuilder(uw.Perlin(0), internal_size=S, ordered=True) as b:
+        assert (b.build(pos[:1]).inds.dtype == np.uint32) == (S > 22)
+        batch = b.build_from_densities(pos, dens)
+    refs = _oracle_batch(o, perm, pos, MODE_FAST, isos=dens)
+    assert max(len(r["verts"]) for r in refs) > 2 * S ** 3
+    _check_batch(batch, refs, exact_positions=True)
+
+
+def test_config4_64cubed_chunks_match_oracle_bitwise(uw):
+    """BASELINE config 4: 64^3 cells per chunk (65^3 samples, SIZE_SCALE = 0.25 exactly).  The large-chunk
+    path evaluates densities in f64 reference order, so EVERYTHING but the powf colour channel is bit-exact."""
+    from oracle import Oracle
+    o = Oracle(64)
+    perm = o.perm_table(0)
+    pos = np.array([[0, 0, -1], [0, 0, 0], [-3, 2, -2], [4, 4, 2], [1, 1, -5], [2, -7, -1]], dtype=np.int32)
+    with uw.ChunkBuilder(uw.Perlin(0), internal_size=64, ordered=True) as b:
+        batch = b.build(pos)
+        dens = b.debug_densities(pos[:2])
+    refs = _oracle_batch(o, perm, pos, MODE_FAST)
+    assert np.array_equal(_bits(dens[0]), _bits(refs[0]["isos"])) and np.array_equal(_bits(dens[1]), _bits(refs[1]["isos"]))
+    assert batch.inds.dtype == np.uint32 and sum(len(r["inds"]) for r in refs) > 100000
+    _check_batch(batch, refs, exact_positions=True)
+    assert batch.chunk(3).flags == 1 and batch.chunk(4).flags == 0 and batch.chunk(4).num_inds() == 0
+    # neighbouring 64^3 chunks agree on their shared face (u_64 = 1.0 exactly, SURVEY App. A.6)
+    d2 = None
+    with uw.ChunkBuilder(uw.Perlin(0), internal_size=64) as b2:
+        d2 = b2.debug_densities(np.array([[0, 0, -1], [1, 0, -1]], dtype=np.int32)).reshape(2, 65, 65, 65)
+    assert np.array_equal(_bits(d2[0][64]), _bits(d2[1][0]))

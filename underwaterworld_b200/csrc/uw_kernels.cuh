@@ -883,15 +883,15 @@ __device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, i
     else                            { out[0] = HI; out[1] = LO; out[2] = X;  }
 }
 
-// vertex of the directed edge `e` of cell (x,y,z): chunk.rs:178-231
-__device__ __forceinline__ void make_vertex(const DevCfg& cfg, const float* s_dens, int x, int y, int z, int e,
-                                            int offx, int offy, int offz, float v[6]) {
+// vertex of the directed edge `e` of cell (x,y,z): chunk.rs:178-231.  dens_at(ax, ay, az) -> density.
+template <class DensAt>
+__device__ __forceinline__ void make_vertex_from(const DevCfg& cfg, DensAt dens_at, int x, int y, int z, int e,
+                                                 int offx, int offy, int offz, float v[6]) {
     const int ca = c_edge_a[e], cb = c_edge_b[e];
     int ax, ay, az, bx, by, bz;
     corner_off(ca, ax, ay, az); corner_off(cb, bx, by, bz);
     ax += x; ay += y; az += z; bx += x; by += y; bz += z;
-    const int L = cfg.L;
-    const float iso_a = s_dens[(ax * L + ay) * L + az], iso_b = s_dens[(bx * L + by) * L + bz];
+    const float iso_a = dens_at(ax, ay, az), iso_b = dens_at(bx, by, bz);
     const float t = __fdiv_rn(__fsub_rn(cfg.iso_level, iso_a), __fsub_rn(iso_b, iso_a));
     const float sax = __fmul_rn((float)ax, cfg.size_scale), say = __fmul_rn((float)ay, cfg.size_scale), saz = __fmul_rn((float)az, cfg.size_scale);
     const float sbx = __fmul_rn((float)bx, cfg.size_scale), sby = __fmul_rn((float)by, cfg.size_scale), sbz = __fmul_rn((float)bz, cfg.size_scale);
@@ -901,6 +901,12 @@ __device__ __forceinline__ void make_vertex(const DevCfg& cfg, const float* s_de
     const float wz = __fadd_rn(mz, (float)offz);
     v[0] = __fadd_rn(mx, (float)offx); v[1] = __fadd_rn(my, (float)offy); v[2] = wz;
     vertex_color(cfg, wz, cb % 3, v + 3);
+}
+
+__device__ __forceinline__ void make_vertex(const DevCfg& cfg, const float* s_dens, int x, int y, int z, int e,
+                                            int offx, int offy, int offz, float v[6]) {
+    const int L = cfg.L;
+    make_vertex_from(cfg, [=](int ax, int ay, int az) { return s_dens[(ax * L + ay) * L + az]; }, x, y, z, e, offx, offy, offz, v);
 }
 
 // owner (first cell in scan order holding the same ORDERED corner pair), SURVEY App. B.4
@@ -1161,6 +1167,192 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
 }
 
 // ---------------------------------------------------------------------------------------
+// LARGE-CHUNK PATH (internal_size 16..64, e.g. BASELINE config 4: 64^3 cells, 65^3 samples = 1.1 MB of
+// densities per chunk -- far beyond shared memory).  Densities are materialised in HBM by the noise
+// kernel; one CTA then walks a chunk's x-slabs IN ORDER, holding two density planes (x, x+1), the sign
+// bits of both, and the (case, vertex base) arrays of the previous and current slab -- everything the
+// reference's scan-order numbering needs, since an edge's owner is never more than
+// one slab back.  COUNT pass -> k_scan_chunks -> EMIT pass (same walk, now writing vertices/indices).
+// ---------------------------------------------------------------------------------------
+struct BigSmem {
+    float* plane[2]; uint32_t* bits[2]; uint32_t* vb[2]; uint8_t* cs[2]; uint32_t* ib; uint16_t* alist; uint32_t* lut;
+};
+
+__host__ __device__ inline size_t big_smem_bytes(const DevCfg& cfg) {
+    const size_t L2p = ((size_t)cfg.L2 + 3) & ~(size_t)3, nw = ((size_t)cfg.L2 + 31) / 32 + 2, cells = (size_t)cfg.S * cfg.S;
+    return 2 * L2p * 4 + 2 * nw * 4 + 2 * cells * 4 + 2 * ((cells + 15) & ~(size_t)15) + cells * 4 + ((cells + 7) & ~(size_t)7) * 2 + 256 * 4;
+}
+
+__device__ __forceinline__ BigSmem big_smem_carve(const DevCfg& cfg, unsigned char* base) {
+    const size_t L2p = ((size_t)cfg.L2 + 3) & ~(size_t)3, nw = ((size_t)cfg.L2 + 31) / 32 + 2, cells = (size_t)cfg.S * cfg.S;
+    BigSmem s;
+    s.plane[0] = (float*)base; base += L2p * 4;
+    s.plane[1] = (float*)base; base += L2p * 4;
+    s.bits[0] = (uint32_t*)base; base += nw * 4;
+    s.bits[1] = (uint32_t*)base; base += nw * 4;
+    s.vb[0] = (uint32_t*)base; base += cells * 4;
+    s.vb[1] = (uint32_t*)base; base += cells * 4;
+    s.ib = (uint32_t*)base; base += cells * 4;
+    s.lut = (uint32_t*)base; base += 256 * 4;
+    s.alist = (uint16_t*)base; base += ((cells + 7) & ~(size_t)7) * 2;
+    s.cs[0] = (uint8_t*)base; base += (cells + 15) & ~(size_t)15;
+    s.cs[1] = (uint8_t*)base;
+    return s;
+}
+
+// two consecutive bits (b, b+1) of a flat bit array
+__device__ __forceinline__ uint32_t two_bits(const uint32_t* bits, int b) {
+    return __funnelshift_r(bits[b >> 5], bits[(b >> 5) + 1], b & 31) & 3u;
+}
+
+template <bool EMIT, typename IndexT>
+__global__ void __launch_bounds__(512) k_extract_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
+                                                     const float* __restrict__ dens, uint32_t n,
+                                                     ChunkCounts* __restrict__ counts,
+                                                     const uw_chunk_desc* __restrict__ descs, const uint32_t* __restrict__ active,
+                                                     const BatchTotals* __restrict__ totals,
+                                                     uw_vert* __restrict__ verts, IndexT* __restrict__ inds) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const BigSmem s = big_smem_carve(cfg, smem_raw);
+    __shared__ uint32_t s_w[64];
+    __shared__ int s_red[2];
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+    const int S = cfg.S, L = cfg.L, L2 = cfg.L2, ncell = S * S;
+    const int CPT = (ncell + NT - 1) / NT;                 // consecutive cells per thread (scan order y, z)
+    for (int t = tid; t < 256; t += NT) s.lut[t] = mc->lut[t];
+    uint32_t n_work = n;
+    if (EMIT) { if (totals->overflow) return; n_work = totals->n_active; }
+
+    for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const uint32_t chunk = EMIT ? active[w] : w;
+        const float* D = dens + (size_t)chunk * cfg.dens_stride;
+        uw_chunk_desc d;
+        if (EMIT) d = descs[chunk];
+        const int offx = EMIT ? d.pos[0] * cfg.chunk_size : 0, offy = EMIT ? d.pos[1] * cfg.chunk_size : 0,
+                  offz = EMIT ? d.pos[2] * cfg.chunk_size : 0;
+        uw_vert* vout = EMIT ? verts + d.vert_offset : nullptr;
+        IndexT* iout = EMIT ? inds + d.index_offset : nullptr;
+        uint32_t vrun = 0, irun = 0;
+        bool all_gt = true, any_lt = false;
+        if (tid < 2) s_red[tid] = tid == 0 ? 1 : 0;
+
+        // loads density plane x into buffer x & 1: floats (EMIT) and sign bits (warp ballots)
+        auto load_plane = [&](int x) {
+            float* pl = s.plane[x & 1];
+            uint32_t* bt = s.bits[x & 1];
+            const float* src = D + (size_t)x * L2;
+            for (int base = tid - lane; base < L2; base += NT) {
+                const int idx = base + lane;
+                const bool ok = idx < L2;
+                float v = 0.f;
+                if (ok) { v = __ldg(src + idx); if (EMIT) pl[idx] = v; }
+                const bool lt = ok && (v < cfg.iso_level);
+                const uint32_t word = __ballot_sync(0xFFFFFFFFu, lt);
+                if (lane == 0) bt[base >> 5] = word;
+                all_gt &= !ok || (v > cfg.iso_level);
+                any_lt |= lt;
+            }
+            if (tid == 0) { bt[(L2 + 31) >> 5] = 0; bt[((L2 + 31) >> 5) + 1] = 0; }
+        };
+        load_plane(0);
+
+        for (int cx = 0; cx < S; ++cx) {
+            load_plane(cx + 1);
+            __syncthreads();
+            const uint32_t* A = s.bits[cx & 1];            // plane x = cx
+            const uint32_t* B = s.bits[(cx + 1) & 1];      // plane x = cx + 1
+            uint8_t* cs_cur = s.cs[cx & 1];
+            uint32_t* vb_cur = s.vb[cx & 1];
+            const uint8_t* cs_prev = s.cs[(cx + 1) & 1];
+            const uint32_t* vb_prev = s.vb[(cx + 1) & 1];
+
+            // ---- classify this slab; per-thread counts over its CPT consecutive cells --------------------
+            const int c0 = tid * CPT;
+            uint32_t nva = 0, ni = 0;
+            for (int q = 0; q < CPT; ++q) {
+                const int cell = c0 + q;
+                if (cell >= ncell) break;
+                const int y = cell / S, z = cell - y * S;
+                const uint32_t nat = two_bits(A, y * L + z) | (two_bits(B, y * L + z) << 2)
+                                   | (two_bits(A, (y + 1) * L + z) << 4) | (two_bits(B, (y + 1) * L + z) << 6);
+                const uint32_t t = s.lut[nat];
+                cs_cur[cell] = (uint8_t)t;
+                if (t >> 8) {
+                    ni += (t >> 8) & 15u;
+                    nva += __popc((t >> 12) & own_mask_of(cx, y, z)) + 0x10000u;        // verts <= 12 * S^2 < 2^16 | surface cells << 16
+                }
+            }
+            uint32_t eva, ei, tva, ti;
+            block_scan2(nva, ni, eva, ei, tva, ti, s_w);
+            const uint32_t slab_nv = tva & 0xFFFFu, slab_na = tva >> 16;
+            if (EMIT) {
+                uint32_t rv = vrun + (eva & 0xFFFFu), ra = eva >> 16, ri = irun + ei;
+                for (int q = 0; q < CPT; ++q) {
+                    const int cell = c0 + q;
+                    if (cell >= ncell) break;
+                    const uint32_t csv = cs_cur[cell];
+                    if (csv != 0u && csv != 255u) {
+                        const int y = cell / S, z = cell - y * S;
+                        vb_cur[cell] = rv; s.ib[cell] = ri;
+                        s.alist[ra++] = (uint16_t)cell;
+                        ri += mc->ninds[csv];
+                        rv += __popc((uint32_t)mc->crossed[csv] & own_mask_of(cx, y, z));
+                    }
+                }
+                __syncthreads();
+                // ---- emit: one thread per surface cell of the slab ------------------------------------------
+                const float* P0 = s.plane[cx & 1];
+                const float* P1 = s.plane[(cx + 1) & 1];
+                auto dens_at = [=](int ax, int ay, int az) { return (ax == cx ? P0 : P1)[ay * L + az]; };
+                for (uint32_t a = tid; a < slab_na; a += NT) {
+                    const int cell = s.alist[a];
+                    const int y = cell / S, z = cell - y * S;
+                    const uint32_t csv = cs_cur[cell];
+                    const uint32_t own = own_mask_of(cx, y, z);
+                    const uint64_t row = __ldg(&mc->rows[csv]);
+                    uint32_t vnext = vb_cur[cell], todo = own;
+                    IndexT* dst = iout + s.ib[cell];
+#pragma unroll 1
+                    for (int k = 0; k < 15; ++k) {
+                        const int e = (int)((row >> (4 * k)) & 0xFull);
+                        if (e == 15) break;
+                        if ((todo >> e) & 1u) {                    // owned edge, first appearance: its vertex
+                            todo &= ~(1u << e);
+                            float v[6];
+                            make_vertex_from(cfg, dens_at, cx, y, z, e, offx, offy, offz, v);
+                            float2* vd = reinterpret_cast<float2*>(vout + vnext);
+                            vd[0] = make_float2(v[0], v[1]); vd[1] = make_float2(v[2], v[3]); vd[2] = make_float2(v[4], v[5]);
+                            ++vnext;
+                        }
+                        int ox, oy, oz, oe;
+                        owner_of(e, cx, y, z, ox, oy, oz, oe);
+                        const int ocell = oy * S + oz;
+                        const uint32_t ocs = ox == cx ? (uint32_t)cs_cur[ocell] : (uint32_t)cs_prev[ocell];
+                        const uint32_t ovb = ox == cx ? vb_cur[ocell] : vb_prev[ocell];
+                        const uint32_t rank = __popc((uint32_t)mc->before[ocs][oe] & own_mask_of(ox, oy, oz));
+                        dst[k] = (IndexT)(ovb + rank);
+                    }
+                }
+            }
+            vrun += slab_nv; irun += ti;
+            (void)slab_na;
+            __syncthreads();                               // buffers (cx & 1) are overwritten two slabs later; cheap safety
+        }
+        if (!EMIT) {
+            const bool w_all = __all_sync(0xFFFFFFFFu, all_gt), w_any = __any_sync(0xFFFFFFFFu, any_lt);
+            if (lane == 0) { if (!w_all) atomicAnd(&s_red[0], 0); if (w_any) atomicOr(&s_red[1], 1); }
+            __syncthreads();
+            if (tid == 0) {
+                ChunkCounts c;
+                c.n_verts = vrun; c.n_inds = irun; c.flags = (s_red[0] ? CF_ALL_GT : 0u) | (s_red[1] ? CF_ANY_LT : 0u); c.pad = 0;
+                counts[chunk] = c;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // FUSED PATH: one persistent kernel does K1..K4 per chunk; densities never leave the SM.
 //
 //   ticket   chunks are handed out by an atomic counter, so a chunk's predecessors are always
@@ -1186,43 +1378,6 @@ struct FusedControl {
     unsigned long long guard;        // f64 guard-band re-evaluations
     BatchTotals totals;
 };
-
-// Scheduling only (results do not depend on it): a stable partition of the request list that puts the
-// chunks whose z layer CAN hold surface (z_lo <= pos.z <= z_hi, derived on the host from the terrace
-// term and |noise| <= 1) first.  Those are several times more expensive than provably blank / solid
-// chunks; handing them out first lets the cheap ones fill the tail of the persistent kernel.
-__global__ void __launch_bounds__(1024) k_order_chunks(const int32_t* __restrict__ pos, uint32_t n, int z_lo, int z_hi,
-                                                       uint32_t* __restrict__ order) {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_total, s_carry_h, s_carry_l;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t cnt = 0;
-    for (uint32_t i = tid; i < n; i += 1024) { const int z = pos[3 * i + 2]; cnt += (z >= z_lo && z <= z_hi); }
-    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-    if (lane == 0) s_w[warp] = cnt;
-    __syncthreads();
-    if (tid == 0) { uint32_t t = 0; for (int w = 0; w < 32; ++w) t += s_w[w]; s_total = t; s_carry_h = 0; s_carry_l = 0; }
-    __syncthreads();
-    const uint32_t n_heavy = s_total;
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + tid;
-        bool heavy = false, valid = i < n;
-        if (valid) { const int z = pos[3 * i + 2]; heavy = (z >= z_lo && z <= z_hi); }
-        const uint32_t bh = __ballot_sync(0xFFFFFFFFu, valid && heavy), bl = __ballot_sync(0xFFFFFFFFu, valid && !heavy);
-        __syncthreads();
-        if (lane == 0) s_w[warp] = __popc(bh) | (__popc(bl) << 16);
-        __syncthreads();
-        uint32_t ph = 0, pl = 0;
-        for (int w = 0; w < warp; ++w) { ph += s_w[w] & 0xFFFFu; pl += s_w[w] >> 16; }
-        const uint32_t below = (1u << lane) - 1u;
-        if (valid) {
-            if (heavy) order[s_carry_h + ph + __popc(bh & below)] = i;
-            else order[n_heavy + s_carry_l + pl + __popc(bl & below)] = i;
-        }
-        __syncthreads();
-        if (tid == 0) { uint32_t th = 0, tl = 0; for (int w = 0; w < 32; ++w) { th += s_w[w] & 0xFFFFu; tl += s_w[w] >> 16; } s_carry_h += th; s_carry_l += tl; }
-    }
-}
 
 template <int ST, int NOCT>
 struct FusedSmem {

@@ -65,7 +65,8 @@ struct uw_ctx {
     fused16_fn_t fused16_fn = nullptr;
     fused32_fn_t fused32_fn = nullptr;
     bool use_fused = false;
-    int z_lo = 1, z_hi = 0;         // chunk z layers that can hold surface (empty range = unknown: no reordering)
+    bool big_path = false;          // internal_size > 15: slab-walking extraction, densities in HBM
+    size_t big_smem = 0; int big_blocks_per_sm = 1;
     bool ordered = false;           // packed arenas follow request order (look-back) vs atomic bump allocation
     size_t fused_smem = 0; int fused_blocks_per_sm = 1;
     ScanSlot* d_scan = nullptr;
@@ -200,31 +201,6 @@ static uw_status setup_tables(uw_ctx* c) {
             }
         }
     }
-    // z layers that can hold surface: iso = terrace(z) + p with |p| <= 1 (each octave is clamped to [-1, 1]);
-    // used only to hand out expensive chunks first (k_order_chunks)
-    {
-        auto layer_range = [&](int pz, float& tmin, float& tmax) {
-            tmin = 3e38f; tmax = -3e38f;
-            for (int k = 0; k < d.L; ++k) {
-                const double local = (double)k * (double)d.size_scale;
-                const float zf = (float)((local + (double)(pz * cf.chunk_size)) / (double)cf.chunk_size);
-                const float adj = (zf * (float)cf.chunk_size) / cf.max_height;
-                const float t = adj - fmodf(adj, cf.adj_z_mod);
-                tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
-            }
-        };
-        const float margin = 1e-3f;
-        int lo = 1, hi = 0;
-        bool found = false;
-        for (int pz = -4096; pz <= 4096; ++pz) {
-            float tmin, tmax;
-            layer_range(pz, tmin, tmax);
-            const bool blank_certain = tmin - 1.0f > cf.iso_level + margin;
-            const bool solid_certain = tmax + 1.0f < cf.iso_level - margin;
-            if (!blank_certain && !solid_certain) { if (!found) { lo = pz; found = true; } hi = pz; }
-        }
-        if (found && lo > -4096 && hi < 4096) { c->z_lo = lo; c->z_hi = hi; } else { c->z_lo = 1; c->z_hi = 0; }
-    }
     return UW_OK;
 }
 
@@ -268,8 +244,8 @@ extern "C" void uw_destroy(uw_ctx* c) {
 extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     if (!cfg || !out) return fail(nullptr, UW_ERR_INVALID, "uw_create: null argument");
     *out = nullptr;
-    if (cfg->internal_size < 1 || cfg->internal_size > UW_SMALL_MAX_L - 1)
-        return fail(nullptr, UW_ERR_UNSUPPORTED, "uw_create: internal_size must be in 1..15 (small-chunk path)");
+    if (cfg->internal_size < 1 || cfg->internal_size > 64)
+        return fail(nullptr, UW_ERR_UNSUPPORTED, "uw_create: internal_size must be in 1..64");
     if (cfg->octaves < 1 || cfg->octaves > UW_MAX_OCT) return fail(nullptr, UW_ERR_INVALID, "uw_create: octaves must be 1..4");
     if (cfg->chunk_size < 1) return fail(nullptr, UW_ERR_INVALID, "uw_create: chunk_size must be positive");
     if (!(cfg->max_height != 0.0f) || !(cfg->adj_z_mod != 0.0f) || !(cfg->max_z != cfg->min_z))
@@ -297,7 +273,9 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->index32 = (cfg->flags & UW_FLAG_INDEX32) != 0 || cfg->internal_size > 22;
     // FP32 factorisation needs chunk-independent fractional parts: chunk_size a power of two
-    c->fast_path = !(cfg->flags & UW_FLAG_EXACT_F64) && is_pow2(cfg->chunk_size);
+    c->big_path = cfg->internal_size > UW_SMALL_MAX_L - 1;
+    // large chunks currently always use the exact f64 noise kernel (any lattice size)
+    c->fast_path = !(cfg->flags & UW_FLAG_EXACT_F64) && is_pow2(cfg->chunk_size) && !c->big_path;
 
     uw_status st = setup_tables(c);
     if (st != UW_OK) return bail(st);
@@ -342,7 +320,17 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
 
     // launch geometry / kernel selection
     const DevCfg& d = c->dcfg;
-    {
+    if (c->big_path) {
+        c->big_smem = big_smem_bytes(d);
+        auto set_attr = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->big_smem); };
+        bool ok = cu(set_attr((const void*)k_extract_big<false, uint16_t>), "attr big count") &&
+                  cu(set_attr((const void*)k_extract_big<true, uint16_t>), "attr big emit16") &&
+                  cu(set_attr((const void*)k_extract_big<true, uint32_t>), "attr big emit32");
+        if (!ok) return bail(UW_ERR_CUDA);
+        int nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_extract_big<true, uint32_t>, 512, c->big_smem) == cudaSuccess && nb > 0)
+            c->big_blocks_per_sm = nb;
+    } else {
         // the specialised kernels bake the axis tables in at compile time (see SpecDims): usable only
         // when the runtime tables (from this configuration) match them bit for bit
         auto spec_ok = [&](auto dims) {
@@ -512,6 +500,29 @@ static uw_status launch_noise(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
 
 static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uint8_t* d_cases, bool only_emit) {
     const DevCfg& d = c->dcfg;
+    if (c->big_path) {
+        const int grid = persistent_grid(c, n, c->big_blocks_per_sm);
+        if (!only_emit) {
+            k_extract_big<false, uint16_t><<<grid, 512, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, nullptr, nullptr,
+                                                                                 nullptr, nullptr, nullptr);
+            c->launches++;
+            CU_TRY(c, cudaGetLastError());
+            if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
+        }
+        k_scan_chunks<<<1, 1024, 0, c->stream>>>(c->d_counts, d_pos, n, c->d_descs, c->d_active, c->d_totals, c->vcap, c->icap);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
+        if (c->index32)
+            k_extract_big<true, uint32_t><<<grid, 512, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, c->d_descs, c->d_active,
+                                                                                c->d_totals, c->d_verts, (uint32_t*)c->d_inds);
+        else
+            k_extract_big<true, uint16_t><<<grid, 512, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, c->d_descs, c->d_active,
+                                                                                c->d_totals, c->d_verts, (uint16_t*)c->d_inds);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        return UW_OK;
+    }
     if (!only_emit) {
         k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, d_cases);
         c->launches++;
@@ -542,15 +553,7 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     c->ctl_used = c->ctl_parity;
     c->ctl_parity ^= 1;
     const int grid = persistent_grid(c, n, c->fused_blocks_per_sm);
-    // heavy-first hand-out order (scheduling only); the ordered-packing mode needs tickets == request order
-    const uint32_t* d_order = nullptr;
-    static const bool no_order = getenv("UW_NO_ORDER") != nullptr;      // experiment switch
-    if (!no_order && !c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= 65536u) {
-        k_order_chunks<<<1, 1024, 0, c->stream>>>(d_pos, n, c->z_lo, c->z_hi, c->d_active);
-        c->launches++;
-        CU_TRY(c, cudaGetLastError());
-        d_order = c->d_active;
-    }
+    const uint32_t* d_order = nullptr;     // optional hand-out permutation (unused: measured neutral at 2048 chunks)
     if (c->index32)
         c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
             c->d_descs, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0);
@@ -821,6 +824,7 @@ extern "C" uw_status uw_debug_densities(uw_ctx* c, const int32_t* pos, uint32_t 
 
 extern "C" uw_status uw_debug_cases(uw_ctx* c, const int32_t* pos, uint32_t n, uint8_t* out) {
     if (!c) return UW_ERR_INVALID;
+    if (c->big_path) return fail(c, UW_ERR_UNSUPPORTED, "uw_debug_cases: not available for internal_size > 15");
     if ((!pos || !out) && n) return fail(c, UW_ERR_INVALID, "uw_debug_cases: null argument");
     if (n == 0) return UW_OK;
     CU_TRY(c, cudaSetDevice(c->device));

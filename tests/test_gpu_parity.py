@@ -423,3 +423,23 @@ def test_config4_64cubed_chunks_match_oracle_bitwise(uw):
     with uw.ChunkBuilder(uw.Perlin(0), internal_size=64) as b2:
         d2 = b2.debug_densities(np.array([[0, 0, -1], [1, 0, -1]], dtype=np.int32)).reshape(2, 65, 65, 65)
     assert np.array_equal(_bits(d2[0][64]), _bits(d2[1][0]))
+
+
+def test_flythrough_scheduler_batches_build_like_single_chunks(uw, builder12_fast, oracle12):
+    """BASELINE config 5 in miniature: the scheduler mirror hands GPU batches in the reference's priority
+    order; every chunk it stores equals the oracle's build of that position."""
+    from underwaterworld_b200 import world as W
+    world = W.World()
+    n_batches = 0
+    for frame, sub, cam in W.scripted_flythrough(90, 60):
+        n_batches += world.update(sub, cam, builder12_fast) > 0
+    assert n_batches >= 3 and world.total_count() > 150
+    perm = oracle12.perm_table(0)
+    some = sorted(world.chunks)[::17]
+    for p in some:
+        r = oracle12.build_chunk(perm, p, MODE_FAST)
+        c = world.chunks[p]
+        assert c.num_inds() == len(r["inds"]) and c.not_blank() == (len(r["inds"]) > 0)
+        if c.not_blank():
+            assert np.array_equal(c.inds_buffer_slice().astype(np.uint32), r["inds"])
+    assert all(world.chunks[p].not_blank() for p in world.chunks_to_render)

@@ -116,8 +116,11 @@ typedef struct uw_batch_view {
     const uw_vert*       verts;    /* [n_verts]                                                */
     const uint16_t*      inds16;   /* [n_inds]  NULL when only u32 indices were emitted        */
     const uint32_t*      inds32;   /* [n_inds]  NULL unless UW_FLAG_INDEX32 / internal_size>22 */
-    const uw_tri*        tris;     /* [n_inds/3] in index order, NULL unless UW_FLAG_TRIS      */
-    const uint32_t*      tri_cell_start; /* [n_chunks*(S^3+1)] per-cell offsets (chunk-local), or NULL */
+    const uw_tri*        tris;     /* [n_inds/3]: triangle t = indices 3t..3t+2 (chunk c's start at
+                                      index_offset/3); NULL unless UW_FLAG_TRIS                */
+    const uint16_t*      tri_cell_start; /* [n_chunks][S^3+1]: first triangle (chunk-local) of every cell in
+                                      scan order x,y,z -- the reference's per-cell Vec<Tri>
+                                      (chunk.rs:167-174); NULL unless UW_FLAG_TRIS             */
 } uw_batch_view;
 
 /* Device-resident result (no host copies): raw device pointers for interop / benchmarking.

@@ -443,3 +443,39 @@ def test_flythrough_scheduler_batches_build_like_single_chunks(uw, builder12_fas
         if c.not_blank():
             assert np.array_equal(c.inds_buffer_slice().astype(np.uint32), r["inds"])
     assert all(world.chunks[p].not_blank() for p in world.chunks_to_render)
+
+
+def test_collision_tris_bit_exact(uw, oracle12):
+    """SURVEY §8f-1 / chunk.rs:167-174,245-250,315-342: per-cell collision triangles (UW_FLAG_TRIS)."""
+    pos = uw.region.box_region((-1, 1), (-1, 1), (-3, 2))
+    perm = oracle12.perm_table(0)
+    for kw in (dict(exact_f64=True, ordered=True), dict(), dict(staged=True)):
+        with uw.ChunkBuilder(uw.Perlin(0), tris=True, **kw) as b:
+            batch = b.build(pos)
+            dens = b.debug_densities(pos)
+        n_tris = 0
+        for i, p in enumerate(pos):
+            r = oracle12.build_chunk(perm, tuple(int(v) for v in p), MODE_FAITHFUL, isos=dens[i], want_tris=True)
+            m = batch.chunk(i)
+            assert np.array_equal(m.inds.astype(np.uint32), r["inds"])
+            assert len(m.tris) == len(r["tris"]) == len(r["inds"]) // 3
+            assert np.array_equal(m.tri_cell_start.astype(np.uint32), r["tri_cell_start"]), f"cell offsets {p}"
+            if len(m.tris):
+                assert np.array_equal(_bits(m.tris["verts"]), _bits(r["tris"]["verts"]))
+                assert np.array_equal(_bits(m.tris["normal"]), _bits(r["tris"]["normal"]))
+                # triangle t == vertices at indices 3t..3t+2
+                assert np.array_equal(_bits(m.tris["verts"]), _bits(m.verts["pos"][m.inds.reshape(-1, 3).astype(np.int64)]))
+            n_tris += len(m.tris)
+        assert n_tris > 3000
+    # Chunk::tris_around
+    with uw.ChunkBuilder(uw.Perlin(0), tris=True) as b:
+        c = uw.Chunk.new((0, 0, -1))
+        c.build_full(b)
+        allt = c.tris_around((0.5, 0.5, 0.5), 12)
+        assert len(allt) == c.num_inds() // 3
+        few = c.tris_around((0.5, 0.5, 0.5), 1)
+        assert 0 < len(few) < len(allt)
+        m = c._mesh
+        cells = [(x * 12 + y) * 12 + z for x in (5, 6, 7) for y in (5, 6, 7) for z in (5, 6, 7)]
+        want = sum(int(m.tri_cell_start[k + 1]) - int(m.tri_cell_start[k]) for k in cells)
+        assert len(few) == want

@@ -27,7 +27,7 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 
 from . import _ffi
-from ._ffi import (CHUNK_BLANK_EARLY, CHUNK_HAS_MESH, CHUNK_U16_OVERFLOW, DESC_DTYPE, VERT_DTYPE, UwError)
+from ._ffi import (CHUNK_BLANK_EARLY, CHUNK_HAS_MESH, CHUNK_U16_OVERFLOW, DESC_DTYPE, TRI_DTYPE, VERT_DTYPE, UwError)
 
 # reference constants, chunk.rs:5-12
 CHUNK_SIZE = 16
@@ -67,6 +67,8 @@ class ChunkMesh:
     flags: int
     verts: np.ndarray          # VERT_DTYPE [vert_count]  == draw::VertColor
     inds: np.ndarray           # uint16 (or uint32) [index_count], chunk-local
+    tris: Optional[np.ndarray] = None            # TRI_DTYPE [index_count / 3]   (UW_FLAG_TRIS)
+    tri_cell_start: Optional[np.ndarray] = None  # uint16 [S^3 + 1], first triangle of every cell (scan order)
 
     @property
     def blank_early(self) -> bool:
@@ -82,8 +84,9 @@ class ChunkMesh:
 class Batch:
     """Finished batch (host copies of the packed buffers)."""
 
-    def __init__(self, descs: np.ndarray, verts: np.ndarray, inds: np.ndarray):
+    def __init__(self, descs: np.ndarray, verts: np.ndarray, inds: np.ndarray, tris=None, tri_cell_start=None):
         self.descs, self.verts, self.inds = descs, verts, inds
+        self.tris, self.tri_cell_start = tris, tri_cell_start
 
     def __len__(self) -> int:
         return int(self.descs.shape[0])
@@ -99,7 +102,10 @@ class Batch:
     def chunk(self, i: int) -> ChunkMesh:
         d = self.descs[i]
         vo, vc, io, ic = int(d["vert_offset"]), int(d["vert_count"]), int(d["index_offset"]), int(d["index_count"])
-        return ChunkMesh(tuple(int(v) for v in d["pos"]), int(d["flags"]), self.verts[vo:vo + vc], self.inds[io:io + ic])
+        tris = tcs = None
+        if self.tris is not None:
+            tris, tcs = self.tris[io // 3:(io + ic) // 3], self.tri_cell_start[i]
+        return ChunkMesh(tuple(int(v) for v in d["pos"]), int(d["flags"]), self.verts[vo:vo + vc], self.inds[io:io + ic], tris, tcs)
 
     def __iter__(self):
         return (self.chunk(i) for i in range(len(self)))
@@ -110,7 +116,7 @@ class ChunkBuilder:
 
     def __init__(self, perlin: Optional[Perlin] = None, *, internal_size: int = INTERNAL_SIZE, device: int = -1,
                  exact_f64: bool = False, index32: bool = False, keep_densities: bool = False,
-                 staged: bool = False, ordered: bool = False, guard_eps: float = 0.0, **consts):
+                 staged: bool = False, ordered: bool = False, tris: bool = False, guard_eps: float = 0.0, **consts):
         self._lib = _ffi.load_library()
         cfg = _ffi.UwConfig()
         self._lib.uw_config_default(C.byref(cfg))
@@ -120,7 +126,7 @@ class ChunkBuilder:
         cfg.guard_eps = guard_eps
         cfg.flags = ((_ffi.FLAG_EXACT_F64 if exact_f64 else 0) | (_ffi.FLAG_INDEX32 if index32 else 0)
                      | (_ffi.FLAG_KEEP_DENSITIES if keep_densities else 0) | (_ffi.FLAG_STAGED if staged else 0)
-                     | (_ffi.FLAG_ORDERED if ordered else 0))
+                     | (_ffi.FLAG_ORDERED if ordered else 0) | (_ffi.FLAG_TRIS if tris else 0))
         for k, v in consts.items():
             if not hasattr(cfg, k):
                 raise TypeError(f"unknown config field {k!r}")
@@ -197,9 +203,17 @@ class ChunkBuilder:
                 inds = np.empty(ni, dtype=np.uint16)
                 if ni:
                     C.memmove(inds.ctypes.data, view.inds16, ni * 2)
+            tris = tcs = None
+            if view.tris:
+                tris = np.empty(ni // 3, dtype=TRI_DTYPE)
+                if ni:
+                    C.memmove(tris.ctypes.data, view.tris, (ni // 3) * TRI_DTYPE.itemsize)
+                tcs = np.empty((n, self.S ** 3 + 1), dtype=np.uint16)
+                if n:
+                    C.memmove(tcs.ctypes.data, view.tri_cell_start, tcs.nbytes)
         finally:
             self._lib.uw_batch_free(handle)
-        return Batch(descs, verts, inds)
+        return Batch(descs, verts, inds, tris, tcs)
 
     def build(self, positions) -> Batch:
         """Chunk::new + Chunk::build_full for every position (host in, host out)."""
@@ -305,6 +319,25 @@ class Chunk:
 
     def num_inds(self) -> int:
         return 0 if self._mesh is None else self._mesh.num_inds()
+
+    def tris_around(self, local_pos_percent: Sequence[float], rng: int) -> np.ndarray:
+        """Chunk::tris_around (chunk.rs:315-342): the collision triangles of every cell within `rng` cells of
+        the cell containing local_pos_percent (each component in [0,1)).  Needs ChunkBuilder(tris=True)."""
+        m = self._mesh
+        if m is None or m.tris is None:
+            raise RuntimeError("tris_around needs a chunk built with ChunkBuilder(tris=True)")
+        S = round((len(m.tri_cell_start) - 1) ** (1.0 / 3.0))
+        mid = [int(np.floor(np.float32(v) * np.float32(S))) for v in local_pos_percent]
+        lo = [max(c - rng, 0) for c in mid]
+        hi = [min(c + rng, S) for c in mid]                      # inclusive, like the reference (cells == S hold nothing)
+        out = []
+        for x in range(lo[0], hi[0] + 1):
+            for y in range(lo[1], hi[1] + 1):
+                for z in range(lo[2], hi[2] + 1):
+                    if x < S and y < S and z < S:
+                        c = (x * S + y) * S + z
+                        out.append(m.tris[int(m.tri_cell_start[c]):int(m.tri_cell_start[c + 1])])
+        return np.concatenate(out) if out else np.zeros(0, dtype=TRI_DTYPE)
 
 
 def build_chunks(builder: ChunkBuilder, positions: Iterable[Sequence[int]]) -> list:

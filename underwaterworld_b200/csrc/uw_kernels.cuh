@@ -883,10 +883,11 @@ __device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, i
     else                            { out[0] = HI; out[1] = LO; out[2] = X;  }
 }
 
-// vertex of the directed edge `e` of cell (x,y,z): chunk.rs:178-231.  dens_at(ax, ay, az) -> density.
+// world position of the vertex on the directed edge `e` of cell (x,y,z): chunk.rs:178-213,224-229.
+// dens_at(ax, ay, az) -> density.  Returns corner_b's cube-local index (chunk.rs:219 needs it).
 template <class DensAt>
-__device__ __forceinline__ void make_vertex_from(const DevCfg& cfg, DensAt dens_at, int x, int y, int z, int e,
-                                                 int offx, int offy, int offz, float v[6]) {
+__device__ __forceinline__ int edge_position(const DevCfg& cfg, DensAt dens_at, int x, int y, int z, int e,
+                                             int offx, int offy, int offz, float p[3]) {
     const int ca = c_edge_a[e], cb = c_edge_b[e];
     int ax, ay, az, bx, by, bz;
     corner_off(ca, ax, ay, az); corner_off(cb, bx, by, bz);
@@ -898,9 +899,28 @@ __device__ __forceinline__ void make_vertex_from(const DevCfg& cfg, DensAt dens_
     const float mx = __fadd_rn(sax, __fmul_rn(t, __fsub_rn(sbx, sax)));
     const float my = __fadd_rn(say, __fmul_rn(t, __fsub_rn(sby, say)));
     const float mz = __fadd_rn(saz, __fmul_rn(t, __fsub_rn(sbz, saz)));
-    const float wz = __fadd_rn(mz, (float)offz);
-    v[0] = __fadd_rn(mx, (float)offx); v[1] = __fadd_rn(my, (float)offy); v[2] = wz;
-    vertex_color(cfg, wz, cb % 3, v + 3);
+    p[0] = __fadd_rn(mx, (float)offx); p[1] = __fadd_rn(my, (float)offy); p[2] = __fadd_rn(mz, (float)offz);
+    return cb;
+}
+
+// vertex (position + colour) of the directed edge `e` of cell (x,y,z): chunk.rs:178-231
+template <class DensAt>
+__device__ __forceinline__ void make_vertex_from(const DevCfg& cfg, DensAt dens_at, int x, int y, int z, int e,
+                                                 int offx, int offy, int offz, float v[6]) {
+    const int cb = edge_position(cfg, dens_at, x, y, z, e, offx, offy, offz, v);
+    vertex_color(cfg, v[2], cb % 3, v + 3);
+}
+
+// util::Tri::new (util.rs:12-21) with cgmath's cross / magnitude / div and safe_normalize (util.rs:61-64); f32, unfused
+__device__ __forceinline__ void tri_normal(const float a[3], const float b[3], const float c[3], float n[3]) {
+    const float e1x = __fsub_rn(b[0], a[0]), e1y = __fsub_rn(b[1], a[1]), e1z = __fsub_rn(b[2], a[2]);
+    const float e2x = __fsub_rn(c[0], a[0]), e2y = __fsub_rn(c[1], a[1]), e2z = __fsub_rn(c[2], a[2]);
+    const float nx = __fsub_rn(__fmul_rn(e1y, e2z), __fmul_rn(e1z, e2y));
+    const float ny = __fsub_rn(__fmul_rn(e1z, e2x), __fmul_rn(e1x, e2z));
+    const float nz = __fsub_rn(__fmul_rn(e1x, e2y), __fmul_rn(e1y, e2x));
+    const float mag = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+    if (mag == 0.0f) { n[0] = nx; n[1] = ny; n[2] = nz; }
+    else { n[0] = __fdiv_rn(nx, mag); n[1] = __fdiv_rn(ny, mag); n[2] = __fdiv_rn(nz, mag); }
 }
 
 __device__ __forceinline__ void make_vertex(const DevCfg& cfg, const float* s_dens, int x, int y, int z, int e,
@@ -992,8 +1012,10 @@ __device__ __forceinline__ uint32_t natural_of(uint32_t q0 /*m00 | m10<<16*/, ui
     return ((a | (a >> 14)) & 0xFu) | (((b | (b >> 14)) & 0xFu) << 4);
 }
 
+// tri_cell (nullable): global u16[S^3 + 1], first triangle of every cell (chunk-local, scan order)
 template <int ST>
-__device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const EmitSmem& s, uint32_t* s_w) {
+__device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const EmitSmem& s, uint32_t* s_w,
+                                                   uint16_t* __restrict__ tri_cell = nullptr) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int S = ST > 0 ? ST : cfg.S, L = S + 1, ncol = S * S;
 
@@ -1028,6 +1050,14 @@ __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const Emit
     uint32_t eva, ei, tva, ti;
     block_scan2(nva, ni, eva, ei, tva, ti, s_w);
 
+    if (tri_cell && col < ncol) {        // per-cell triangle offsets (the reference's per-cell Vec<Tri>, chunk.rs:167-174)
+        uint32_t rt = ei;
+        for (int z = 0; z < S; ++z) {
+            tri_cell[col * S + z] = (uint16_t)(rt / 3u);
+            if ((smask >> z) & 1u) rt += (s.lut[natural_of(q0, q1, z)] >> 8) & 15u;
+        }
+        if (col == ncol - 1) tri_cell[ncol * S] = (uint16_t)(ti / 3u);
+    }
     // ---- C: surface cells only ------------------------------------------------------------------------
     uint32_t rv = eva & 0xFFFFu, ra = eva >> 16, ri = ei;
     while (smask) {
@@ -1118,6 +1148,40 @@ __device__ __forceinline__ void emit_indices(const DevCfg& cfg, const McTables* 
     }
 }
 
+// F (UW_FLAG_TRIS): the reference's collision triangles, one thread per surface cell; triangle t of the
+// chunk is (indices 3t..3t+2), its corners recomputed from the cell's own edges (same ordered corner
+// pairs and densities as the vertex buffer -> bit-identical positions)
+template <int ST>
+__device__ __forceinline__ void emit_tris(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
+                                          const ChunkShape sh, int px, int py, int pz, uw_tri* __restrict__ tout) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int S = ST > 0 ? ST : cfg.S, L = S + 1;
+    const int offx = px * cfg.chunk_size, offy = py * cfg.chunk_size, offz = pz * cfg.chunk_size;
+    const float* dens = s.dens;
+    auto dens_at = [=](int ax, int ay, int az) { return dens[(ax * L + ay) * L + az]; };
+    for (uint32_t a = tid; a < sh.n_act; a += NT) {
+        const int cell = s.alist[a];
+        const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+        const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
+        float* dst = reinterpret_cast<float*>(tout + s.ibase[cell] / 3u);
+#pragma unroll 1
+        for (int t = 0; t < 5; ++t) {
+            const int e0 = (int)((row >> (12 * t)) & 0xFull);
+            if (e0 == 15) break;
+            const int e1 = (int)((row >> (12 * t + 4)) & 0xFull), e2 = (int)((row >> (12 * t + 8)) & 0xFull);
+            float v[12];
+            edge_position(cfg, dens_at, x, y, z, e0, offx, offy, offz, v);
+            edge_position(cfg, dens_at, x, y, z, e1, offx, offy, offz, v + 3);
+            edge_position(cfg, dens_at, x, y, z, e2, offx, offy, offz, v + 6);
+            tri_normal(v, v + 3, v + 6, v + 9);
+            float4* d4 = reinterpret_cast<float4*>(dst + 12 * t);       // uw_tri is 48 B; the array base is 16-B aligned
+            d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+            d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+            d4[2] = make_float4(v[8], v[9], v[10], v[11]);
+        }
+    }
+}
+
 // everything after the first fill + barrier
 template <int ST, typename IndexT>
 __device__ __forceinline__ void emit_rest(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
@@ -1140,7 +1204,8 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
                                                     const uw_chunk_desc* __restrict__ descs,
                                                     const uint32_t* __restrict__ active,
                                                     const BatchTotals* __restrict__ totals,
-                                                    uw_vert* __restrict__ verts, IndexT* __restrict__ inds) {
+                                                    uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
+                                                    uw_tri* __restrict__ tris, uint16_t* __restrict__ tri_cell) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const EmitSmem s = emit_smem_carve(cfg, smem_raw);
     __shared__ int s_red[2];
@@ -1158,10 +1223,12 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
         load_signs<true>(cfg, dens + (size_t)chunk * cfg.dens_stride, s.dens, s.bits, s_red);
         for (int c = tid; c < L * L; c += NT) s.mask[c] = col_mask(s.bits, c, L);
         __syncthreads();
-        const ChunkShape sh = emit_prepare<ST>(cfg, s, s_w);
+        const int ncell = (L - 1) * (L - 1) * (L - 1);
+        const ChunkShape sh = emit_prepare<ST>(cfg, s, s_w, tri_cell ? tri_cell + (size_t)chunk * (ncell + 1) : nullptr);
         emit_fill<ST>(cfg, mc, s, sh, 0);
         __syncthreads();
         emit_rest<ST, IndexT>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
+        if (tris) emit_tris<ST>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], tris + d.index_offset / 3u);
         __syncthreads();
     }
 }
@@ -1455,7 +1522,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
               uw_chunk_desc* __restrict__ descs,
               uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
               unsigned long long vcap, unsigned long long icap,
-              float* __restrict__ dens_out /*nullable: debug tap*/, int ordered) {
+              float* __restrict__ dens_out /*nullable: debug tap*/, int ordered,
+              uw_tri* __restrict__ tris /*nullable: UW_FLAG_TRIS*/, uint16_t* __restrict__ tri_cell /*nullable*/) {
     using D = SpecDims<ST, NOCT>;
     BatchTotals* const totals = &ctr->totals;
     unsigned long long* const guard_count = &ctr->guard;
@@ -1540,7 +1608,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         // ---- K2: cases, counts, per-cell bases (block-uniform skip when no sample is inside) -------------
         ChunkShape sh;
         sh.n_vert = 0; sh.n_ind = 0; sh.n_act = 0;
-        if (fl & CF_ANY_LT) sh = emit_prepare<ST>(cfg, es, sm.w);
+        if (fl & CF_ANY_LT) sh = emit_prepare<ST>(cfg, es, sm.w, tri_cell ? tri_cell + (size_t)chunk * (ST * ST * ST + 1) : nullptr);
         const uint32_t nv = sh.n_vert, ni = sh.n_ind;
         PHASE_MARK(2);                                     // K2 prepare
 
@@ -1575,8 +1643,10 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             __syncthreads();
             PHASE_MARK(4);                                 // K4 D1 fill
             ev = sm.part[0] >> 32; ei = sm.part[0] & 0xFFFFFFFFull;
-            if (ev + nv <= vcap && ei + ni <= icap)
+            if (ev + nv <= vcap && ei + ni <= icap) {
                 emit_rest<ST, IndexT>(cfg, mc, es, sh, px, py, pz, verts + ev, inds + ei);
+                if (tris) emit_tris<ST>(cfg, mc, es, sh, px, py, pz, tris + ei / 3u);
+            }
             PHASE_MARK(5);                                 // K4 D2 + E (thread 0's own share)
         }
         if (tid == 0) {

@@ -44,6 +44,9 @@ struct uw_ctx {
     unsigned long long vcap = 0, icap = 0;
     uw_vert* d_verts = nullptr;
     void* d_inds = nullptr;
+    bool tris = false;              // UW_FLAG_TRIS: per-cell collision triangles
+    uw_tri* d_tris = nullptr;       // [icap / 3]
+    uint16_t* d_tri_cell = nullptr; // [cap_chunks][S^3 + 1]
 
     // pinned host staging
     int32_t* h_pos = nullptr; size_t h_pos_cap = 0;
@@ -54,14 +57,14 @@ struct uw_ctx {
 
     // launch geometry / kernel selection
     typedef void (*noise_fn_t)(DevCfg, AxisTables, const uint8_t*, const int32_t*, uint32_t, float*, unsigned long long*);
-    typedef void (*emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*);
-    typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*);
+    typedef void (*emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*, uw_tri*, uint16_t*);
+    typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uw_tri*, uint16_t*);
     typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, const uint32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint16_t*, unsigned long long,
-                                 unsigned long long, float*, int);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*);
     typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, const uint32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint32_t*, unsigned long long,
-                                 unsigned long long, float*, int);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*);
     fused16_fn_t fused16_fn = nullptr;
     fused32_fn_t fused32_fn = nullptr;
     bool use_fused = false;
@@ -229,7 +232,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_pos); cudaFree(c->d_dens); cudaFree(c->d_counts);
     cudaFree(c->d_descs); cudaFree(c->d_active); cudaFree(c->d_cases); cudaFree(c->d_totals); cudaFree(c->d_guard);
-    cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_scan); cudaFree(c->d_ctl);
+    cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_tris); cudaFree(c->d_tri_cell); cudaFree(c->d_scan); cudaFree(c->d_ctl);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_pos) cudaFreeHost(c->h_pos);
     if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -274,6 +277,8 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     c->index32 = (cfg->flags & UW_FLAG_INDEX32) != 0 || cfg->internal_size > 22;
     // FP32 factorisation needs chunk-independent fractional parts: chunk_size a power of two
     c->big_path = cfg->internal_size > UW_SMALL_MAX_L - 1;
+    c->tris = (cfg->flags & UW_FLAG_TRIS) != 0;
+    if (c->tris && c->big_path) { c->err = "uw_create: UW_FLAG_TRIS is not available for internal_size > 15"; return bail(UW_ERR_UNSUPPORTED); }
     // large chunks currently always use the exact f64 noise kernel (any lattice size)
     c->fast_path = !(cfg->flags & UW_FLAG_EXACT_F64) && is_pow2(cfg->chunk_size) && !c->big_path;
 
@@ -431,6 +436,7 @@ static uw_status ensure_chunks(uw_ctx* c, uint32_t n) {
     CU_TRY(c, regrow(&c->d_descs, cap));
     CU_TRY(c, regrow(&c->d_active, cap));
     CU_TRY(c, regrow(&c->d_scan, cap));
+    if (c->tris) CU_TRY(c, regrow(&c->d_tri_cell, (size_t)cap * ((size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1)));
     if (!c->d_ctl) {
         CU_TRY(c, cudaMalloc(&c->d_ctl, 2 * sizeof(FusedControl)));
         CU_TRY(c, cudaMemset(c->d_ctl, 0, 2 * sizeof(FusedControl)));
@@ -455,6 +461,7 @@ static uw_status ensure_outputs(uw_ctx* c, unsigned long long nv, unsigned long 
         CU_TRY(c, cudaStreamSynchronize(c->stream));
         if (c->d_inds) { cudaFree(c->d_inds); c->d_inds = nullptr; }
         CU_TRY(c, cudaMalloc(&c->d_inds, (size_t)cap * isz));
+        if (c->tris) CU_TRY(c, regrow(&c->d_tris, (size_t)cap / 3 + 1));
         c->icap = cap;
     }
     return UW_OK;
@@ -536,10 +543,10 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
     const int grid = persistent_grid(c, n, c->emit_blocks_per_sm);
     if (c->index32)
         c->emit32_fn<<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
-                                                            c->d_verts, (uint32_t*)c->d_inds);
+                                                            c->d_verts, (uint32_t*)c->d_inds, c->d_tris, c->d_tri_cell);
     else
         c->emit16_fn<<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
-                                                            c->d_verts, (uint16_t*)c->d_inds);
+                                                            c->d_verts, (uint16_t*)c->d_inds, c->d_tris, c->d_tri_cell);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;
@@ -556,10 +563,10 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     const uint32_t* d_order = nullptr;     // optional hand-out permutation (unused: measured neutral at 2048 chunks)
     if (c->index32)
         c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
-            c->d_descs, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0);
+            c->d_descs, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell);
     else
         c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
-            c->d_descs, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0);
+            c->d_descs, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;
@@ -571,7 +578,10 @@ static uw_status enqueue_build(uw_ctx* c, const int32_t* d_pos, uint32_t n, bool
     uw_status st = ensure_outputs(c, (unsigned long long)n * 192 + 4096, (unsigned long long)n * 640 + 16384);
     if (st != UW_OK) return st;
     c->launches = 0;
-    CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
+    if (c->tris)      // cells of chunks that never reach the emit stage keep offset 0
+        CU_TRY(c, cudaMemsetAsync(c->d_tri_cell, 0, (size_t)n * ((size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1) * 2, c->stream));
+    if (!(c->use_fused && !from_densities))      // the fused kernel counts guard re-evaluations in its control block
+        CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
     c->last_fused = false;
     if (c->use_fused && !from_densities) {
         if (c->profiling) for (int e = 0; e < 4; ++e) CU_TRY(c, cudaEventRecord(c->ev[e], c->stream));
@@ -677,15 +687,23 @@ static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
     const size_t off_desc = 0;
     const size_t off_vert = (sizeof(uw_chunk_desc) * (size_t)b->n + 255) & ~(size_t)255;
     const size_t off_ind = (off_vert + sizeof(uw_vert) * (size_t)t.n_verts + 255) & ~(size_t)255;
-    const size_t bytes = off_ind + isz * (size_t)t.n_inds + 256;
+    const size_t ncell1 = (size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1;
+    const size_t off_tri = (off_ind + isz * (size_t)t.n_inds + 255) & ~(size_t)255;
+    const size_t off_tcs = (off_tri + (c->tris ? sizeof(uw_tri) * (size_t)(t.n_inds / 3) : 0) + 255) & ~(size_t)255;
+    const size_t bytes = off_tcs + (c->tris ? ncell1 * 2 * (size_t)b->n : 0) + 256;
     st = pinned_get(c, bytes, &b->arena);
     if (st != UW_OK) return st;
     char* base = (char*)b->arena.ptr;
     CU_TRY(c, cudaMemcpyAsync(base + off_desc, c->d_descs, sizeof(uw_chunk_desc) * (size_t)b->n, cudaMemcpyDeviceToHost, c->stream));
     if (t.n_verts) CU_TRY(c, cudaMemcpyAsync(base + off_vert, c->d_verts, sizeof(uw_vert) * (size_t)t.n_verts, cudaMemcpyDeviceToHost, c->stream));
     if (t.n_inds) CU_TRY(c, cudaMemcpyAsync(base + off_ind, c->d_inds, isz * (size_t)t.n_inds, cudaMemcpyDeviceToHost, c->stream));
+    if (c->tris) {
+        if (t.n_inds) CU_TRY(c, cudaMemcpyAsync(base + off_tri, c->d_tris, sizeof(uw_tri) * (size_t)(t.n_inds / 3), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(base + off_tcs, c->d_tri_cell, ncell1 * 2 * (size_t)b->n, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     memset(&b->view, 0, sizeof b->view);
+    if (c->tris) { b->view.tris = (const uw_tri*)(base + off_tri); b->view.tri_cell_start = (const uint16_t*)(base + off_tcs); }
     b->view.n_chunks = b->n; b->view.n_verts = t.n_verts; b->view.n_inds = t.n_inds;
     b->view.descs = (const uw_chunk_desc*)(base + off_desc);
     b->view.verts = (const uw_vert*)(base + off_vert);

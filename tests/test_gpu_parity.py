@@ -410,7 +410,7 @@ def test_config4_64cubed_chunks_match_oracle_bitwise(uw):
     o = Oracle(64)
     perm = o.perm_table(0)
     pos = np.array([[0, 0, -1], [0, 0, 0], [-3, 2, -2], [4, 4, 2], [1, 1, -5], [2, -7, -1]], dtype=np.int32)
-    with uw.ChunkBuilder(uw.Perlin(0), internal_size=64, ordered=True) as b:
+    with uw.ChunkBuilder(uw.Perlin(0), internal_size=64, ordered=True, exact_f64=True) as b:
         batch = b.build(pos)
         dens = b.debug_densities(pos[:2])
     refs = _oracle_batch(o, perm, pos, MODE_FAST)
@@ -420,7 +420,7 @@ def test_config4_64cubed_chunks_match_oracle_bitwise(uw):
     assert batch.chunk(3).flags == 1 and batch.chunk(4).flags == 0 and batch.chunk(4).num_inds() == 0
     # neighbouring 64^3 chunks agree on their shared face (u_64 = 1.0 exactly)
     d2 = None
-    with uw.ChunkBuilder(uw.Perlin(0), internal_size=64) as b2:
+    with uw.ChunkBuilder(uw.Perlin(0), internal_size=64, exact_f64=True) as b2:
         d2 = b2.debug_densities(np.array([[0, 0, -1], [1, 0, -1]], dtype=np.int32)).reshape(2, 65, 65, 65)
     assert np.array_equal(_bits(d2[0][64]), _bits(d2[1][0]))
 
@@ -479,3 +479,25 @@ def test_collision_tris_bit_exact(uw, oracle12):
         cells = [(x * 12 + y) * 12 + z for x in (5, 6, 7) for y in (5, 6, 7) for z in (5, 6, 7)]
         want = sum(int(m.tri_cell_start[k + 1]) - int(m.tri_cell_start[k]) for k in cells)
         assert len(few) == want
+
+
+def test_config4_fp32_noise_topology_bit_exact(uw):
+    """64^3 chunks through the FP32 plane-tiled noise kernel (+ f64 guard band): densities within tolerance,
+    classification identical, and the mesh equals the oracle's mesh of the GPU's densities bit for bit."""
+    from oracle import Oracle
+    o = Oracle(64)
+    perm = o.perm_table(0)
+    pos = np.array([[0, 0, -1], [0, 0, 0], [-3, 2, -2], [4, 4, 2], [1, 1, -5], [2, -7, -1], [100, -50, 1]], dtype=np.int32)
+    with uw.ChunkBuilder(uw.Perlin(0), internal_size=64, ordered=True) as b:
+        batch = b.build(pos)
+        gdens = b.debug_densities(pos)
+        guards = b.guard_count()
+    want = np.stack([o.densities(perm, p) for p in pos])
+    assert np.abs(gdens.astype(np.float64) - want).max() <= DENS_TOL
+    iso = np.float32(-0.1)
+    assert np.array_equal(gdens < iso, want < iso) and np.array_equal(gdens > iso, want > iso)
+    assert 0 < guards < 1e-3 * gdens.size
+    refs = _oracle_batch(o, perm, pos, MODE_FAST)                       # oracle's own densities: topology
+    for i, r in enumerate(refs):
+        assert np.array_equal(batch.chunk(i).inds, r["inds"]) and batch.chunk(i).flags & 3 == r["flags"] & 3
+    _check_batch(batch, _oracle_batch(o, perm, pos, MODE_FAST, isos=gdens), exact_positions=True)

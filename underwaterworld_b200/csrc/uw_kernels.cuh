@@ -1234,6 +1234,171 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
 }
 
 // ---------------------------------------------------------------------------------------
+// K1 for large chunks (e.g. 65^3 samples): the same tensor-product factorisation as noise_chunk_spec,
+// tiled over the chunk's (i, j) columns.  A unit is 256 consecutive columns of one chunk (they touch at
+// most PLMAX x-planes, so stage X is tiny); every thread walks its whole z column with the per-sample
+// weights as compile-time immediates, parks the results in a per-warp shared-memory tile and the warp
+// flushes the tile with contiguous stores (a column is 260 contiguous bytes in HBM).
+// ---------------------------------------------------------------------------------------
+template <int ST, int NOCT>
+struct BigNoiseSmem {
+    using D = SpecDims<ST, NOCT>;
+    static constexpr int NT = 256, NW = NT / 32;
+    static constexpr int PLMAX = (NT + D::L - 2) / D::L + 1;           // x-planes 256 consecutive columns can touch
+    static constexpr int G2SUM = (NOCT >= 1 ? 9 : 0) + (NOCT >= 2 ? 16 : 0) + (NOCT >= 3 ? 36 : 0) + (NOCT >= 4 ? 100 : 0);
+    static constexpr int HALF = (D::L + 1) / 2;                         // z samples per tile flush
+    float4 lat[D::LAT];
+    float4 X[PLMAX * G2SUM];
+    float4 axis[NOCT][D::L + 1];
+    float4 grad[16];
+    float terr[D::L + 3];
+    uint8_t perm[256];
+    float tile[NW][32][HALF + 1 - (HALF & 1)];                          // odd row stride: conflict-free column writes
+};
+
+template <int ST, int NOCT>
+__global__ void __launch_bounds__(256, 3)
+k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axis /*[NOCT][L]: d, d-1, fade, -*/,
+            const uint8_t* __restrict__ g_perm, const int32_t* __restrict__ pos, uint32_t n,
+            float* __restrict__ dens, unsigned long long* __restrict__ guard_count) {
+    using D = SpecDims<ST, NOCT>;
+    using SM = BigNoiseSmem<ST, NOCT>;
+    constexpr int L = D::L, L2 = L * L, NT = SM::NT, HALF = SM::HALF, TS = HALF + 1 - (HALF & 1);
+    constexpr int UPC = (L2 + NT - 1) / NT;                             // units per chunk
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int t = tid; t < 256; t += NT) sm.perm[t] = g_perm[t];
+    if (tid < 16) sm.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
+    for (int t = tid; t < NOCT * L; t += NT) sm.axis[t / L][t % L] = g_axis[t];
+    __syncthreads();
+
+    constexpr float inv_max = 1.0f / (2.0f - 1.0f / (float)(1 << (NOCT - 1)));
+    const unsigned long long n_units = (unsigned long long)n * UPC;
+    for (unsigned long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const uint32_t chunk = (uint32_t)(u / UPC);
+        const int col0 = (int)(u - (unsigned long long)chunk * UPC) * NT;
+        const int ncols = min(NT, L2 - col0);
+        const int i_min = col0 / L, npl = (col0 + ncols - 1) / L - i_min + 1;
+        const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];
+
+        // ---- stage H ----------------------------------------------------------------------------
+#pragma unroll
+        for (int o = 0; o < NOCT; ++o) {
+            const int G = D::G(o), F = 1 << o, base = D::lat_base(o);
+            for (int t = tid; t < G * G * G; t += NT) {
+                const int cx = t / (G * G), r = t - cx * G * G, cy = r / G, cz = r - cy * G;
+                const uint32_t h = sm.perm[sm.perm[sm.perm[(F * px + cx) & 255] ^ ((F * py + cy) & 255)] ^ ((F * pz + cz) & 255)];
+                sm.lat[base + t] = sm.grad[h & 15u];
+            }
+        }
+        if (tid < L) {
+            float adj, fm;
+            terrace_terms(cfg, tid, pz, adj, fm);
+            sm.terr[tid] = __fsub_rn(adj, fm);
+        }
+        __syncthreads();
+        // ---- stage X (only the planes this unit touches) ------------------------------------------
+        {
+            int xb = 0;
+#pragma unroll
+            for (int o = 0; o < NOCT; ++o) {
+                const int G = D::G(o), lb = D::lat_base(o);
+                const float sc = 1.1547005383792515f * inv_max / (float)(1 << o);
+                for (int t = tid; t < npl * G * G; t += NT) {
+                    const int pl = t / (G * G), r = t - pl * G * G;
+                    const int i = i_min + pl, c = (i << o) / ST;
+                    const float4 g0 = sm.lat[lb + c * G * G + r], g1 = sm.lat[lb + (c + 1) * G * G + r];
+                    const float4 ax = sm.axis[o][i];
+                    const float q0 = g0.x * ax.x, q1 = g1.x * ax.y;
+                    float4 e;
+                    e.x = fmaf(ax.z, q1 - q0, q0) * sc;
+                    e.y = fmaf(ax.z, g1.y - g0.y, g0.y) * sc;
+                    e.z = fmaf(ax.z, g1.z - g0.z, g0.z) * sc;
+                    e.w = 0.f;
+                    sm.X[xb + t] = e;
+                }
+                xb += SM::PLMAX * G * G;
+            }
+        }
+        __syncthreads();
+        // ---- stage YZ ---------------------------------------------------------------------------------
+        const int col = col0 + tid;
+        const bool live = tid < ncols;
+        const int i = live ? col / L : i_min, j = live ? col - i * L : 0;
+        float R0[NOCT], S0[NOCT], R1[NOCT], S1[NOCT], Cc[NOCT], Dd[NOCT];
+        const float4* xrow[NOCT];
+        float dy[NOCT], dy1[NOCT], wy[NOCT];
+        {
+            int xb = 0;
+#pragma unroll
+            for (int o = 0; o < NOCT; ++o) {
+                const int G = D::G(o);
+                xrow[o] = sm.X + xb + ((i - i_min) * G + ((j << o) / ST)) * G;
+                const float4 ay = sm.axis[o][j];
+                dy[o] = ay.x; dy1[o] = ay.y; wy[o] = ay.z;
+                xb += SM::PLMAX * G * G;
+            }
+        }
+        auto ystage = [&](int o, int cz, float& R, float& Sz) {
+            const int G = D::G(o);
+            const float4 E0 = xrow[o][cz];
+            const float4 E1 = xrow[o][G + cz];
+            const float A0 = fmaf(E0.y, dy[o], E0.x);
+            const float A1 = fmaf(E1.y, dy1[o], E1.x);
+            R = fmaf(wy[o], A1 - A0, A0);
+            Sz = fmaf(wy[o], E1.z - E0.z, E0.z);
+        };
+        const float isl = cfg.iso_level, eps = cfg.guard_eps;
+        float* trow = &sm.tile[warp][lane][0];
+        float* gout = dens + (size_t)chunk * cfg.dens_stride;
+        const int wcol0 = col0 + warp * 32;
+        unsigned long long near = 0;
+        // flush the warp's tile: `cnt` z samples starting at kbase of up to 32 consecutive columns
+        auto flush = [&](int kbase, int cnt) {
+            while (near) {                                               // rare: exact f64 re-evaluation
+                const int kk = __ffsll((long long)near) - 1;
+                near &= near - 1;
+                trow[kk] = x_iso_lattice(cfg, sm.perm, px, py, pz, i, j, kbase + kk);
+                atomicAdd(guard_count, 1ull);
+            }
+            __syncwarp();
+            for (int e = lane; e < 32 * cnt; e += 32) {
+                const int c = e / cnt, kk = e - c * cnt;
+                if (wcol0 + c < L2) gout[(size_t)(wcol0 + c) * L + kbase + kk] = sm.tile[warp][c][kk];
+            }
+            __syncwarp();
+        };
+#pragma unroll
+        for (int k = 0; k < L; ++k) {
+            float total = 0.f;
+#pragma unroll
+            for (int o = 0; o < NOCT; ++o) {
+                const int c = D::cell(o, k);
+                const bool first = (k == 0), step = (k > 0) && (c != D::cell(o, k > 0 ? k - 1 : 0));
+                if (first) { ystage(o, c, R0[o], S0[o]); ystage(o, c + 1, R1[o], S1[o]); }
+                else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; ystage(o, c + 1, R1[o], S1[o]); }
+                if (first || step) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
+                const float d = D::tab_d(o, k), w = D::tab_w(o, k);
+                float v = fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o]));
+                const float lim = inv_max / (float)(1 << o);
+                v = fminf(fmaxf(v, -lim), lim);
+                total += v;
+            }
+            const float iso = total + sm.terr[k];
+            const int kk = k < HALF ? k : k - HALF;
+            trow[kk] = iso;
+            if (live && fabsf(iso - isl) < eps) near |= 1ull << kk;
+            if (k == HALF - 1) flush(0, HALF);
+        }
+        flush(HALF, L - HALF);
+        __syncthreads();                                                 // lat / X are rewritten by the next unit
+        (void)TS;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // LARGE-CHUNK PATH (internal_size 16..64, e.g. BASELINE config 4: 64^3 cells, 65^3 samples = 1.1 MB of
 // densities per chunk -- far beyond shared memory).  Densities are materialised in HBM by the noise
 // kernel; one CTA then walks a chunk's x-slabs IN ORDER, holding two density planes (x, x+1), the sign

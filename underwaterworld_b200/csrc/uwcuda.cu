@@ -29,6 +29,11 @@ struct uw_ctx {
     bool own_stream = false;
     uint8_t perm[256];
     uint8_t* d_perm = nullptr;
+    std::vector<float> ax_d, ax_d1, ax_w;   // [octaves][L] axis tables (f64-computed), any L
+    std::vector<int> ax_c;
+    float4* d_axis = nullptr;               // device copy [octaves][L] (d, d-1, fade, 0) for the large-chunk noise kernel
+    bool big_fast_noise = false;            // FP32 plane-tiled noise available for this configuration
+    size_t big_noise_smem = 0; int big_noise_blocks_per_sm = 1;
     McTables* d_mc = nullptr;
 
     // grow-only device buffers
@@ -187,24 +192,42 @@ static uw_status setup_tables(uw_ctx* c) {
     }
     // per-axis tables in f64, reference operation order (chunk.rs:107-108, perlin_util.rs:13)
     memset(&c->tab, 0, sizeof c->tab);
-    if (d.L <= UW_AXIS_PAD) {
-        for (int o = 0; o < d.octaves; ++o) {
-            const double F = (double)(1 << o);
-            for (int i = 0; i < d.L; ++i) {
-                const double local = (double)i * (double)d.size_scale;
-                const double u = (local + 0.0) / (double)cf.chunk_size;
-                const double p = u * F;
-                const double f = floor(p);
-                const double dd = p - f;
-                if (f < 0.0 || f > F) return fail(c, UW_ERR_INVALID, "axis table: lattice cell out of range");
-                c->tab.c[o][i] = (int)f;
-                c->tab.d[o][i] = (float)dd;
-                c->tab.d1[o][i] = (float)(dd + (-1.0));
-                c->tab.w[o][i] = (float)fade_f64(dd);
+    c->ax_d.assign((size_t)d.octaves * d.L, 0.f); c->ax_d1 = c->ax_d; c->ax_w = c->ax_d;
+    c->ax_c.assign((size_t)d.octaves * d.L, 0);
+    for (int o = 0; o < d.octaves; ++o) {
+        const double F = (double)(1 << o);
+        for (int i = 0; i < d.L; ++i) {
+            const double local = (double)i * (double)d.size_scale;
+            const double u = (local + 0.0) / (double)cf.chunk_size;
+            const double p = u * F;
+            const double f = floor(p);
+            const double dd = p - f;
+            if (f < 0.0 || f > F) return fail(c, UW_ERR_INVALID, "axis table: lattice cell out of range");
+            const size_t k = (size_t)o * d.L + i;
+            c->ax_c[k] = (int)f; c->ax_d[k] = (float)dd; c->ax_d1[k] = (float)(dd + (-1.0)); c->ax_w[k] = (float)fade_f64(dd);
+            if (d.L <= UW_AXIS_PAD) {
+                c->tab.c[o][i] = c->ax_c[k]; c->tab.d[o][i] = c->ax_d[k]; c->tab.d1[o][i] = c->ax_d1[k]; c->tab.w[o][i] = c->ax_w[k];
             }
         }
     }
     return UW_OK;
+}
+
+// The specialised kernels bake the axis tables in at compile time (SpecDims): usable only when this
+// configuration's runtime f64 tables match them bit for bit.
+template <class DD>
+static bool spec_tables_match(const uw_ctx* c, DD) {
+    const DevCfg& d = c->dcfg;
+    if (d.S != DD::S || d.octaves != 3 || !c->fast_path) return false;
+    bool ok = true;
+    for (int o = 0; o < 3; ++o)
+        for (int i = 0; i < DD::L; ++i) {
+            const size_t k = (size_t)o * d.L + i;
+            const float dd = DD::tab_d(o, i), ww = DD::tab_w(o, i);
+            ok &= c->ax_c[k] == DD::cell(o, i) && c->ax_c[k] == DD::tab_c(o, i);
+            ok &= memcmp(&dd, &c->ax_d[k], 4) == 0 && memcmp(&ww, &c->ax_w[k], 4) == 0;
+        }
+    return ok;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -230,7 +253,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_pos); cudaFree(c->d_dens); cudaFree(c->d_counts);
+    cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_axis); cudaFree(c->d_pos); cudaFree(c->d_dens); cudaFree(c->d_counts);
     cudaFree(c->d_descs); cudaFree(c->d_active); cudaFree(c->d_cases); cudaFree(c->d_totals); cudaFree(c->d_guard);
     cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_tris); cudaFree(c->d_tri_cell); cudaFree(c->d_scan); cudaFree(c->d_ctl);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -279,8 +302,9 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     c->big_path = cfg->internal_size > UW_SMALL_MAX_L - 1;
     c->tris = (cfg->flags & UW_FLAG_TRIS) != 0;
     if (c->tris && c->big_path) { c->err = "uw_create: UW_FLAG_TRIS is not available for internal_size > 15"; return bail(UW_ERR_UNSUPPORTED); }
-    // large chunks currently always use the exact f64 noise kernel (any lattice size)
-    c->fast_path = !(cfg->flags & UW_FLAG_EXACT_F64) && is_pow2(cfg->chunk_size) && !c->big_path;
+    // FP32 factorised noise needs chunk-independent fractional parts: chunk_size a power of two.  Large chunks
+    // have an FP32 kernel for internal_size 64 (BASELINE config 4); other large sizes use the exact f64 kernel.
+    c->fast_path = !(cfg->flags & UW_FLAG_EXACT_F64) && is_pow2(cfg->chunk_size);
 
     uw_status st = setup_tables(c);
     if (st != UW_OK) return bail(st);
@@ -326,6 +350,21 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     // launch geometry / kernel selection
     const DevCfg& d = c->dcfg;
     if (c->big_path) {
+        if (spec_tables_match(c, SpecDims<64, 3>())) {
+            std::vector<float4> h((size_t)3 * d.L);
+            for (size_t k = 0; k < h.size(); ++k) h[k] = make_float4(c->ax_d[k], c->ax_d1[k], c->ax_w[k], 0.f);
+            c->big_noise_smem = sizeof(BigNoiseSmem<64, 3>);
+            bool okn = cu(cudaMalloc(&c->d_axis, h.size() * sizeof(float4)), "cudaMalloc axis") &&
+                       cu(cudaMemcpy(c->d_axis, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice), "memcpy axis") &&
+                       cu(cudaFuncSetAttribute((const void*)k_noise_big<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->big_noise_smem), "attr noise big");
+            if (!okn) return bail(UW_ERR_CUDA);
+            int nbn = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbn, (const void*)k_noise_big<64, 3>, 256, c->big_noise_smem) == cudaSuccess && nbn > 0)
+                c->big_noise_blocks_per_sm = nbn;
+            c->big_fast_noise = true;
+        } else {
+            c->fast_path = false;
+        }
         c->big_smem = big_smem_bytes(d);
         auto set_attr = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->big_smem); };
         bool ok = cu(set_attr((const void*)k_extract_big<false, uint16_t>), "attr big count") &&
@@ -338,18 +377,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     } else {
         // the specialised kernels bake the axis tables in at compile time (see SpecDims): usable only
         // when the runtime tables (from this configuration) match them bit for bit
-        auto spec_ok = [&](auto dims) {
-            using DD = decltype(dims);
-            if (d.S != DD::S || d.octaves != 3 || !c->fast_path) return false;
-            bool ok = true;
-            for (int o = 0; o < 3; ++o)
-                for (int i = 0; i < DD::L; ++i) {
-                    const float dd = DD::tab_d(o, i), ww = DD::tab_w(o, i);
-                    ok &= c->tab.c[o][i] == DD::cell(o, i) && c->tab.c[o][i] == DD::tab_c(o, i);
-                    ok &= memcmp(&dd, &c->tab.d[o][i], 4) == 0 && memcmp(&ww, &c->tab.w[o][i], 4) == 0;
-                }
-            return ok;
-        };
+        auto spec_ok = [&](auto dims) { return spec_tables_match(c, dims); };
         c->noise_threads = ((d.L2 + 31) / 32) * 32;
         c->noise_smem = noise_smem_bytes(d);
         c->noise_fn = k_noise_small<0, 0>;
@@ -490,7 +518,11 @@ static int persistent_grid(const uw_ctx* c, uint32_t n, int blocks_per_sm) {
 
 static uw_status launch_noise(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
     const DevCfg& d = c->dcfg;
-    if (c->fast_path) {
+    if (c->big_path && c->big_fast_noise && c->fast_path) {
+        const unsigned long long units = (unsigned long long)n * ((d.L2 + 255) / 256);
+        const unsigned long long full = (unsigned long long)c->num_sms * c->big_noise_blocks_per_sm;
+        k_noise_big<64, 3><<<(int)(units < full ? units : full), 256, c->big_noise_smem, c->stream>>>(d, c->d_axis, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
+    } else if (c->fast_path && !c->big_path) {
         const int grid = persistent_grid(c, n, c->noise_blocks_per_sm);
         c->noise_fn<<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
     } else {

@@ -418,8 +418,8 @@ template <int ST, int NOCT>
 struct SpecDims {
     static constexpr int S = ST, L = ST + 1;
     __host__ __device__ static constexpr int G(int o) { return (1 << o) + 2; }
-    __host__ __device__ static constexpr int lat_base(int o) { return o == 0 ? 0 : lat_base(o - 1) + G(o - 1) * G(o - 1) * G(o - 1); }
-    __host__ __device__ static constexpr int x_base(int o) { return o == 0 ? 0 : x_base(o - 1) + L * G(o - 1) * G(o - 1); }
+    __host__ __device__ static constexpr int lat_base(int o) { return o == 0 ? 0 : o == 1 ? 27 : o == 2 ? 91 : o == 3 ? 307 : 1307; }   // prefix of G^3
+    __host__ __device__ static constexpr int x_base(int o) { return L * (o == 0 ? 0 : o == 1 ? 9 : o == 2 ? 25 : o == 3 ? 61 : 161); }  // L * prefix of G^2
     static constexpr int LAT = lat_base(NOCT), XN = x_base(NOCT);
     static constexpr int DSTRIDE = (L * L * L + 3) & ~3;
     static constexpr int NT = ((L * L + 31) / 32) * 32;
@@ -461,7 +461,8 @@ struct SpecSmem {
 // Returns (block-uniform) CF_ALL_GT | CF_ANY_LT.  All threads must call; ends with a barrier.
 template <int ST, int NOCT>
 __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const AxisTables& tab, SpecSmem<ST, NOCT>& sm,
-                                                     int px, int py, int pz, unsigned long long* guard_count PHASE_ARG) {
+                                                     int px, int py, int pz, unsigned long long* guard_count PHASE_ARG,
+                                                     uint32_t* next_ticket_ctr = nullptr, uint32_t* next_ticket = nullptr) {
     using D = SpecDims<ST, NOCT>;
     constexpr int L = D::L;
     const int tid = threadIdx.x;
@@ -510,6 +511,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     }
     __syncthreads();
     PHASE_MARK(12);
+    // the next chunk ticket is requested here (by thread 0) so that the atomic's round trip hides under
+    // the z-column stage instead of stalling the whole CTA at the top of the next iteration
+    if (next_ticket_ctr && tid == 0) *next_ticket = atomicAdd(next_ticket_ctr, 1u);
 
     // ---- stage YZ -------------------------------------------------------------------------------
     if (tid < L * L) {
@@ -1015,7 +1019,8 @@ __device__ __forceinline__ uint32_t natural_of(uint32_t q0 /*m00 | m10<<16*/, ui
 // tri_cell (nullable): global u16[S^3 + 1], first triangle of every cell (chunk-local, scan order)
 template <int ST>
 __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const EmitSmem& s, uint32_t* s_w,
-                                                   uint16_t* __restrict__ tri_cell = nullptr) {
+                                                   uint16_t* __restrict__ tri_cell = nullptr,
+                                                   unsigned long long* alloc_ctr = nullptr, unsigned long long* packed = nullptr) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int S = ST > 0 ? ST : cfg.S, L = S + 1, ncol = S * S;
 
@@ -1049,6 +1054,9 @@ __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const Emit
     }
     uint32_t eva, ei, tva, ti;
     block_scan2(nva, ni, eva, ei, tva, ti, s_w);
+    // completion-order packing: claim this chunk's range of the arenas now (one 64-bit atomic); the
+    // round trip hides under phases C and D1
+    if (alloc_ctr && tid == 0 && ti > 0) *packed = atomicAdd(alloc_ctr, ((unsigned long long)(tva & 0xFFFFu) << 32) | ti);
 
     if (tri_cell && col < ncol) {        // per-cell triangle offsets (the reference's per-cell Vec<Tri>, chunk.rs:167-174)
         uint32_t rt = ei;
@@ -1719,51 +1727,36 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     static_assert(offsetof(NS, xpad) == offsetof(NS, X) + sizeof(sm.n.X), "X and xpad must be adjacent");
     static_assert(sizeof(sm.n.lat) + sizeof(sm.n.X) + sizeof(sm.n.xpad) >= (size_t)L * L * L * UW_EDGE_KINDS * 2, "vid must fit");
 
-#ifndef UW_TICKET_PREFETCH
-#define UW_TICKET_PREFETCH 0
-#endif
-#if UW_TICKET_PREFETCH
-    // chunk tickets are prefetched one iteration ahead so that the atomic's and the position load's
-    // round trips overlap the previous chunk's work
+    // first ticket; later ones are requested inside K1 (see noise_chunk_spec) and published at the end of
+    // the iteration, so chunks are still handed out on demand (committing a whole chunk ahead was measured
+    // slower: with ~3.5 chunks per CTA the tail grows by up to one chunk)
     if (tid == 0) {
-        const uint32_t c0 = atomicAdd(&ctr->ticket, 1u);
+        const uint32_t t0 = atomicAdd(&ctr->ticket, 1u);
+        const uint32_t c0 = (t0 < n && order) ? order[t0] : t0;
         sm.cur[0] = (int)c0;
-        if (c0 < n) { sm.cur[1] = pos[3 * c0]; sm.cur[2] = pos[3 * c0 + 1]; sm.cur[3] = pos[3 * c0 + 2]; }
+        if (t0 < n) { sm.cur[1] = pos[3 * c0]; sm.cur[2] = pos[3 * c0 + 1]; sm.cur[3] = pos[3 * c0 + 2]; }
     }
     __syncthreads();
-#endif
-
 #ifdef UW_PHASE_TIMING
     long long t_phase = clock64();
     if (tid == 0 && blockIdx.x < 1024) { g_cta[blockIdx.x][0] = gtimer(); g_cta[blockIdx.x][2] = 0; g_cta[blockIdx.x][3] = 0; }
 #endif
     while (true) {
-#if !UW_TICKET_PREFETCH
-        if (tid == 0) {
-            const uint32_t t0 = atomicAdd(&ctr->ticket, 1u);
-            uint32_t c0 = t0;
-            if (t0 < n && order) c0 = order[t0];
-            sm.cur[0] = (int)c0;
-            if (t0 < n) { sm.cur[1] = pos[3 * c0]; sm.cur[2] = pos[3 * c0 + 1]; sm.cur[3] = pos[3 * c0 + 2]; }
-        }
-        __syncthreads();
-#endif
         const uint32_t chunk = (uint32_t)sm.cur[0];
         if (chunk >= n) break;
         const int px = sm.cur[1], py = sm.cur[2], pz = sm.cur[3];
         PHASE_MARK(0);                                     // ticket + position
         uint32_t nxt = 0;
-#if UW_TICKET_PREFETCH
-        if (tid == 0) nxt = atomicAdd(&ctr->ticket, 1u);                 // consumed at the end of this iteration
-#endif
 
         // ---- K1 ---------------------------------------------------------------------------------
-        const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS);
+        const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS, &ctr->ticket, &nxt);
         PHASE_MARK(1);                                     // K1 noise
         int nx = 0, ny = 0, nz = 0;
-#if UW_TICKET_PREFETCH
-        if (tid == 0 && nxt < n) { nx = pos[3 * nxt]; ny = pos[3 * nxt + 1]; nz = pos[3 * nxt + 2]; }
-#endif
+        uint32_t nchunk = nxt;
+        if (tid == 0 && nxt < n) {                         // next chunk's position: in flight during K2..K4
+            if (order) nchunk = order[nxt];
+            nx = pos[3 * nchunk]; ny = pos[3 * nchunk + 1]; nz = pos[3 * nchunk + 2];
+        }
         if (dens_out) {
             float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);
             const float4* src = reinterpret_cast<const float4*>(sm.n.dens);
@@ -1773,7 +1766,10 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         // ---- K2: cases, counts, per-cell bases (block-uniform skip when no sample is inside) -------------
         ChunkShape sh;
         sh.n_vert = 0; sh.n_ind = 0; sh.n_act = 0;
-        if (fl & CF_ANY_LT) sh = emit_prepare<ST>(cfg, es, sm.w, tri_cell ? tri_cell + (size_t)chunk * (ST * ST * ST + 1) : nullptr);
+        unsigned long long packed = 0;
+        if (fl & CF_ANY_LT)
+            sh = emit_prepare<ST>(cfg, es, sm.w, tri_cell ? tri_cell + (size_t)chunk * (ST * ST * ST + 1) : nullptr,
+                                  ordered ? nullptr : &ctr->alloc, &packed);
         const uint32_t nv = sh.n_vert, ni = sh.n_ind;
         PHASE_MARK(2);                                     // K2 prepare
 
@@ -1783,7 +1779,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         //  unordered: one 64-bit atomic bump allocation -> no inter-CTA dependency; each chunk's OWN
         //             buffers are identical either way, only their placement in the arena differs.
         //             The atomic is issued here and its result consumed after the D1 fill.
-        unsigned long long ev = 0, ei = 0, packed = 0;
+        unsigned long long ev = 0, ei = 0;
         if (ordered) {
             if (tid == 0) {
                 const unsigned long long tag = chunk == 0 ? SCAN_PFX : SCAN_AGG;
@@ -1796,8 +1792,6 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
                 atomicExch(&scan[chunk].i, SCAN_PFX | (ei + ni));
             }
             packed = (ev << 32) | ei;
-        } else if (ni > 0 && tid == 0) {
-            packed = atomicAdd(&ctr->alloc, ((unsigned long long)nv << 32) | ni);
         }
 
         // ---- K4 ---------------------------------------------------------------------------------
@@ -1830,11 +1824,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
                     totals->overflow = 1u;
             }
             if (!ordered && ni > 0 && (ev + nv > vcap || ei + ni > icap)) totals->overflow = 1u;
-#if UW_TICKET_PREFETCH
-            sm.cur[0] = (int)nxt; sm.cur[1] = nx; sm.cur[2] = ny; sm.cur[3] = nz;
-#endif
+            sm.cur[0] = (int)nchunk; sm.cur[1] = nx; sm.cur[2] = ny; sm.cur[3] = nz;
         }
-        (void)nxt; (void)nx; (void)ny; (void)nz;
         __syncthreads();                                   // chunk fully emitted, smem reusable, next ticket visible
         PHASE_MARK(6);                                     // tail: descriptor + waiting for the other warps
 #ifdef UW_PHASE_TIMING

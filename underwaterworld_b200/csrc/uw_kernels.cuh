@@ -401,6 +401,72 @@ __global__ void __launch_bounds__(256) k_noise_small(const __grid_constant__ Dev
     }
 }
 
+// Control block of one fused launch.  Two blocks alternate between launches: the last CTA of launch k
+// zeroes the block of launch k+1, so no memset sits on the launch path.
+struct BatchTotals {
+    unsigned long long n_verts, n_inds;
+    uint32_t n_active, overflow, n_blank, n_mesh;
+};
+struct FusedControl {
+    uint32_t ticket, done;
+    uint32_t defer_n, prim_done;     // heavy-first hand-out: deferred (provably trivial) chunks, primaries decided
+    unsigned long long alloc;        // n_verts << 32 | n_inds (completion-order packing)
+    unsigned long long guard;        // f64 guard-band re-evaluations
+    BatchTotals totals;
+};
+
+// Chunk hand-out for the persistent kernel (executed by ONE thread).  Tickets 0..n-1 walk the request
+// list; a chunk whose z layer provably holds no surface (z outside [z_lo, z_hi]: blank or solid whatever the
+// noise does, |noise| <= 1) is several times cheaper than a surface chunk, so it is parked in `defer_list`
+// and handed out by tickets >= n, after every potentially expensive chunk has been started.  With only ~3.5
+// chunks per CTA this trims the tail of the kernel; results do not depend on the order.
+struct Ticket { uint32_t chunk; int px, py, pz; };
+#define TICKET_DONE 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+__device__ __noinline__ Ticket take_ticket(FusedControl* ctr, const int32_t* __restrict__ pos, uint32_t n,
+                                           uint32_t* defer_list, int z_lo, int z_hi) {
+    Ticket tk;
+    tk.chunk = TICKET_DONE; tk.px = tk.py = tk.pz = 0;
+    const bool defer_on = defer_list != nullptr;
+    while (true) {
+        const uint32_t t = atomicAdd(&ctr->ticket, 1u);
+        uint32_t c;
+        if (t < n) {
+            c = t;
+            tk.px = pos[3 * c]; tk.py = pos[3 * c + 1]; tk.pz = pos[3 * c + 2];
+            if (defer_on && (tk.pz < z_lo || tk.pz > z_hi)) {
+                const uint32_t slot = atomicAdd(&ctr->defer_n, 1u);
+                atomicExch(&defer_list[slot], c + 1u);
+                __threadfence();
+                atomicAdd(&ctr->prim_done, 1u);
+                continue;
+            }
+            if (defer_on) atomicAdd(&ctr->prim_done, 1u);
+            tk.chunk = c;
+            return tk;
+        }
+        if (!defer_on || t - n >= n) return tk;
+        const uint32_t idx = t - n;
+        uint32_t e;
+        while (true) {
+            e = ld_volatile_u32(&defer_list[idx]);
+            if (e) break;
+            if (ld_volatile_u32(&ctr->prim_done) >= n) { e = ld_volatile_u32(&defer_list[idx]); break; }
+        }
+        if (!e) return tk;                       // every primary is decided and this slot was never filled: no work left
+        c = e - 1u;
+        tk.px = pos[3 * c]; tk.py = pos[3 * c + 1]; tk.pz = pos[3 * c + 2];
+        tk.chunk = c;
+        return tk;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // K1 (fast path, compile-time specialised): same algorithm as k_noise_small with S and the
 // octave count as template parameters, so that every loop bound, lattice size and -- crucially --
@@ -462,7 +528,9 @@ struct SpecSmem {
 template <int ST, int NOCT>
 __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const AxisTables& tab, SpecSmem<ST, NOCT>& sm,
                                                      int px, int py, int pz, unsigned long long* guard_count PHASE_ARG,
-                                                     uint32_t* next_ticket_ctr = nullptr, uint32_t* next_ticket = nullptr) {
+                                                     FusedControl* tk_ctr = nullptr, Ticket* tk_out = nullptr,
+                                                     const int32_t* tk_pos = nullptr, uint32_t tk_n = 0,
+                                                     uint32_t* tk_defer = nullptr, int tk_zlo = 0, int tk_zhi = 0) {
     using D = SpecDims<ST, NOCT>;
     constexpr int L = D::L;
     const int tid = threadIdx.x;
@@ -513,7 +581,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     PHASE_MARK(12);
     // the next chunk ticket is requested here (by thread 0) so that the atomic's round trip hides under
     // the z-column stage instead of stalling the whole CTA at the top of the next iteration
-    if (next_ticket_ctr && tid == 0) *next_ticket = atomicAdd(next_ticket_ctr, 1u);
+    // (the LAST thread does it: its warp has idle lanes in the column stage, and divergent paths of a warp
+    // interleave, so the global round trips overlap that warp's own work too)
+    if (tk_ctr && tid == NT - 1) *tk_out = take_ticket(tk_ctr, tk_pos, tk_n, tk_defer, tk_zlo, tk_zhi);
 
     // ---- stage YZ -------------------------------------------------------------------------------
     if (tid < L * L) {
@@ -770,11 +840,6 @@ __global__ void __launch_bounds__(256) k_classify_small(const __grid_constant__ 
 // K3: chunk-level exclusive scan of (V, I) -> descriptors, totals, active-chunk list.
 // Single CTA, 1024 threads, 4 chunks per thread per round with a running carry.
 // ---------------------------------------------------------------------------------------
-struct BatchTotals {
-    unsigned long long n_verts, n_inds;
-    uint32_t n_active, overflow, n_blank, n_mesh;
-};
-
 __global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restrict__ counts,
                                                       const int32_t* __restrict__ pos, uint32_t n,
                                                       uw_chunk_desc* __restrict__ descs,
@@ -1610,15 +1675,6 @@ struct ScanSlot { unsigned long long v, i; };     // bits 63..62: 0 = empty, 1 =
 #define SCAN_PFX  (2ull << 62)
 #define SCAN_VAL  ((1ull << 62) - 1ull)
 
-// Control block of one fused launch.  Two blocks alternate between launches: the last CTA of launch k
-// zeroes the block of launch k+1, so no memset sits on the launch path.
-struct FusedControl {
-    uint32_t ticket, done;
-    unsigned long long alloc;        // n_verts << 32 | n_inds (completion-order packing)
-    unsigned long long guard;        // f64 guard-band re-evaluations
-    BatchTotals totals;
-};
-
 template <int ST, int NOCT>
 struct FusedSmem {
     SpecSmem<ST, NOCT> n;                             // n.lat / n.X are dead after K1 and reused by K4 (vid)
@@ -1696,7 +1752,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
               uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
               unsigned long long vcap, unsigned long long icap,
               float* __restrict__ dens_out /*nullable: debug tap*/, int ordered,
-              uw_tri* __restrict__ tris /*nullable: UW_FLAG_TRIS*/, uint16_t* __restrict__ tri_cell /*nullable*/) {
+              uw_tri* __restrict__ tris /*nullable: UW_FLAG_TRIS*/, uint16_t* __restrict__ tri_cell /*nullable*/,
+              uint32_t* __restrict__ defer_list /*nullable: heavy-first hand-out*/, int z_lo, int z_hi) {
     using D = SpecDims<ST, NOCT>;
     BatchTotals* const totals = &ctr->totals;
     unsigned long long* const guard_count = &ctr->guard;
@@ -1730,11 +1787,10 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // first ticket; later ones are requested inside K1 (see noise_chunk_spec) and published at the end of
     // the iteration, so chunks are still handed out on demand (committing a whole chunk ahead was measured
     // slower: with ~3.5 chunks per CTA the tail grows by up to one chunk)
-    if (tid == 0) {
-        const uint32_t t0 = atomicAdd(&ctr->ticket, 1u);
-        const uint32_t c0 = (t0 < n && order) ? order[t0] : t0;
-        sm.cur[0] = (int)c0;
-        if (t0 < n) { sm.cur[1] = pos[3 * c0]; sm.cur[2] = pos[3 * c0 + 1]; sm.cur[3] = pos[3 * c0 + 2]; }
+    if (order) defer_list = nullptr;
+    if (tid == D::NT - 1) {
+        const Ticket t0 = take_ticket(ctr, pos, n, defer_list, z_lo, z_hi);
+        sm.cur[0] = (int)t0.chunk; sm.cur[1] = t0.px; sm.cur[2] = t0.py; sm.cur[3] = t0.pz;
     }
     __syncthreads();
 #ifdef UW_PHASE_TIMING
@@ -1743,20 +1799,16 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
 #endif
     while (true) {
         const uint32_t chunk = (uint32_t)sm.cur[0];
-        if (chunk >= n) break;
+        if (chunk == TICKET_DONE) break;
         const int px = sm.cur[1], py = sm.cur[2], pz = sm.cur[3];
         PHASE_MARK(0);                                     // ticket + position
-        uint32_t nxt = 0;
+        Ticket nxt;
+        nxt.chunk = TICKET_DONE; nxt.px = nxt.py = nxt.pz = 0;
 
         // ---- K1 ---------------------------------------------------------------------------------
-        const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS, &ctr->ticket, &nxt);
+        const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS,
+                                                       ctr, &nxt, pos, n, defer_list, z_lo, z_hi);
         PHASE_MARK(1);                                     // K1 noise
-        int nx = 0, ny = 0, nz = 0;
-        uint32_t nchunk = nxt;
-        if (tid == 0 && nxt < n) {                         // next chunk's position: in flight during K2..K4
-            if (order) nchunk = order[nxt];
-            nx = pos[3 * nchunk]; ny = pos[3 * nchunk + 1]; nz = pos[3 * nchunk + 2];
-        }
         if (dens_out) {
             float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);
             const float4* src = reinterpret_cast<const float4*>(sm.n.dens);
@@ -1824,8 +1876,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
                     totals->overflow = 1u;
             }
             if (!ordered && ni > 0 && (ev + nv > vcap || ei + ni > icap)) totals->overflow = 1u;
-            sm.cur[0] = (int)nchunk; sm.cur[1] = nx; sm.cur[2] = ny; sm.cur[3] = nz;
         }
+        if (tid == D::NT - 1) { sm.cur[0] = (int)nxt.chunk; sm.cur[1] = nxt.px; sm.cur[2] = nxt.py; sm.cur[3] = nxt.pz; }
         __syncthreads();                                   // chunk fully emitted, smem reusable, next ticket visible
         PHASE_MARK(6);                                     // tail: descriptor + waiting for the other warps
 #ifdef UW_PHASE_TIMING
@@ -1833,11 +1885,21 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
                         if (blockIdx.x < 1024) { g_cta[blockIdx.x][1] = gtimer(); g_cta[blockIdx.x][2] += 1; g_cta[blockIdx.x][3] += (ni > 0); } }
 #endif
     }
-    // last CTA out resets the other control block for the next launch
+    // last CTA out resets the other control block (and the used part of the defer list) for the next launch
+    __syncthreads();                                       // every thread has seen TICKET_DONE in sm.cur[0]
     if (tid == 0) {
         __threadfence();
-        if (atomicAdd(&ctr->done, 1u) == gridDim.x - 1) {
-            ctr_next->ticket = 0; ctr_next->done = 0; ctr_next->alloc = 0; ctr_next->guard = 0;
+        sm.cur[0] = (atomicAdd(&ctr->done, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sm.cur[0]) {
+        if (defer_list) {
+            const uint32_t used = ld_volatile_u32(&ctr->defer_n);
+            for (uint32_t i = tid; i < used; i += D::NT) defer_list[i] = 0u;
+        }
+        if (tid == 0) {
+            ctr_next->ticket = 0; ctr_next->done = 0; ctr_next->defer_n = 0; ctr_next->prim_done = 0;
+            ctr_next->alloc = 0; ctr_next->guard = 0;
             BatchTotals z; z.n_verts = 0; z.n_inds = 0; z.n_active = 0; z.overflow = 0; z.n_blank = 0; z.n_mesh = 0;
             ctr_next->totals = z;
         }

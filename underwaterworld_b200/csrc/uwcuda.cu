@@ -66,13 +66,15 @@ struct uw_ctx {
     typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uw_tri*, uint16_t*);
     typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, const uint32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint16_t*, unsigned long long,
-                                 unsigned long long, float*, int, uw_tri*, uint16_t*);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int);
     typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, const uint32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint32_t*, unsigned long long,
-                                 unsigned long long, float*, int, uw_tri*, uint16_t*);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int);
     fused16_fn_t fused16_fn = nullptr;
     fused32_fn_t fused32_fn = nullptr;
     bool use_fused = false;
+    int z_lo = 1, z_hi = 0;         // chunk z layers that can hold surface (empty range = unknown: no deferral)
+    uint32_t* d_defer = nullptr;    // [cap_chunks] deferred-chunk list of the fused kernel (kept zeroed between launches)
     bool big_path = false;          // internal_size > 15: slab-walking extraction, densities in HBM
     size_t big_smem = 0; int big_blocks_per_sm = 1;
     bool ordered = false;           // packed arenas follow request order (look-back) vs atomic bump allocation
@@ -210,6 +212,27 @@ static uw_status setup_tables(uw_ctx* c) {
             }
         }
     }
+    // z layers that can hold surface: iso = terrace(z) + p with |p| <= 1 (every octave is clamped to [-1, 1]);
+    // used only to hand out the expensive chunks first (take_ticket)
+    {
+        const float margin = 1e-3f;
+        int lo = 1, hi = 0;
+        bool found = false;
+        for (int pz = -4096; pz <= 4096; ++pz) {
+            float tmin = 3e38f, tmax = -3e38f;
+            for (int k = 0; k < d.L; ++k) {
+                const double local = (double)k * (double)d.size_scale;
+                const float zf = (float)((local + (double)(pz * cf.chunk_size)) / (double)cf.chunk_size);
+                const float adj = (zf * (float)cf.chunk_size) / cf.max_height;
+                const float t = adj - fmodf(adj, cf.adj_z_mod);
+                tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
+            }
+            const bool blank_certain = tmin - 1.0f > cf.iso_level + margin;
+            const bool solid_certain = tmax + 1.0f < cf.iso_level - margin;
+            if (!blank_certain && !solid_certain) { if (!found) { lo = pz; found = true; } hi = pz; }
+        }
+        if (found && lo > -4096 && hi < 4096) { c->z_lo = lo; c->z_hi = hi; } else { c->z_lo = 1; c->z_hi = 0; }
+    }
     return UW_OK;
 }
 
@@ -255,7 +278,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_axis); cudaFree(c->d_pos); cudaFree(c->d_dens); cudaFree(c->d_counts);
     cudaFree(c->d_descs); cudaFree(c->d_active); cudaFree(c->d_cases); cudaFree(c->d_totals); cudaFree(c->d_guard);
-    cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_tris); cudaFree(c->d_tri_cell); cudaFree(c->d_scan); cudaFree(c->d_ctl);
+    cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_tris); cudaFree(c->d_tri_cell); cudaFree(c->d_scan); cudaFree(c->d_ctl); cudaFree(c->d_defer);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_pos) cudaFreeHost(c->h_pos);
     if (c->h_totals) cudaFreeHost(c->h_totals);
@@ -464,6 +487,8 @@ static uw_status ensure_chunks(uw_ctx* c, uint32_t n) {
     CU_TRY(c, regrow(&c->d_descs, cap));
     CU_TRY(c, regrow(&c->d_active, cap));
     CU_TRY(c, regrow(&c->d_scan, cap));
+    CU_TRY(c, regrow(&c->d_defer, cap));
+    CU_TRY(c, cudaMemset(c->d_defer, 0, (size_t)cap * sizeof(uint32_t)));
     if (c->tris) CU_TRY(c, regrow(&c->d_tri_cell, (size_t)cap * ((size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1)));
     if (!c->d_ctl) {
         CU_TRY(c, cudaMalloc(&c->d_ctl, 2 * sizeof(FusedControl)));
@@ -592,13 +617,17 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     c->ctl_used = c->ctl_parity;
     c->ctl_parity ^= 1;
     const int grid = persistent_grid(c, n, c->fused_blocks_per_sm);
-    const uint32_t* d_order = nullptr;     // optional hand-out permutation (unused: measured neutral at 2048 chunks)
+    const uint32_t* d_order = nullptr;     // optional explicit hand-out permutation (unused)
+    // heavy-first hand-out (scheduling only): provably trivial z layers are deferred inside the kernel; the
+    // ordered-packing mode needs tickets == request order.  Only worth it when CTAs get just a few chunks each.
+    static const bool no_defer = getenv("UW_NO_DEFER") != nullptr;      // experiment switch
+    uint32_t* d_defer = (!no_defer && !c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= 16u * (uint32_t)grid) ? c->d_defer : nullptr;
     if (c->index32)
         c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
-            c->d_descs, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell);
+            c->d_descs, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell, d_defer, c->z_lo, c->z_hi);
     else
         c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
-            c->d_descs, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell);
+            c->d_descs, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell, d_defer, c->z_lo, c->z_hi);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;

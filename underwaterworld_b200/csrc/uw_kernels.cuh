@@ -1510,59 +1510,135 @@ __device__ __forceinline__ uint32_t two_bits(const uint32_t* bits, int b) {
     return __funnelshift_r(bits[b >> 5], bits[(b >> 5) + 1], b & 31) & 3u;
 }
 
-template <bool EMIT, typename IndexT>
-__global__ void __launch_bounds__(512) k_extract_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
-                                                     const float* __restrict__ dens, uint32_t n,
-                                                     ChunkCounts* __restrict__ counts,
-                                                     const uw_chunk_desc* __restrict__ descs, const uint32_t* __restrict__ active,
-                                                     const BatchTotals* __restrict__ totals,
-                                                     uw_vert* __restrict__ verts, IndexT* __restrict__ inds) {
+#define UW_BIG_NT 512
+#define UW_BIG_NLD 9          // ceil(65 * 65 / 512): plane elements per thread
+
+// COUNT pass: per-chunk vertex / index totals and the blank / no-surface vote.  Totals do not depend on
+// the scan order, so no state is carried between slabs: two sign-bit planes in shared memory, per-thread
+// counters, one block reduction per chunk.  The next plane's loads are issued before the current slab is
+// classified so that their DRAM latency hides behind the bit work.
+__global__ void __launch_bounds__(UW_BIG_NT) k_count_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
+                                                         const float* __restrict__ dens, uint32_t n,
+                                                         ChunkCounts* __restrict__ counts) {
+    __shared__ uint32_t s_bits[2][(65 * 65 + 31) / 32 + 2];
+    __shared__ uint32_t s_lut[256];
+    __shared__ uint32_t s_acc[4];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int S = cfg.S, L = cfg.L, L2 = cfg.L2, ncell = S * S;
+    for (int t = tid; t < 256; t += UW_BIG_NT) s_lut[t] = mc->lut[t];
+
+    for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
+        const float* D = dens + (size_t)chunk * cfg.dens_stride;
+        if (tid < 4) s_acc[tid] = tid == 2 ? 1u : 0u;       // [0] verts, [1] inds, [2] all_gt, [3] any_lt
+        float pre[UW_BIG_NLD];
+        bool all_gt = true, any_lt = false;
+        uint32_t nv = 0, ni = 0;
+        auto issue = [&](int x) {
+            const float* src = D + (size_t)x * L2;
+#pragma unroll
+            for (int q = 0; q < UW_BIG_NLD; ++q) { const int idx = q * UW_BIG_NT + tid; pre[q] = idx < L2 ? __ldg(src + idx) : 0.f; }
+        };
+        auto commit = [&](int x) {
+            uint32_t* bt = s_bits[x & 1];
+#pragma unroll
+            for (int q = 0; q < UW_BIG_NLD; ++q) {
+                const int base = q * UW_BIG_NT + tid - lane;
+                if (base < L2) {                                          // warp-uniform
+                    const bool ok = base + lane < L2;
+                    const bool lt = ok && (pre[q] < cfg.iso_level);
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, lt);
+                    if (lane == 0) bt[base >> 5] = word;
+                    all_gt &= !ok || (pre[q] > cfg.iso_level);
+                    any_lt |= lt;
+                }
+            }
+            if (tid == 0) { bt[(L2 + 31) >> 5] = 0; bt[((L2 + 31) >> 5) + 1] = 0; }
+        };
+        issue(0); commit(0); issue(1);
+        for (int cx = 0; cx < S; ++cx) {
+            commit(cx + 1);
+            if (cx + 2 <= S) issue(cx + 2);
+            __syncthreads();
+            const uint32_t* A = s_bits[cx & 1];
+            const uint32_t* B = s_bits[(cx + 1) & 1];
+            for (int cell = tid; cell < ncell; cell += UW_BIG_NT) {
+                const int y = cell / S, z = cell - y * S;
+                const uint32_t nat = two_bits(A, y * L + z) | (two_bits(B, y * L + z) << 2)
+                                   | (two_bits(A, (y + 1) * L + z) << 4) | (two_bits(B, (y + 1) * L + z) << 6);
+                const uint32_t t = s_lut[nat];
+                if (t >> 8) { ni += (t >> 8) & 15u; nv += __popc((t >> 12) & own_mask_of(cx, y, z)); }
+            }
+            __syncthreads();
+        }
+        nv = __reduce_add_sync(0xFFFFFFFFu, nv); ni = __reduce_add_sync(0xFFFFFFFFu, ni);
+        const bool w_all = __all_sync(0xFFFFFFFFu, all_gt), w_any = __any_sync(0xFFFFFFFFu, any_lt);
+        if (lane == 0) {
+            atomicAdd(&s_acc[0], nv); atomicAdd(&s_acc[1], ni);
+            if (!w_all) atomicAnd(&s_acc[2], 0u);
+            if (w_any) atomicOr(&s_acc[3], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            ChunkCounts c;
+            c.n_verts = s_acc[0]; c.n_inds = s_acc[1]; c.flags = (s_acc[2] ? CF_ALL_GT : 0u) | (s_acc[3] ? CF_ANY_LT : 0u); c.pad = 0;
+            counts[chunk] = c;
+        }
+        __syncthreads();
+    }
+}
+
+// EMIT pass over the active chunks (see the section header).
+template <typename IndexT>
+__global__ void __launch_bounds__(UW_BIG_NT) k_emit_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
+                                                        const float* __restrict__ dens,
+                                                        const uw_chunk_desc* __restrict__ descs, const uint32_t* __restrict__ active,
+                                                        const BatchTotals* __restrict__ totals,
+                                                        uw_vert* __restrict__ verts, IndexT* __restrict__ inds) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const BigSmem s = big_smem_carve(cfg, smem_raw);
     __shared__ uint32_t s_w[64];
-    __shared__ int s_red[2];
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     const int S = cfg.S, L = cfg.L, L2 = cfg.L2, ncell = S * S;
     const int CPT = (ncell + NT - 1) / NT;                 // consecutive cells per thread (scan order y, z)
     for (int t = tid; t < 256; t += NT) s.lut[t] = mc->lut[t];
-    uint32_t n_work = n;
-    if (EMIT) { if (totals->overflow) return; n_work = totals->n_active; }
+    if (totals->overflow) return;                          // host grows the arenas and relaunches
+    const uint32_t n_work = totals->n_active;
 
     for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const uint32_t chunk = EMIT ? active[w] : w;
+        const uint32_t chunk = active[w];
         const float* D = dens + (size_t)chunk * cfg.dens_stride;
-        uw_chunk_desc d;
-        if (EMIT) d = descs[chunk];
-        const int offx = EMIT ? d.pos[0] * cfg.chunk_size : 0, offy = EMIT ? d.pos[1] * cfg.chunk_size : 0,
-                  offz = EMIT ? d.pos[2] * cfg.chunk_size : 0;
-        uw_vert* vout = EMIT ? verts + d.vert_offset : nullptr;
-        IndexT* iout = EMIT ? inds + d.index_offset : nullptr;
+        const uw_chunk_desc d = descs[chunk];
+        const int offx = d.pos[0] * cfg.chunk_size, offy = d.pos[1] * cfg.chunk_size, offz = d.pos[2] * cfg.chunk_size;
+        uw_vert* vout = verts + d.vert_offset;
+        IndexT* iout = inds + d.index_offset;
         uint32_t vrun = 0, irun = 0;
-        bool all_gt = true, any_lt = false;
-        if (tid < 2) s_red[tid] = tid == 0 ? 1 : 0;
-
-        // loads density plane x into buffer x & 1: floats (EMIT) and sign bits (warp ballots)
-        auto load_plane = [&](int x) {
+        float pre[UW_BIG_NLD];
+        auto issue = [&](int x) {
+            const float* src = D + (size_t)x * L2;
+#pragma unroll
+            for (int q = 0; q < UW_BIG_NLD; ++q) { const int idx = q * UW_BIG_NT + tid; pre[q] = idx < L2 ? __ldg(src + idx) : 0.f; }
+        };
+        // plane x -> buffer x & 1: floats and sign bits (warp ballots)
+        auto commit = [&](int x) {
             float* pl = s.plane[x & 1];
             uint32_t* bt = s.bits[x & 1];
-            const float* src = D + (size_t)x * L2;
-            for (int base = tid - lane; base < L2; base += NT) {
-                const int idx = base + lane;
-                const bool ok = idx < L2;
-                float v = 0.f;
-                if (ok) { v = __ldg(src + idx); if (EMIT) pl[idx] = v; }
-                const bool lt = ok && (v < cfg.iso_level);
-                const uint32_t word = __ballot_sync(0xFFFFFFFFu, lt);
-                if (lane == 0) bt[base >> 5] = word;
-                all_gt &= !ok || (v > cfg.iso_level);
-                any_lt |= lt;
+#pragma unroll
+            for (int q = 0; q < UW_BIG_NLD; ++q) {
+                const int base = q * UW_BIG_NT + tid - lane;
+                if (base < L2) {                                          // warp-uniform
+                    const bool ok = base + lane < L2;
+                    if (ok) pl[base + lane] = pre[q];
+                    const uint32_t word = __ballot_sync(0xFFFFFFFFu, ok && (pre[q] < cfg.iso_level));
+                    if (lane == 0) bt[base >> 5] = word;
+                }
             }
             if (tid == 0) { bt[(L2 + 31) >> 5] = 0; bt[((L2 + 31) >> 5) + 1] = 0; }
         };
-        load_plane(0);
+        issue(0); commit(0); issue(1);
 
         for (int cx = 0; cx < S; ++cx) {
-            load_plane(cx + 1);
+            commit(cx + 1);
+            if (cx + 2 <= S) issue(cx + 2);                // in flight while this slab is classified and emitted
             __syncthreads();
             const uint32_t* A = s.bits[cx & 1];            // plane x = cx
             const uint32_t* B = s.bits[(cx + 1) & 1];      // plane x = cx + 1
@@ -1590,7 +1666,7 @@ __global__ void __launch_bounds__(512) k_extract_big(const __grid_constant__ Dev
             uint32_t eva, ei, tva, ti;
             block_scan2(nva, ni, eva, ei, tva, ti, s_w);
             const uint32_t slab_nv = tva & 0xFFFFu, slab_na = tva >> 16;
-            if (EMIT) {
+            if (slab_na) {                                  // block-uniform
                 uint32_t rv = vrun + (eva & 0xFFFFu), ra = eva >> 16, ri = irun + ei;
                 for (int q = 0; q < CPT; ++q) {
                     const int cell = c0 + q;
@@ -1640,18 +1716,7 @@ __global__ void __launch_bounds__(512) k_extract_big(const __grid_constant__ Dev
                 }
             }
             vrun += slab_nv; irun += ti;
-            (void)slab_na;
-            __syncthreads();                               // buffers (cx & 1) are overwritten two slabs later; cheap safety
-        }
-        if (!EMIT) {
-            const bool w_all = __all_sync(0xFFFFFFFFu, all_gt), w_any = __any_sync(0xFFFFFFFFu, any_lt);
-            if (lane == 0) { if (!w_all) atomicAnd(&s_red[0], 0); if (w_any) atomicOr(&s_red[1], 1); }
-            __syncthreads();
-            if (tid == 0) {
-                ChunkCounts c;
-                c.n_verts = vrun; c.n_inds = irun; c.flags = (s_red[0] ? CF_ALL_GT : 0u) | (s_red[1] ? CF_ANY_LT : 0u); c.pad = 0;
-                counts[chunk] = c;
-            }
+            __syncthreads();                               // buffers (cx & 1) are overwritten by the next commit
         }
         __syncthreads();
     }

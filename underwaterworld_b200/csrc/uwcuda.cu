@@ -76,7 +76,7 @@ struct uw_ctx {
     int z_lo = 1, z_hi = 0;         // chunk z layers that can hold surface (empty range = unknown: no deferral)
     uint32_t* d_defer = nullptr;    // [cap_chunks] deferred-chunk list of the fused kernel (kept zeroed between launches)
     bool big_path = false;          // internal_size > 15: slab-walking extraction, densities in HBM
-    size_t big_smem = 0; int big_blocks_per_sm = 1;
+    size_t big_smem = 0; int big_blocks_per_sm = 1, big_count_blocks_per_sm = 1;
     bool ordered = false;           // packed arenas follow request order (look-back) vs atomic bump allocation
     size_t fused_smem = 0; int fused_blocks_per_sm = 1;
     ScanSlot* d_scan = nullptr;
@@ -390,13 +390,14 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         }
         c->big_smem = big_smem_bytes(d);
         auto set_attr = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->big_smem); };
-        bool ok = cu(set_attr((const void*)k_extract_big<false, uint16_t>), "attr big count") &&
-                  cu(set_attr((const void*)k_extract_big<true, uint16_t>), "attr big emit16") &&
-                  cu(set_attr((const void*)k_extract_big<true, uint32_t>), "attr big emit32");
+        bool ok = cu(set_attr((const void*)k_emit_big<uint16_t>), "attr big emit16") &&
+                  cu(set_attr((const void*)k_emit_big<uint32_t>), "attr big emit32");
         if (!ok) return bail(UW_ERR_CUDA);
         int nb = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_extract_big<true, uint32_t>, 512, c->big_smem) == cudaSuccess && nb > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_emit_big<uint32_t>, UW_BIG_NT, c->big_smem) == cudaSuccess && nb > 0)
             c->big_blocks_per_sm = nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_count_big, UW_BIG_NT, 0) == cudaSuccess && nb > 0)
+            c->big_count_blocks_per_sm = nb;
     } else {
         // the specialised kernels bake the axis tables in at compile time (see SpecDims): usable only
         // when the runtime tables (from this configuration) match them bit for bit
@@ -567,8 +568,7 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
     if (c->big_path) {
         const int grid = persistent_grid(c, n, c->big_blocks_per_sm);
         if (!only_emit) {
-            k_extract_big<false, uint16_t><<<grid, 512, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, nullptr, nullptr,
-                                                                                 nullptr, nullptr, nullptr);
+            k_count_big<<<persistent_grid(c, n, c->big_count_blocks_per_sm), UW_BIG_NT, 0, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts);
             c->launches++;
             CU_TRY(c, cudaGetLastError());
             if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
@@ -578,11 +578,11 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
         CU_TRY(c, cudaGetLastError());
         if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
         if (c->index32)
-            k_extract_big<true, uint32_t><<<grid, 512, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, c->d_descs, c->d_active,
-                                                                                c->d_totals, c->d_verts, (uint32_t*)c->d_inds);
+            k_emit_big<uint32_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active,
+                                                                             c->d_totals, c->d_verts, (uint32_t*)c->d_inds);
         else
-            k_extract_big<true, uint16_t><<<grid, 512, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, c->d_descs, c->d_active,
-                                                                                c->d_totals, c->d_verts, (uint16_t*)c->d_inds);
+            k_emit_big<uint16_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active,
+                                                                             c->d_totals, c->d_verts, (uint16_t*)c->d_inds);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         return UW_OK;

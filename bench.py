@@ -95,7 +95,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def __enter__(self):
         if self.nv:
@@ -268,15 +268,18 @@ def run_ours(args):
             torch.cuda.synchronize()
             e2e_step()
         barrier()
-        e2e_s = 0.0
+        e2e_t = []
         nv = ni = 0
         for i in range(K):
             flush.fill_(i & 0xFF)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             nv, ni = e2e_step()
-            e2e_s += time.perf_counter() - t0
+            e2e_t.append(time.perf_counter() - t0)
         barrier()
+        # host-timed: the median is robust against the clock-sampling thread and other host noise
+        e2e_s = float(np.median(e2e_t)) * K
+        e2e_mean_ms = 1e3 * float(np.mean(e2e_t))
     ms_per_step = max_over_ranks(sum(step_ms) / K)
     e2e_ms = max_over_ranks(1e3 * e2e_s / K)
     total_chunks = n * world
@@ -344,6 +347,52 @@ def run_ours(args):
                     "noise_algorithmic_tflops": noise_flops / (stage_ms["noise"] / 1e3) / 1e12 if stage_ms["noise"] > 0 else None,
                     "note": "UW_FLAG_STAGED: same stages as four kernels with densities materialised in HBM"}}
 
+    # ---- north_star targets, measured where they are defined (rank 0 only; a few extra milliseconds) ----------
+    north_star = None
+    if rank == 0:
+        from underwaterworld_b200 import region as _region
+        big = _region.box_region((-32, 32), (-32, 32), (-4, 4))            # 32768 chunks: enough waves to amortise latency
+        d_big = torch.from_numpy(big).cuda()
+        stg = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local, staged=True)
+        stg.set_stream(stream.cuda_stream)
+        stg.set_profiling(True)
+        t_big = {"noise_ms": 0.0, "classify_ms": 0.0, "emit_ms": 0.0}
+        for i in range(5):
+            stg.build_device(d_big.data_ptr(), len(big)); stg.sync()
+            if i >= 2:
+                tt = stg.stage_times()
+                for k in t_big:
+                    t_big[k] += tt[k] / 3
+        vb = stg.device_view()
+        nb_act = None
+        stg.close()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(2):
+            builder.build_device(d_big.data_ptr(), len(big)); builder.sync()
+        e0.record(stream)
+        for i in range(5):
+            builder.build_device(d_big.data_ptr(), len(big))
+        e1.record(stream); builder.sync()
+        fused_big_ms = e0.elapsed_time(e1) / 5
+        ext_bytes = len(big) * 4 * L3 * 2 + 24 * int(vb.n_verts) + 2 * int(vb.n_inds)     # staged: densities read by classify + emit, mesh out
+        north_star = {
+            "batch_chunks": len(big),
+            "noise_stage": {"kernel": "k_noise_spec<12,3> (staged pipeline)", "ms": t_big["noise_ms"],
+                            "algorithmic_tflops": len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12,
+                            "frac_of_nominal_fp32_peak": len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12 / FP32_NOMINAL_TFLOPS,
+                            "density_write_gbs": len(big) * 4 * L3 / (t_big["noise_ms"] / 1e3) / 1e9},
+            "extraction_stages": {"kernels": "k_classify_small + k_scan_chunks + k_emit_small (staged pipeline)",
+                                  "ms": t_big["classify_ms"] + t_big["emit_ms"],
+                                  "algorithmic_gbs": ext_bytes / ((t_big["classify_ms"] + t_big["emit_ms"]) / 1e3) / 1e9,
+                                  "frac_of_measured_hbm": ext_bytes / ((t_big["classify_ms"] + t_big["emit_ms"]) / 1e3) / 1e9 / peak},
+            "fused_kernel": {"ms": fused_big_ms, "chunks_per_s": len(big) / (fused_big_ms / 1e3),
+                             "voxels_per_s": len(big) * CELLS / (fused_big_ms / 1e3),
+                             "algorithmic_tflops": len(big) * L3 * FLOP_PER_SAMPLE / (fused_big_ms / 1e3) / 1e12,
+                             "frac_of_nominal_fp32_peak": len(big) * L3 * FLOP_PER_SAMPLE / (fused_big_ms / 1e3) / 1e12 / FP32_NOMINAL_TFLOPS},
+            "note": "targets: >= 60 % of peak FP32 in the noise stage, >= 50 % of peak HBM in the extraction stages. "
+                    "FLOPs are the reference's algorithmic count (285 per sample); the kernels execute ~3x fewer instructions."}
+        del d_big
+
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -370,11 +419,13 @@ def run_ours(args):
                        "chunks_per_gpu": n, "cells_per_chunk": CELLS, "samples_per_chunk": L3,
                        "l2": "flushed between timed steps (256 MB write)", "parallelism": f"chunk-slabs x{world}"},
             "e2e": {"value": e2e_value, "unit": "voxels/s", "chunks_per_s": total_chunks / (e2e_ms / 1e3),
-                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "ms_per_step": e2e_ms, "ms_per_step_mean": e2e_mean_ms, "timing": "host perf_counter around uw_build, median of K steps",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step) * K,
             "kernels_per_step": ["k_order_chunks", "k_build_fused"],
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "north_star": north_star,
             "clocks": sampler.summary(),
             "mesh": {"n_verts": n_verts, "n_inds": n_inds, "chunks_with_mesh": n_active, "chunks_blank_early": n_blank,
                      "guard_band_reevals": int(guards)},

@@ -59,3 +59,37 @@ def test_weak_scaling_regions_are_disjoint():
     a, b = region.weak_region(16, (-8, 8), (-4, 4), 0), region.weak_region(16, (-8, 8), (-4, 4), 1)
     assert len(a) == len(b) == 2048
     assert not set(map(tuple, a)) & set(map(tuple, b))
+
+
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from underwaterworld_b200.gather import gather_meshes
+    rng = np.random.default_rng(rank)
+    n_chunks, n_verts, n_inds = 5 + rank, 100 * (rank + 1), 0 if rank == 1 else 300     # ragged, one rank has no indices
+    d = torch.from_numpy(rng.integers(0, 255, n_chunks * 32, dtype=np.uint8))
+    v = torch.from_numpy(rng.integers(0, 255, n_verts * 24, dtype=np.uint8))
+    i = torch.from_numpy(rng.integers(0, 255, n_inds * 2, dtype=np.uint8))
+    got = gather_meshes(d, v, i, dst=0)
+    if rank == 0:
+        assert got is not None and len(got) == world
+        for r, (gd, gv, gi) in enumerate(got):
+            rr = np.random.default_rng(r)
+            nc, nv, ni = 5 + r, 100 * (r + 1), 0 if r == 1 else 300
+            assert np.array_equal(gd.numpy(), rr.integers(0, 255, nc * 32, dtype=np.uint8))
+            assert np.array_equal(gv.numpy(), rr.integers(0, 255, nv * 24, dtype=np.uint8))
+            assert np.array_equal(gi.numpy(), rr.integers(0, 255, ni * 2, dtype=np.uint8))
+        open(os.path.join(out_dir, "ok"), "w").write("ok")
+    else:
+        assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_mesh_gather_to_render_rank_gloo(tmp_path):
+    """Optional gather of finished meshes to the rendering rank: sizes by all_gather, ragged
+    payloads by send/recv; here over gloo with host tensors, on the GPU box over NCCL / NVLink."""
+    mp.spawn(_gather_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    assert (tmp_path / "ok").exists()

@@ -56,24 +56,22 @@ def gather_meshes(descs: torch.Tensor, verts: torch.Tensor, inds: torch.Tensor, 
     mine = torch.tensor([descs.numel(), verts.numel(), inds.numel()], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, mine, group=group)
+    ops = []
+    out = None
     if rank != dst:
-        for t in (descs, verts, inds):
-            if t.numel():
-                dist.send(t.contiguous(), dst, group=group)
-        return None
-    out = []
-    for r in range(world):
-        if r == dst:
-            out.append((descs, verts, inds))
-            continue
-        bufs = []
-        for k in range(3):
-            n = int(sizes[r][k].item())
-            b = torch.empty(n, dtype=torch.uint8, device=dev)
-            if n:
-                dist.recv(b, r, group=group)
-            bufs.append(b)
-        out.append(tuple(bufs))
+        ops = [dist.P2POp(dist.isend, t.contiguous(), dst, group) for t in (descs, verts, inds) if t.numel()]
+    else:
+        out = []
+        for r in range(world):
+            if r == dst:
+                out.append((descs, verts, inds))
+                continue
+            bufs = [torch.empty(int(sizes[r][k].item()), dtype=torch.uint8, device=dev) for k in range(3)]
+            ops += [dist.P2POp(dist.irecv, b, r, group) for b in bufs if b.numel()]
+            out.append(tuple(bufs))
+    if ops:                                  # one batched group: the transfers run concurrently over NVLink
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     return out
 
 

@@ -51,6 +51,11 @@ typedef enum uw_status {
                                      completion order (one atomic bump allocation per chunk, ~17 % faster,
                                      no inter-CTA dependency).  Every chunk's OWN buffers are identical in
                                      both modes; only vert_offset / index_offset differ.              */
+#define UW_FLAG_ANALYTIC_SKIP 0x40u /* chunks whose z layer provably holds no surface (every octave of the noise is
+                                     clamped to [-1, 1], so iso = terrace(z) + p cannot reach iso_level there) are
+                                     answered without evaluating the noise: blank-early above, solid below.  The
+                                     reference encodes the same fact as world::MIN_Z / MAX_Z (world.rs:11-12,161).
+                                     Outputs are identical; off by default so that benchmarks evaluate every sample. */
 #define UW_FLAG_TRIS        0x8u  /* also emit the per-cell collision triangle lists (chunk.rs:167-174,
                                      245-250) -- SURVEY §8f-1                                       */
 

@@ -501,3 +501,20 @@ def test_config4_fp32_noise_topology_bit_exact(uw):
     for i, r in enumerate(refs):
         assert np.array_equal(batch.chunk(i).inds, r["inds"]) and batch.chunk(i).flags & 3 == r["flags"] & 3
     _check_batch(batch, _oracle_batch(o, perm, pos, MODE_FAST, isos=gdens), exact_positions=True)
+
+
+def test_analytic_skip_gives_identical_results(uw, builder12_fast):
+    """UW_FLAG_ANALYTIC_SKIP: provably blank / solid z layers are answered without evaluating the noise;
+    every descriptor and every chunk's buffers are unchanged (SURVEY 8d "analytic skipping is legal")."""
+    pos = uw.region.box_region((-4, 4), (-4, 4), (-9, 9))         # z from far below to far above the surface
+    want = builder12_fast.build(pos)
+    with uw.ChunkBuilder(uw.Perlin(0), analytic_skip=True) as b:
+        got = b.build(pos)
+    for f in ("pos", "flags", "vert_count", "index_count"):
+        assert np.array_equal(got.descs[f], want.descs[f]), f
+    assert got.n_verts == want.n_verts and got.n_inds == want.n_inds
+    for i in range(len(pos)):
+        a, w = got.chunk(i), want.chunk(i)
+        assert np.array_equal(a.inds, w.inds) and np.array_equal(a.verts.view(np.uint8), w.verts.view(np.uint8))
+    z = pos[:, 2]
+    assert (want.descs["flags"][z >= 2] == 1).all() and (want.descs["index_count"][z <= -4] == 0).all()

@@ -18,6 +18,7 @@ FLAG_KEEP_DENSITIES = 0x4
 FLAG_TRIS = 0x8
 FLAG_STAGED = 0x10
 FLAG_ORDERED = 0x20
+FLAG_ANALYTIC_SKIP = 0x40
 
 CHUNK_BLANK_EARLY = 0x1
 CHUNK_HAS_MESH = 0x2

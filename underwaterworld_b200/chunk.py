@@ -116,7 +116,7 @@ class ChunkBuilder:
 
     def __init__(self, perlin: Optional[Perlin] = None, *, internal_size: int = INTERNAL_SIZE, device: int = -1,
                  exact_f64: bool = False, index32: bool = False, keep_densities: bool = False,
-                 staged: bool = False, ordered: bool = False, tris: bool = False, guard_eps: float = 0.0, **consts):
+                 staged: bool = False, ordered: bool = False, tris: bool = False, analytic_skip: bool = False, guard_eps: float = 0.0, **consts):
         self._lib = _ffi.load_library()
         cfg = _ffi.UwConfig()
         self._lib.uw_config_default(C.byref(cfg))
@@ -126,7 +126,8 @@ class ChunkBuilder:
         cfg.guard_eps = guard_eps
         cfg.flags = ((_ffi.FLAG_EXACT_F64 if exact_f64 else 0) | (_ffi.FLAG_INDEX32 if index32 else 0)
                      | (_ffi.FLAG_KEEP_DENSITIES if keep_densities else 0) | (_ffi.FLAG_STAGED if staged else 0)
-                     | (_ffi.FLAG_ORDERED if ordered else 0) | (_ffi.FLAG_TRIS if tris else 0))
+                     | (_ffi.FLAG_ORDERED if ordered else 0) | (_ffi.FLAG_TRIS if tris else 0)
+                     | (_ffi.FLAG_ANALYTIC_SKIP if analytic_skip else 0))
         for k, v in consts.items():
             if not hasattr(cfg, k):
                 raise TypeError(f"unknown config field {k!r}")

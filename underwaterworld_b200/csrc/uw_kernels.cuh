@@ -429,8 +429,10 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     return v;
 }
 
+// skip_descs != nullptr (UW_FLAG_ANALYTIC_SKIP): a provably trivial chunk is answered right here -- blank-early
+// above the surface layers, solid (no mesh) below -- and never handed out.
 __device__ __noinline__ Ticket take_ticket(FusedControl* ctr, const int32_t* __restrict__ pos, uint32_t n,
-                                           uint32_t* defer_list, int z_lo, int z_hi) {
+                                           uint32_t* defer_list, int z_lo, int z_hi, uw_chunk_desc* skip_descs = nullptr) {
     Ticket tk;
     tk.chunk = TICKET_DONE; tk.px = tk.py = tk.pz = 0;
     const bool defer_on = defer_list != nullptr;
@@ -440,6 +442,16 @@ __device__ __noinline__ Ticket take_ticket(FusedControl* ctr, const int32_t* __r
         if (t < n) {
             c = t;
             tk.px = pos[3 * c]; tk.py = pos[3 * c + 1]; tk.pz = pos[3 * c + 2];
+            if (skip_descs && (tk.pz < z_lo || tk.pz > z_hi)) {
+                uw_chunk_desc d;
+                d.pos[0] = tk.px; d.pos[1] = tk.py; d.pos[2] = tk.pz;
+                d.flags = tk.pz > z_hi ? UW_CHUNK_BLANK_EARLY : 0u;
+                d.vert_offset = 0; d.vert_count = 0; d.index_offset = 0; d.index_count = 0;
+                skip_descs[c] = d;
+                if (tk.pz > z_hi) atomicAdd(&ctr->totals.n_blank, 1u);
+                if (defer_on) atomicAdd(&ctr->prim_done, 1u);
+                continue;
+            }
             if (defer_on && (tk.pz < z_lo || tk.pz > z_hi)) {
                 const uint32_t slot = atomicAdd(&ctr->defer_n, 1u);
                 atomicExch(&defer_list[slot], c + 1u);
@@ -530,7 +542,8 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
                                                      int px, int py, int pz, unsigned long long* guard_count PHASE_ARG,
                                                      FusedControl* tk_ctr = nullptr, Ticket* tk_out = nullptr,
                                                      const int32_t* tk_pos = nullptr, uint32_t tk_n = 0,
-                                                     uint32_t* tk_defer = nullptr, int tk_zlo = 0, int tk_zhi = 0) {
+                                                     uint32_t* tk_defer = nullptr, int tk_zlo = 0, int tk_zhi = 0,
+                                                     uw_chunk_desc* tk_skip = nullptr) {
     using D = SpecDims<ST, NOCT>;
     constexpr int L = D::L;
     const int tid = threadIdx.x;
@@ -583,7 +596,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     // the z-column stage instead of stalling the whole CTA at the top of the next iteration
     // (the LAST thread does it: its warp has idle lanes in the column stage, and divergent paths of a warp
     // interleave, so the global round trips overlap that warp's own work too)
-    if (tk_ctr && tid == NT - 1) *tk_out = take_ticket(tk_ctr, tk_pos, tk_n, tk_defer, tk_zlo, tk_zhi);
+    if (tk_ctr && tid == NT - 1) *tk_out = take_ticket(tk_ctr, tk_pos, tk_n, tk_defer, tk_zlo, tk_zhi, tk_skip);
 
     // ---- stage YZ -------------------------------------------------------------------------------
     if (tid < L * L) {
@@ -1818,7 +1831,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
               unsigned long long vcap, unsigned long long icap,
               float* __restrict__ dens_out /*nullable: debug tap*/, int ordered,
               uw_tri* __restrict__ tris /*nullable: UW_FLAG_TRIS*/, uint16_t* __restrict__ tri_cell /*nullable*/,
-              uint32_t* __restrict__ defer_list /*nullable: heavy-first hand-out*/, int z_lo, int z_hi) {
+              uint32_t* __restrict__ defer_list /*nullable: heavy-first hand-out*/, int z_lo, int z_hi, int analytic_skip) {
     using D = SpecDims<ST, NOCT>;
     BatchTotals* const totals = &ctr->totals;
     unsigned long long* const guard_count = &ctr->guard;
@@ -1853,8 +1866,9 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // the iteration, so chunks are still handed out on demand (committing a whole chunk ahead was measured
     // slower: with ~3.5 chunks per CTA the tail grows by up to one chunk)
     if (order) defer_list = nullptr;
+    uw_chunk_desc* const skip_descs = (analytic_skip && !ordered && z_hi >= z_lo) ? descs : nullptr;
     if (tid == D::NT - 1) {
-        const Ticket t0 = take_ticket(ctr, pos, n, defer_list, z_lo, z_hi);
+        const Ticket t0 = take_ticket(ctr, pos, n, defer_list, z_lo, z_hi, skip_descs);
         sm.cur[0] = (int)t0.chunk; sm.cur[1] = t0.px; sm.cur[2] = t0.py; sm.cur[3] = t0.pz;
     }
     __syncthreads();
@@ -1872,7 +1886,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
 
         // ---- K1 ---------------------------------------------------------------------------------
         const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS,
-                                                       ctr, &nxt, pos, n, defer_list, z_lo, z_hi);
+                                                       ctr, &nxt, pos, n, defer_list, z_lo, z_hi, skip_descs);
         PHASE_MARK(1);                                     // K1 noise
         if (dens_out) {
             float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);

@@ -761,6 +761,8 @@ __device__ __forceinline__ uint32_t load_signs(const DevCfg& cfg, const float* _
 // exclusive prefix and the block totals.  NT <= 1024.
 __device__ __forceinline__ void block_scan2(uint32_t v, uint32_t i, uint32_t& ev, uint32_t& ei,
                                             uint32_t& tv, uint32_t& ti, uint32_t* s_w /*[64]*/) {
+    // ONE barrier: warp scans by shuffle, warp totals to shared memory, then every thread sums the totals of
+    // the warps before its own.  The caller must have a barrier between two calls that reuse s_w (all do).
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
     uint32_t sv = v, si = i;
 #pragma unroll
@@ -770,20 +772,14 @@ __device__ __forceinline__ void block_scan2(uint32_t v, uint32_t i, uint32_t& ev
     }
     if (lane == 31) { s_w[warp] = sv; s_w[32 + warp] = si; }
     __syncthreads();
-    if (warp == 0) {
-        uint32_t a = lane < nw ? s_w[lane] : 0u, b = lane < nw ? s_w[32 + lane] : 0u;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, a, d), y = __shfl_up_sync(0xFFFFFFFFu, b, d);
-            if (lane >= d) { a += x; b += y; }
-        }
-        s_w[lane] = a; s_w[32 + lane] = b;           // inclusive warp totals
+    uint32_t wv = 0, wi = 0, av = 0, ai = 0;
+    for (int w = 0; w < nw; ++w) {
+        const uint32_t a = s_w[w], b = s_w[32 + w];
+        av += a; ai += b;
+        if (w < warp) { wv += a; wi += b; }
     }
-    __syncthreads();
-    const uint32_t wv = warp ? s_w[warp - 1] : 0u, wi = warp ? s_w[32 + warp - 1] : 0u;
     ev = wv + sv - v; ei = wi + si - i;
-    tv = s_w[nw - 1]; ti = s_w[32 + nw - 1];
-    __syncthreads();
+    tv = av; ti = ai;
 }
 
 // ---------------------------------------------------------------------------------------

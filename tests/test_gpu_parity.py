@@ -518,3 +518,46 @@ def test_analytic_skip_gives_identical_results(uw, builder12_fast):
         assert np.array_equal(a.inds, w.inds) and np.array_equal(a.verts.view(np.uint8), w.verts.view(np.uint8))
     z = pos[:, 2]
     assert (want.descs["flags"][z >= 2] == 1).all() and (want.descs["index_count"][z <= -4] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# non-default constants: the runtime-table kernels (k_noise_small<0,0>), the exact-f64 fallback for
+# configurations the FP32 factorisation does not cover, and the large-chunk path at odd sizes
+# ---------------------------------------------------------------------------------------------
+_CONFIGS = [
+    dict(internal_size=5),
+    dict(internal_size=7, octaves=1),
+    dict(internal_size=9, octaves=2, iso_level=0.05),
+    dict(internal_size=15, octaves=4, iso_level=-0.3),
+    dict(internal_size=12, chunk_size=32, max_height=64.0),
+    dict(internal_size=12, chunk_size=8, max_height=8.0, adj_z_mod=0.5),
+    dict(internal_size=6, chunk_size=24),                       # chunk_size not a power of two -> exact f64 noise
+    dict(internal_size=8, adj_z_mod=0.3),                       # terrace step not a power of two -> fmodf path
+    dict(internal_size=12, min_hue=10.0, max_hue=300.0, saturation=0.9, base_value=0.2, min_z=-4.0, max_z=3.0),
+    dict(internal_size=19, octaves=2),                          # large-chunk path, u16 indices, f64 noise
+    dict(internal_size=24, octaves=4, iso_level=0.0),           # large-chunk path, u32 indices
+]
+
+
+@pytest.mark.parametrize("cfg", _CONFIGS, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()))
+def test_non_default_constants_match_oracle(uw, cfg):
+    from oracle import Oracle
+    S = cfg["internal_size"]
+    o = Oracle(**cfg)
+    perm = o.perm_table(7)
+    cs = cfg.get("chunk_size", 16)
+    zs = (-2, -1, 0, 1) if cs == 16 else (-3, -1, 0, 2)
+    pos = np.array([(x, y, z) for x in (-1, 3) for y in (0, 2) for z in zs], dtype=np.int32)
+    with uw.ChunkBuilder(uw.Perlin(7), ordered=True, **cfg) as b:
+        batch = b.build(pos)
+        gdens = b.debug_densities(pos)
+    want = np.stack([o.densities(perm, p) for p in pos])
+    assert np.abs(gdens.astype(np.float64) - want).max() <= DENS_TOL
+    iso = np.float32(cfg.get("iso_level", -0.1))
+    assert np.array_equal(gdens < iso, want < iso) and np.array_equal(gdens > iso, want > iso)
+    refs = _oracle_batch(o, perm, pos, MODE_FAST)                    # oracle's own densities: topology bit-exact
+    for i, r in enumerate(refs):
+        m = batch.chunk(i)
+        assert m.flags & 3 == r["flags"] & 3 and np.array_equal(m.inds.astype(np.uint32), r["inds"]), f"chunk {pos[i]}"
+    assert sum(len(r["inds"]) for r in refs) > 0
+    _check_batch(batch, _oracle_batch(o, perm, pos, MODE_FAST, isos=gdens), exact_positions=True)

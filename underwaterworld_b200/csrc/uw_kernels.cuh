@@ -1820,7 +1820,7 @@ template <int ST, int NOCT, typename IndexT>
 __global__ void __launch_bounds__(SpecDims<ST, NOCT>::NT, UW_FUSED_MINB)
 k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTables tab,
               const uint8_t* __restrict__ g_perm, const McTables* __restrict__ mc,
-              const int32_t* __restrict__ pos, const uint32_t* __restrict__ order /*nullable*/, uint32_t n,
+              const int32_t* __restrict__ pos, uint32_t n,
               ScanSlot* __restrict__ scan, FusedControl* __restrict__ ctr, FusedControl* __restrict__ ctr_next,
               uw_chunk_desc* __restrict__ descs,
               uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
@@ -1861,7 +1861,6 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // first ticket; later ones are requested inside K1 (see noise_chunk_spec) and published at the end of
     // the iteration, so chunks are still handed out on demand (committing a whole chunk ahead was measured
     // slower: with ~3.5 chunks per CTA the tail grows by up to one chunk)
-    if (order) defer_list = nullptr;
     uw_chunk_desc* const skip_descs = (analytic_skip && !ordered && z_hi >= z_lo) ? descs : nullptr;
     if (tid == D::NT - 1) {
         const Ticket t0 = take_ticket(ctr, pos, n, defer_list, z_lo, z_hi, skip_descs);

@@ -64,10 +64,10 @@ struct uw_ctx {
     typedef void (*noise_fn_t)(DevCfg, AxisTables, const uint8_t*, const int32_t*, uint32_t, float*, unsigned long long*);
     typedef void (*emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*, uw_tri*, uint16_t*);
     typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uw_tri*, uint16_t*);
-    typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, const uint32_t*, uint32_t, ScanSlot*,
+    typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint16_t*, unsigned long long,
                                  unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int, int);
-    typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, const uint32_t*, uint32_t, ScanSlot*,
+    typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint32_t*, unsigned long long,
                                  unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int, int);
     fused16_fn_t fused16_fn = nullptr;
@@ -617,16 +617,14 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     c->ctl_used = c->ctl_parity;
     c->ctl_parity ^= 1;
     const int grid = persistent_grid(c, n, c->fused_blocks_per_sm);
-    const uint32_t* d_order = nullptr;     // optional explicit hand-out permutation (unused)
     // heavy-first hand-out (scheduling only): provably trivial z layers are deferred inside the kernel; the
     // ordered-packing mode needs tickets == request order.  Only worth it when CTAs get just a few chunks each.
-    static const bool no_defer = getenv("UW_NO_DEFER") != nullptr;      // experiment switch
-    uint32_t* d_defer = (!no_defer && !c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= 16u * (uint32_t)grid) ? c->d_defer : nullptr;
+    uint32_t* d_defer = (!c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= 16u * (uint32_t)grid) ? c->d_defer : nullptr;
     if (c->index32)
-        c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
+        c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, ctl, ctl_next,
             c->d_descs, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell, d_defer, c->z_lo, c->z_hi, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0);
     else
-        c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, d_order, n, c->d_scan, ctl, ctl_next,
+        c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, ctl, ctl_next,
             c->d_descs, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell, d_defer, c->z_lo, c->z_hi, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0);
     c->launches++;
     CU_TRY(c, cudaGetLastError());

@@ -318,6 +318,7 @@ def run_ours(args):
     guards = builder.guard_count()
 
     peak, peak_src = measured_peaks()
+    ffma_tflops = builder.ffma_peak_tflops()                 # measured FP32 peak (FFMA chains), beside the nominal one
     out_bytes = n * 32 + 24 * n_verts + 2 * n_inds
     alg_bytes = {
         "fused": n * 12 + out_bytes,                                    # positions in, descriptors + mesh out
@@ -331,14 +332,17 @@ def run_ours(args):
     noise_flops = n * L3 * FLOP_PER_SAMPLE
     roofline = {"kernel": "k_build_fused<12,3,u16> (noise + classify + scan + emit in one persistent kernel)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r01_ncu_fused_full.txt
+                # (ncu --set full): 126 KB read, writes still resident in the 126 MB L2 when the kernel ends
+                "traffic": 126464, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes["fused"], "avg_launch_ms": fused_ms,
                 "note": "densities never leave the SM, so compulsory HBM traffic is only positions in and mesh out; "
                         "at 2048 chunks the kernel is issue/latency-bound (see profiles/), not HBM-bound",
                 "fp32_view": {
                     "algorithmic_tflops": noise_flops / (fused_ms / 1e3) / 1e12 if fused_ms > 0 else None,
-                    "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
+                    "nominal_peak_tflops": FP32_NOMINAL_TFLOPS, "measured_ffma_peak_tflops": ffma_tflops,
                     "frac_of_nominal": noise_flops / (fused_ms / 1e3) / 1e12 / FP32_NOMINAL_TFLOPS if fused_ms > 0 else None,
+                    "frac_of_measured_ffma": noise_flops / (fused_ms / 1e3) / 1e12 / ffma_tflops if fused_ms > 0 and ffma_tflops > 0 else None,
                     "note": "285 FLOP/sample is the reference's op count (SURVEY 8d) over the WHOLE fused kernel time; "
                             "the tensor-product factorisation executes ~3x fewer"},
                 "staged_pipeline": {
@@ -380,6 +384,7 @@ def run_ours(args):
             "noise_stage": {"kernel": "k_noise_spec<12,3> (staged pipeline)", "ms": t_big["noise_ms"],
                             "algorithmic_tflops": len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12,
                             "frac_of_nominal_fp32_peak": len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12 / FP32_NOMINAL_TFLOPS,
+                            "frac_of_measured_ffma_peak": len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12 / ffma_tflops,
                             "density_write_gbs": len(big) * 4 * L3 / (t_big["noise_ms"] / 1e3) / 1e9},
             "extraction_stages": {"kernels": "k_classify_small + k_scan_chunks + k_emit_small (staged pipeline)",
                                   "ms": t_big["classify_ms"] + t_big["emit_ms"],
@@ -411,6 +416,9 @@ def run_ours(args):
         line = {
             "metric": "voxels/s (Perlin + MC mesh build)", "value": value, "unit": "voxels/s",
             "chunks_per_s": total_chunks / (ms_per_step / 1e3),
+            "nontrivial": {"chunks_with_mesh_per_s": n_active * world / (ms_per_step / 1e3),
+                           "voxels_per_s": n_active * world * CELLS / (ms_per_step / 1e3),
+                           "note": "same time, counting only chunks that end with a mesh (rank 0's share x N)"},
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 noise + f64 guard band / f32 mesh / u16 indices", "data": "synthetic",

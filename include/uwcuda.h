@@ -202,6 +202,9 @@ uw_status   uw_get_stage_times(uw_ctx* ctx, uw_stage_times* out);
 uw_status   uw_set_profiling(uw_ctx* ctx, int enabled);
 /* Number of f64 guard-band re-evaluations in the last build (valid after sync). */
 uw_status   uw_get_guard_count(uw_ctx* ctx, uint64_t* out);
+/* Measurement aid: sustained FFMA rate of the device (TFLOP/s, 2 FLOP per FFMA) -- the "measured FP32
+ * peak" beside the nominal 148 x 128 x 2 x 1.965 GHz = 74.4 TFLOP/s in the noise-stage roofline. */
+uw_status   uw_debug_ffma_peak(uw_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

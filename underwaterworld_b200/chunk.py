@@ -179,6 +179,12 @@ class ChunkBuilder:
         self._check(self._lib.uw_get_stage_times(self._ctx, C.byref(t)))
         return {k: getattr(t, k) for k, _ in t._fields_}
 
+    def ffma_peak_tflops(self) -> float:
+        """Measured FFMA-chain throughput of the device (measurement aid for the FP32 roofline)."""
+        v = C.c_double()
+        self._check(self._lib.uw_debug_ffma_peak(self._ctx, C.byref(v)))
+        return v.value
+
     def guard_count(self) -> int:
         v = C.c_uint64()
         self._check(self._lib.uw_get_guard_count(self._ctx, C.byref(v)))

@@ -1979,3 +1979,21 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// Measurement aid (not on the product path): FFMA-chain microbenchmark for the "measured FP32 peak" the
+// noise-stage roofline is quoted against.  16 independent chains per thread.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ffma_peak(float* __restrict__ out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) x[q] = (float)(threadIdx.x + q) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) x[q] = fmaf(x[q], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += x[q];
+    if (s == 123.456f) out[0] = s;                 // keeps the chains alive, never true in practice
+}

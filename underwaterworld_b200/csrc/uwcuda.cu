@@ -946,6 +946,28 @@ extern "C" uw_status uw_iso_at(uw_ctx* c, const double* pts, uint32_t n, float* 
     return UW_OK;
 }
 
+// Measurement aid: sustained FFMA rate of the device in TFLOP/s (2 FLOP per FFMA), CUDA-event timed.
+extern "C" uw_status uw_debug_ffma_peak(uw_ctx* c, double* tflops) {
+    if (!c || !tflops) return UW_ERR_INVALID;
+    CU_TRY(c, cudaSetDevice(c->device));
+    float* d_out = nullptr;
+    CU_TRY(c, cudaMalloc(&d_out, 4));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 8192, blocks = c->num_sms * 8;
+    k_ffma_peak<<<blocks, 256, 0, c->stream>>>(d_out, 64, 1.0001f, 1e-4f);          // warm-up
+    cudaEventRecord(e0, c->stream);
+    k_ffma_peak<<<blocks, 256, 0, c->stream>>>(d_out, iters, 1.0001f, 1e-4f);
+    cudaEventRecord(e1, c->stream);
+    cudaError_t err = cudaStreamSynchronize(c->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+    if (err != cudaSuccess) return fail(c, UW_ERR_CUDA, std::string("uw_debug_ffma_peak: ") + cudaGetErrorString(err));
+    *tflops = 2.0 * 16.0 * (double)iters * 256.0 * (double)blocks / ((double)ms * 1e-3) / 1e12;
+    return UW_OK;
+}
+
 #ifdef UW_PHASE_TIMING
 // debug builds only (-DUW_PHASE_TIMING): accumulated per-phase cycle counts of thread 0 of every CTA
 extern "C" int uw_debug_phase_cycles(unsigned long long out[16], int reset) {

@@ -1033,7 +1033,9 @@ __device__ __forceinline__ void owner_of(int e, int x, int y, int z, int& ox, in
 //            E  one thread per surface cell: index = vid[(corner_a, direction) of the slot's edge]
 // ---------------------------------------------------------------------------------------
 #define UW_SMALL_MAX_CELLS ((UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1))
+#ifndef UW_VLIST_CAP
 #define UW_VLIST_CAP 4096
+#endif
 #define UW_EDGE_KINDS 5      // +x, -x, +y, +z, -z  (-y never occurs: edges 8..11 all run +y)
 
 struct EmitSmem {
@@ -1147,7 +1149,7 @@ __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const Emit
         smask &= smask - 1;
         const int cell = col * S + z;
         const uint32_t t = s.lut[natural_of(q0, q1, z)];
-        s.vbase[cell] = (uint16_t)rv; s.ibase[cell] = (uint16_t)ri;
+        s.vbase[ra] = (uint16_t)rv; s.ibase[ra] = (uint16_t)ri;        // indexed by surface-cell rank, like alist
         s.alist[ra++] = (uint16_t)cell;
         ri += (t >> 8) & 15u;
         rv += __popc((t >> 12) & (z == 0 ? own0 : ownn));
@@ -1173,7 +1175,7 @@ __device__ __forceinline__ void emit_fill(const DevCfg& cfg, const McTables* __r
         const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
         const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
         const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
-        uint32_t vnext = s.vbase[cell], todo = own;     // owned edges not yet numbered
+        uint32_t vnext = s.vbase[a], todo = own;        // owned edges not yet numbered
 #pragma unroll
         for (int k = 0; k < 15; ++k) {
             const uint32_t e = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
@@ -1220,7 +1222,7 @@ __device__ __forceinline__ void emit_indices(const DevCfg& cfg, const McTables* 
         const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
         const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
         const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
-        IndexT* dst = iout + s.ibase[cell];
+        IndexT* dst = iout + s.ibase[a];
 #pragma unroll
         for (int k = 0; k < 15; ++k) {
             const uint32_t e = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
@@ -1245,7 +1247,7 @@ __device__ __forceinline__ void emit_tris(const DevCfg& cfg, const McTables* __r
         const int cell = s.alist[a];
         const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
         const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
-        float* dst = reinterpret_cast<float*>(tout + s.ibase[cell] / 3u);
+        float* dst = reinterpret_cast<float*>(tout + s.ibase[a] / 3u);
 #pragma unroll 1
         for (int t = 0; t < 5; ++t) {
             const int e0 = (int)((row >> (12 * t)) & 0xFull);
@@ -1753,7 +1755,7 @@ template <int ST, int NOCT>
 struct FusedSmem {
     SpecSmem<ST, NOCT> n;                             // n.lat / n.X are dead after K1 and reused by K4 (vid)
     uint16_t vlist[UW_VLIST_CAP];
-    uint16_t vbase[ST * ST * ST + 8];
+    uint16_t vbase[ST * ST * ST + 8];                 // vbase / ibase / alist: one entry per SURFACE cell (worst case: all)
     uint16_t ibase[ST * ST * ST + 8];
     uint16_t alist[ST * ST * ST + 8];
     uint32_t lut[256];

@@ -12,8 +12,9 @@ K2 classify -> K3 scan -> K4 emit) over one batch of chunk positions:
 
 value  = voxels/s (cells/s) device-resident: positions already in HBM, outputs stay in HBM,
          timed with CUDA events on the launching stream, L2 flushed between steps.
-e2e    = the same metric through the C ABI with HOST buffers (uw_build: pinned H2D of the
-         positions, the kernels, D2H of descriptors + vertices + indices into pinned host memory).
+e2e    = the same metric through the C ABI with HOST buffers (pinned H2D of the positions, the kernel, D2H of
+         descriptors + vertices + indices into pinned host memory), K builds software-pipelined two deep
+         (uw_build_async / uw_batch_wait); the blocking single-call latency is reported beside it.
 --impl reference  times the CPU oracle (oracle/, faithful mode = the reference's algorithm,
          all host threads) on a bounded sample of the same workload.  The reference itself is
          Rust and cannot be compiled in this image (no cargo/rustc) -- see DESIGN.md.
@@ -278,10 +279,45 @@ def run_ours(args):
             e2e_t.append(time.perf_counter() - t0)
         barrier()
         # host-timed: the median is robust against the clock-sampling thread and other host noise
-        e2e_s = float(np.median(e2e_t)) * K
+        single_ms = 1e3 * float(np.median(e2e_t))
         e2e_mean_ms = 1e3 * float(np.mean(e2e_t))
+
+        # The same K host builds, software-pipelined the way a streaming caller uses the ABI: submit batch k+1
+        # (uw_build_async), then collect batch k (uw_batch_wait) -- batch k's D2H runs on the library's copy
+        # stream underneath batch k+1's kernel.  One wall-clock region around all K steps, nothing in flight at
+        # either end; every step's H2D and D2H is inside it.
+        def pipelined(steps):
+            prev = C.c_void_p()
+            if lib.uw_build_async(ctx, pos.ctypes.data, n, C.byref(prev)) != 0:
+                raise RuntimeError(lib.uw_last_error(ctx).decode())
+            for _ in range(1, steps):
+                nxt = C.c_void_p()
+                if lib.uw_build_async(ctx, pos.ctypes.data, n, C.byref(nxt)) != 0:
+                    raise RuntimeError(lib.uw_last_error(ctx).decode())
+                if lib.uw_batch_wait(prev) != 0:
+                    raise RuntimeError(lib.uw_last_error(ctx).decode())
+                lib.uw_batch_view_get(prev, C.byref(view))
+                lib.uw_batch_free(prev)
+                prev = nxt
+            if lib.uw_batch_wait(prev) != 0:
+                raise RuntimeError(lib.uw_last_error(ctx).decode())
+            lib.uw_batch_view_get(prev, C.byref(view))
+            lib.uw_batch_free(prev)
+
+        pipelined(max(W, 3))
+        pipe_t = []
+        for _ in range(3):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            pipelined(K)
+            pipe_t.append(time.perf_counter() - t0)
+        barrier()
+        e2e_s = float(np.median(pipe_t))
     ms_per_step = max_over_ranks(sum(step_ms) / K)
     e2e_ms = max_over_ranks(1e3 * e2e_s / K)
+    single_ms = max_over_ranks(single_ms)
     total_chunks = n * world
     value = total_chunks * CELLS / (ms_per_step / 1e3)
     e2e_value = total_chunks * CELLS / (e2e_ms / 1e3)
@@ -427,10 +463,15 @@ def run_ours(args):
                        "chunks_per_gpu": n, "cells_per_chunk": CELLS, "samples_per_chunk": L3,
                        "l2": "flushed between timed steps (256 MB write)", "parallelism": f"chunk-slabs x{world}"},
             "e2e": {"value": e2e_value, "unit": "voxels/s", "chunks_per_s": total_chunks / (e2e_ms / 1e3),
-                    "ms_per_step": e2e_ms, "ms_per_step_mean": e2e_mean_ms, "timing": "host perf_counter around uw_build, median of K steps",
+                    "ms_per_step": e2e_ms,
+                    "timing": "host perf_counter around K software-pipelined host builds (uw_build_async k+1, uw_batch_wait k; "
+                              "two batches in flight, D2H of batch k under the kernel of batch k+1), median of 3 runs",
+                    "single_call": {"ms_per_step": single_ms, "ms_per_step_mean": e2e_mean_ms,
+                                    "chunks_per_s": total_chunks / (single_ms / 1e3),
+                                    "timing": "blocking uw_build, host perf_counter, median of K steps, L2 flushed between steps"},
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_step) * K,
-            "kernels_per_step": ["k_order_chunks", "k_build_fused"],
+            "kernels_per_step": ["k_build_fused"],
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "north_star": north_star,

@@ -168,7 +168,10 @@ uw_status   uw_perm_table(const uw_ctx* ctx, uint8_t out[256]);
 /* ---- the hot path: Chunk::new + Chunk::build_full for n chunks (chunk.rs:89-103,266-313) -- */
 /* chunk_pos_xyz: n x 3 int32, HOST memory.  Blocking: returns with the batch complete. */
 uw_status   uw_build(uw_ctx* ctx, const int32_t* chunk_pos_xyz, uint32_t n, uw_batch** out);
-/* Same, but returns once work is enqueued; uw_batch_wait() completes it. */
+/* Same, but returns once work is enqueued; uw_batch_wait() completes it.  Up to TWO batches may be in flight on
+ * the default (fused, internal_size 10/12) path: submit batch k+1, then wait on batch k -- batch k's copies to the
+ * host run on a second stream underneath batch k+1's kernel.  A third submit (or a second one on the staged /
+ * large-chunk paths, or any device-resident / debug call while a batch is in flight) returns UW_ERR_NOT_READY. */
 uw_status   uw_build_async(uw_ctx* ctx, const int32_t* chunk_pos_xyz, uint32_t n, uw_batch** out);
 uw_status   uw_batch_wait(uw_batch* b);
 uw_status   uw_batch_view_get(const uw_batch* b, uw_batch_view* out);

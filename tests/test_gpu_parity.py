@@ -343,6 +343,34 @@ def test_index32_and_async(uw, oracle12):
     assert np.array_equal(batch.inds, np.concatenate([r["inds"] for r in refs]))
 
 
+def test_two_async_batches_overlap(uw, builder12):
+    """Software pipeline of the host API: batch k+1 is submitted before batch k is collected (two buffer sets,
+    copies on a second stream).  Results equal the blocking builds; a third submit is refused."""
+    regions = [uw.region.box_region((-6 + 3 * k, -3 + 3 * k), (-4, 4), (-3, 1)) for k in range(5)]
+    want = [builder12.build(r) for r in regions]
+    got = []
+    prev = builder12.build_async(regions[0])
+    for k in range(1, len(regions)):
+        nxt = builder12.build_async(regions[k])
+        if k == 1:
+            with pytest.raises(uw.UwError):
+                builder12.build_async(regions[0])            # two already in flight
+            with pytest.raises(uw.UwError):
+                builder12.build_device(0, 0)
+        got.append(builder12.wait(prev))
+        prev = nxt
+    got.append(builder12.wait(prev))
+    for w, g in zip(want, got):
+        assert np.array_equal(w.descs["pos"], g.descs["pos"])
+        assert np.array_equal(w.descs["vert_count"], g.descs["vert_count"])
+        assert np.array_equal(w.descs["index_count"], g.descs["index_count"])
+        for i in range(0, len(w.descs), 7):                   # packing order is completion order: compare per chunk
+            a, b = w.chunk(i), g.chunk(i)
+            assert np.array_equal(a.inds, b.inds) and a.verts.tobytes() == b.verts.tobytes()
+    # the builder is reusable afterwards
+    assert builder12.build(regions[0]).n_inds == want[0].n_inds
+
+
 def test_large_batch_properties(uw, builder12):
     """Config-3-sized slab properties that need no oracle: index range, packing, determinism,
     triangle soup equality between FP32 and exact-f64 topology."""

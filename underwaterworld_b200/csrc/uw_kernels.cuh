@@ -415,6 +415,13 @@ struct FusedControl {
     BatchTotals totals;
 };
 
+// What the host reads back after a fused launch; written by the last CTA out to a per-batch slot, so that a
+// later launch (which zeroes and reuses the control blocks) cannot disturb it.
+struct FusedSummary {
+    unsigned long long alloc, guard;
+    BatchTotals totals;
+};
+
 // Chunk hand-out for the persistent kernel (executed by ONE thread).  Tickets 0..n-1 walk the request
 // list; a chunk whose z layer provably holds no surface (z outside [z_lo, z_hi]: blank or solid whatever the
 // noise does, |noise| <= 1) is several times cheaper than a surface chunk, so it is parked in `defer_list`
@@ -1829,7 +1836,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
               unsigned long long vcap, unsigned long long icap,
               float* __restrict__ dens_out /*nullable: debug tap*/, int ordered,
               uw_tri* __restrict__ tris /*nullable: UW_FLAG_TRIS*/, uint16_t* __restrict__ tri_cell /*nullable*/,
-              uint32_t* __restrict__ defer_list /*nullable: heavy-first hand-out*/, int z_lo, int z_hi, int analytic_skip) {
+              uint32_t* __restrict__ defer_list /*nullable: heavy-first hand-out*/, int z_lo, int z_hi, int analytic_skip,
+              FusedSummary* __restrict__ sum_out) {
     using D = SpecDims<ST, NOCT>;
     BatchTotals* const totals = &ctr->totals;
     unsigned long long* const guard_count = &ctr->guard;
@@ -1974,6 +1982,16 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             for (uint32_t i = tid; i < used; i += D::NT) defer_list[i] = 0u;
         }
         if (tid == 0) {
+            FusedSummary sm_out;                     // every other CTA fenced its writes before bumping `done`
+            sm_out.alloc = atomicAdd(&ctr->alloc, 0ull);
+            sm_out.guard = atomicAdd(&ctr->guard, 0ull);
+            sm_out.totals.n_verts = atomicAdd(&ctr->totals.n_verts, 0ull);
+            sm_out.totals.n_inds = atomicAdd(&ctr->totals.n_inds, 0ull);
+            sm_out.totals.n_active = atomicAdd(&ctr->totals.n_active, 0u);
+            sm_out.totals.overflow = atomicAdd(&ctr->totals.overflow, 0u);
+            sm_out.totals.n_blank = atomicAdd(&ctr->totals.n_blank, 0u);
+            sm_out.totals.n_mesh = 0;
+            *sum_out = sm_out;                       // host-mapped memory: visible to the host at kernel completion
             ctr_next->ticket = 0; ctr_next->done = 0; ctr_next->defer_n = 0; ctr_next->prim_done = 0;
             ctr_next->alloc = 0; ctr_next->guard = 0;
             BatchTotals z; z.n_verts = 0; z.n_inds = 0; z.n_active = 0; z.overflow = 0; z.n_blank = 0; z.n_mesh = 0;

@@ -36,28 +36,45 @@ struct uw_ctx {
     size_t big_noise_smem = 0; int big_noise_blocks_per_sm = 1;
     McTables* d_mc = nullptr;
 
-    // grow-only device buffers
-    uint32_t cap_chunks = 0;
-    int32_t* d_pos = nullptr;
-    float* d_dens = nullptr;
-    ChunkCounts* d_counts = nullptr;
-    uw_chunk_desc* d_descs = nullptr;
-    uint32_t* d_active = nullptr;
-    uint8_t* d_cases = nullptr;  uint32_t cap_cases_chunks = 0;
+    bool tris = false;              // UW_FLAG_TRIS: per-cell collision triangles
+    // grow-only per-batch buffers: TWO sets, so that a host build's D2H copies (set A, copy stream) overlap the
+    // next batch's kernel (set B, compute stream).  B() is the set of the build being enqueued / last enqueued.
+    struct BufSet {
+        uint32_t cap_chunks = 0;
+        int32_t* d_pos = nullptr;
+        float* d_dens = nullptr;        // only the staged / large-chunk / debug paths materialise densities
+        uint32_t cap_dens_chunks = 0;
+        ChunkCounts* d_counts = nullptr;
+        uw_chunk_desc* d_descs = nullptr;
+        uint32_t* d_active = nullptr;
+        uint8_t* d_cases = nullptr;  uint32_t cap_cases_chunks = 0;
+        ScanSlot* d_scan = nullptr;
+        uint32_t* d_defer = nullptr;    // deferred-chunk list of the fused kernel (kept zeroed between launches)
+        unsigned long long vcap = 0, icap = 0;
+        uw_vert* d_verts = nullptr;
+        void* d_inds = nullptr;
+        uw_tri* d_tris = nullptr;       // [icap / 3]
+        uint16_t* d_tri_cell = nullptr; // [cap_chunks][S^3 + 1]
+        int32_t* h_pos = nullptr; size_t h_pos_cap = 0;   // pinned staging of the request
+        FusedSummary* h_sum = nullptr;  // pinned + mapped: the last CTA of the fused kernel writes it over PCIe
+        cudaEvent_t done = nullptr;     // recorded after the set's kernels
+        bool busy = false;              // an async batch that has not been collected owns this set
+        // state of the set's last build
+        uint32_t last_n = 0;
+        const int32_t* last_pos_dev = nullptr;
+        bool last_fused = false;
+        bool pending = false;           // kernels enqueued, totals not yet validated
+        BatchTotals result = {};        // validated totals of the last finished build
+    } sets[2];
+    int cur = 0;
+    BufSet& B() { return sets[cur]; }
     BatchTotals* d_totals = nullptr;
     unsigned long long* d_guard = nullptr;
-    unsigned long long vcap = 0, icap = 0;
-    uw_vert* d_verts = nullptr;
-    void* d_inds = nullptr;
-    bool tris = false;              // UW_FLAG_TRIS: per-cell collision triangles
-    uw_tri* d_tris = nullptr;       // [icap / 3]
-    uint16_t* d_tri_cell = nullptr; // [cap_chunks][S^3 + 1]
+    cudaStream_t copy_stream = nullptr;
 
     // pinned host staging
-    int32_t* h_pos = nullptr; size_t h_pos_cap = 0;
     BatchTotals* h_totals = nullptr;
     unsigned long long* h_guard = nullptr;
-    unsigned long long* h_alloc = nullptr;
     std::vector<PinnedBlock> pool;
 
     // launch geometry / kernel selection
@@ -66,23 +83,20 @@ struct uw_ctx {
     typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uw_tri*, uint16_t*);
     typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint16_t*, unsigned long long,
-                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int, int);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int, int, FusedSummary*);
     typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint32_t*, unsigned long long,
-                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int, int);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int, int, FusedSummary*);
     fused16_fn_t fused16_fn = nullptr;
     fused32_fn_t fused32_fn = nullptr;
     bool use_fused = false;
     int z_lo = 1, z_hi = 0;         // chunk z layers that can hold surface (empty range = unknown: no deferral)
-    uint32_t* d_defer = nullptr;    // [cap_chunks] deferred-chunk list of the fused kernel (kept zeroed between launches)
     bool big_path = false;          // internal_size > 15: slab-walking extraction, densities in HBM
     size_t big_smem = 0; int big_blocks_per_sm = 1, big_count_blocks_per_sm = 1;
     bool ordered = false;           // packed arenas follow request order (look-back) vs atomic bump allocation
     size_t fused_smem = 0; int fused_blocks_per_sm = 1;
-    ScanSlot* d_scan = nullptr;
-    FusedControl* d_ctl = nullptr;  // two blocks, alternating per launch
-    FusedControl* h_ctl = nullptr;  // pinned copy of the block used by the last launch
-    int ctl_parity = 0, ctl_used = 0;
+    FusedControl* d_ctl = nullptr;  // two blocks, alternating per launch (each launch zeroes the other one)
+    int ctl_parity = 0;
     noise_fn_t noise_fn = nullptr;
     emit16_fn_t emit16_fn = nullptr;
     emit32_fn_t emit32_fn = nullptr;
@@ -91,12 +105,6 @@ struct uw_ctx {
     int emit_blocks_per_sm = 1; size_t emit_smem = 0;
     int classify_blocks_per_sm = 1;
 
-    // state of the last build
-    uint32_t last_n = 0;
-    const int32_t* last_pos_dev = nullptr;
-    bool last_fused = false;
-    bool pending = false;           // kernels enqueued, totals not yet validated
-    bool async_in_flight = false;
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     uw_stage_times times;
@@ -108,6 +116,7 @@ struct uw_ctx {
 struct uw_batch {
     uw_ctx* ctx;
     uint32_t n;
+    int set;            // buffer set the batch's kernels write (-1: empty batch)
     bool ready;
     PinnedBlock arena;
     uw_batch_view view;
@@ -276,16 +285,21 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_axis); cudaFree(c->d_pos); cudaFree(c->d_dens); cudaFree(c->d_counts);
-    cudaFree(c->d_descs); cudaFree(c->d_active); cudaFree(c->d_cases); cudaFree(c->d_totals); cudaFree(c->d_guard);
-    cudaFree(c->d_verts); cudaFree(c->d_inds); cudaFree(c->d_tris); cudaFree(c->d_tri_cell); cudaFree(c->d_scan); cudaFree(c->d_ctl); cudaFree(c->d_defer);
-    if (c->h_ctl) cudaFreeHost(c->h_ctl);
-    if (c->h_pos) cudaFreeHost(c->h_pos);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_axis); cudaFree(c->d_totals); cudaFree(c->d_guard); cudaFree(c->d_ctl);
+    for (auto& b : c->sets) {
+        cudaFree(b.d_pos); cudaFree(b.d_dens); cudaFree(b.d_counts); cudaFree(b.d_descs); cudaFree(b.d_active);
+        cudaFree(b.d_cases); cudaFree(b.d_verts); cudaFree(b.d_inds); cudaFree(b.d_tris); cudaFree(b.d_tri_cell);
+        cudaFree(b.d_scan); cudaFree(b.d_defer);
+        if (b.h_pos) cudaFreeHost(b.h_pos);
+        if (b.h_sum) cudaFreeHost(b.h_sum);
+        if (b.done) cudaEventDestroy(b.done);
+    }
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_guard) cudaFreeHost(c->h_guard);
-    if (c->h_alloc) cudaFreeHost(c->h_alloc);
     for (auto& b : c->pool) cudaFreeHost(b.ptr);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -339,6 +353,13 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     };
     if (!cu(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(UW_ERR_CUDA);
     c->own_stream = true;
+    if (!cu(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate copy")) return bail(UW_ERR_CUDA);
+    for (auto& b : c->sets) {
+        if (!cu(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming), "cudaEventCreate done")) return bail(UW_ERR_CUDA);
+        if (!cu(cudaHostAlloc(&b.h_sum, sizeof(FusedSummary), cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc summary")) return bail(UW_ERR_OOM);
+    }
+    if (!cu(cudaMalloc(&c->d_ctl, 2 * sizeof(FusedControl)), "cudaMalloc control")) return bail(UW_ERR_OOM);
+    if (!cu(cudaMemset(c->d_ctl, 0, 2 * sizeof(FusedControl)), "memset control")) return bail(UW_ERR_CUDA);
     if (!cu(cudaMalloc(&c->d_perm, 256), "cudaMalloc perm")) return bail(UW_ERR_OOM);
     if (!cu(cudaMemcpy(c->d_perm, c->perm, 256, cudaMemcpyHostToDevice), "memcpy perm")) return bail(UW_ERR_CUDA);
     {
@@ -367,7 +388,6 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     if (!cu(cudaMemset(c->d_guard, 0, sizeof(unsigned long long)), "memset guard")) return bail(UW_ERR_CUDA);
     if (!cu(cudaHostAlloc(&c->h_totals, sizeof(BatchTotals), cudaHostAllocDefault), "cudaHostAlloc totals")) return bail(UW_ERR_OOM);
     if (!cu(cudaHostAlloc(&c->h_guard, sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc guard")) return bail(UW_ERR_OOM);
-    if (!cu(cudaHostAlloc(&c->h_alloc, sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc alloc")) return bail(UW_ERR_OOM);
     for (auto& ev : c->ev) if (!cu(cudaEventCreate(&ev), "cudaEventCreate")) return bail(UW_ERR_CUDA);
 
     // launch geometry / kernel selection
@@ -477,46 +497,50 @@ static cudaError_t regrow(T** p, size_t count) {
 }
 
 static uw_status ensure_chunks(uw_ctx* c, uint32_t n) {
-    if (n <= c->cap_chunks) return UW_OK;
-    uint32_t cap = c->cap_chunks ? c->cap_chunks : 256;
+    if (n <= c->B().cap_chunks) return UW_OK;
+    uint32_t cap = c->B().cap_chunks ? c->B().cap_chunks : 256;
     while (cap < n) cap *= 2;
     if (cap > n && (uint64_t)cap * c->dcfg.dens_stride * 4 > (8ull << 30)) cap = n;   // no 2x slack on multi-GB batches
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    CU_TRY(c, regrow(&c->d_pos, (size_t)cap * 3));
-    CU_TRY(c, regrow(&c->d_dens, (size_t)cap * c->dcfg.dens_stride));
-    CU_TRY(c, regrow(&c->d_counts, cap));
-    CU_TRY(c, regrow(&c->d_descs, cap));
-    CU_TRY(c, regrow(&c->d_active, cap));
-    CU_TRY(c, regrow(&c->d_scan, cap));
-    CU_TRY(c, regrow(&c->d_defer, cap));
-    CU_TRY(c, cudaMemset(c->d_defer, 0, (size_t)cap * sizeof(uint32_t)));
-    if (c->tris) CU_TRY(c, regrow(&c->d_tri_cell, (size_t)cap * ((size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1)));
-    if (!c->d_ctl) {
-        CU_TRY(c, cudaMalloc(&c->d_ctl, 2 * sizeof(FusedControl)));
-        CU_TRY(c, cudaMemset(c->d_ctl, 0, 2 * sizeof(FusedControl)));
-        CU_TRY(c, cudaHostAlloc(&c->h_ctl, sizeof(FusedControl), cudaHostAllocDefault));
-    }
-    c->cap_chunks = cap;
+    CU_TRY(c, regrow(&c->B().d_pos, (size_t)cap * 3));
+    CU_TRY(c, regrow(&c->B().d_counts, cap));
+    CU_TRY(c, regrow(&c->B().d_descs, cap));
+    CU_TRY(c, regrow(&c->B().d_active, cap));
+    CU_TRY(c, regrow(&c->B().d_scan, cap));
+    CU_TRY(c, regrow(&c->B().d_defer, cap));
+    CU_TRY(c, cudaMemset(c->B().d_defer, 0, (size_t)cap * sizeof(uint32_t)));
+    if (c->tris) CU_TRY(c, regrow(&c->B().d_tri_cell, (size_t)cap * ((size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1)));
+    c->B().cap_chunks = cap;
+    return UW_OK;
+}
+
+// The density field lives in HBM only on the staged / large-chunk / debug paths (the fused kernel keeps it in
+// shared memory): allocated on first use, sized like the chunk arrays.
+static uw_status ensure_dens(uw_ctx* c) {
+    if (c->B().cap_dens_chunks >= c->B().cap_chunks) return UW_OK;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, regrow(&c->B().d_dens, (size_t)c->B().cap_chunks * c->dcfg.dens_stride));
+    c->B().cap_dens_chunks = c->B().cap_chunks;
     return UW_OK;
 }
 
 static uw_status ensure_outputs(uw_ctx* c, unsigned long long nv, unsigned long long ni) {
     const size_t isz = c->index32 ? 4 : 2;
-    if (nv > c->vcap) {
-        unsigned long long cap = c->vcap ? c->vcap : 4096;
+    if (nv > c->B().vcap) {
+        unsigned long long cap = c->B().vcap ? c->B().vcap : 4096;
         while (cap < nv) cap *= 2;
         CU_TRY(c, cudaStreamSynchronize(c->stream));
-        CU_TRY(c, regrow(&c->d_verts, (size_t)cap));
-        c->vcap = cap;
+        CU_TRY(c, regrow(&c->B().d_verts, (size_t)cap));
+        c->B().vcap = cap;
     }
-    if (ni > c->icap) {
-        unsigned long long cap = c->icap ? c->icap : 16384;
+    if (ni > c->B().icap) {
+        unsigned long long cap = c->B().icap ? c->B().icap : 16384;
         while (cap < ni) cap *= 2;
         CU_TRY(c, cudaStreamSynchronize(c->stream));
-        if (c->d_inds) { cudaFree(c->d_inds); c->d_inds = nullptr; }
-        CU_TRY(c, cudaMalloc(&c->d_inds, (size_t)cap * isz));
-        if (c->tris) CU_TRY(c, regrow(&c->d_tris, (size_t)cap / 3 + 1));
-        c->icap = cap;
+        if (c->B().d_inds) { cudaFree(c->B().d_inds); c->B().d_inds = nullptr; }
+        CU_TRY(c, cudaMalloc(&c->B().d_inds, (size_t)cap * isz));
+        if (c->tris) CU_TRY(c, regrow(&c->B().d_tris, (size_t)cap / 3 + 1));
+        c->B().icap = cap;
     }
     return UW_OK;
 }
@@ -547,16 +571,16 @@ static uw_status launch_noise(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
     if (c->big_path && c->big_fast_noise && c->fast_path) {
         const unsigned long long units = (unsigned long long)n * ((d.L2 + 255) / 256);
         const unsigned long long full = (unsigned long long)c->num_sms * c->big_noise_blocks_per_sm;
-        k_noise_big<64, 3><<<(int)(units < full ? units : full), 256, c->big_noise_smem, c->stream>>>(d, c->d_axis, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
+        k_noise_big<64, 3><<<(int)(units < full ? units : full), 256, c->big_noise_smem, c->stream>>>(d, c->d_axis, c->d_perm, d_pos, n, c->B().d_dens, c->d_guard);
     } else if (c->fast_path && !c->big_path) {
         const int grid = persistent_grid(c, n, c->noise_blocks_per_sm);
-        c->noise_fn<<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->d_dens, c->d_guard);
+        c->noise_fn<<<grid, c->noise_threads, c->noise_smem, c->stream>>>(d, c->tab, c->d_perm, d_pos, n, c->B().d_dens, c->d_guard);
     } else {
         const unsigned long long total = (unsigned long long)n * d.L3;
         unsigned long long blocks = (total + 255) / 256;
         const unsigned long long maxb = (unsigned long long)c->num_sms * 8;
         if (blocks > maxb) blocks = maxb;
-        k_noise_exact<<<(int)blocks, 256, 0, c->stream>>>(d, c->d_perm, d_pos, n, c->d_dens);
+        k_noise_exact<<<(int)blocks, 256, 0, c->stream>>>(d, c->d_perm, d_pos, n, c->B().d_dens);
     }
     c->launches++;
     CU_TRY(c, cudaGetLastError());
@@ -568,42 +592,42 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
     if (c->big_path) {
         const int grid = persistent_grid(c, n, c->big_blocks_per_sm);
         if (!only_emit) {
-            k_count_big<<<persistent_grid(c, n, c->big_count_blocks_per_sm), UW_BIG_NT, 0, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts);
+            k_count_big<<<persistent_grid(c, n, c->big_count_blocks_per_sm), UW_BIG_NT, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts);
             c->launches++;
             CU_TRY(c, cudaGetLastError());
             if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
         }
-        k_scan_chunks<<<1, 1024, 0, c->stream>>>(c->d_counts, d_pos, n, c->d_descs, c->d_active, c->d_totals, c->vcap, c->icap);
+        k_scan_chunks<<<1, 1024, 0, c->stream>>>(c->B().d_counts, d_pos, n, c->B().d_descs, c->B().d_active, c->d_totals, c->B().vcap, c->B().icap);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
         if (c->index32)
-            k_emit_big<uint32_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active,
-                                                                             c->d_totals, c->d_verts, (uint32_t*)c->d_inds);
+            k_emit_big<uint32_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
+                                                                             c->d_totals, c->B().d_verts, (uint32_t*)c->B().d_inds);
         else
-            k_emit_big<uint16_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active,
-                                                                             c->d_totals, c->d_verts, (uint16_t*)c->d_inds);
+            k_emit_big<uint16_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
+                                                                             c->d_totals, c->B().d_verts, (uint16_t*)c->B().d_inds);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         return UW_OK;
     }
     if (!only_emit) {
-        k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, d_cases);
+        k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts, d_cases);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
     }
-    k_scan_chunks<<<1, 1024, 0, c->stream>>>(c->d_counts, d_pos, n, c->d_descs, c->d_active, c->d_totals, c->vcap, c->icap);
+    k_scan_chunks<<<1, 1024, 0, c->stream>>>(c->B().d_counts, d_pos, n, c->B().d_descs, c->B().d_active, c->d_totals, c->B().vcap, c->B().icap);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
     const int grid = persistent_grid(c, n, c->emit_blocks_per_sm);
     if (c->index32)
-        c->emit32_fn<<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
-                                                            c->d_verts, (uint32_t*)c->d_inds, c->d_tris, c->d_tri_cell);
+        c->emit32_fn<<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active, c->d_totals,
+                                                            c->B().d_verts, (uint32_t*)c->B().d_inds, c->B().d_tris, c->B().d_tri_cell);
     else
-        c->emit16_fn<<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->d_dens, c->d_descs, c->d_active, c->d_totals,
-                                                            c->d_verts, (uint16_t*)c->d_inds, c->d_tris, c->d_tri_cell);
+        c->emit16_fn<<<grid, 256, c->emit_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active, c->d_totals,
+                                                            c->B().d_verts, (uint16_t*)c->B().d_inds, c->B().d_tris, c->B().d_tri_cell);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;
@@ -611,108 +635,117 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
 
 static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float* d_dens_out) {
     const DevCfg& d = c->dcfg;
-    if (c->ordered) CU_TRY(c, cudaMemsetAsync(c->d_scan, 0, sizeof(ScanSlot) * (size_t)n, c->stream));
+    if (c->ordered) CU_TRY(c, cudaMemsetAsync(c->B().d_scan, 0, sizeof(ScanSlot) * (size_t)n, c->stream));
     FusedControl* ctl = c->d_ctl + c->ctl_parity;
     FusedControl* ctl_next = c->d_ctl + (c->ctl_parity ^ 1);
-    c->ctl_used = c->ctl_parity;
     c->ctl_parity ^= 1;
     const int grid = persistent_grid(c, n, c->fused_blocks_per_sm);
     // heavy-first hand-out (scheduling only): provably trivial z layers are deferred inside the kernel; the
     // ordered-packing mode needs tickets == request order.  Only worth it when CTAs get just a few chunks each.
-    uint32_t* d_defer = (!c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= 16u * (uint32_t)grid) ? c->d_defer : nullptr;
+    uint32_t* d_defer = (!c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= 16u * (uint32_t)grid) ? c->B().d_defer : nullptr;
     if (c->index32)
-        c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, ctl, ctl_next,
-            c->d_descs, c->d_verts, (uint32_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell, d_defer, c->z_lo, c->z_hi, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0);
+        c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
+            c->B().d_descs, c->B().d_verts, (uint32_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_defer, c->z_lo, c->z_hi, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
     else
-        c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->d_scan, ctl, ctl_next,
-            c->d_descs, c->d_verts, (uint16_t*)c->d_inds, c->vcap, c->icap, d_dens_out, c->ordered ? 1 : 0, c->d_tris, c->d_tri_cell, d_defer, c->z_lo, c->z_hi, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0);
+        c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
+            c->B().d_descs, c->B().d_verts, (uint16_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_defer, c->z_lo, c->z_hi, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;
 }
 
-// enqueue the whole pipeline for n chunks whose positions are at d_pos (device)
+// enqueue the whole pipeline for n chunks whose positions are at d_pos (device), into the current buffer set
 static uw_status enqueue_build(uw_ctx* c, const int32_t* d_pos, uint32_t n, bool from_densities) {
     // initial output capacity guess: grows (and the emit stage is re-run) on overflow
     uw_status st = ensure_outputs(c, (unsigned long long)n * 192 + 4096, (unsigned long long)n * 640 + 16384);
     if (st != UW_OK) return st;
+    const bool fused = c->use_fused && !from_densities;
+    const bool keep = (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) != 0;
+    if (!fused || keep) { st = ensure_dens(c); if (st != UW_OK) return st; }
     c->launches = 0;
     if (c->tris)      // cells of chunks that never reach the emit stage keep offset 0
-        CU_TRY(c, cudaMemsetAsync(c->d_tri_cell, 0, (size_t)n * ((size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1) * 2, c->stream));
-    if (!(c->use_fused && !from_densities))      // the fused kernel counts guard re-evaluations in its control block
+        CU_TRY(c, cudaMemsetAsync(c->B().d_tri_cell, 0, (size_t)n * ((size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1) * 2, c->stream));
+    if (!fused)       // the fused kernel counts guard re-evaluations in its control block
         CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
-    c->last_fused = false;
-    if (c->use_fused && !from_densities) {
+    c->B().last_fused = fused;
+    if (fused) {
         if (c->profiling) for (int e = 0; e < 4; ++e) CU_TRY(c, cudaEventRecord(c->ev[e], c->stream));
-        st = launch_fused(c, d_pos, n, (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) ? c->d_dens : nullptr);
+        st = launch_fused(c, d_pos, n, keep ? c->B().d_dens : nullptr);
         if (st != UW_OK) return st;
-        if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[4], c->stream));
-        c->last_n = n; c->last_pos_dev = d_pos; c->pending = true; c->last_fused = true;
-        return UW_OK;
-    }
-    if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
-    if (!from_densities) {
-        st = launch_noise(c, d_pos, n);
-        if (st != UW_OK) return st;
-    }
-    if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
-    uint8_t* d_cases = nullptr;
-    if (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) {
-        if (n > c->cap_cases_chunks) {
-            CU_TRY(c, cudaStreamSynchronize(c->stream));
-            CU_TRY(c, regrow(&c->d_cases, (size_t)n * c->dcfg.S * c->dcfg.S * c->dcfg.S));
-            c->cap_cases_chunks = n;
+    } else {
+        if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
+        if (!from_densities) {
+            st = launch_noise(c, d_pos, n);
+            if (st != UW_OK) return st;
         }
-        d_cases = c->d_cases;
+        if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
+        uint8_t* d_cases = nullptr;
+        if (keep) {
+            if (n > c->B().cap_cases_chunks) {
+                CU_TRY(c, cudaStreamSynchronize(c->stream));
+                CU_TRY(c, regrow(&c->B().d_cases, (size_t)n * c->dcfg.S * c->dcfg.S * c->dcfg.S));
+                c->B().cap_cases_chunks = n;
+            }
+            d_cases = c->B().d_cases;
+        }
+        st = launch_extract(c, d_pos, n, d_cases, false);
+        if (st != UW_OK) return st;
     }
-    st = launch_extract(c, d_pos, n, d_cases, false);
-    if (st != UW_OK) return st;
     if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[4], c->stream));
-    c->last_n = n; c->last_pos_dev = d_pos; c->pending = true;
+    CU_TRY(c, cudaEventRecord(c->B().done, c->stream));
+    c->B().last_n = n; c->B().last_pos_dev = d_pos; c->B().pending = true;
     return UW_OK;
 }
 
-// wait for the enqueued build; on output-arena overflow grow and re-run scan+emit
+// Wait for the current set's enqueued build and validate its totals; on output-arena overflow grow and re-run
+// the emitting stage.  Read-backs go through the copy stream, so a later batch already running on the compute
+// stream does not delay them.
 static uw_status finish_build(uw_ctx* c) {
-    if (!c->pending) return UW_OK;
+    uw_ctx::BufSet& B = c->B();
+    if (!B.pending) return UW_OK;
+    BatchTotals t = {};
+    unsigned long long guard = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
-        if (c->last_fused) {
-            CU_TRY(c, cudaMemcpyAsync(c->h_ctl, c->d_ctl + c->ctl_used, sizeof(FusedControl), cudaMemcpyDeviceToHost, c->stream));
-            CU_TRY(c, cudaStreamSynchronize(c->stream));
-            *c->h_totals = c->h_ctl->totals;
-            *c->h_guard = c->h_ctl->guard;
+        CU_TRY(c, cudaEventSynchronize(B.done));      // everything issued from here on is ordered after the set's kernels
+        if (B.last_fused) {
+            t = B.h_sum->totals;                      // written straight to host memory by the kernel
+            guard = B.h_sum->guard;
             if (!c->ordered) {
-                c->h_totals->n_verts = c->h_ctl->alloc >> 32; c->h_totals->n_inds = c->h_ctl->alloc & 0xFFFFFFFFull;
-                if (c->h_totals->n_verts > c->vcap || c->h_totals->n_inds > c->icap) c->h_totals->overflow = 1;
+                t.n_verts = B.h_sum->alloc >> 32; t.n_inds = B.h_sum->alloc & 0xFFFFFFFFull;
+                if (t.n_verts > B.vcap || t.n_inds > B.icap) t.overflow = 1;
             }
         } else {
-            CU_TRY(c, cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(BatchTotals), cudaMemcpyDeviceToHost, c->stream));
-            CU_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            CU_TRY(c, cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(BatchTotals), cudaMemcpyDeviceToHost, c->copy_stream));
+            CU_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->copy_stream));
+            CU_TRY(c, cudaStreamSynchronize(c->copy_stream));
+            t = *c->h_totals;
+            guard = *c->h_guard;
         }
-        if (!c->h_totals->overflow) break;
-        if (c->h_totals->n_verts > 0xFFFFFFFFull || c->h_totals->n_inds > 0xFFFFFFFFull)
+        if (!t.overflow) break;
+        if (t.n_verts > 0xFFFFFFFFull || t.n_inds > 0xFFFFFFFFull)
             return fail(c, UW_ERR_INVALID, "batch too large: packed vertex/index offsets exceed 32 bits; split the batch");
-        uw_status st = ensure_outputs(c, c->h_totals->n_verts, c->h_totals->n_inds);
+        uw_status st = ensure_outputs(c, t.n_verts, t.n_inds);
         if (st != UW_OK) return st;
-        if (c->last_fused) {
-            st = launch_fused(c, c->last_pos_dev, c->last_n, (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) ? c->d_dens : nullptr);
+        if (B.last_fused) {
+            st = launch_fused(c, B.last_pos_dev, B.last_n, (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) ? B.d_dens : nullptr);
         } else {
-            st = launch_extract(c, c->last_pos_dev, c->last_n, nullptr, true);
+            st = launch_extract(c, B.last_pos_dev, B.last_n, nullptr, true);
         }
         if (st != UW_OK) return st;
+        CU_TRY(c, cudaEventRecord(B.done, c->stream));
     }
-    if (c->h_totals->overflow) return fail(c, UW_ERR_CUDA, "output arena overflow persisted");
-    c->guard_total = *c->h_guard;
-    c->pending = false;
+    if (t.overflow) return fail(c, UW_ERR_CUDA, "output arena overflow persisted");
+    B.result = t;
+    c->guard_total = guard;
+    B.pending = false;
     if (c->profiling) {
-        float a = 0, b = 0, d = 0, e = 0, t = 0;
+        float a = 0, b = 0, d = 0, e = 0, tt = 0;
         cudaEventElapsedTime(&a, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
         cudaEventElapsedTime(&d, c->ev[2], c->ev[3]);
         cudaEventElapsedTime(&e, c->ev[3], c->ev[4]);
-        cudaEventElapsedTime(&t, c->ev[0], c->ev[4]);
-        c->times.noise_ms = a; c->times.classify_ms = b; c->times.scan_ms = d; c->times.emit_ms = e; c->times.total_ms = t;
+        cudaEventElapsedTime(&tt, c->ev[0], c->ev[4]);
+        c->times.noise_ms = a; c->times.classify_ms = b; c->times.scan_ms = d; c->times.emit_ms = e; c->times.total_ms = tt;
     }
     c->times.launches = c->launches;
     return UW_OK;
@@ -725,23 +758,28 @@ static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n) {
         if (pos[i] > (1 << 24) || pos[i] < -(1 << 24))
             return fail(c, UW_ERR_INVALID, "chunk position out of supported range (|pos| <= 2^24)");
     }
-    if ((size_t)n * 3 > c->h_pos_cap) {
-        if (c->h_pos) cudaFreeHost(c->h_pos);
-        c->h_pos = nullptr;
-        size_t cap = c->h_pos_cap ? c->h_pos_cap : 4096;
+    if ((size_t)n * 3 > c->B().h_pos_cap) {
+        if (c->B().h_pos) cudaFreeHost(c->B().h_pos);
+        c->B().h_pos = nullptr;
+        size_t cap = c->B().h_pos_cap ? c->B().h_pos_cap : 4096;
         while (cap < (size_t)n * 3) cap *= 2;
-        CU_TRY(c, cudaHostAlloc(&c->h_pos, cap * sizeof(int32_t), cudaHostAllocDefault));
-        c->h_pos_cap = cap;
+        CU_TRY(c, cudaHostAlloc(&c->B().h_pos, cap * sizeof(int32_t), cudaHostAllocDefault));
+        c->B().h_pos_cap = cap;
     }
-    memcpy(c->h_pos, pos, (size_t)n * 3 * sizeof(int32_t));
-    CU_TRY(c, cudaMemcpyAsync(c->d_pos, c->h_pos, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    memcpy(c->B().h_pos, pos, (size_t)n * 3 * sizeof(int32_t));
+    CU_TRY(c, cudaMemcpyAsync(c->B().d_pos, c->B().h_pos, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     return UW_OK;
 }
 
+// Copy batch b's result (it owns buffer set b->set) into a pinned arena, on the copy stream.
 static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
+    const int saved = c->cur;
+    c->cur = b->set;
+    uw_ctx::BufSet& B = c->B();
+    auto done = [&](uw_status st) { c->cur = saved; return st; };
     uw_status st = finish_build(c);
-    if (st != UW_OK) return st;
-    const BatchTotals t = *c->h_totals;
+    if (st != UW_OK) return done(st);
+    const BatchTotals t = B.result;
     const size_t isz = c->index32 ? 4 : 2;
     const size_t off_desc = 0;
     const size_t off_vert = (sizeof(uw_chunk_desc) * (size_t)b->n + 255) & ~(size_t)255;
@@ -751,16 +789,18 @@ static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
     const size_t off_tcs = (off_tri + (c->tris ? sizeof(uw_tri) * (size_t)(t.n_inds / 3) : 0) + 255) & ~(size_t)255;
     const size_t bytes = off_tcs + (c->tris ? ncell1 * 2 * (size_t)b->n : 0) + 256;
     st = pinned_get(c, bytes, &b->arena);
-    if (st != UW_OK) return st;
+    if (st != UW_OK) return done(st);
     char* base = (char*)b->arena.ptr;
-    CU_TRY(c, cudaMemcpyAsync(base + off_desc, c->d_descs, sizeof(uw_chunk_desc) * (size_t)b->n, cudaMemcpyDeviceToHost, c->stream));
-    if (t.n_verts) CU_TRY(c, cudaMemcpyAsync(base + off_vert, c->d_verts, sizeof(uw_vert) * (size_t)t.n_verts, cudaMemcpyDeviceToHost, c->stream));
-    if (t.n_inds) CU_TRY(c, cudaMemcpyAsync(base + off_ind, c->d_inds, isz * (size_t)t.n_inds, cudaMemcpyDeviceToHost, c->stream));
-    if (c->tris) {
-        if (t.n_inds) CU_TRY(c, cudaMemcpyAsync(base + off_tri, c->d_tris, sizeof(uw_tri) * (size_t)(t.n_inds / 3), cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(c, cudaMemcpyAsync(base + off_tcs, c->d_tri_cell, ncell1 * 2 * (size_t)b->n, cudaMemcpyDeviceToHost, c->stream));
+    cudaStream_t cs = c->copy_stream;      // finish_build waited for the set's kernels
+    cudaError_t e = cudaMemcpyAsync(base + off_desc, B.d_descs, sizeof(uw_chunk_desc) * (size_t)b->n, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && t.n_verts) e = cudaMemcpyAsync(base + off_vert, B.d_verts, sizeof(uw_vert) * (size_t)t.n_verts, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && t.n_inds) e = cudaMemcpyAsync(base + off_ind, B.d_inds, isz * (size_t)t.n_inds, cudaMemcpyDeviceToHost, cs);
+    if (e == cudaSuccess && c->tris) {
+        if (t.n_inds) e = cudaMemcpyAsync(base + off_tri, B.d_tris, sizeof(uw_tri) * (size_t)(t.n_inds / 3), cudaMemcpyDeviceToHost, cs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(base + off_tcs, B.d_tri_cell, ncell1 * 2 * (size_t)b->n, cudaMemcpyDeviceToHost, cs);
     }
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+    if (e != cudaSuccess) return done(fail(c, UW_ERR_CUDA, std::string("collect_batch: ") + cudaGetErrorString(e)));
     memset(&b->view, 0, sizeof b->view);
     if (c->tris) { b->view.tris = (const uw_tri*)(base + off_tri); b->view.tri_cell_start = (const uint16_t*)(base + off_tcs); }
     b->view.n_chunks = b->n; b->view.n_verts = t.n_verts; b->view.n_inds = t.n_inds;
@@ -769,34 +809,54 @@ static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
     if (c->index32) b->view.inds32 = (const uint32_t*)(base + off_ind);
     else b->view.inds16 = (const uint16_t*)(base + off_ind);
     b->ready = true;
-    c->async_in_flight = false;
-    return UW_OK;
+    B.busy = false;
+    return done(UW_OK);
+}
+
+// Batches in flight: the fused small-chunk path keeps all per-batch state in its buffer set, so two batches may
+// overlap (one computing, one draining over PCIe); the multi-kernel paths share the scan totals and run one at a time.
+static int pick_set(uw_ctx* c, bool from_densities) {
+    const int nbusy = (c->sets[0].busy ? 1 : 0) + (c->sets[1].busy ? 1 : 0);
+    const int max_in_flight = (c->use_fused && !from_densities) ? 2 : 1;
+    if (nbusy >= max_in_flight) return -1;
+    if (nbusy == 0) return c->cur;          // keep reusing the warm set
+    return c->sets[0].busy ? 1 : 0;
 }
 
 static uw_status build_common(uw_ctx* c, const int32_t* pos, const float* dens, uint32_t n, uw_batch** out, bool async) {
     if (!c) return UW_ERR_INVALID;
     if (!out || (!pos && n)) return fail(c, UW_ERR_INVALID, "uw_build: null argument");
     *out = nullptr;
-    if (c->async_in_flight) return fail(c, UW_ERR_NOT_READY, "uw_build: a previous async batch has not been waited on");
+    const int set = pick_set(c, dens != nullptr);
+    if (set < 0) return fail(c, UW_ERR_NOT_READY, "uw_build: too many async batches in flight; wait on (or free) an earlier one");
     CU_TRY(c, cudaSetDevice(c->device));
     uw_batch* b = new uw_batch();
-    b->ctx = c; b->n = n; b->ready = false; b->arena.ptr = nullptr; b->arena.bytes = 0;
+    b->ctx = c; b->n = n; b->set = -1; b->ready = false; b->arena.ptr = nullptr; b->arena.bytes = 0;
     memset(&b->view, 0, sizeof b->view);
     if (n == 0) { b->ready = true; *out = b; return UW_OK; }
+    c->cur = set;
+    b->set = set;
     uw_status st = ensure_chunks(c, n);
     if (st == UW_OK) st = stage_positions(c, pos, n);
     if (st == UW_OK && dens) {
+        st = ensure_dens(c);
         const DevCfg& d = c->dcfg;
-        cudaError_t e = cudaMemcpy2DAsync(c->d_dens, (size_t)d.dens_stride * 4, dens, (size_t)d.L3 * 4, (size_t)d.L3 * 4, n,
-                                          cudaMemcpyHostToDevice, c->stream);
+        cudaError_t e = st == UW_OK ? cudaMemcpy2DAsync(c->B().d_dens, (size_t)d.dens_stride * 4, dens, (size_t)d.L3 * 4, (size_t)d.L3 * 4, n,
+                                                        cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
         if (e != cudaSuccess) st = fail(c, UW_ERR_CUDA, std::string("cudaMemcpy2DAsync densities: ") + cudaGetErrorString(e));
     }
-    if (st == UW_OK) st = enqueue_build(c, c->d_pos, n, dens != nullptr);
+    if (st == UW_OK) st = enqueue_build(c, c->B().d_pos, n, dens != nullptr);
     if (st == UW_OK) {
-        if (async) c->async_in_flight = true;
-        else st = collect_batch(c, b);
+        c->B().busy = true;
+        if (!async) st = collect_batch(c, b);
     }
-    if (st != UW_OK) { delete b; return st; }
+    if (st != UW_OK) {
+        cudaStreamSynchronize(c->stream);
+        c->sets[set].busy = false; c->sets[set].pending = false;
+        if (b->arena.ptr) c->pool.push_back(b->arena);
+        delete b;
+        return st;
+    }
     *out = b;
     return UW_OK;
 }
@@ -828,7 +888,11 @@ extern "C" uw_status uw_batch_view_get(const uw_batch* b, uw_batch_view* out) {
 
 extern "C" void uw_batch_free(uw_batch* b) {
     if (!b) return;
-    if (!b->ready && b->ctx) { cudaSetDevice(b->ctx->device); cudaStreamSynchronize(b->ctx->stream); b->ctx->async_in_flight = false; b->ctx->pending = false; }
+    if (!b->ready && b->ctx && b->set >= 0) {      // abandoned async batch: let its kernels drain, release the set
+        cudaSetDevice(b->ctx->device);
+        cudaStreamSynchronize(b->ctx->stream);
+        b->ctx->sets[b->set].busy = false; b->ctx->sets[b->set].pending = false;
+    }
     if (b->arena.ptr) b->ctx->pool.push_back(b->arena);
     delete b;
 }
@@ -836,9 +900,9 @@ extern "C" void uw_batch_free(uw_batch* b) {
 extern "C" uw_status uw_build_device(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
     if (!c) return UW_ERR_INVALID;
     if (!d_pos && n) return fail(c, UW_ERR_INVALID, "uw_build_device: null positions");
-    if (c->async_in_flight) return fail(c, UW_ERR_NOT_READY, "uw_build_device: an async batch is in flight");
+    if (c->sets[0].busy || c->sets[1].busy) return fail(c, UW_ERR_NOT_READY, "uw_build_device: an async batch is in flight");
     CU_TRY(c, cudaSetDevice(c->device));
-    if (n == 0) { c->last_n = 0; c->pending = false; memset(c->h_totals, 0, sizeof(BatchTotals)); return UW_OK; }
+    if (n == 0) { c->B().last_n = 0; c->B().pending = false; c->B().result = BatchTotals{}; return UW_OK; }
     uw_status st = ensure_chunks(c, n);
     if (st != UW_OK) return st;
     return enqueue_build(c, d_pos, n, false);
@@ -847,21 +911,21 @@ extern "C" uw_status uw_build_device(uw_ctx* c, const int32_t* d_pos, uint32_t n
 extern "C" uw_status uw_sync(uw_ctx* c) {
     if (!c) return UW_ERR_INVALID;
     CU_TRY(c, cudaSetDevice(c->device));
-    if (c->pending) return finish_build(c);
+    if (c->B().pending) return finish_build(c);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return UW_OK;
 }
 
 extern "C" uw_status uw_device_view_get(uw_ctx* c, uw_device_view* out) {
     if (!c || !out) return UW_ERR_INVALID;
-    if (c->pending) return fail(c, UW_ERR_NOT_READY, "uw_device_view_get: call uw_sync first");
+    if (c->B().pending) return fail(c, UW_ERR_NOT_READY, "uw_device_view_get: call uw_sync first");
     memset(out, 0, sizeof *out);
-    out->n_chunks = c->last_n;
-    out->n_verts = c->last_n ? c->h_totals->n_verts : 0;
-    out->n_inds = c->last_n ? c->h_totals->n_inds : 0;
-    out->d_descs = c->d_descs; out->d_verts = c->d_verts;
-    if (c->index32) out->d_inds32 = c->d_inds; else out->d_inds16 = c->d_inds;
-    out->d_densities = c->d_dens; out->density_stride = c->dcfg.dens_stride;
+    out->n_chunks = c->B().last_n;
+    out->n_verts = c->B().last_n ? c->B().result.n_verts : 0;
+    out->n_inds = c->B().last_n ? c->B().result.n_inds : 0;
+    out->d_descs = c->B().d_descs; out->d_verts = c->B().d_verts;
+    if (c->index32) out->d_inds32 = c->B().d_inds; else out->d_inds16 = c->B().d_inds;
+    out->d_densities = c->B().d_dens; out->density_stride = c->dcfg.dens_stride;
     return UW_OK;
 }
 
@@ -885,13 +949,15 @@ extern "C" uw_status uw_debug_densities(uw_ctx* c, const int32_t* pos, uint32_t 
     if ((!pos || !out) && n) return fail(c, UW_ERR_INVALID, "uw_debug_densities: null argument");
     if (n == 0) return UW_OK;
     CU_TRY(c, cudaSetDevice(c->device));
+    if (c->sets[0].busy || c->sets[1].busy) return fail(c, UW_ERR_NOT_READY, "uw_debug_densities: an async batch is in flight");
     uw_status st = ensure_chunks(c, n);
+    if (st == UW_OK) st = ensure_dens(c);
     if (st == UW_OK) st = stage_positions(c, pos, n);
     if (st == UW_OK) CU_TRY(c, cudaMemsetAsync(c->d_guard, 0, sizeof(unsigned long long), c->stream));
-    if (st == UW_OK) st = launch_noise(c, c->d_pos, n);
+    if (st == UW_OK) st = launch_noise(c, c->B().d_pos, n);
     if (st != UW_OK) return st;
     const DevCfg& d = c->dcfg;
-    CU_TRY(c, cudaMemcpy2DAsync(out, (size_t)d.L3 * 4, c->d_dens, (size_t)d.dens_stride * 4, (size_t)d.L3 * 4, n,
+    CU_TRY(c, cudaMemcpy2DAsync(out, (size_t)d.L3 * 4, c->B().d_dens, (size_t)d.dens_stride * 4, (size_t)d.L3 * 4, n,
                                 cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaMemcpyAsync(c->h_guard, c->d_guard, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -905,20 +971,22 @@ extern "C" uw_status uw_debug_cases(uw_ctx* c, const int32_t* pos, uint32_t n, u
     if ((!pos || !out) && n) return fail(c, UW_ERR_INVALID, "uw_debug_cases: null argument");
     if (n == 0) return UW_OK;
     CU_TRY(c, cudaSetDevice(c->device));
+    if (c->sets[0].busy || c->sets[1].busy) return fail(c, UW_ERR_NOT_READY, "uw_debug_cases: an async batch is in flight");
     uw_status st = ensure_chunks(c, n);
+    if (st == UW_OK) st = ensure_dens(c);
     if (st == UW_OK) st = stage_positions(c, pos, n);
-    if (st == UW_OK) st = launch_noise(c, c->d_pos, n);
+    if (st == UW_OK) st = launch_noise(c, c->B().d_pos, n);
     if (st != UW_OK) return st;
     const DevCfg& d = c->dcfg;
     const size_t S3 = (size_t)d.S * d.S * d.S;
-    if (n > c->cap_cases_chunks) {
+    if (n > c->B().cap_cases_chunks) {
         CU_TRY(c, cudaStreamSynchronize(c->stream));
-        CU_TRY(c, regrow(&c->d_cases, (size_t)n * S3));
-        c->cap_cases_chunks = n;
+        CU_TRY(c, regrow(&c->B().d_cases, (size_t)n * S3));
+        c->B().cap_cases_chunks = n;
     }
-    k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->d_dens, n, c->d_counts, c->d_cases);
+    k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts, c->B().d_cases);
     CU_TRY(c, cudaGetLastError());
-    CU_TRY(c, cudaMemcpyAsync(out, c->d_cases, (size_t)n * S3, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(out, c->B().d_cases, (size_t)n * S3, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return UW_OK;
 }

@@ -852,86 +852,266 @@ __global__ void __launch_bounds__(256) k_classify_small(const __grid_constant__ 
     }
 }
 
+// Compile-time-sized variant of load_signs (lattice L = ST + 1, NT threads): the loop is fully unrolled, so all
+// of a thread's loads of the chunk are in flight together and the memory latency is paid once per chunk
+// instead of once per 32-sample word.  Per-warp flags go to s_flag[NT / 32]; ends with a barrier.
+template <int ST, int NT, bool KEEP>
+__device__ __forceinline__ uint32_t load_signs_spec(float iso, const float* __restrict__ src, float* s_dens,
+                                                    uint32_t* s_bits, uint32_t* s_flag) {
+    constexpr int L = ST + 1, L3 = L * L * L, NLD = (L3 + NT - 1) / NT, NW = NT / 32, NWORD = (L3 + 31) / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float v[NLD];
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+        const int idx = tid + NT * k;
+        v[k] = ((k + 1) * NT <= L3 || idx < L3) ? __ldg(src + idx) : 0.f;
+    }
+    bool all_gt = true, any_lt = false;
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+        const int idx = tid + NT * k;
+        const bool ok = (k + 1) * NT <= L3 || idx < L3;
+        if (KEEP && ok) s_dens[idx] = v[k];
+        const bool lt = ok && (v[k] < iso);
+        all_gt &= !ok || (v[k] > iso); any_lt |= lt;
+        const uint32_t w = __ballot_sync(0xFFFFFFFFu, lt);
+        if (lane == 0 && NT * k + 32 * warp < L3) s_bits[(NT * k >> 5) + warp] = w;
+    }
+    if (tid == 0) { s_bits[NWORD] = 0; s_bits[NWORD + 1] = 0; }      // padding read by col_mask's funnel shift
+    const bool w_all = __all_sync(0xFFFFFFFFu, all_gt);
+    const bool w_any = __any_sync(0xFFFFFFFFu, any_lt);
+    if (lane == 0) s_flag[warp] = (w_all ? CF_ALL_GT : 0u) | (w_any ? CF_ANY_LT : 0u);
+    __syncthreads();
+    uint32_t a = CF_ALL_GT, o = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { const uint32_t f = s_flag[w]; a &= f; o |= f; }
+    return a | (o & CF_ANY_LT);
+}
+
+// 8-bit corner pattern of cell z of a column: bits (m00 z, m00 z+1, m10 z, m10 z+1, m01 z, m01 z+1, m11 z, m11 z+1)
+__device__ __forceinline__ uint32_t natural_of(uint32_t q0 /*m00 | m10<<16*/, uint32_t q1 /*m01 | m11<<16*/, int z) {
+    const uint32_t a = (q0 >> z) & 0x00030003u, b = (q1 >> z) & 0x00030003u;
+    return ((a | (a >> 14)) & 0xFu) | (((b | (b >> 14)) & 0xFu) << 4);
+}
+
+// K2, compile-time sizes (internal_size 12 / 10), HBM-bound by construction: one CTA per chunk, two threads per
+// (x, y) column; the NEXT chunk's densities are already in flight (registers) while this chunk's columns are
+// counted, the 256-entry pattern table lives in shared memory, and there is ONE barrier per chunk (sign words,
+// warp flags and warp partials rotate through three slots; thread 0 writes chunk k's counts during chunk k+1).
+#ifndef UW_CLS_MINB
+#define UW_CLS_MINB 7
+#endif
+template <int ST>
+struct ClsDims {
+    static constexpr int S = ST, L = ST + 1, L3 = L * L * L, NCOL = ST * ST;
+    static constexpr int NT = ((2 * NCOL + 31) / 32) * 32, NW = NT / 32;
+    static constexpr int NLD = (L3 + NT - 1) / NT, NWORD = (L3 + 31) / 32;
+    static constexpr int HALF = (ST + 1) / 2;
+};
+
+template <int ST>
+__global__ void __launch_bounds__(ClsDims<ST>::NT, UW_CLS_MINB) k_classify_spec(const __grid_constant__ DevCfg cfg,
+                                                                   const McTables* __restrict__ mc,
+                                                                   const float* __restrict__ dens, uint32_t n,
+                                                                   ChunkCounts* __restrict__ counts) {
+    using D = ClsDims<ST>;
+    constexpr int S = D::S, L = D::L, L3 = D::L3, NT = D::NT, NW = D::NW, NLD = D::NLD;
+    __shared__ uint32_t s_bits[3][D::NWORD + 2];
+    __shared__ uint32_t s_flag[3][NW];
+    __shared__ uint32_t s_part[3][NW];
+    __shared__ uint32_t s_lut[256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < 256; t += NT) s_lut[t] = mc->lut[t];
+    if (tid < 3) { s_bits[tid][D::NWORD] = 0; s_bits[tid][D::NWORD + 1] = 0; }
+    const float iso = cfg.iso_level;
+    const size_t stride = cfg.dens_stride;
+
+    const bool has_col = tid < 2 * D::NCOL;
+    const int col = has_col ? (tid >= D::NCOL ? tid - D::NCOL : tid) : 0;
+    const int x = col / S, y = col - x * S;
+    const int z0 = tid >= D::NCOL ? D::HALF : 0, z1 = tid >= D::NCOL ? S : D::HALF;
+    const uint32_t ownn = 0x4F0u | (y == 0 ? 0x00Fu : 0u) | (x == 0 ? 0x800u : 0u);      // SURVEY App. B.4, z > 0
+    const uint32_t own0 = ownn | 0x200u | (x == 0 ? 0x100u : 0u);
+
+    auto finalize = [&](uint32_t chunk, int slot) {
+        uint32_t a = CF_ALL_GT, o = 0, acc = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { const uint32_t f = s_flag[slot][w]; a &= f; o |= f; acc += s_part[slot][w]; }
+        uint4 c;
+        c.x = acc >> 16; c.y = acc & 0xFFFFu; c.z = a | (o & CF_ANY_LT); c.w = 0;
+        *reinterpret_cast<uint4*>(counts + chunk) = c;
+    };
+
+    float v[NLD];
+    uint32_t chunk = blockIdx.x;
+    if (chunk < n) {
+        const float* src = dens + (size_t)chunk * stride;
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) {
+            const int idx = tid + NT * k;
+            v[k] = ((k + 1) * NT <= L3 || idx < L3) ? __ldg(src + idx) : 0.f;
+        }
+    }
+    __syncthreads();
+    uint32_t prev = 0xFFFFFFFFu;
+    int slot = 0, pslot = 2;
+    for (; chunk < n; chunk += gridDim.x) {
+        bool all_gt = true, any_lt = false;
+#pragma unroll
+        for (int k = 0; k < NLD; ++k) {
+            const bool ok = (k + 1) * NT <= L3 || tid + NT * k < L3;
+            const bool lt = ok && (v[k] < iso);
+            all_gt &= !ok || (v[k] > iso); any_lt |= lt;
+            const uint32_t w = __ballot_sync(0xFFFFFFFFu, lt);
+            if (lane == 0 && NT * k + 32 * warp < L3) s_bits[slot][(NT * k >> 5) + warp] = w;
+        }
+        const bool w_all = __all_sync(0xFFFFFFFFu, all_gt);
+        const bool w_any = __any_sync(0xFFFFFFFFu, any_lt);
+        if (lane == 0) s_flag[slot][warp] = (w_all ? CF_ALL_GT : 0u) | (w_any ? CF_ANY_LT : 0u);
+        const uint32_t next = chunk + gridDim.x;
+        if (next < n) {                                   // in flight underneath the column work below
+            const float* src = dens + (size_t)next * stride;
+#pragma unroll
+            for (int k = 0; k < NLD; ++k) {
+                const int idx = tid + NT * k;
+                v[k] = ((k + 1) * NT <= L3 || idx < L3) ? __ldg(src + idx) : 0.f;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && prev != 0xFFFFFFFFu) finalize(prev, pslot);
+        uint32_t o = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) o |= s_flag[slot][w];
+        uint32_t acc = 0;                                  // n_inds | n_verts << 16
+        if ((o & CF_ANY_LT) && has_col) {
+            const uint32_t* bits = s_bits[slot];
+            const uint32_t q0 = col_mask(bits, x * L + y, L) | (col_mask(bits, (x + 1) * L + y, L) << 16);
+            const uint32_t q1 = col_mask(bits, x * L + y + 1, L) | (col_mask(bits, (x + 1) * L + y + 1, L) << 16);
+            const uint32_t any = q0 | q1, all = q0 & q1, full = (1u << L) - 1u;
+            if (any != 0u && (all & (all >> 16) & full) != full) {
+#pragma unroll
+                for (int z = z0; z < z1; ++z) {
+                    const uint32_t t = s_lut[natural_of(q0, q1, z)];            // case | ninds << 8 | crossed << 12
+                    if (t >> 8) acc += ((t >> 8) & 15u) + (__popc((t >> 12) & (z == 0 ? own0 : ownn)) << 16);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+        if (lane == 0) s_part[slot][warp] = acc;
+        prev = chunk; pslot = slot; slot = slot == 2 ? 0 : slot + 1;
+    }
+    __syncthreads();
+    if (tid == 0 && prev != 0xFFFFFFFFu) finalize(prev, pslot);
+}
+
 // ---------------------------------------------------------------------------------------
 // K3: chunk-level exclusive scan of (V, I) -> descriptors, totals, active-chunk list.
-// Single CTA, 1024 threads, 4 chunks per thread per round with a running carry.
+// One CTA per tile of 1024 chunks (one chunk per thread, coalesced 16-B loads / 32-B stores).  Tiles are taken
+// by ticket, so every tile's predecessors are already running: a tile publishes its totals (data, fence, epoch
+// flag), then sums the published totals of ALL earlier tiles -- one per thread, no chain -- and writes its chunks.
+// The flags carry the launch epoch, so nothing is cleared between launches; the last CTA out resets the tickets.
 // ---------------------------------------------------------------------------------------
+struct ScanPart { unsigned long long v, i; uint32_t a, blank; };
+struct ScanCtl { uint32_t ticket, done, pad0, pad1; };
+
 __global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restrict__ counts,
                                                       const int32_t* __restrict__ pos, uint32_t n,
                                                       uw_chunk_desc* __restrict__ descs,
                                                       uint32_t* __restrict__ active,
                                                       BatchTotals* __restrict__ totals,
-                                                      unsigned long long vcap, unsigned long long icap) {
-    __shared__ uint32_t s_w[96];
-    __shared__ unsigned long long s_carry[2];
-    __shared__ uint32_t s_carry_a, s_nblank;
+                                                      unsigned long long vcap, unsigned long long icap,
+                                                      ScanPart* __restrict__ part, uint32_t* __restrict__ flag,
+                                                      ScanCtl* __restrict__ ctl, uint32_t epoch) {
+    __shared__ uint32_t s_w[4][32];
+    __shared__ unsigned long long s_c[2][32];
+    __shared__ uint32_t s_ca[2][32];
+    __shared__ uint32_t s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry[0] = 0; s_carry[1] = 0; s_carry_a = 0; s_nblank = 0; }
+    if (tid == 0) s_tile = atomicAdd(&ctl->ticket, 1u);
     __syncthreads();
-    uint32_t my_blank = 0;
-    constexpr int PER = 4;
-    for (uint32_t base = 0; base < n; base += 1024 * PER) {
-        ChunkCounts c[PER];
-        uint32_t sv = 0, si = 0, sa = 0;
+    const uint32_t tile = s_tile, ntiles = gridDim.x;
+    const uint32_t idx = tile * 1024u + tid;
+    uint4 c = make_uint4(0u, 0u, 0u, 0u);                    // ChunkCounts {n_verts, n_inds, flags, pad}
+    if (idx < n) c = *reinterpret_cast<const uint4*>(counts + idx);
+    int32_t px = 0, py = 0, pz = 0;
+    if (idx < n) { px = pos[3 * idx]; py = pos[3 * idx + 1]; pz = pos[3 * idx + 2]; }
+    const uint32_t act = c.y > 0 ? 1u : 0u, blank = (idx < n && (c.z & CF_ALL_GT)) ? 1u : 0u;
+
+    // tile-local inclusive scans of (verts, inds, active, blank)
+    uint32_t xv = c.x, xi = c.y, xa = act | (blank << 16);
 #pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            const uint32_t idx = base + tid * PER + q;
-            if (idx < n) c[q] = counts[idx]; else { c[q].n_verts = 0; c[q].n_inds = 0; c[q].flags = 0; }
-            sv += c[q].n_verts; si += c[q].n_inds; sa += (c[q].n_inds > 0);
-            if (idx < n && (c[q].flags & CF_ALL_GT)) ++my_blank;
-        }
-        // warp inclusive scans of (sv, si, sa)
-        uint32_t xv = sv, xi = si, xa = sa;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, xv, d), b = __shfl_up_sync(0xFFFFFFFFu, xi, d),
+                       e = __shfl_up_sync(0xFFFFFFFFu, xa, d);
+        if (lane >= d) { xv += a; xi += b; xa += e; }
+    }
+    if (lane == 31) { s_w[0][warp] = xv; s_w[1][warp] = xi; s_w[2][warp] = xa; }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t a = s_w[0][lane], b = s_w[1][lane], e = s_w[2][lane];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, xv, d), b = __shfl_up_sync(0xFFFFFFFFu, xi, d),
-                           e = __shfl_up_sync(0xFFFFFFFFu, xa, d);
-            if (lane >= d) { xv += a; xi += b; xa += e; }
+            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, a, d), y = __shfl_up_sync(0xFFFFFFFFu, b, d),
+                           z = __shfl_up_sync(0xFFFFFFFFu, e, d);
+            if (lane >= d) { a += x; b += y; e += z; }
         }
-        if (lane == 31) { s_w[warp] = xv; s_w[32 + warp] = xi; s_w[64 + warp] = xa; }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t a = s_w[lane], b = s_w[32 + lane], e = s_w[64 + lane];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, a, d), y = __shfl_up_sync(0xFFFFFFFFu, b, d),
-                               z = __shfl_up_sync(0xFFFFFFFFu, e, d);
-                if (lane >= d) { a += x; b += y; e += z; }
-            }
-            s_w[lane] = a; s_w[32 + lane] = b; s_w[64 + lane] = e;
+        s_w[0][lane] = a; s_w[1][lane] = b; s_w[2][lane] = e;
+        if (lane == 31) {                                    // tile totals: publish, then the epoch flag
+            ScanPart p;
+            p.v = a; p.i = b; p.a = e & 0xFFFFu; p.blank = e >> 16;
+            part[tile] = p;
+            __threadfence();
+            asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(flag + tile), "r"(epoch) : "memory");
         }
-        __syncthreads();
-        unsigned long long ov = s_carry[0] + (warp ? s_w[warp - 1] : 0u) + (xv - sv);
-        unsigned long long oi = s_carry[1] + (warp ? s_w[32 + warp - 1] : 0u) + (xi - si);
-        uint32_t oa = s_carry_a + (warp ? s_w[64 + warp - 1] : 0u) + (xa - sa);
-#pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            const uint32_t idx = base + tid * PER + q;
-            if (idx < n) {
-                uw_chunk_desc d;
-                d.pos[0] = pos[3 * idx]; d.pos[1] = pos[3 * idx + 1]; d.pos[2] = pos[3 * idx + 2];
-                d.flags = ((c[q].flags & CF_ALL_GT) ? UW_CHUNK_BLANK_EARLY : 0u)
-                        | (c[q].n_inds > 0 ? UW_CHUNK_HAS_MESH : 0u)
-                        | (c[q].n_verts > 65536u ? UW_CHUNK_U16_OVERFLOW : 0u);
-                d.vert_offset = (uint32_t)ov; d.vert_count = c[q].n_verts;
-                d.index_offset = (uint32_t)oi; d.index_count = c[q].n_inds;
-                descs[idx] = d;
-                if (c[q].n_inds > 0) active[oa++] = idx;
-                ov += c[q].n_verts; oi += c[q].n_inds;
-            }
-        }
-        __syncthreads();
-        if (tid == 1023) { s_carry[0] = ov; s_carry[1] = oi; s_carry_a = oa; }
-        __syncthreads();
     }
-    if (my_blank) atomicAdd(&s_nblank, my_blank);
     __syncthreads();
-    if (tid == 0) {
+    const uint32_t lv = (warp ? s_w[0][warp - 1] : 0u) + xv - c.x;          // exclusive, tile-local
+    const uint32_t li = (warp ? s_w[1][warp - 1] : 0u) + xi - c.y;
+    const uint32_t la = ((warp ? s_w[2][warp - 1] : 0u) + xa - (act | (blank << 16))) & 0xFFFFu;
+    const uint32_t tile_v = s_w[0][31], tile_i = s_w[1][31], tile_a = s_w[2][31] & 0xFFFFu, tile_b = s_w[2][31] >> 16;
+
+    // carry = sum of all earlier tiles' totals
+    unsigned long long cv = 0, ci = 0;
+    uint32_t ca = 0, cb = 0;
+    for (uint32_t t = tid; t < tile; t += 1024u) {
+        while (ld_volatile_u32(flag + t) != epoch) { }
+        __threadfence();
+        const volatile ScanPart* p = part + t;
+        cv += p->v; ci += p->i; ca += p->a; cb += p->blank;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        cv += __shfl_xor_sync(0xFFFFFFFFu, cv, d); ci += __shfl_xor_sync(0xFFFFFFFFu, ci, d);
+        ca += __shfl_xor_sync(0xFFFFFFFFu, ca, d); cb += __shfl_xor_sync(0xFFFFFFFFu, cb, d);
+    }
+    if (lane == 0) { s_c[0][warp] = cv; s_c[1][warp] = ci; s_ca[0][warp] = ca; s_ca[1][warp] = cb; }
+    __syncthreads();
+    cv = 0; ci = 0; ca = 0; cb = 0;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) { cv += s_c[0][w]; ci += s_c[1][w]; ca += s_ca[0][w]; cb += s_ca[1][w]; }
+
+    if (idx < n) {
+        const unsigned long long ov = cv + lv, oi = ci + li;
+        uint4 d0, d1;
+        d0.x = (uint32_t)px; d0.y = (uint32_t)py; d0.z = (uint32_t)pz;
+        d0.w = ((c.z & CF_ALL_GT) ? UW_CHUNK_BLANK_EARLY : 0u) | (c.y > 0 ? UW_CHUNK_HAS_MESH : 0u)
+             | (c.x > 65536u ? UW_CHUNK_U16_OVERFLOW : 0u);
+        d1.x = (uint32_t)ov; d1.y = c.x; d1.z = (uint32_t)oi; d1.w = c.y;
+        uint4* dst = reinterpret_cast<uint4*>(descs + idx);  // uw_chunk_desc: pos[3], flags, vert_offset, vert_count, index_offset, index_count
+        dst[0] = d0; dst[1] = d1;
+        if (act) active[ca + la] = idx;
+    }
+    if (tile == ntiles - 1 && tid == 0) {
         BatchTotals t;
-        t.n_verts = s_carry[0]; t.n_inds = s_carry[1]; t.n_active = s_carry_a;
-        t.overflow = (s_carry[0] > vcap || s_carry[1] > icap || s_carry[0] > 0xFFFFFFFFull || s_carry[1] > 0xFFFFFFFFull) ? 1u : 0u;
-        t.n_blank = s_nblank; t.n_mesh = s_carry_a;
+        t.n_verts = cv + tile_v; t.n_inds = ci + tile_i; t.n_active = ca + tile_a;
+        t.overflow = (t.n_verts > vcap || t.n_inds > icap || t.n_verts > 0xFFFFFFFFull || t.n_inds > 0xFFFFFFFFull) ? 1u : 0u;
+        t.n_blank = cb + tile_b; t.n_mesh = t.n_active;
         *totals = t;
+    }
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(&ctl->done, 1u) == ntiles - 1) { ctl->ticket = 0; ctl->done = 0; }
     }
 }
 
@@ -1092,12 +1272,6 @@ __device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned 
 }
 
 struct ChunkShape { uint32_t n_vert, n_ind, n_act; };
-
-// 8-bit corner pattern of cell z of a column: bits (m00 z, m00 z+1, m10 z, m10 z+1, m01 z, m01 z+1, m11 z, m11 z+1)
-__device__ __forceinline__ uint32_t natural_of(uint32_t q0 /*m00 | m10<<16*/, uint32_t q1 /*m01 | m11<<16*/, int z) {
-    const uint32_t a = (q0 >> z) & 0x00030003u, b = (q1 >> z) & 0x00030003u;
-    return ((a | (a >> 14)) & 0xFu) | (((b | (b >> 14)) & 0xFu) << 4);
-}
 
 // tri_cell (nullable): global u16[S^3 + 1], first triangle of every cell (chunk-local, scan order)
 template <int ST>
@@ -1311,7 +1485,8 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
     for (uint32_t a = blockIdx.x; a < n_active; a += gridDim.x) {
         const uint32_t chunk = active[a];
         const uw_chunk_desc d = descs[chunk];
-        load_signs<true>(cfg, dens + (size_t)chunk * cfg.dens_stride, s.dens, s.bits, s_red);
+        if constexpr (ST > 0) load_signs_spec<ST, 256, true>(cfg.iso_level, dens + (size_t)chunk * cfg.dens_stride, s.dens, s.bits, s_w);
+        else                  load_signs<true>(cfg, dens + (size_t)chunk * cfg.dens_stride, s.dens, s.bits, s_red);
         for (int c = tid; c < L * L; c += NT) s.mask[c] = col_mask(s.bits, c, L);
         __syncthreads();
         const int ncell = (L - 1) * (L - 1) * (L - 1);
@@ -1528,6 +1703,11 @@ __device__ __forceinline__ uint32_t two_bits(const uint32_t* bits, int b) {
     return __funnelshift_r(bits[b >> 5], bits[(b >> 5) + 1], b & 31) & 3u;
 }
 
+// bits b .. b+15 of a flat bit array
+__device__ __forceinline__ uint32_t bits16(const uint32_t* bits, int b) {
+    return __funnelshift_r(bits[b >> 5], bits[(b >> 5) + 1], b & 31) & 0xFFFFu;
+}
+
 #define UW_BIG_NT 512
 #define UW_BIG_NLD 9          // ceil(65 * 65 / 512): plane elements per thread
 
@@ -1543,6 +1723,8 @@ __global__ void __launch_bounds__(UW_BIG_NT) k_count_big(const __grid_constant__
     __shared__ uint32_t s_acc[4];
     const int tid = threadIdx.x, lane = tid & 31;
     const int S = cfg.S, L = cfg.L, L2 = cfg.L2, ncell = S * S;
+    const int CPT = (ncell + UW_BIG_NT - 1) / UW_BIG_NT;
+    const bool row_runs = CPT <= 15 && S % CPT == 0;
     for (int t = tid; t < 256; t += UW_BIG_NT) s_lut[t] = mc->lut[t];
 
     for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
@@ -1579,12 +1761,31 @@ __global__ void __launch_bounds__(UW_BIG_NT) k_count_big(const __grid_constant__
             __syncthreads();
             const uint32_t* A = s_bits[cx & 1];
             const uint32_t* B = s_bits[(cx + 1) & 1];
-            for (int cell = tid; cell < ncell; cell += UW_BIG_NT) {
-                const int y = cell / S, z = cell - y * S;
-                const uint32_t nat = two_bits(A, y * L + z) | (two_bits(B, y * L + z) << 2)
-                                   | (two_bits(A, (y + 1) * L + z) << 4) | (two_bits(B, (y + 1) * L + z) << 6);
-                const uint32_t t = s_lut[nat];
-                if (t >> 8) { ni += (t >> 8) & 15u; nv += __popc((t >> 12) & own_mask_of(cx, y, z)); }
+            if (row_runs) {
+                // a thread's CPT consecutive cells lie in one (y) row: one 4-column mask fetch per thread and slab,
+                // and a run with no sign change (the common case) costs nothing more
+                const int c0 = tid * CPT;
+                if (c0 < ncell) {
+                    const int y = c0 / S, z0 = c0 - y * S, b = y * L + z0;
+                    const uint32_t keep = (2u << CPT) - 1u;                    // CPT + 1 samples
+                    const uint32_t q0 = (bits16(A, b) & keep) | ((bits16(B, b) & keep) << 16);
+                    const uint32_t q1 = (bits16(A, b + L) & keep) | ((bits16(B, b + L) & keep) << 16);
+                    const uint32_t any = q0 | q1, all = q0 & q1;
+                    if (any != 0u && (all & (all >> 16) & keep) != keep) {
+                        for (int q = 0; q < CPT; ++q) {
+                            const uint32_t t = s_lut[natural_of(q0, q1, q)];
+                            if (t >> 8) { ni += (t >> 8) & 15u; nv += __popc((t >> 12) & own_mask_of(cx, y, z0 + q)); }
+                        }
+                    }
+                }
+            } else {
+                for (int cell = tid; cell < ncell; cell += UW_BIG_NT) {
+                    const int y = cell / S, z = cell - y * S;
+                    const uint32_t nat = two_bits(A, y * L + z) | (two_bits(B, y * L + z) << 2)
+                                       | (two_bits(A, (y + 1) * L + z) << 4) | (two_bits(B, (y + 1) * L + z) << 6);
+                    const uint32_t t = s_lut[nat];
+                    if (t >> 8) { ni += (t >> 8) & 15u; nv += __popc((t >> 12) & own_mask_of(cx, y, z)); }
+                }
             }
             __syncthreads();
         }
@@ -1618,6 +1819,7 @@ __global__ void __launch_bounds__(UW_BIG_NT) k_emit_big(const __grid_constant__ 
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     const int S = cfg.S, L = cfg.L, L2 = cfg.L2, ncell = S * S;
     const int CPT = (ncell + NT - 1) / NT;                 // consecutive cells per thread (scan order y, z)
+    const bool row_runs = CPT <= 15 && S % CPT == 0;       // a thread's run never straddles two rows
     for (int t = tid; t < 256; t += NT) s.lut[t] = mc->lut[t];
     if (totals->overflow) return;                          // host grows the arenas and relaunches
     const uint32_t n_work = totals->n_active;
@@ -1668,17 +1870,40 @@ __global__ void __launch_bounds__(UW_BIG_NT) k_emit_big(const __grid_constant__ 
             // ---- classify this slab; per-thread counts over its CPT consecutive cells --------------------
             const int c0 = tid * CPT;
             uint32_t nva = 0, ni = 0;
-            for (int q = 0; q < CPT; ++q) {
-                const int cell = c0 + q;
-                if (cell >= ncell) break;
-                const int y = cell / S, z = cell - y * S;
-                const uint32_t nat = two_bits(A, y * L + z) | (two_bits(B, y * L + z) << 2)
-                                   | (two_bits(A, (y + 1) * L + z) << 4) | (two_bits(B, (y + 1) * L + z) << 6);
-                const uint32_t t = s.lut[nat];
-                cs_cur[cell] = (uint8_t)t;
-                if (t >> 8) {
-                    ni += (t >> 8) & 15u;
-                    nva += __popc((t >> 12) & own_mask_of(cx, y, z)) + 0x10000u;        // verts <= 12 * S^2 < 2^16 | surface cells << 16
+            if (row_runs) {
+                if (c0 < ncell) {
+                    const int y = c0 / S, z0 = c0 - y * S, b = y * L + z0;
+                    const uint32_t keep = (2u << CPT) - 1u;
+                    const uint32_t q0 = (bits16(A, b) & keep) | ((bits16(B, b) & keep) << 16);
+                    const uint32_t q1 = (bits16(A, b + L) & keep) | ((bits16(B, b + L) & keep) << 16);
+                    const uint32_t any = q0 | q1, all = q0 & q1;
+                    if (any == 0u || (all & (all >> 16) & keep) == keep) {
+                        const uint8_t fill = any ? 255 : 0;
+                        for (int q = 0; q < CPT; ++q) cs_cur[c0 + q] = fill;
+                    } else {
+                        for (int q = 0; q < CPT; ++q) {
+                            const uint32_t t = s.lut[natural_of(q0, q1, q)];
+                            cs_cur[c0 + q] = (uint8_t)t;
+                            if (t >> 8) {
+                                ni += (t >> 8) & 15u;
+                                nva += __popc((t >> 12) & own_mask_of(cx, y, z0 + q)) + 0x10000u;
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int q = 0; q < CPT; ++q) {
+                    const int cell = c0 + q;
+                    if (cell >= ncell) break;
+                    const int y = cell / S, z = cell - y * S;
+                    const uint32_t nat = two_bits(A, y * L + z) | (two_bits(B, y * L + z) << 2)
+                                       | (two_bits(A, (y + 1) * L + z) << 4) | (two_bits(B, (y + 1) * L + z) << 6);
+                    const uint32_t t = s.lut[nat];
+                    cs_cur[cell] = (uint8_t)t;
+                    if (t >> 8) {
+                        ni += (t >> 8) & 15u;
+                        nva += __popc((t >> 12) & own_mask_of(cx, y, z)) + 0x10000u;        // verts <= 12 * S^2 < 2^16 | surface cells << 16
+                    }
                 }
             }
             uint32_t eva, ei, tva, ti;

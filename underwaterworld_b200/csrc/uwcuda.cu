@@ -70,6 +70,12 @@ struct uw_ctx {
     BufSet& B() { return sets[cur]; }
     BatchTotals* d_totals = nullptr;
     unsigned long long* d_guard = nullptr;
+    // chunk-level scan (staged / large-chunk paths): per-tile totals + epoch flags, see k_scan_chunks
+    ScanPart* d_scan_part = nullptr; uint32_t* d_scan_flag = nullptr; ScanCtl* d_scan_ctl = nullptr;
+    uint32_t scan_tiles_cap = 0, scan_epoch = 0;
+    typedef void (*classify_fn_t)(DevCfg, const McTables*, const float*, uint32_t, ChunkCounts*);
+    classify_fn_t classify_fn = nullptr;     // compile-time-sized classify (internal_size 12 / 10)
+    int classify_spec_threads = 0, classify_spec_blocks_per_sm = 1;
     cudaStream_t copy_stream = nullptr;
 
     // pinned host staging
@@ -287,6 +293,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_axis); cudaFree(c->d_totals); cudaFree(c->d_guard); cudaFree(c->d_ctl);
+    cudaFree(c->d_scan_part); cudaFree(c->d_scan_flag); cudaFree(c->d_scan_ctl);
     for (auto& b : c->sets) {
         cudaFree(b.d_pos); cudaFree(b.d_dens); cudaFree(b.d_counts); cudaFree(b.d_descs); cudaFree(b.d_active);
         cudaFree(b.d_cases); cudaFree(b.d_verts); cudaFree(b.d_inds); cudaFree(b.d_tris); cudaFree(b.d_tri_cell);
@@ -461,6 +468,10 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
             c->emit_blocks_per_sm = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_classify_small, 256, 0) == cudaSuccess && nb > 0)
             c->classify_blocks_per_sm = nb;
+        if (d.S == 12)      { c->classify_fn = k_classify_spec<12>; c->classify_spec_threads = ClsDims<12>::NT; }
+        else if (d.S == 10) { c->classify_fn = k_classify_spec<10>; c->classify_spec_threads = ClsDims<10>::NT; }
+        if (c->classify_fn && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->classify_fn, c->classify_spec_threads, 0) == cudaSuccess && nb > 0)
+            c->classify_spec_blocks_per_sm = nb;
     }
     *out = c;
     return UW_OK;
@@ -587,6 +598,33 @@ static uw_status launch_noise(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
     return UW_OK;
 }
 
+static uw_status launch_scan(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
+    const uint32_t tiles = (n + 1023u) / 1024u;
+    if (tiles > c->scan_tiles_cap) {
+        uint32_t cap = c->scan_tiles_cap ? c->scan_tiles_cap : 64;
+        while (cap < tiles) cap *= 2;
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        CU_TRY(c, regrow(&c->d_scan_part, cap));
+        CU_TRY(c, regrow(&c->d_scan_flag, cap));
+        CU_TRY(c, cudaMemset(c->d_scan_flag, 0, (size_t)cap * sizeof(uint32_t)));
+        if (!c->d_scan_ctl) {
+            CU_TRY(c, cudaMalloc(&c->d_scan_ctl, sizeof(ScanCtl)));
+            CU_TRY(c, cudaMemset(c->d_scan_ctl, 0, sizeof(ScanCtl)));
+        }
+        c->scan_tiles_cap = cap;
+        c->scan_epoch = 0;
+    }
+    if (++c->scan_epoch == 0) {                       // epoch wrapped: flags of 2^32 launches ago would alias
+        CU_TRY(c, cudaMemsetAsync(c->d_scan_flag, 0, (size_t)c->scan_tiles_cap * sizeof(uint32_t), c->stream));
+        c->scan_epoch = 1;
+    }
+    k_scan_chunks<<<tiles, 1024, 0, c->stream>>>(c->B().d_counts, d_pos, n, c->B().d_descs, c->B().d_active, c->d_totals,
+                                                 c->B().vcap, c->B().icap, c->d_scan_part, c->d_scan_flag, c->d_scan_ctl, c->scan_epoch);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return UW_OK;
+}
+
 static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uint8_t* d_cases, bool only_emit) {
     const DevCfg& d = c->dcfg;
     if (c->big_path) {
@@ -597,9 +635,7 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
             CU_TRY(c, cudaGetLastError());
             if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
         }
-        k_scan_chunks<<<1, 1024, 0, c->stream>>>(c->B().d_counts, d_pos, n, c->B().d_descs, c->B().d_active, c->d_totals, c->B().vcap, c->B().icap);
-        c->launches++;
-        CU_TRY(c, cudaGetLastError());
+        { uw_status sst = launch_scan(c, d_pos, n); if (sst != UW_OK) return sst; }
         if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
         if (c->index32)
             k_emit_big<uint32_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
@@ -612,14 +648,15 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
         return UW_OK;
     }
     if (!only_emit) {
-        k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts, d_cases);
+        if (c->classify_fn && !d_cases)
+            c->classify_fn<<<persistent_grid(c, n, c->classify_spec_blocks_per_sm), c->classify_spec_threads, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts);
+        else
+            k_classify_small<<<persistent_grid(c, n, c->classify_blocks_per_sm), 256, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts, d_cases);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
     }
-    k_scan_chunks<<<1, 1024, 0, c->stream>>>(c->B().d_counts, d_pos, n, c->B().d_descs, c->B().d_active, c->d_totals, c->B().vcap, c->B().icap);
-    c->launches++;
-    CU_TRY(c, cudaGetLastError());
+    { uw_status sst = launch_scan(c, d_pos, n); if (sst != UW_OK) return sst; }
     if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
     const int grid = persistent_grid(c, n, c->emit_blocks_per_sm);
     if (c->index32)

@@ -894,10 +894,32 @@ __device__ __forceinline__ uint32_t natural_of(uint32_t q0 /*m00 | m10<<16*/, ui
     return ((a | (a >> 14)) & 0xFu) | (((b | (b >> 14)) & 0xFu) << 4);
 }
 
-// K2, compile-time sizes (internal_size 12 / 10), HBM-bound by construction: one CTA per chunk, two threads per
-// (x, y) column; the NEXT chunk's densities are already in flight (registers) while this chunk's columns are
-// counted, the 256-entry pattern table lives in shared memory, and there is ONE barrier per chunk (sign words,
-// warp flags and warp partials rotate through three slots; thread 0 writes chunk k's counts during chunk k+1).
+// ---- bulk async copy (TMA engine, no tensor map) + mbarrier helpers --------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-B aligned; completion is signalled on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// K2, compile-time sizes (internal_size 12 / 10), built to be HBM-bound: one CTA per chunk, two threads per
+// (x, y) column.  Densities arrive through a 3-stage ring of bulk async copies (one elected thread, mbarrier
+// completion), so up to three chunks per CTA are in flight while the current one is counted; the 256-entry
+// pattern table lives in shared memory, and there is ONE block barrier per chunk (sign words, warp flags and
+// warp partials rotate through three slots; thread 0 writes chunk k's counts during chunk k+1).
 #ifndef UW_CLS_MINB
 #define UW_CLS_MINB 7
 #endif
@@ -907,15 +929,19 @@ struct ClsDims {
     static constexpr int NT = ((2 * NCOL + 31) / 32) * 32, NW = NT / 32;
     static constexpr int NLD = (L3 + NT - 1) / NT, NWORD = (L3 + 31) / 32;
     static constexpr int HALF = (ST + 1) / 2;
+    static constexpr int NSTAGE = 3;
+    static constexpr int BYTES = ((L3 * 4 + 15) / 16) * 16;          // <= dens_stride * 4 (stride is padded to 4 floats)
 };
 
 template <int ST>
 __global__ void __launch_bounds__(ClsDims<ST>::NT, UW_CLS_MINB) k_classify_spec(const __grid_constant__ DevCfg cfg,
-                                                                   const McTables* __restrict__ mc,
-                                                                   const float* __restrict__ dens, uint32_t n,
-                                                                   ChunkCounts* __restrict__ counts) {
+                                                                                const McTables* __restrict__ mc,
+                                                                                const float* __restrict__ dens, uint32_t n,
+                                                                                ChunkCounts* __restrict__ counts) {
     using D = ClsDims<ST>;
-    constexpr int S = D::S, L = D::L, L3 = D::L3, NT = D::NT, NW = D::NW, NLD = D::NLD;
+    constexpr int S = D::S, L = D::L, L3 = D::L3, NT = D::NT, NW = D::NW, NLD = D::NLD, NSTAGE = D::NSTAGE;
+    __shared__ __align__(16) float s_dens[NSTAGE][D::BYTES / 4];
+    __shared__ __align__(8) uint64_t s_bar[NSTAGE];
     __shared__ uint32_t s_bits[3][D::NWORD + 2];
     __shared__ uint32_t s_flag[3][NW];
     __shared__ uint32_t s_part[3][NW];
@@ -925,6 +951,16 @@ __global__ void __launch_bounds__(ClsDims<ST>::NT, UW_CLS_MINB) k_classify_spec(
     if (tid < 3) { s_bits[tid][D::NWORD] = 0; s_bits[tid][D::NWORD + 1] = 0; }
     const float iso = cfg.iso_level;
     const size_t stride = cfg.dens_stride;
+    const uint32_t grid = gridDim.x;
+
+    if (tid == 0) {
+        for (int st = 0; st < NSTAGE; ++st) mbar_init(&s_bar[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int st = 0; st < NSTAGE; ++st) {
+            const uint64_t ch = (uint64_t)blockIdx.x + (uint64_t)st * grid;
+            if (ch < n) { mbar_expect_tx(&s_bar[st], D::BYTES); bulk_g2s(s_dens[st], dens + ch * stride, D::BYTES, &s_bar[st]); }
+        }
+    }
 
     const bool has_col = tid < 2 * D::NCOL;
     const int col = has_col ? (tid >= D::NCOL ? tid - D::NCOL : tid) : 0;
@@ -942,48 +978,33 @@ __global__ void __launch_bounds__(ClsDims<ST>::NT, UW_CLS_MINB) k_classify_spec(
         *reinterpret_cast<uint4*>(counts + chunk) = c;
     };
 
-    float v[NLD];
-    uint32_t chunk = blockIdx.x;
-    if (chunk < n) {
-        const float* src = dens + (size_t)chunk * stride;
-#pragma unroll
-        for (int k = 0; k < NLD; ++k) {
-            const int idx = tid + NT * k;
-            v[k] = ((k + 1) * NT <= L3 || idx < L3) ? __ldg(src + idx) : 0.f;
-        }
-    }
-    __syncthreads();
-    uint32_t prev = 0xFFFFFFFFu;
-    int slot = 0, pslot = 2;
-    for (; chunk < n; chunk += gridDim.x) {
+    __syncthreads();                                     // barriers initialised, table loaded
+    uint32_t prev = 0xFFFFFFFFu, it = 0;
+    int slot = 0, pslot = 2;                             // slot == it % 3 (ring stage and scratch slot alike)
+    for (uint32_t chunk = blockIdx.x; chunk < n; chunk += grid, ++it) {
+        mbar_wait(&s_bar[slot], (it / NSTAGE) & 1u);
+        const float* src = s_dens[slot];
         bool all_gt = true, any_lt = false;
 #pragma unroll
         for (int k = 0; k < NLD; ++k) {
             const bool ok = (k + 1) * NT <= L3 || tid + NT * k < L3;
-            const bool lt = ok && (v[k] < iso);
-            all_gt &= !ok || (v[k] > iso); any_lt |= lt;
+            const float v = ok ? src[tid + NT * k] : 0.f;
+            const bool lt = ok && (v < iso);
+            all_gt &= !ok || (v > iso); any_lt |= lt;
             const uint32_t w = __ballot_sync(0xFFFFFFFFu, lt);
             if (lane == 0 && NT * k + 32 * warp < L3) s_bits[slot][(NT * k >> 5) + warp] = w;
         }
         const bool w_all = __all_sync(0xFFFFFFFFu, all_gt);
         const bool w_any = __any_sync(0xFFFFFFFFu, any_lt);
         if (lane == 0) s_flag[slot][warp] = (w_all ? CF_ALL_GT : 0u) | (w_any ? CF_ANY_LT : 0u);
-        const uint32_t next = chunk + gridDim.x;
-        if (next < n) {                                   // in flight underneath the column work below
-            const float* src = dens + (size_t)next * stride;
-#pragma unroll
-            for (int k = 0; k < NLD; ++k) {
-                const int idx = tid + NT * k;
-                v[k] = ((k + 1) * NT <= L3 || idx < L3) ? __ldg(src + idx) : 0.f;
-            }
+        const int has_lt = __syncthreads_or(w_any);      // sign words visible; every thread is done with this stage
+        if (tid == 0) {
+            const uint64_t nx = (uint64_t)chunk + (uint64_t)NSTAGE * grid;      // refill the stage just drained
+            if (nx < n) { mbar_expect_tx(&s_bar[slot], D::BYTES); bulk_g2s(s_dens[slot], dens + nx * stride, D::BYTES, &s_bar[slot]); }
+            if (prev != 0xFFFFFFFFu) finalize(prev, pslot);
         }
-        __syncthreads();
-        if (tid == 0 && prev != 0xFFFFFFFFu) finalize(prev, pslot);
-        uint32_t o = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) o |= s_flag[slot][w];
         uint32_t acc = 0;                                  // n_inds | n_verts << 16
-        if ((o & CF_ANY_LT) && has_col) {
+        if (has_lt && has_col) {
             const uint32_t* bits = s_bits[slot];
             const uint32_t q0 = col_mask(bits, x * L + y, L) | (col_mask(bits, (x + 1) * L + y, L) << 16);
             const uint32_t q1 = col_mask(bits, x * L + y + 1, L) | (col_mask(bits, (x + 1) * L + y + 1, L) << 16);
@@ -1013,7 +1034,7 @@ __global__ void __launch_bounds__(ClsDims<ST>::NT, UW_CLS_MINB) k_classify_spec(
 // The flags carry the launch epoch, so nothing is cleared between launches; the last CTA out resets the tickets.
 // ---------------------------------------------------------------------------------------
 struct ScanPart { unsigned long long v, i; uint32_t a, blank; };
-struct ScanCtl { uint32_t ticket, done, pad0, pad1; };
+struct ScanCtl { uint32_t ticket, done, emit_ticket, pad1; };   // emit_ticket: work hand-out of the following emit kernel
 
 __global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restrict__ counts,
                                                       const int32_t* __restrict__ pos, uint32_t n,
@@ -1111,7 +1132,7 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restr
     }
     if (tid == 0) {
         __threadfence();
-        if (atomicAdd(&ctl->done, 1u) == ntiles - 1) { ctl->ticket = 0; ctl->done = 0; }
+        if (atomicAdd(&ctl->done, 1u) == ntiles - 1) { ctl->ticket = 0; ctl->done = 0; ctl->emit_ticket = 0; }
     }
 }
 
@@ -1672,28 +1693,38 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
 // reference's scan-order numbering needs, since an edge's owner is never more than
 // one slab back.  COUNT pass -> k_scan_chunks -> EMIT pass (same walk, now writing vertices/indices).
 // ---------------------------------------------------------------------------------------
+#define UW_BIG_VCAP 4096     // slab vertex-list tile (entries)
 struct BigSmem {
-    float* plane[2]; uint32_t* bits[2]; uint32_t* vb[2]; uint8_t* cs[2]; uint32_t* ib; uint16_t* alist; uint32_t* lut;
+    float* plane[2]; uint32_t* bits[2]; uint16_t* vb[2]; uint8_t* cs[2]; uint16_t* ib; uint16_t* alist; uint16_t* vlist;
+    uint32_t* lut; uint64_t* rows; uint16_t* before; uint16_t* crossed; uint8_t* nind;
 };
 
 __host__ __device__ inline size_t big_smem_bytes(const DevCfg& cfg) {
-    const size_t L2p = ((size_t)cfg.L2 + 3) & ~(size_t)3, nw = ((size_t)cfg.L2 + 31) / 32 + 2, cells = (size_t)cfg.S * cfg.S;
-    return 2 * L2p * 4 + 2 * nw * 4 + 2 * cells * 4 + 2 * ((cells + 15) & ~(size_t)15) + cells * 4 + ((cells + 7) & ~(size_t)7) * 2 + 256 * 4;
+    const size_t L2p = ((size_t)cfg.L2 + 3) & ~(size_t)3, nw = (((size_t)cfg.L2 + 31) / 32 + 3) & ~(size_t)1;
+    const size_t cells2 = ((size_t)cfg.S * cfg.S + 7) & ~(size_t)7;
+    return 2 * L2p * 4 + 256 * 8 + 256 * 4 + 2 * nw * 4 + 256 * 12 * 2 + 256 * 2 + 256
+         + 4 * cells2 * 2 + UW_BIG_VCAP * 2 + 2 * ((cells2 + 15) & ~(size_t)15);
 }
 
 __device__ __forceinline__ BigSmem big_smem_carve(const DevCfg& cfg, unsigned char* base) {
-    const size_t L2p = ((size_t)cfg.L2 + 3) & ~(size_t)3, nw = ((size_t)cfg.L2 + 31) / 32 + 2, cells = (size_t)cfg.S * cfg.S;
+    const size_t L2p = ((size_t)cfg.L2 + 3) & ~(size_t)3, nw = (((size_t)cfg.L2 + 31) / 32 + 3) & ~(size_t)1;
+    const size_t cells2 = ((size_t)cfg.S * cfg.S + 7) & ~(size_t)7;
     BigSmem s;
     s.plane[0] = (float*)base; base += L2p * 4;
     s.plane[1] = (float*)base; base += L2p * 4;
+    s.rows = (uint64_t*)base; base += 256 * 8;
+    s.lut = (uint32_t*)base; base += 256 * 4;
     s.bits[0] = (uint32_t*)base; base += nw * 4;
     s.bits[1] = (uint32_t*)base; base += nw * 4;
-    s.vb[0] = (uint32_t*)base; base += cells * 4;
-    s.vb[1] = (uint32_t*)base; base += cells * 4;
-    s.ib = (uint32_t*)base; base += cells * 4;
-    s.lut = (uint32_t*)base; base += 256 * 4;
-    s.alist = (uint16_t*)base; base += ((cells + 7) & ~(size_t)7) * 2;
-    s.cs[0] = (uint8_t*)base; base += (cells + 15) & ~(size_t)15;
+    s.before = (uint16_t*)base; base += 256 * 12 * 2;
+    s.crossed = (uint16_t*)base; base += 256 * 2;
+    s.nind = (uint8_t*)base; base += 256;
+    s.vb[0] = (uint16_t*)base; base += cells2 * 2;
+    s.vb[1] = (uint16_t*)base; base += cells2 * 2;
+    s.ib = (uint16_t*)base; base += cells2 * 2;
+    s.alist = (uint16_t*)base; base += cells2 * 2;
+    s.vlist = (uint16_t*)base; base += UW_BIG_VCAP * 2;
+    s.cs[0] = (uint8_t*)base; base += (cells2 + 15) & ~(size_t)15;
     s.cs[1] = (uint8_t*)base;
     return s;
 }
@@ -1806,32 +1837,45 @@ __global__ void __launch_bounds__(UW_BIG_NT) k_count_big(const __grid_constant__
     }
 }
 
-// EMIT pass over the active chunks (see the section header).
+// EMIT pass over the active chunks (see the section header).  Chunks are taken by ticket (their costs differ by
+// the amount of surface they hold).  Per slab: classify + block scan -> per-cell vertex bases and the slab's
+// surface-cell list; then one thread per SURFACE CELL writes its indices (owner lookups against the current /
+// previous slab, every table in shared memory) and lists its owned edges; then one thread per VERTEX does the
+// edge lerp + colour.  Slab-relative u16 bases keep the footprint at two CTAs per SM.
 template <typename IndexT>
-__global__ void __launch_bounds__(UW_BIG_NT) k_emit_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
-                                                        const float* __restrict__ dens,
-                                                        const uw_chunk_desc* __restrict__ descs, const uint32_t* __restrict__ active,
-                                                        const BatchTotals* __restrict__ totals,
-                                                        uw_vert* __restrict__ verts, IndexT* __restrict__ inds) {
+__global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
+                                                           const float* __restrict__ dens,
+                                                           const uw_chunk_desc* __restrict__ descs, const uint32_t* __restrict__ active,
+                                                           const BatchTotals* __restrict__ totals,
+                                                           uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
+                                                           uint32_t* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const BigSmem s = big_smem_carve(cfg, smem_raw);
     __shared__ uint32_t s_w[64];
+    __shared__ uint32_t s_next;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
     const int S = cfg.S, L = cfg.L, L2 = cfg.L2, ncell = S * S;
     const int CPT = (ncell + NT - 1) / NT;                 // consecutive cells per thread (scan order y, z)
     const bool row_runs = CPT <= 15 && S % CPT == 0;       // a thread's run never straddles two rows
-    for (int t = tid; t < 256; t += NT) s.lut[t] = mc->lut[t];
+    for (int t = tid; t < 256; t += NT) {
+        s.lut[t] = mc->lut[t]; s.rows[t] = mc->rows[t]; s.crossed[t] = mc->crossed[t]; s.nind[t] = mc->ninds[t];
+    }
+    for (int t = tid; t < 256 * 12; t += NT) s.before[t] = mc->before[t / 12][t % 12];
     if (totals->overflow) return;                          // host grows the arenas and relaunches
     const uint32_t n_work = totals->n_active;
 
-    for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+    for (;;) {
+        if (tid == 0) s_next = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t w = s_next;
+        if (w >= n_work) break;
         const uint32_t chunk = active[w];
         const float* D = dens + (size_t)chunk * cfg.dens_stride;
         const uw_chunk_desc d = descs[chunk];
         const int offx = d.pos[0] * cfg.chunk_size, offy = d.pos[1] * cfg.chunk_size, offz = d.pos[2] * cfg.chunk_size;
         uw_vert* vout = verts + d.vert_offset;
         IndexT* iout = inds + d.index_offset;
-        uint32_t vrun = 0, irun = 0;
+        uint32_t vrun = 0, irun = 0, vrun_prev = 0;        // chunk-local running bases: this slab's, the previous slab's
         float pre[UW_BIG_NLD];
         auto issue = [&](int x) {
             const float* src = D + (size_t)x * L2;
@@ -1863,9 +1907,9 @@ __global__ void __launch_bounds__(UW_BIG_NT) k_emit_big(const __grid_constant__ 
             const uint32_t* A = s.bits[cx & 1];            // plane x = cx
             const uint32_t* B = s.bits[(cx + 1) & 1];      // plane x = cx + 1
             uint8_t* cs_cur = s.cs[cx & 1];
-            uint32_t* vb_cur = s.vb[cx & 1];
+            uint16_t* vb_cur = s.vb[cx & 1];
             const uint8_t* cs_prev = s.cs[(cx + 1) & 1];
-            const uint32_t* vb_prev = s.vb[(cx + 1) & 1];
+            const uint16_t* vb_prev = s.vb[(cx + 1) & 1];
 
             // ---- classify this slab; per-thread counts over its CPT consecutive cells --------------------
             const int c0 = tid * CPT;
@@ -1910,58 +1954,74 @@ __global__ void __launch_bounds__(UW_BIG_NT) k_emit_big(const __grid_constant__ 
             block_scan2(nva, ni, eva, ei, tva, ti, s_w);
             const uint32_t slab_nv = tva & 0xFFFFu, slab_na = tva >> 16;
             if (slab_na) {                                  // block-uniform
-                uint32_t rv = vrun + (eva & 0xFFFFu), ra = eva >> 16, ri = irun + ei;
-                for (int q = 0; q < CPT; ++q) {
-                    const int cell = c0 + q;
-                    if (cell >= ncell) break;
-                    const uint32_t csv = cs_cur[cell];
-                    if (csv != 0u && csv != 255u) {
-                        const int y = cell / S, z = cell - y * S;
-                        vb_cur[cell] = rv; s.ib[cell] = ri;
-                        s.alist[ra++] = (uint16_t)cell;
-                        ri += mc->ninds[csv];
-                        rv += __popc((uint32_t)mc->crossed[csv] & own_mask_of(cx, y, z));
+                if (nva) {                                  // slab-relative bases of this thread's surface cells
+                    uint32_t rv = eva & 0xFFFFu, ra = eva >> 16, ri = ei;
+                    for (int q = 0; q < CPT; ++q) {
+                        const int cell = c0 + q;
+                        if (cell >= ncell) break;
+                        const uint32_t csv = cs_cur[cell];
+                        if (csv != 0u && csv != 255u) {
+                            const int y = cell / S, z = cell - y * S;
+                            vb_cur[cell] = (uint16_t)rv; s.ib[ra] = (uint16_t)ri;
+                            s.alist[ra++] = (uint16_t)cell;
+                            ri += s.nind[csv];
+                            rv += __popc((uint32_t)s.crossed[csv] & own_mask_of(cx, y, z));
+                        }
                     }
                 }
                 __syncthreads();
-                // ---- emit: one thread per surface cell of the slab ------------------------------------------
                 const float* P0 = s.plane[cx & 1];
                 const float* P1 = s.plane[(cx + 1) & 1];
                 auto dens_at = [=](int ax, int ay, int az) { return (ax == cx ? P0 : P1)[ay * L + az]; };
-                for (uint32_t a = tid; a < slab_na; a += NT) {
-                    const int cell = s.alist[a];
-                    const int y = cell / S, z = cell - y * S;
-                    const uint32_t csv = cs_cur[cell];
-                    const uint32_t own = own_mask_of(cx, y, z);
-                    const uint64_t row = __ldg(&mc->rows[csv]);
-                    uint32_t vnext = vb_cur[cell], todo = own;
-                    IndexT* dst = iout + s.ib[cell];
+                for (uint32_t v0 = 0; v0 < (slab_nv ? slab_nv : 1u); v0 += UW_BIG_VCAP) {
+                    if (v0) __syncthreads();                // the previous tile's vertex threads are done with vlist
+                    // ---- one thread per surface cell: indices (first tile) + this tile of the owned-edge list ----
+                    for (uint32_t a = tid; a < slab_na; a += NT) {
+                        const int cell = s.alist[a];
+                        const int y = cell / S, z = cell - y * S;
+                        const uint32_t csv = cs_cur[cell];
+                        const uint64_t row = s.rows[csv];
+                        uint32_t vnext = vb_cur[cell], todo = own_mask_of(cx, y, z);
+                        IndexT* dst = iout + irun + s.ib[a];
 #pragma unroll 1
-                    for (int k = 0; k < 15; ++k) {
-                        const int e = (int)((row >> (4 * k)) & 0xFull);
-                        if (e == 15) break;
-                        if ((todo >> e) & 1u) {                    // owned edge, first appearance: its vertex
-                            todo &= ~(1u << e);
-                            float v[6];
-                            make_vertex_from(cfg, dens_at, cx, y, z, e, offx, offy, offz, v);
-                            float2* vd = reinterpret_cast<float2*>(vout + vnext);
-                            vd[0] = make_float2(v[0], v[1]); vd[1] = make_float2(v[2], v[3]); vd[2] = make_float2(v[4], v[5]);
-                            ++vnext;
+                        for (int k = 0; k < 15; ++k) {
+                            const int e = (int)((row >> (4 * k)) & 0xFull);
+                            if (e == 15) break;
+                            if ((todo >> e) & 1u) {                    // owned edge, first appearance: its vertex
+                                todo &= ~(1u << e);
+                                const uint32_t slot = vnext - v0;
+                                if (slot < UW_BIG_VCAP) s.vlist[slot] = (uint16_t)(cell | (e << 12));
+                                ++vnext;
+                            }
+                            if (v0 == 0) {
+                                int ox, oy, oz, oe;
+                                owner_of(e, cx, y, z, ox, oy, oz, oe);
+                                const int ocell = oy * S + oz;
+                                const uint32_t ocs = ox == cx ? (uint32_t)cs_cur[ocell] : (uint32_t)cs_prev[ocell];
+                                const uint32_t ovb = ox == cx ? vrun + vb_cur[ocell] : vrun_prev + vb_prev[ocell];
+                                const uint32_t rank = __popc((uint32_t)s.before[ocs * 12 + oe] & own_mask_of(ox, oy, oz));
+                                dst[k] = (IndexT)(ovb + rank);
+                            }
                         }
-                        int ox, oy, oz, oe;
-                        owner_of(e, cx, y, z, ox, oy, oz, oe);
-                        const int ocell = oy * S + oz;
-                        const uint32_t ocs = ox == cx ? (uint32_t)cs_cur[ocell] : (uint32_t)cs_prev[ocell];
-                        const uint32_t ovb = ox == cx ? vb_cur[ocell] : vb_prev[ocell];
-                        const uint32_t rank = __popc((uint32_t)mc->before[ocs][oe] & own_mask_of(ox, oy, oz));
-                        dst[k] = (IndexT)(ovb + rank);
+                    }
+                    __syncthreads();
+                    // ---- one thread per vertex of the tile ------------------------------------------------------
+                    const uint32_t cnt = min((uint32_t)UW_BIG_VCAP, slab_nv - v0);
+                    for (uint32_t t = tid; t < cnt; t += NT) {
+                        const uint32_t ent = s.vlist[t];
+                        const int cell = ent & 0xFFF, e = ent >> 12;
+                        const int y = cell / S, z = cell - y * S;
+                        float v[6];
+                        make_vertex_from(cfg, dens_at, cx, y, z, e, offx, offy, offz, v);
+                        float2* vd = reinterpret_cast<float2*>(vout + vrun + v0 + t);
+                        vd[0] = make_float2(v[0], v[1]); vd[1] = make_float2(v[2], v[3]); vd[2] = make_float2(v[4], v[5]);
                     }
                 }
             }
+            vrun_prev = vrun;
             vrun += slab_nv; irun += ti;
             __syncthreads();                               // buffers (cx & 1) are overwritten by the next commit
         }
-        __syncthreads();
     }
 }
 

@@ -639,10 +639,10 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
         if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
         if (c->index32)
             k_emit_big<uint32_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
-                                                                             c->d_totals, c->B().d_verts, (uint32_t*)c->B().d_inds);
+                                                                             c->d_totals, c->B().d_verts, (uint32_t*)c->B().d_inds, &c->d_scan_ctl->emit_ticket);
         else
             k_emit_big<uint16_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
-                                                                             c->d_totals, c->B().d_verts, (uint16_t*)c->B().d_inds);
+                                                                             c->d_totals, c->B().d_verts, (uint16_t*)c->B().d_inds, &c->d_scan_ctl->emit_ticket);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         return UW_OK;

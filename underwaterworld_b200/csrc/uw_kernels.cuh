@@ -1740,20 +1740,24 @@ __device__ __forceinline__ uint32_t bits16(const uint32_t* bits, int b) {
 }
 
 #define UW_BIG_NT 512
+#ifndef UW_BIG_COUNT_MINB
+#define UW_BIG_COUNT_MINB 3
+#endif
 #define UW_BIG_NLD 9          // ceil(65 * 65 / 512): plane elements per thread
 
 // COUNT pass: per-chunk vertex / index totals and the blank / no-surface vote.  Totals do not depend on
 // the scan order, so no state is carried between slabs: two sign-bit planes in shared memory, per-thread
 // counters, one block reduction per chunk.  The next plane's loads are issued before the current slab is
 // classified so that their DRAM latency hides behind the bit work.
-__global__ void __launch_bounds__(UW_BIG_NT) k_count_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
+template <int ST /*compile-time internal_size, 0 = runtime*/>
+__global__ void __launch_bounds__(UW_BIG_NT, UW_BIG_COUNT_MINB) k_count_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
                                                          const float* __restrict__ dens, uint32_t n,
                                                          ChunkCounts* __restrict__ counts) {
     __shared__ uint32_t s_bits[2][(65 * 65 + 31) / 32 + 2];
     __shared__ uint32_t s_lut[256];
     __shared__ uint32_t s_acc[4];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int S = cfg.S, L = cfg.L, L2 = cfg.L2, ncell = S * S;
+    const int S = ST > 0 ? ST : cfg.S, L = S + 1, L2 = L * L, ncell = S * S;
     const int CPT = (ncell + UW_BIG_NT - 1) / UW_BIG_NT;
     const bool row_runs = CPT <= 15 && S % CPT == 0;
     for (int t = tid; t < 256; t += UW_BIG_NT) s_lut[t] = mc->lut[t];
@@ -1842,7 +1846,7 @@ __global__ void __launch_bounds__(UW_BIG_NT) k_count_big(const __grid_constant__
 // surface-cell list; then one thread per SURFACE CELL writes its indices (owner lookups against the current /
 // previous slab, every table in shared memory) and lists its owned edges; then one thread per VERTEX does the
 // edge lerp + colour.  Slab-relative u16 bases keep the footprint at two CTAs per SM.
-template <typename IndexT>
+template <typename IndexT, int ST /*compile-time internal_size, 0 = runtime*/>
 __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
                                                            const float* __restrict__ dens,
                                                            const uw_chunk_desc* __restrict__ descs, const uint32_t* __restrict__ active,
@@ -1853,8 +1857,8 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
     const BigSmem s = big_smem_carve(cfg, smem_raw);
     __shared__ uint32_t s_w[64];
     __shared__ uint32_t s_next;
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
-    const int S = cfg.S, L = cfg.L, L2 = cfg.L2, ncell = S * S;
+    const int tid = threadIdx.x, NT = UW_BIG_NT, lane = tid & 31;
+    const int S = ST > 0 ? ST : cfg.S, L = S + 1, L2 = L * L, ncell = S * S;
     const int CPT = (ncell + NT - 1) / NT;                 // consecutive cells per thread (scan order y, z)
     const bool row_runs = CPT <= 15 && S % CPT == 0;       // a thread's run never straddles two rows
     for (int t = tid; t < 256; t += NT) {

@@ -73,7 +73,12 @@ struct uw_ctx {
     // chunk-level scan (staged / large-chunk paths): per-tile totals + epoch flags, see k_scan_chunks
     ScanPart* d_scan_part = nullptr; uint32_t* d_scan_flag = nullptr; ScanCtl* d_scan_ctl = nullptr;
     uint32_t scan_tiles_cap = 0, scan_epoch = 0;
+    typedef void (*big_emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*, uint32_t*);
+    typedef void (*big_emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uint32_t*);
     typedef void (*classify_fn_t)(DevCfg, const McTables*, const float*, uint32_t, ChunkCounts*);
+    big_emit16_fn_t big_emit16_fn = nullptr;
+    big_emit32_fn_t big_emit32_fn = nullptr;
+    classify_fn_t big_count_fn = nullptr;
     classify_fn_t classify_fn = nullptr;     // compile-time-sized classify (internal_size 12 / 10)
     int classify_spec_threads = 0, classify_spec_blocks_per_sm = 1;
     cudaStream_t copy_stream = nullptr;
@@ -417,13 +422,15 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         }
         c->big_smem = big_smem_bytes(d);
         auto set_attr = [&](const void* f) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->big_smem); };
-        bool ok = cu(set_attr((const void*)k_emit_big<uint16_t>), "attr big emit16") &&
-                  cu(set_attr((const void*)k_emit_big<uint32_t>), "attr big emit32");
+        if (d.S == 64) { c->big_emit16_fn = k_emit_big<uint16_t, 64>; c->big_emit32_fn = k_emit_big<uint32_t, 64>; c->big_count_fn = k_count_big<64>; }
+        else           { c->big_emit16_fn = k_emit_big<uint16_t, 0>;  c->big_emit32_fn = k_emit_big<uint32_t, 0>;  c->big_count_fn = k_count_big<0>; }
+        bool ok = cu(set_attr((const void*)c->big_emit16_fn), "attr big emit16") &&
+                  cu(set_attr((const void*)c->big_emit32_fn), "attr big emit32");
         if (!ok) return bail(UW_ERR_CUDA);
         int nb = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_emit_big<uint32_t>, UW_BIG_NT, c->big_smem) == cudaSuccess && nb > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->big_emit32_fn, UW_BIG_NT, c->big_smem) == cudaSuccess && nb > 0)
             c->big_blocks_per_sm = nb;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k_count_big, UW_BIG_NT, 0) == cudaSuccess && nb > 0)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->big_count_fn, UW_BIG_NT, 0) == cudaSuccess && nb > 0)
             c->big_count_blocks_per_sm = nb;
     } else {
         // the specialised kernels bake the axis tables in at compile time (see SpecDims): usable only
@@ -630,7 +637,7 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
     if (c->big_path) {
         const int grid = persistent_grid(c, n, c->big_blocks_per_sm);
         if (!only_emit) {
-            k_count_big<<<persistent_grid(c, n, c->big_count_blocks_per_sm), UW_BIG_NT, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts);
+            c->big_count_fn<<<persistent_grid(c, n, c->big_count_blocks_per_sm), UW_BIG_NT, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts);
             c->launches++;
             CU_TRY(c, cudaGetLastError());
             if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
@@ -638,10 +645,10 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
         { uw_status sst = launch_scan(c, d_pos, n); if (sst != UW_OK) return sst; }
         if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
         if (c->index32)
-            k_emit_big<uint32_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
+            c->big_emit32_fn<<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
                                                                              c->d_totals, c->B().d_verts, (uint32_t*)c->B().d_inds, &c->d_scan_ctl->emit_ticket);
         else
-            k_emit_big<uint16_t><<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
+            c->big_emit16_fn<<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
                                                                              c->d_totals, c->B().d_verts, (uint16_t*)c->B().d_inds, &c->d_scan_ctl->emit_ticket);
         c->launches++;
         CU_TRY(c, cudaGetLastError());

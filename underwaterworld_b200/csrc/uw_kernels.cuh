@@ -780,10 +780,23 @@ __device__ __forceinline__ void block_scan2(uint32_t v, uint32_t i, uint32_t& ev
     if (lane == 31) { s_w[warp] = sv; s_w[32 + warp] = si; }
     __syncthreads();
     uint32_t wv = 0, wi = 0, av = 0, ai = 0;
-    for (int w = 0; w < nw; ++w) {
-        const uint32_t a = s_w[w], b = s_w[32 + w];
-        av += a; ai += b;
-        if (w < warp) { wv += a; wi += b; }
+    if (nw > 8) {
+        // many warps: every warp scans the warp totals itself (lane l holds warp l's total) instead of looping
+        uint32_t a = lane < nw ? s_w[lane] : 0u, b = lane < nw ? s_w[32 + lane] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, a, d), y = __shfl_up_sync(0xFFFFFFFFu, b, d);
+            if (lane >= d) { a += x; b += y; }
+        }
+        av = __shfl_sync(0xFFFFFFFFu, a, nw - 1); ai = __shfl_sync(0xFFFFFFFFu, b, nw - 1);
+        const uint32_t pa = __shfl_sync(0xFFFFFFFFu, a, warp > 0 ? warp - 1 : 0), pb = __shfl_sync(0xFFFFFFFFu, b, warp > 0 ? warp - 1 : 0);
+        if (warp > 0) { wv = pa; wi = pb; }
+    } else {
+        for (int w = 0; w < nw; ++w) {
+            const uint32_t a = s_w[w], b = s_w[32 + w];
+            av += a; ai += b;
+            if (w < warp) { wv += a; wi += b; }
+        }
     }
     ev = wv + sv - v; ei = wi + si - i;
     tv = av; ti = ai;
@@ -1752,10 +1765,12 @@ __device__ __forceinline__ uint32_t bits16(const uint32_t* bits, int b) {
 template <int ST /*compile-time internal_size, 0 = runtime*/>
 __global__ void __launch_bounds__(UW_BIG_NT, UW_BIG_COUNT_MINB) k_count_big(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
                                                          const float* __restrict__ dens, uint32_t n,
-                                                         ChunkCounts* __restrict__ counts) {
+                                                         ChunkCounts* __restrict__ counts,
+                                                         uint2* __restrict__ quarters /*[n][4]: (verts, inds) of each x-quarter*/) {
     __shared__ uint32_t s_bits[2][(65 * 65 + 31) / 32 + 2];
     __shared__ uint32_t s_lut[256];
     __shared__ uint32_t s_acc[4];
+    __shared__ uint32_t s_q[4][2];
     const int tid = threadIdx.x, lane = tid & 31;
     const int S = ST > 0 ? ST : cfg.S, L = S + 1, L2 = L * L, ncell = S * S;
     const int CPT = (ncell + UW_BIG_NT - 1) / UW_BIG_NT;
@@ -1765,6 +1780,8 @@ __global__ void __launch_bounds__(UW_BIG_NT, UW_BIG_COUNT_MINB) k_count_big(cons
     for (uint32_t chunk = blockIdx.x; chunk < n; chunk += gridDim.x) {
         const float* D = dens + (size_t)chunk * cfg.dens_stride;
         if (tid < 4) s_acc[tid] = tid == 2 ? 1u : 0u;       // [0] verts, [1] inds, [2] all_gt, [3] any_lt
+        if (tid < 8) s_q[tid >> 1][tid & 1] = 0u;
+        const int qlen = (S & 3) == 0 ? S >> 2 : S;         // x-quarters (the emit pass may split a chunk there)
         float pre[UW_BIG_NLD];
         bool all_gt = true, any_lt = false;
         uint32_t nv = 0, ni = 0;
@@ -1822,21 +1839,26 @@ __global__ void __launch_bounds__(UW_BIG_NT, UW_BIG_COUNT_MINB) k_count_big(cons
                     if (t >> 8) { ni += (t >> 8) & 15u; nv += __popc((t >> 12) & own_mask_of(cx, y, z)); }
                 }
             }
+            if ((cx + 1) % qlen == 0) {                     // quarter boundary: flush the per-thread counters
+                nv = __reduce_add_sync(0xFFFFFFFFu, nv); ni = __reduce_add_sync(0xFFFFFFFFu, ni);
+                if (lane == 0 && (nv | ni)) { atomicAdd(&s_q[cx / qlen][0], nv); atomicAdd(&s_q[cx / qlen][1], ni); }
+                nv = 0; ni = 0;
+            }
             __syncthreads();
         }
-        nv = __reduce_add_sync(0xFFFFFFFFu, nv); ni = __reduce_add_sync(0xFFFFFFFFu, ni);
         const bool w_all = __all_sync(0xFFFFFFFFu, all_gt), w_any = __any_sync(0xFFFFFFFFu, any_lt);
         if (lane == 0) {
-            atomicAdd(&s_acc[0], nv); atomicAdd(&s_acc[1], ni);
             if (!w_all) atomicAnd(&s_acc[2], 0u);
             if (w_any) atomicOr(&s_acc[3], 1u);
         }
         __syncthreads();
         if (tid == 0) {
             ChunkCounts c;
-            c.n_verts = s_acc[0]; c.n_inds = s_acc[1]; c.flags = (s_acc[2] ? CF_ALL_GT : 0u) | (s_acc[3] ? CF_ANY_LT : 0u); c.pad = 0;
+            c.n_verts = s_q[0][0] + s_q[1][0] + s_q[2][0] + s_q[3][0]; c.n_inds = s_q[0][1] + s_q[1][1] + s_q[2][1] + s_q[3][1];
+            c.flags = (s_acc[2] ? CF_ALL_GT : 0u) | (s_acc[3] ? CF_ANY_LT : 0u); c.pad = 0;
             counts[chunk] = c;
         }
+        if (tid < 4) quarters[(size_t)chunk * 4 + tid] = make_uint2(s_q[tid][0], s_q[tid][1]);
         __syncthreads();
     }
 }
@@ -1852,7 +1874,7 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
                                                            const uw_chunk_desc* __restrict__ descs, const uint32_t* __restrict__ active,
                                                            const BatchTotals* __restrict__ totals,
                                                            uw_vert* __restrict__ verts, IndexT* __restrict__ inds,
-                                                           uint32_t* __restrict__ ticket) {
+                                                           uint32_t* __restrict__ ticket, const uint2* __restrict__ quarters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const BigSmem s = big_smem_carve(cfg, smem_raw);
     __shared__ uint32_t s_w[64];
@@ -1866,14 +1888,32 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
     }
     for (int t = tid; t < 256 * 12; t += NT) s.before[t] = mc->before[t / 12][t % 12];
     if (totals->overflow) return;                          // host grows the arenas and relaunches
-    const uint32_t n_work = totals->n_active;
+    // Work unit = (active chunk, x-part): with only a few chunks per CTA the last wave would sit half empty, so a
+    // chunk is cut into 2 or 4 x-ranges when that shortens the schedule.  A part that starts inside the chunk
+    // re-classifies the slab before its range (no output) to rebuild the owner state, and takes its running
+    // vertex / index bases from the count pass's per-quarter totals.
+    const uint32_t n_active = totals->n_active;
+    uint32_t parts = 1;
+    if ((S & 3) == 0 && n_active > 0) {
+        float best = 1e30f;
+        for (uint32_t p = 1; p <= 4; p <<= 1) {
+            const float waves = (float)((n_active * p + gridDim.x - 1) / gridDim.x);
+            const float cost = waves * ((float)S / (float)p + (p > 1 ? 1.f : 0.f));
+            if (cost < best * 0.97f) { best = cost; parts = p; }
+        }
+    }
+    const uint32_t n_work = n_active * parts;
+    const int xlen = S / (int)parts;
 
     for (;;) {
         if (tid == 0) s_next = atomicAdd(ticket, 1u);
         __syncthreads();
         const uint32_t w = s_next;
         if (w >= n_work) break;
-        const uint32_t chunk = active[w];
+        const uint32_t chunk = active[w / parts];
+        const int part = (int)(w % parts), x0 = part * xlen, x1 = x0 + xlen, xs = part ? x0 - 1 : 0;
+        uint32_t pv = 0, pi = 0;                           // vertices / indices of the chunk before slab x0
+        for (int q = 0; q < part * (4 / (int)parts); ++q) { const uint2 t = quarters[(size_t)chunk * 4 + q]; pv += t.x; pi += t.y; }
         const float* D = dens + (size_t)chunk * cfg.dens_stride;
         const uw_chunk_desc d = descs[chunk];
         const int offx = d.pos[0] * cfg.chunk_size, offy = d.pos[1] * cfg.chunk_size, offz = d.pos[2] * cfg.chunk_size;
@@ -1902,11 +1942,12 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
             }
             if (tid == 0) { bt[(L2 + 31) >> 5] = 0; bt[((L2 + 31) >> 5) + 1] = 0; }
         };
-        issue(0); commit(0); issue(1);
+        issue(xs); commit(xs); issue(xs + 1);
 
-        for (int cx = 0; cx < S; ++cx) {
+        for (int cx = xs; cx < x1; ++cx) {
+            const bool warm = cx < x0;                     // owner state only, nothing is written
             commit(cx + 1);
-            if (cx + 2 <= S) issue(cx + 2);                // in flight while this slab is classified and emitted
+            if (cx + 2 <= x1) issue(cx + 2);               // in flight while this slab is classified and emitted
             __syncthreads();
             const uint32_t* A = s.bits[cx & 1];            // plane x = cx
             const uint32_t* B = s.bits[(cx + 1) & 1];      // plane x = cx + 1
@@ -1925,7 +1966,24 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
                     const uint32_t q0 = (bits16(A, b) & keep) | ((bits16(B, b) & keep) << 16);
                     const uint32_t q1 = (bits16(A, b + L) & keep) | ((bits16(B, b + L) & keep) << 16);
                     const uint32_t any = q0 | q1, all = q0 & q1;
-                    if (any == 0u || (all & (all >> 16) & keep) == keep) {
+                    if constexpr (ST == 64) {                // CPT == 8: the run's case bytes leave as one 8-byte store
+                        uint32_t w0 = 0, w1 = 0;
+                        if (any == 0u || (all & (all >> 16) & keep) == keep) {
+                            w0 = w1 = any ? 0xFFFFFFFFu : 0u;
+                        } else {
+                            const uint32_t ownn = own_mask_of(cx, y, 1), own0 = own_mask_of(cx, y, 0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const uint32_t t = s.lut[natural_of(q0, q1, q)];
+                                if (q < 4) w0 |= (t & 0xFFu) << (8 * q); else w1 |= (t & 0xFFu) << (8 * (q - 4));
+                                if (t >> 8) {
+                                    ni += (t >> 8) & 15u;
+                                    nva += __popc((t >> 12) & (z0 + q == 0 ? own0 : ownn)) + 0x10000u;
+                                }
+                            }
+                        }
+                        *reinterpret_cast<uint2*>(cs_cur + c0) = make_uint2(w0, w1);
+                    } else if (any == 0u || (all & (all >> 16) & keep) == keep) {
                         const uint8_t fill = any ? 255 : 0;
                         for (int q = 0; q < CPT; ++q) cs_cur[c0 + q] = fill;
                     } else {
@@ -1957,6 +2015,7 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
             uint32_t eva, ei, tva, ti;
             block_scan2(nva, ni, eva, ei, tva, ti, s_w);
             const uint32_t slab_nv = tva & 0xFFFFu, slab_na = tva >> 16;
+            if (warm) { vrun = pv - slab_nv; irun = pi - ti; }
             if (slab_na) {                                  // block-uniform
                 if (nva) {                                  // slab-relative bases of this thread's surface cells
                     uint32_t rv = eva & 0xFFFFu, ra = eva >> 16, ri = ei;
@@ -1977,7 +2036,7 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
                 const float* P0 = s.plane[cx & 1];
                 const float* P1 = s.plane[(cx + 1) & 1];
                 auto dens_at = [=](int ax, int ay, int az) { return (ax == cx ? P0 : P1)[ay * L + az]; };
-                for (uint32_t v0 = 0; v0 < (slab_nv ? slab_nv : 1u); v0 += UW_BIG_VCAP) {
+                for (uint32_t v0 = 0; !warm && v0 < (slab_nv ? slab_nv : 1u); v0 += UW_BIG_VCAP) {
                     if (v0) __syncthreads();                // the previous tile's vertex threads are done with vlist
                     // ---- one thread per surface cell: indices (first tile) + this tile of the owned-edge list ----
                     for (uint32_t a = tid; a < slab_na; a += NT) {

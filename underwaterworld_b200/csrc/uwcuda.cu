@@ -45,6 +45,7 @@ struct uw_ctx {
         float* d_dens = nullptr;        // only the staged / large-chunk / debug paths materialise densities
         uint32_t cap_dens_chunks = 0;
         ChunkCounts* d_counts = nullptr;
+        uint2* d_quarters = nullptr;    // large-chunk path: per-chunk (verts, inds) of each x-quarter
         uw_chunk_desc* d_descs = nullptr;
         uint32_t* d_active = nullptr;
         uint8_t* d_cases = nullptr;  uint32_t cap_cases_chunks = 0;
@@ -73,12 +74,13 @@ struct uw_ctx {
     // chunk-level scan (staged / large-chunk paths): per-tile totals + epoch flags, see k_scan_chunks
     ScanPart* d_scan_part = nullptr; uint32_t* d_scan_flag = nullptr; ScanCtl* d_scan_ctl = nullptr;
     uint32_t scan_tiles_cap = 0, scan_epoch = 0;
-    typedef void (*big_emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*, uint32_t*);
-    typedef void (*big_emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uint32_t*);
+    typedef void (*big_emit16_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint16_t*, uint32_t*, const uint2*);
+    typedef void (*big_emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uint32_t*, const uint2*);
+    typedef void (*big_count_fn_t)(DevCfg, const McTables*, const float*, uint32_t, ChunkCounts*, uint2*);
     typedef void (*classify_fn_t)(DevCfg, const McTables*, const float*, uint32_t, ChunkCounts*);
     big_emit16_fn_t big_emit16_fn = nullptr;
     big_emit32_fn_t big_emit32_fn = nullptr;
-    classify_fn_t big_count_fn = nullptr;
+    big_count_fn_t big_count_fn = nullptr;
     classify_fn_t classify_fn = nullptr;     // compile-time-sized classify (internal_size 12 / 10)
     int classify_spec_threads = 0, classify_spec_blocks_per_sm = 1;
     cudaStream_t copy_stream = nullptr;
@@ -300,7 +302,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_axis); cudaFree(c->d_totals); cudaFree(c->d_guard); cudaFree(c->d_ctl);
     cudaFree(c->d_scan_part); cudaFree(c->d_scan_flag); cudaFree(c->d_scan_ctl);
     for (auto& b : c->sets) {
-        cudaFree(b.d_pos); cudaFree(b.d_dens); cudaFree(b.d_counts); cudaFree(b.d_descs); cudaFree(b.d_active);
+        cudaFree(b.d_pos); cudaFree(b.d_dens); cudaFree(b.d_counts); cudaFree(b.d_quarters); cudaFree(b.d_descs); cudaFree(b.d_active);
         cudaFree(b.d_cases); cudaFree(b.d_verts); cudaFree(b.d_inds); cudaFree(b.d_tris); cudaFree(b.d_tri_cell);
         cudaFree(b.d_scan); cudaFree(b.d_defer);
         if (b.h_pos) cudaFreeHost(b.h_pos);
@@ -522,6 +524,7 @@ static uw_status ensure_chunks(uw_ctx* c, uint32_t n) {
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, regrow(&c->B().d_pos, (size_t)cap * 3));
     CU_TRY(c, regrow(&c->B().d_counts, cap));
+    if (c->big_path) CU_TRY(c, regrow(&c->B().d_quarters, (size_t)cap * 4));
     CU_TRY(c, regrow(&c->B().d_descs, cap));
     CU_TRY(c, regrow(&c->B().d_active, cap));
     CU_TRY(c, regrow(&c->B().d_scan, cap));
@@ -637,7 +640,7 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
     if (c->big_path) {
         const int grid = persistent_grid(c, n, c->big_blocks_per_sm);
         if (!only_emit) {
-            c->big_count_fn<<<persistent_grid(c, n, c->big_count_blocks_per_sm), UW_BIG_NT, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts);
+            c->big_count_fn<<<persistent_grid(c, n, c->big_count_blocks_per_sm), UW_BIG_NT, 0, c->stream>>>(d, c->d_mc, c->B().d_dens, n, c->B().d_counts, c->B().d_quarters);
             c->launches++;
             CU_TRY(c, cudaGetLastError());
             if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
@@ -646,10 +649,10 @@ static uw_status launch_extract(uw_ctx* c, const int32_t* d_pos, uint32_t n, uin
         if (c->profiling && !only_emit) CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
         if (c->index32)
             c->big_emit32_fn<<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
-                                                                             c->d_totals, c->B().d_verts, (uint32_t*)c->B().d_inds, &c->d_scan_ctl->emit_ticket);
+                                                                             c->d_totals, c->B().d_verts, (uint32_t*)c->B().d_inds, &c->d_scan_ctl->emit_ticket, c->B().d_quarters);
         else
             c->big_emit16_fn<<<grid, UW_BIG_NT, c->big_smem, c->stream>>>(d, c->d_mc, c->B().d_dens, c->B().d_descs, c->B().d_active,
-                                                                             c->d_totals, c->B().d_verts, (uint16_t*)c->B().d_inds, &c->d_scan_ctl->emit_ticket);
+                                                                             c->d_totals, c->B().d_verts, (uint16_t*)c->B().d_inds, &c->d_scan_ctl->emit_ticket, c->B().d_quarters);
         c->launches++;
         CU_TRY(c, cudaGetLastError());
         return UW_OK;

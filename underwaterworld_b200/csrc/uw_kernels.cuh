@@ -407,9 +407,11 @@ struct BatchTotals {
     unsigned long long n_verts, n_inds;
     uint32_t n_active, overflow, n_blank, n_mesh;
 };
+#define UW_NCLS 8                    // hand-out classes: 0 = expected heaviest z layer ... UW_NCLS - 1 = provably trivial
 struct FusedControl {
     uint32_t ticket, done;
-    uint32_t defer_n, prim_done;     // heavy-first hand-out: deferred (provably trivial) chunks, primaries decided
+    uint32_t classified, cls_ticket; // cost-ordered hand-out: chunks filed into their class list so far, filing work claimed
+    uint32_t cls_n[UW_NCLS];         // entries per class list
     unsigned long long alloc;        // n_verts << 32 | n_inds (completion-order packing)
     unsigned long long guard;        // f64 guard-band re-evaluations
     BatchTotals totals;
@@ -422,13 +424,27 @@ struct FusedSummary {
     BatchTotals totals;
 };
 
-// Chunk hand-out for the persistent kernel (executed by ONE thread).  Tickets 0..n-1 walk the request
-// list; a chunk whose z layer provably holds no surface (z outside [z_lo, z_hi]: blank or solid whatever the
-// noise does, |noise| <= 1) is several times cheaper than a surface chunk, so it is parked in `defer_list`
-// and handed out by tickets >= n, after every potentially expensive chunk has been started.  With only ~3.5
-// chunks per CTA this trims the tail of the kernel; results do not depend on the order.
+// Chunk hand-out for the persistent kernel.
+//
+// Request order (order == nullptr): tickets 0..n-1 walk the request list.
+//
+// Cost order (order != nullptr; used when a CTA gets only a few chunks, so the tail decides the run time): a
+// chunk's cost is set by how much surface it holds, and that is mostly a function of its z layer -- iso =
+// terrace(z) + noise -- so the host ranks the layers by the likelihood of surface (class 0 = heaviest; layers
+// that provably hold none, |noise| <= 1, are the last class).  Every CTA first files a few chunks of the request
+// into per-class lists (order[class][slot] = chunk index + position); tickets then walk class 0, class 1, ...:
+// the expensive chunks all start in the first wave and the cheap ones fill the gaps at the end.  Results do not
+// depend on the order.
 struct Ticket { uint32_t chunk; int px, py, pz; };
 #define TICKET_DONE 0xFFFFFFFFu
+
+struct Handout {
+    FusedControl* ctr; const int32_t* pos; uint32_t n;
+    uint4* order;                      // [UW_NCLS][n] or nullptr
+    uint32_t* state;                   // shared memory, UW_NCLS + 1 words: class-list prefix sums once known, [UW_NCLS] = ready
+    int z_lo, z_hi; unsigned long long zcls;   // class of layer z_lo + i in bits 4i..4i+3
+    uw_chunk_desc* skip;               // UW_FLAG_ANALYTIC_SKIP: provably trivial chunks are answered without being handed out
+};
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
@@ -436,51 +452,77 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     return v;
 }
 
-// skip_descs != nullptr (UW_FLAG_ANALYTIC_SKIP): a provably trivial chunk is answered right here -- blank-early
-// above the surface layers, solid (no mesh) below -- and never handed out.
-__device__ __noinline__ Ticket take_ticket(FusedControl* ctr, const int32_t* __restrict__ pos, uint32_t n,
-                                           uint32_t* defer_list, int z_lo, int z_hi, uw_chunk_desc* skip_descs = nullptr) {
+__device__ __forceinline__ bool answer_trivial(const Handout& h, uint32_t c, int px, int py, int pz) {
+    if (!h.skip || (pz >= h.z_lo && pz <= h.z_hi)) return false;
+    uw_chunk_desc d;
+    d.pos[0] = px; d.pos[1] = py; d.pos[2] = pz;
+    d.flags = pz > h.z_hi ? UW_CHUNK_BLANK_EARLY : 0u;      // blank-early above the surface layers, solid (no mesh) below
+    d.vert_offset = 0; d.vert_count = 0; d.index_offset = 0; d.index_count = 0;
+    h.skip[c] = d;
+    if (pz > h.z_hi) atomicAdd(&h.ctr->totals.n_blank, 1u);
+    return true;
+}
+
+// cost order, step 1 (all threads of a CTA, before its first ticket): file the request into the class lists.
+// Filing work is itself claimed by ticket (blockDim chunks at a time), so the lists are completed by whichever
+// CTAs are running -- the wait in take_ticket never depends on a CTA that has not been scheduled yet.
+__device__ __forceinline__ void handout_classify(const Handout& h) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        if (threadIdx.x == 0) h.state[0] = atomicAdd(&h.ctr->cls_ticket, blockDim.x);
+        __syncthreads();
+        const uint32_t c0 = h.state[0];
+        __syncthreads();
+        if (c0 >= h.n) break;
+        const uint32_t c = c0 + threadIdx.x;
+        int px = 0, py = 0, pz = 0;
+        bool valid = c < h.n;
+        if (valid) { px = h.pos[3 * c]; py = h.pos[3 * c + 1]; pz = h.pos[3 * c + 2]; }
+        if (valid && answer_trivial(h, c, px, py, pz)) valid = false;
+        const int dz = pz - h.z_lo;
+        const uint32_t cls = (pz < h.z_lo || pz > h.z_hi) ? UW_NCLS - 1 : dz < 16 ? (uint32_t)((h.zcls >> (4 * dz)) & 15ull) : UW_NCLS - 2;
+        const uint32_t act = __ballot_sync(0xFFFFFFFFu, valid);
+        if (valid) {                                       // one atomic per (warp, class)
+            const uint32_t peers = __match_any_sync(act, cls);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&h.ctr->cls_n[cls], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint32_t slot = base + __popc(peers & ((1u << lane) - 1u));
+            h.order[(size_t)cls * h.n + slot] = make_uint4(c, (uint32_t)px, (uint32_t)py, (uint32_t)pz);
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(&h.ctr->classified, min((uint32_t)blockDim.x, h.n - c0));
+    }
+}
+
+// executed by ONE thread
+__device__ __noinline__ Ticket take_ticket(const Handout& h) {
     Ticket tk;
     tk.chunk = TICKET_DONE; tk.px = tk.py = tk.pz = 0;
-    const bool defer_on = defer_list != nullptr;
+    if (h.order) {
+        const uint32_t t = atomicAdd(&h.ctr->ticket, 1u);
+        if (!h.state[UW_NCLS]) {                       // first ticket of this CTA: wait for the lists, keep their prefix sums
+            while (ld_volatile_u32(&h.ctr->classified) < h.n) { }
+            __threadfence();
+            uint32_t run = 0;
+            for (int k = 0; k < UW_NCLS; ++k) { run += ld_volatile_u32(&h.ctr->cls_n[k]); h.state[k] = run; }
+            h.state[UW_NCLS] = 1u;
+        }
+        if (t >= h.state[UW_NCLS - 1]) return tk;
+        int cls = 0;
+        while (t >= h.state[cls]) ++cls;
+        const uint32_t before = cls ? h.state[cls - 1] : 0u;
+        const uint4 e = __ldcg(&h.order[(size_t)cls * h.n + (t - before)]);
+        tk.chunk = e.x; tk.px = (int)e.y; tk.py = (int)e.z; tk.pz = (int)e.w;
+        return tk;
+    }
     while (true) {
-        const uint32_t t = atomicAdd(&ctr->ticket, 1u);
-        uint32_t c;
-        if (t < n) {
-            c = t;
-            tk.px = pos[3 * c]; tk.py = pos[3 * c + 1]; tk.pz = pos[3 * c + 2];
-            if (skip_descs && (tk.pz < z_lo || tk.pz > z_hi)) {
-                uw_chunk_desc d;
-                d.pos[0] = tk.px; d.pos[1] = tk.py; d.pos[2] = tk.pz;
-                d.flags = tk.pz > z_hi ? UW_CHUNK_BLANK_EARLY : 0u;
-                d.vert_offset = 0; d.vert_count = 0; d.index_offset = 0; d.index_count = 0;
-                skip_descs[c] = d;
-                if (tk.pz > z_hi) atomicAdd(&ctr->totals.n_blank, 1u);
-                if (defer_on) atomicAdd(&ctr->prim_done, 1u);
-                continue;
-            }
-            if (defer_on && (tk.pz < z_lo || tk.pz > z_hi)) {
-                const uint32_t slot = atomicAdd(&ctr->defer_n, 1u);
-                atomicExch(&defer_list[slot], c + 1u);
-                __threadfence();
-                atomicAdd(&ctr->prim_done, 1u);
-                continue;
-            }
-            if (defer_on) atomicAdd(&ctr->prim_done, 1u);
-            tk.chunk = c;
-            return tk;
-        }
-        if (!defer_on || t - n >= n) return tk;
-        const uint32_t idx = t - n;
-        uint32_t e;
-        while (true) {
-            e = ld_volatile_u32(&defer_list[idx]);
-            if (e) break;
-            if (ld_volatile_u32(&ctr->prim_done) >= n) { e = ld_volatile_u32(&defer_list[idx]); break; }
-        }
-        if (!e) return tk;                       // every primary is decided and this slot was never filled: no work left
-        c = e - 1u;
-        tk.px = pos[3 * c]; tk.py = pos[3 * c + 1]; tk.pz = pos[3 * c + 2];
+        const uint32_t c = atomicAdd(&h.ctr->ticket, 1u);
+        if (c >= h.n) return tk;
+        tk.px = h.pos[3 * c]; tk.py = h.pos[3 * c + 1]; tk.pz = h.pos[3 * c + 2];
+        if (answer_trivial(h, c, tk.px, tk.py, tk.pz)) continue;
         tk.chunk = c;
         return tk;
     }
@@ -547,10 +589,7 @@ struct SpecSmem {
 template <int ST, int NOCT>
 __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const AxisTables& tab, SpecSmem<ST, NOCT>& sm,
                                                      int px, int py, int pz, unsigned long long* guard_count PHASE_ARG,
-                                                     FusedControl* tk_ctr = nullptr, Ticket* tk_out = nullptr,
-                                                     const int32_t* tk_pos = nullptr, uint32_t tk_n = 0,
-                                                     uint32_t* tk_defer = nullptr, int tk_zlo = 0, int tk_zhi = 0,
-                                                     uw_chunk_desc* tk_skip = nullptr) {
+                                                     const Handout* hand = nullptr, Ticket* tk_out = nullptr) {
     using D = SpecDims<ST, NOCT>;
     constexpr int L = D::L;
     const int tid = threadIdx.x;
@@ -603,7 +642,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     // the z-column stage instead of stalling the whole CTA at the top of the next iteration
     // (the LAST thread does it: its warp has idle lanes in the column stage, and divergent paths of a warp
     // interleave, so the global round trips overlap that warp's own work too)
-    if (tk_ctr && tid == NT - 1) *tk_out = take_ticket(tk_ctr, tk_pos, tk_n, tk_defer, tk_zlo, tk_zhi, tk_skip);
+    if (hand && tid == NT - 1) *tk_out = take_ticket(*hand);
 
     // ---- stage YZ -------------------------------------------------------------------------------
     if (tid < L * L) {
@@ -2119,6 +2158,7 @@ struct FusedSmem {
     uint32_t w[64];
     unsigned long long part[4 * 8];
     int cur[4];                                       // current ticket: chunk index, chunk position
+    uint32_t hand[UW_NCLS + 1];                       // cost-ordered hand-out: class-list prefix sums, ready flag
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -2184,8 +2224,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
               unsigned long long vcap, unsigned long long icap,
               float* __restrict__ dens_out /*nullable: debug tap*/, int ordered,
               uw_tri* __restrict__ tris /*nullable: UW_FLAG_TRIS*/, uint16_t* __restrict__ tri_cell /*nullable*/,
-              uint32_t* __restrict__ defer_list /*nullable: heavy-first hand-out*/, int z_lo, int z_hi, int analytic_skip,
-              FusedSummary* __restrict__ sum_out) {
+              uint4* __restrict__ order /*nullable: cost-ordered hand-out, [UW_NCLS][n]*/, int z_lo, int z_hi,
+              unsigned long long zcls, int analytic_skip, FusedSummary* __restrict__ sum_out) {
     using D = SpecDims<ST, NOCT>;
     BatchTotals* const totals = &ctr->totals;
     unsigned long long* const guard_count = &ctr->guard;
@@ -2219,9 +2259,15 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // first ticket; later ones are requested inside K1 (see noise_chunk_spec) and published at the end of
     // the iteration, so chunks are still handed out on demand (committing a whole chunk ahead was measured
     // slower: with ~3.5 chunks per CTA the tail grows by up to one chunk)
-    uw_chunk_desc* const skip_descs = (analytic_skip && !ordered && z_hi >= z_lo) ? descs : nullptr;
+    Handout hand;
+    hand.ctr = ctr; hand.pos = pos; hand.n = n; hand.order = order; hand.state = sm.hand;
+    hand.z_lo = z_lo; hand.z_hi = z_hi; hand.zcls = zcls;
+    hand.skip = (analytic_skip && !ordered && z_hi >= z_lo) ? descs : nullptr;
+    if (tid == 0) sm.hand[UW_NCLS] = 0u;
+    if (order) handout_classify(hand);
+    __syncthreads();
     if (tid == D::NT - 1) {
-        const Ticket t0 = take_ticket(ctr, pos, n, defer_list, z_lo, z_hi, skip_descs);
+        const Ticket t0 = take_ticket(hand);
         sm.cur[0] = (int)t0.chunk; sm.cur[1] = t0.px; sm.cur[2] = t0.py; sm.cur[3] = t0.pz;
     }
     __syncthreads();
@@ -2239,7 +2285,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
 
         // ---- K1 ---------------------------------------------------------------------------------
         const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS,
-                                                       ctr, &nxt, pos, n, defer_list, z_lo, z_hi, skip_descs);
+                                                       &hand, &nxt);
         PHASE_MARK(1);                                     // K1 noise
         if (dens_out) {
             float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);
@@ -2317,7 +2363,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
                         if (blockIdx.x < 1024) { g_cta[blockIdx.x][1] = gtimer(); g_cta[blockIdx.x][2] += 1; g_cta[blockIdx.x][3] += (ni > 0); } }
 #endif
     }
-    // last CTA out resets the other control block (and the used part of the defer list) for the next launch
+    // last CTA out resets the other control block for the next launch
     __syncthreads();                                       // every thread has seen TICKET_DONE in sm.cur[0]
     if (tid == 0) {
         __threadfence();
@@ -2325,10 +2371,6 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     }
     __syncthreads();
     if (sm.cur[0]) {
-        if (defer_list) {
-            const uint32_t used = ld_volatile_u32(&ctr->defer_n);
-            for (uint32_t i = tid; i < used; i += D::NT) defer_list[i] = 0u;
-        }
         if (tid == 0) {
             FusedSummary sm_out;                     // every other CTA fenced its writes before bumping `done`
             sm_out.alloc = atomicAdd(&ctr->alloc, 0ull);
@@ -2340,7 +2382,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             sm_out.totals.n_blank = atomicAdd(&ctr->totals.n_blank, 0u);
             sm_out.totals.n_mesh = 0;
             *sum_out = sm_out;                       // host-mapped memory: visible to the host at kernel completion
-            ctr_next->ticket = 0; ctr_next->done = 0; ctr_next->defer_n = 0; ctr_next->prim_done = 0;
+            ctr_next->ticket = 0; ctr_next->done = 0; ctr_next->classified = 0; ctr_next->cls_ticket = 0;
+            for (int k = 0; k < UW_NCLS; ++k) ctr_next->cls_n[k] = 0;
             ctr_next->alloc = 0; ctr_next->guard = 0;
             BatchTotals z; z.n_verts = 0; z.n_inds = 0; z.n_active = 0; z.overflow = 0; z.n_blank = 0; z.n_mesh = 0;
             ctr_next->totals = z;

@@ -8,6 +8,8 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <utility>
 
 #include "uw_kernels.cuh"
 
@@ -50,7 +52,7 @@ struct uw_ctx {
         uint32_t* d_active = nullptr;
         uint8_t* d_cases = nullptr;  uint32_t cap_cases_chunks = 0;
         ScanSlot* d_scan = nullptr;
-        uint32_t* d_defer = nullptr;    // deferred-chunk list of the fused kernel (kept zeroed between launches)
+        uint4* d_order = nullptr;       // cost-ordered hand-out lists of the fused kernel, [UW_NCLS][order_cap]
         unsigned long long vcap = 0, icap = 0;
         uw_vert* d_verts = nullptr;
         void* d_inds = nullptr;
@@ -96,14 +98,16 @@ struct uw_ctx {
     typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uw_tri*, uint16_t*);
     typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint16_t*, unsigned long long,
-                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int, int, FusedSummary*);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint4*, int, int, unsigned long long, int, FusedSummary*);
     typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint32_t*, unsigned long long,
-                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint32_t*, int, int, int, FusedSummary*);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint4*, int, int, unsigned long long, int, FusedSummary*);
     fused16_fn_t fused16_fn = nullptr;
     fused32_fn_t fused32_fn = nullptr;
     bool use_fused = false;
-    int z_lo = 1, z_hi = 0;         // chunk z layers that can hold surface (empty range = unknown: no deferral)
+    int z_lo = 1, z_hi = 0;         // chunk z layers that can hold surface (empty range = unknown: request-order hand-out)
+    unsigned long long zcls = 0;    // hand-out class of layer z_lo + i in bits 4i..4i+3 (0 = most likely to hold surface)
+    size_t order_cap = 0;           // largest batch that is handed out in cost order
     bool big_path = false;          // internal_size > 15: slab-walking extraction, densities in HBM
     size_t big_smem = 0; int big_blocks_per_sm = 1, big_count_blocks_per_sm = 1;
     bool ordered = false;           // packed arenas follow request order (look-back) vs atomic bump allocation
@@ -254,6 +258,30 @@ static uw_status setup_tables(uw_ctx* c) {
             if (!blank_certain && !solid_certain) { if (!found) { lo = pz; found = true; } hi = pz; }
         }
         if (found && lo > -4096 && hi < 4096) { c->z_lo = lo; c->z_hi = hi; } else { c->z_lo = 1; c->z_hi = 0; }
+        // Rank those layers by how likely they are to hold surface: the noise term is roughly N(0, 0.25), so a
+        // lattice level z contributes exp(-((iso - terrace(z)) / 0.25)^2 / 2).  Scheduling only (take_ticket).
+        c->zcls = 0;
+        const int nl = c->z_hi - c->z_lo + 1;
+        if (nl > 0) {
+            std::vector<std::pair<double, int>> w;
+            for (int pz = c->z_lo; pz <= c->z_hi && pz < c->z_lo + 16; ++pz) {
+                double acc = 0.0;
+                for (int k = 0; k < d.L; ++k) {
+                    const double local = (double)k * (double)d.size_scale;
+                    const float zf = (float)((local + (double)(pz * cf.chunk_size)) / (double)cf.chunk_size);
+                    const float adj = (zf * (float)cf.chunk_size) / cf.max_height;
+                    const float t = adj - fmodf(adj, cf.adj_z_mod);
+                    const double u = ((double)cf.iso_level - (double)t) / 0.25;
+                    acc += exp(-0.5 * u * u);
+                }
+                w.push_back({-acc, pz - c->z_lo});
+            }
+            std::sort(w.begin(), w.end());
+            for (size_t r = 0; r < w.size(); ++r) {
+                const unsigned long long cls = r < (size_t)(UW_NCLS - 2) ? r : (size_t)(UW_NCLS - 2);
+                c->zcls |= cls << (4 * w[r].second);
+            }
+        }
     }
     return UW_OK;
 }
@@ -304,7 +332,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     for (auto& b : c->sets) {
         cudaFree(b.d_pos); cudaFree(b.d_dens); cudaFree(b.d_counts); cudaFree(b.d_quarters); cudaFree(b.d_descs); cudaFree(b.d_active);
         cudaFree(b.d_cases); cudaFree(b.d_verts); cudaFree(b.d_inds); cudaFree(b.d_tris); cudaFree(b.d_tri_cell);
-        cudaFree(b.d_scan); cudaFree(b.d_defer);
+        cudaFree(b.d_scan); cudaFree(b.d_order);
         if (b.h_pos) cudaFreeHost(b.h_pos);
         if (b.h_sum) cudaFreeHost(b.h_sum);
         if (b.done) cudaEventDestroy(b.done);
@@ -471,6 +499,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         int nb = 1;
         if (c->fused16_fn && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->fused16_fn, c->noise_threads, c->fused_smem) == cudaSuccess && nb > 0)
             c->fused_blocks_per_sm = nb;
+        c->order_cap = (size_t)16 * c->num_sms * c->fused_blocks_per_sm;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->noise_fn, c->noise_threads, c->noise_smem) == cudaSuccess && nb > 0)
             c->noise_blocks_per_sm = nb;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->emit16_fn, 256, c->emit_smem) == cudaSuccess && nb > 0)
@@ -528,8 +557,8 @@ static uw_status ensure_chunks(uw_ctx* c, uint32_t n) {
     CU_TRY(c, regrow(&c->B().d_descs, cap));
     CU_TRY(c, regrow(&c->B().d_active, cap));
     CU_TRY(c, regrow(&c->B().d_scan, cap));
-    CU_TRY(c, regrow(&c->B().d_defer, cap));
-    CU_TRY(c, cudaMemset(c->B().d_defer, 0, (size_t)cap * sizeof(uint32_t)));
+    if (c->use_fused && !c->B().d_order)
+        CU_TRY(c, cudaMalloc(&c->B().d_order, (size_t)UW_NCLS * c->order_cap * sizeof(uint4)));
     if (c->tris) CU_TRY(c, regrow(&c->B().d_tri_cell, (size_t)cap * ((size_t)c->dcfg.S * c->dcfg.S * c->dcfg.S + 1)));
     c->B().cap_chunks = cap;
     return UW_OK;
@@ -689,13 +718,13 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     const int grid = persistent_grid(c, n, c->fused_blocks_per_sm);
     // heavy-first hand-out (scheduling only): provably trivial z layers are deferred inside the kernel; the
     // ordered-packing mode needs tickets == request order.  Only worth it when CTAs get just a few chunks each.
-    uint32_t* d_defer = (!c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= 16u * (uint32_t)grid) ? c->B().d_defer : nullptr;
+    uint4* d_order = (!c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= c->order_cap) ? c->B().d_order : nullptr;
     if (c->index32)
         c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
-            c->B().d_descs, c->B().d_verts, (uint32_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_defer, c->z_lo, c->z_hi, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
+            c->B().d_descs, c->B().d_verts, (uint32_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
     else
         c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
-            c->B().d_descs, c->B().d_verts, (uint16_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_defer, c->z_lo, c->z_hi, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
+            c->B().d_descs, c->B().d_verts, (uint16_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;

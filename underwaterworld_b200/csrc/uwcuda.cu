@@ -987,8 +987,8 @@ extern "C" uw_status uw_build_device(uw_ctx* c, const int32_t* d_pos, uint32_t n
 extern "C" uw_status uw_sync(uw_ctx* c) {
     if (!c) return UW_ERR_INVALID;
     CU_TRY(c, cudaSetDevice(c->device));
-    if (c->B().pending) return finish_build(c);
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->B().pending) { uw_status st = finish_build(c); if (st != UW_OK) return st; }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));      // also covers whatever the caller put on the stream after the build
     return UW_OK;
 }
 

@@ -18,3 +18,19 @@ with uw.ChunkBuilder(uw.Perlin(0), internal_size=64) as b:
 with uw.ChunkBuilder(uw.Perlin(0), internal_size=20) as b:
     print("S=20", b.build(pos[30:36]).n_inds)
 print("done")
+# paths that need larger batches: cost-ordered hand-out (n > resident CTAs), multi-tile chunk scan (n > 1024),
+# staged S=10 (k_classify_spec<10>), and two host batches in flight
+big = uw.region.box_region((-6, 6), (-6, 6), (-4, 4))       # 1152 chunks
+with uw.ChunkBuilder(uw.Perlin(0)) as b, uw.ChunkBuilder(uw.Perlin(0), staged=True) as s, uw.ChunkBuilder(uw.Perlin(0), ordered=True) as o:
+    fb, sb, ob = b.build(big), s.build(big), o.build(big)
+    same = all(fb.chunk(i).inds.tobytes() == sb.chunk(i).inds.tobytes() == ob.chunk(i).inds.tobytes()
+               and fb.chunk(i).verts.tobytes() == sb.chunk(i).verts.tobytes() for i in range(len(big)))
+    print("1152 chunks: fused(cost order) / staged(2 scan tiles) / ordered identical per chunk:", same, fb.n_inds)
+    h0 = b.build_async(big[:600]); h1 = b.build_async(big[600:])
+    a0 = b.wait(h0); a1 = b.wait(h1)
+    print("two batches in flight:", a0.n_inds + a1.n_inds == fb.n_inds)
+with uw.ChunkBuilder(uw.Perlin(0), internal_size=10, staged=True) as s10, uw.ChunkBuilder(uw.Perlin(0), internal_size=10) as f10:
+    print("S=10 staged == fused:", s10.build(pos).n_inds == f10.build(pos).n_inds)
+with uw.ChunkBuilder(uw.Perlin(0), analytic_skip=True) as b:
+    print("analytic skip, cost order:", b.build(big).n_inds == fb.n_inds)
+print("done 2")

@@ -2159,6 +2159,7 @@ struct FusedSmem {
     unsigned long long part[4 * 8];
     int cur[4];                                       // current ticket: chunk index, chunk position
     uint32_t hand[UW_NCLS + 1];                       // cost-ordered hand-out: class-list prefix sums, ready flag
+    Handout handout;
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -2259,11 +2260,16 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // first ticket; later ones are requested inside K1 (see noise_chunk_spec) and published at the end of
     // the iteration, so chunks are still handed out on demand (committing a whole chunk ahead was measured
     // slower: with ~3.5 chunks per CTA the tail grows by up to one chunk)
-    Handout hand;
-    hand.ctr = ctr; hand.pos = pos; hand.n = n; hand.order = order; hand.state = sm.hand;
-    hand.z_lo = z_lo; hand.z_hi = z_hi; hand.zcls = zcls;
-    hand.skip = (analytic_skip && !ordered && z_hi >= z_lo) ? descs : nullptr;
-    if (tid == 0) sm.hand[UW_NCLS] = 0u;
+    // hand-out parameters live in shared memory: the ticket code runs in ONE thread, deep inside K1, and must not
+    // cost the other phases any registers
+    Handout& hand = sm.handout;
+    if (tid == 0) {
+        hand.ctr = ctr; hand.pos = pos; hand.n = n; hand.order = order; hand.state = sm.hand;
+        hand.z_lo = z_lo; hand.z_hi = z_hi; hand.zcls = zcls;
+        hand.skip = (analytic_skip && !ordered && z_hi >= z_lo) ? descs : nullptr;
+        sm.hand[UW_NCLS] = 0u;
+    }
+    __syncthreads();
     if (order) handout_classify(hand);
     __syncthreads();
     if (tid == D::NT - 1) {

@@ -12,7 +12,8 @@
 //   Chunk::verts_buffer_slice()          src/chunk.rs:346   -> chunk.verts_buffer_slice()
 //   Chunk::inds_buffer_slice()           src/chunk.rs:347   -> chunk.inds_buffer_slice()
 //   Chunk::num_inds()                    src/chunk.rs:348   -> chunk.num_inds()
-//   World::build_full_step (one chunk)   src/world.rs:113   -> uw::build_chunks(builder, positions) (a batch)
+//   World::build_full_step (one chunk)   src/world.rs:113   -> uw::build_chunks(builder, positions) (a batch),
+//                                                            uw::build_chunks_pipelined (a stream of batches)
 //
 // Link with -luwcuda.  No CPU fallback: constructing a ChunkBuilder without a CUDA device throws.
 #pragma once
@@ -156,6 +157,38 @@ inline std::vector<Chunk> build_chunks(const ChunkBuilder& b, const std::vector<
     }
     uw_batch_free(batch);
     return out;
+}
+
+// Streaming variant for a loader that hands over many batches: batch k+1 is submitted (uw_build_async) before
+// batch k is collected (uw_batch_wait), so k's copy to the host overlaps k+1's kernel.  `sink(k, chunks)` is called
+// in batch order.
+template <class Sink>
+inline void build_chunks_pipelined(const ChunkBuilder& b, const std::vector<std::vector<std::array<int32_t, 3>>>& batches, Sink sink) {
+    auto submit = [&](const std::vector<std::array<int32_t, 3>>& pos) {
+        uw_batch* h = nullptr;
+        b.check(uw_build_async(b.ctx(), pos.empty() ? nullptr : pos[0].data(), (uint32_t)pos.size(), &h), "uw_build_async");
+        return h;
+    };
+    auto collect = [&](size_t k, uw_batch* h) {
+        struct Guard { uw_batch* h; ~Guard() { uw_batch_free(h); } } guard{h};
+        b.check(uw_batch_wait(h), "uw_batch_wait");
+        std::vector<Chunk> out;
+        out.reserve(batches[k].size());
+        for (uint32_t i = 0; i < batches[k].size(); ++i) {
+            out.emplace_back(batches[k][i]);
+            out.back().adopt(b, h, i);
+        }
+        sink(k, std::move(out));
+    };
+    if (batches.empty()) return;
+    uw_batch* prev = submit(batches[0]);
+    for (size_t k = 1; k < batches.size(); ++k) {
+        uw_batch* next = nullptr;
+        try { next = submit(batches[k]); } catch (...) { uw_batch_free(prev); throw; }
+        try { collect(k - 1, prev); } catch (...) { uw_batch_free(next); throw; }
+        prev = next;
+    }
+    collect(batches.size() - 1, prev);
 }
 
 }  // namespace uw

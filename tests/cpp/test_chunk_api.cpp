@@ -37,6 +37,23 @@ int main(int argc, char** argv) {
             if (c.num_inds() != batch[i].num_inds() || c.not_blank() != batch[i].not_blank()) { printf("BATCH MISMATCH %zu\n", i); return 4; }
             if (c.not_blank() && memcmp(c.inds_buffer_slice().data(), batch[i].inds_buffer_slice().data(), c.num_inds() * 2)) return 5;
         }
+        // ... and as a stream of batches with two in flight
+        {
+            std::vector<std::vector<std::array<int32_t, 3>>> stream;
+            for (int k = 0; k < 4; ++k) stream.push_back({positions[k], positions[(k + 1) % positions.size()], {k, -k, -1}});
+            size_t seen = 0, bad = 0;
+            uw::build_chunks_pipelined(builder, stream, [&](size_t k, std::vector<uw::Chunk> chunks) {
+                if (k != seen++) ++bad;
+                for (size_t i = 0; i < chunks.size(); ++i) {
+                    uw::Chunk c(stream[k][i]);
+                    c.build_full(builder);
+                    if (c.num_inds() != chunks[i].num_inds()) ++bad;
+                    else if (c.not_blank() && memcmp(c.inds_buffer_slice().data(), chunks[i].inds_buffer_slice().data(), c.num_inds() * 2)) ++bad;
+                }
+            });
+            printf("pipelined batches=%zu bad=%zu\n", seen, bad);
+            if (seen != stream.size() || bad) return 6;
+        }
         // the reference panics when slicing a blank chunk's buffers (chunk.rs:346): here it throws
         uw::Chunk blank({0, 0, 5});
         blank.build_full(builder);

@@ -347,6 +347,9 @@ def run_ours(args):
     staged = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local, staged=True)
     acc = stage_profile(staged)                              # the same stages as four kernels, for attribution
     staged.close()
+    skipper = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local, analytic_skip=True)
+    skip_ms = stage_profile(skipper)["total_ms"]             # reported beside the headline, never as the headline
+    skipper.close()
     hb = builder.build(pos)                                  # host path once, for the mesh statistics
     n_active = int((hb.descs["index_count"] > 0).sum())
     n_blank = int((hb.descs["flags"] & 1).sum())
@@ -483,6 +486,11 @@ def run_ours(args):
             "kernels_per_step": ["k_build_fused"],
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "analytic_skip_variant": {
+                "ms_per_step": skip_ms, "chunks_per_s": n / (skip_ms / 1e3) if skip_ms > 0 else None,
+                "note": "UW_FLAG_ANALYTIC_SKIP (off by default, NOT the headline): z layers that provably hold no surface "
+                        "(|noise| <= 1) are answered without evaluating the noise; outputs identical (tests), "
+                        "but their samples are not evaluated, so no noise FLOPs may be credited for them"},
             "north_star": north_star,
             "clocks": sampler.summary(),
             "mesh": {"n_verts": n_verts, "n_inds": n_inds, "chunks_with_mesh": n_active, "chunks_blank_early": n_blank,

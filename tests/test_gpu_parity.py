@@ -398,6 +398,70 @@ def test_large_batch_properties(uw, builder12):
     np.testing.assert_allclose(batch.verts["pos"], exact.verts["pos"], rtol=0, atol=5e-2)
 
 
+def test_config3_full_region_invariants_on_device(uw):
+    """BASELINE config 3 at full size (524 288 chunks, one launch, outputs stay in HBM): size-independent
+    properties checked with torch on the device -- arena packing is a partition, every index addresses a vertex
+    of its own chunk, every vertex is referenced and lies inside its chunk, provably blank / solid layers end the
+    way the reference ends them, two runs (different completion orders) agree chunk by chunk, and the
+    analytic-skip variant produces the same descriptors and the same per-chunk content."""
+    import torch
+    from underwaterworld_b200.gather import device_batch_tensors
+    pos = uw.region.config_positions("large")
+    assert len(pos) == 524288
+    d_pos = torch.from_numpy(pos).cuda()
+
+    def run(builder):
+        builder.build_device(d_pos.data_ptr(), len(pos))
+        builder.sync()
+        descs, verts, inds = device_batch_tensors(builder)
+        d = descs.view(torch.int32).reshape(-1, 8).to(torch.int64)
+        vo, vc, io, ic = d[:, 4], d[:, 5], d[:, 6], d[:, 7]
+        flags = d[:, 3]
+        nv, ni = verts.numel() // 24, inds.numel() // 2
+        assert int(vc.sum()) == nv and int(ic.sum()) == ni and bool((ic % 3 == 0).all())
+        assert bool(((flags & 2) != 0).eq(ic > 0).all())
+        act = torch.nonzero(ic > 0).flatten()
+        order = act[torch.argsort(vo[act])]
+        # the packed arenas are partitioned by the surface chunks' ranges (completion order)
+        assert int(vo[order[0]]) == 0 and bool((vo[order][1:] == (vo[order] + vc[order])[:-1]).all())
+        iorder = act[torch.argsort(io[act])]
+        assert int(io[iorder[0]]) == 0 and bool((io[iorder][1:] == (io[iorder] + ic[iorder])[:-1]).all())
+        # per index: owner chunk (by arena order), local range check, vertex usage
+        i_owner = torch.repeat_interleave(iorder, ic[iorder])
+        idx = inds.view(torch.int16).to(torch.int64) & 0xFFFF
+        assert bool((idx < vc[i_owner]).all())
+        used = torch.zeros(nv, dtype=torch.bool, device="cuda")
+        used[idx + vo[i_owner]] = True
+        assert bool(used.all())
+        del used
+        v_owner = torch.repeat_interleave(order, vc[order])
+        vf = verts.view(torch.float32).reshape(-1, 6)
+        lo = (d[v_owner, 0:3] * 16).to(torch.float32)
+        assert bool((vf[:, 0:3] >= lo - 1e-4).all()) and bool((vf[:, 0:3] <= lo + 16.0 + 1e-4).all())
+        assert bool((vf[:, 3:6] >= 0).all()) and bool((vf[:, 3:6] <= 1).all())
+        # order-free per-chunk content sums (bit patterns as integers)
+        vsum = torch.zeros(len(pos), dtype=torch.int64, device="cuda")
+        vsum.index_add_(0, v_owner, verts.view(torch.int32).reshape(-1, 6).to(torch.int64).sum(dim=1))
+        isum = torch.zeros(len(pos), dtype=torch.int64, device="cuda")
+        isum.index_add_(0, i_owner, idx)
+        return dict(pos=d[:, 0:3].clone(), flags=flags.clone(), vc=vc.clone(), ic=ic.clone(), vsum=vsum, isum=isum, nv=nv, ni=ni)
+
+    with uw.ChunkBuilder(uw.Perlin(0)) as b:
+        a = run(b)
+        c = run(b)
+    assert bool((a["pos"].cpu() == torch.from_numpy(pos).to(torch.int64)).all())
+    z = a["pos"][:, 2]
+    assert bool((a["flags"][z >= 2] == 1).all())                 # provably blank: early-out, no mesh (chunk.rs:276-280)
+    assert bool((a["flags"][z <= -4] == 0).all())                # provably solid: mesh stage runs, emits nothing
+    assert a["nv"] > 20_000_000 and a["ni"] > 80_000_000
+    for k in ("flags", "vc", "ic", "vsum", "isum"):
+        assert bool((a[k] == c[k]).all()), k
+    with uw.ChunkBuilder(uw.Perlin(0), analytic_skip=True) as s:
+        e = run(s)
+    for k in ("pos", "flags", "vc", "ic", "vsum", "isum"):
+        assert bool((a[k] == e[k]).all()), k
+
+
 def test_device_resident_build_matches_host_build(uw, builder12):
     import torch
     pos = uw.region.box_region((-2, 2), (-2, 2), (-2, 1))

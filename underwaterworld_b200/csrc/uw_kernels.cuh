@@ -528,6 +528,35 @@ __device__ __noinline__ Ticket take_ticket(const Handout& h) {
     }
 }
 
+// Split-phase hand-out for the steady state (the CTA's first ticket goes through take_ticket, which also sets up
+// h.state): ticket_begin issues the atomic, ticket_fetch turns its result into (chunk, position) loads, and
+// nothing waits until the values are first USED -- the caller keeps whole stages of K1 between the three steps,
+// so both global round trips overlap compute without relying on how divergent paths of a warp are scheduled.
+__device__ __forceinline__ uint32_t ticket_begin(const Handout& h) { return atomicAdd(&h.ctr->ticket, 1u); }
+
+__device__ __forceinline__ Ticket ticket_fetch(const Handout& h, uint32_t t) {
+    Ticket tk;
+    tk.chunk = TICKET_DONE; tk.px = tk.py = tk.pz = 0;
+    if (h.order) {
+        if (t < h.state[UW_NCLS - 1]) {
+            int cls = 0;
+            while (t >= h.state[cls]) ++cls;
+            const uint32_t before = cls ? h.state[cls - 1] : 0u;
+            const uint4 e = __ldcg(&h.order[(size_t)cls * h.n + (t - before)]);
+            tk.chunk = e.x; tk.px = (int)e.y; tk.py = (int)e.z; tk.pz = (int)e.w;
+        }
+        return tk;
+    }
+    if (t < h.n) {
+        tk.px = h.pos[3 * t]; tk.py = h.pos[3 * t + 1]; tk.pz = h.pos[3 * t + 2];
+        if (h.skip) {                                  // UW_FLAG_ANALYTIC_SKIP: may have to move on to the next ticket (blocking)
+            if (answer_trivial(h, t, tk.px, tk.py, tk.pz)) return take_ticket(h);
+        }
+        tk.chunk = t;
+    }
+    return tk;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1 (fast path, compile-time specialised): same algorithm as k_noise_small with S and the
 // octave count as template parameters, so that every loop bound, lattice size and -- crucially --
@@ -594,6 +623,10 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     constexpr int L = D::L;
     const int tid = threadIdx.x;
     constexpr int NT = D::NT;
+    // the NEXT chunk's ticket: atomic issued here, (chunk, position) loads after stage X, values first touched by
+    // the caller at the end of the iteration -- see ticket_begin / ticket_fetch
+    uint32_t tk_t = 0;
+    if (hand && tid == NT - 1) tk_t = ticket_begin(*hand);
 
     // ---- stage H --------------------------------------------------------------------------------
 #pragma unroll
@@ -638,11 +671,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     }
     __syncthreads();
     PHASE_MARK(12);
-    // the next chunk ticket is requested here (by thread 0) so that the atomic's round trip hides under
-    // the z-column stage instead of stalling the whole CTA at the top of the next iteration
-    // (the LAST thread does it: its warp has idle lanes in the column stage, and divergent paths of a warp
-    // interleave, so the global round trips overlap that warp's own work too)
-    if (hand && tid == NT - 1) *tk_out = take_ticket(*hand);
+    if (hand && tid == NT - 1) *tk_out = ticket_fetch(*hand, tk_t);
 
     // ---- stage YZ -------------------------------------------------------------------------------
     if (tid < L * L) {

@@ -34,3 +34,10 @@ st, en = (a[:, 0] - t0) / 1e3, (a[:, 1] - t0) / 1e3
 print(f"CTA start us: min {st.min():.1f} max {st.max():.1f};  end us: min {en.min():.1f} median {np.median(en):.1f} max {en.max():.1f}")
 print(f"chunks per CTA: min {a[:,2].min():.0f} mean {a[:,2].mean():.2f} max {a[:,2].max():.0f}; heavy per CTA: min {a[:,3].min():.0f} mean {a[:,3].mean():.2f} max {a[:,3].max():.0f}")
 print("end-time histogram (us):", np.histogram(en, bins=8)[0].tolist(), np.round(np.histogram(en, bins=8)[1], 1).tolist())
+order = np.argsort(-en)[:12]
+print("latest CTAs (end us, start us, chunks, mesh chunks):", [(round(float(en[i]), 1), round(float(st[i]), 1), int(a[i, 2]), int(a[i, 3])) for i in order])
+one = en[a[:, 2] == 1]
+print("CTAs with exactly 1 chunk:", len(one), "end us max", one.max() if len(one) else None)
+for k in (1, 2, 3, 4, 5):
+    sel = a[:, 2] == k
+    if sel.any(): print(f"  CTAs with {k} chunks: {int(sel.sum())}, end us mean {en[sel].mean():.1f} max {en[sel].max():.1f}, mesh chunks mean {a[sel, 3].mean():.2f}")

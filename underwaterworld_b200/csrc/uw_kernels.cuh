@@ -2264,16 +2264,6 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     const int tid = threadIdx.x;
     constexpr int L = D::L;
 
-    for (int t = tid; t < 256; t += D::NT) sm.n.perm[t] = g_perm[t];
-    if (tid < 16) sm.n.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
-    for (int t = tid; t < NOCT * L; t += D::NT) {
-        const int o = t / L, i = t - o * L;
-        sm.n.axis[o][i] = make_float4(tab.d[o][i], tab.d1[o][i], tab.w[o][i], 0.f);
-    }
-
-    for (int t = tid; t < 256; t += D::NT) sm.lut[t] = mc->lut[t];
-    fill_edge_offsets(sm.eoff, L);
-
     // the vertex-id table of K4 aliases the K1 lattice/X tables (dead once noise_chunk_spec has returned;
     // lat and X are adjacent members of SpecSmem)
     EmitSmem es;
@@ -2299,10 +2289,23 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         sm.hand[UW_NCLS] = 0u;
     }
     __syncthreads();
+    // start-up order matters at 2048 chunks (the prologue is ~10 % of the kernel): first the global round trips of
+    // the hand-out (filing the request / the first ticket's atomic), then the table loads underneath them
+    uint32_t t_first = 0;
     if (order) handout_classify(hand);
-    __syncthreads();
+    else if (tid == D::NT - 1) t_first = ticket_begin(hand);
+
+    for (int t = tid; t < 256; t += D::NT) sm.n.perm[t] = g_perm[t];
+    if (tid < 16) sm.n.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
+    for (int t = tid; t < NOCT * L; t += D::NT) {
+        const int o = t / L, i = t - o * L;
+        sm.n.axis[o][i] = make_float4(tab.d[o][i], tab.d1[o][i], tab.w[o][i], 0.f);
+    }
+    for (int t = tid; t < 256; t += D::NT) sm.lut[t] = mc->lut[t];
+    fill_edge_offsets(sm.eoff, L);
+
     if (tid == D::NT - 1) {
-        const Ticket t0 = take_ticket(hand);
+        const Ticket t0 = order ? take_ticket(hand) : ticket_fetch(hand, t_first);
         sm.cur[0] = (int)t0.chunk; sm.cur[1] = t0.px; sm.cur[2] = t0.py; sm.cur[3] = t0.pz;
     }
     __syncthreads();

@@ -497,19 +497,23 @@ __device__ __forceinline__ void handout_classify(const Handout& h) {
     }
 }
 
+// cost order, step 2 (ONE thread, once per CTA): wait until the whole request is filed, keep the lists' prefix sums
+__device__ __forceinline__ void handout_ready(const Handout& h) {
+    if (h.state[UW_NCLS]) return;
+    while (ld_volatile_u32(&h.ctr->classified) < h.n) { }
+    __threadfence();
+    uint32_t run = 0;
+    for (int k = 0; k < UW_NCLS; ++k) { run += ld_volatile_u32(&h.ctr->cls_n[k]); h.state[k] = run; }
+    h.state[UW_NCLS] = 1u;
+}
+
 // executed by ONE thread
 __device__ __noinline__ Ticket take_ticket(const Handout& h) {
     Ticket tk;
     tk.chunk = TICKET_DONE; tk.px = tk.py = tk.pz = 0;
     if (h.order) {
         const uint32_t t = atomicAdd(&h.ctr->ticket, 1u);
-        if (!h.state[UW_NCLS]) {                       // first ticket of this CTA: wait for the lists, keep their prefix sums
-            while (ld_volatile_u32(&h.ctr->classified) < h.n) { }
-            __threadfence();
-            uint32_t run = 0;
-            for (int k = 0; k < UW_NCLS; ++k) { run += ld_volatile_u32(&h.ctr->cls_n[k]); h.state[k] = run; }
-            h.state[UW_NCLS] = 1u;
-        }
+        handout_ready(h);
         if (t >= h.state[UW_NCLS - 1]) return tk;
         int cls = 0;
         while (t >= h.state[cls]) ++cls;
@@ -2292,8 +2296,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // start-up order matters at 2048 chunks (the prologue is ~10 % of the kernel): first the global round trips of
     // the hand-out (filing the request / the first ticket's atomic), then the table loads underneath them
     uint32_t t_first = 0;
+    if (tid == D::NT - 1) t_first = ticket_begin(hand);
     if (order) handout_classify(hand);
-    else if (tid == D::NT - 1) t_first = ticket_begin(hand);
 
     for (int t = tid; t < 256; t += D::NT) sm.n.perm[t] = g_perm[t];
     if (tid < 16) sm.n.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
@@ -2305,7 +2309,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     fill_edge_offsets(sm.eoff, L);
 
     if (tid == D::NT - 1) {
-        const Ticket t0 = order ? take_ticket(hand) : ticket_fetch(hand, t_first);
+        if (order) handout_ready(hand);
+        const Ticket t0 = ticket_fetch(hand, t_first);
         sm.cur[0] = (int)t0.chunk; sm.cur[1] = t0.px; sm.cur[2] = t0.py; sm.cur[3] = t0.pz;
     }
     __syncthreads();

@@ -194,6 +194,19 @@ def run_ours(args):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    # One process per GPU: run (and first-touch pinned host memory) on the CPUs next to this rank's GPU, as a
+    # production launcher would -- on a two-socket box a remote pinned arena halves the D2H rate of the host path.
+    numa = "unpinned (single rank: the CPU baseline of this run uses every host core)"
+    try:
+        if world == 1:
+            raise RuntimeError("single rank")
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = f"nvmlDeviceSetCpuAffinity(gpu {local}): {len(os.sched_getaffinity(0))} cpus"
+    except Exception as e:                                   # not fatal: the numbers are simply measured unpinned
+        if world > 1:
+            numa = f"unpinned ({type(e).__name__})"
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -479,7 +492,8 @@ def run_ours(args):
             "config": {"workload": "spawn-neighbourhood 16x16x8 = 2048 chunks of 12^3 per GPU (BASELINE configs[1]; "
                                    "rank r owns x in [-8+16r, 8+16r)), seed 0, octaves 3, iso -0.1",
                        "chunks_per_gpu": n, "cells_per_chunk": CELLS, "samples_per_chunk": L3,
-                       "l2": "flushed between timed steps (256 MB write)", "parallelism": f"chunk-slabs x{world}"},
+                       "l2": "flushed between timed steps (256 MB write)", "parallelism": f"chunk-slabs x{world}",
+                       "host_affinity": numa},
             "e2e": {"value": e2e_value, "unit": "voxels/s", "chunks_per_s": total_chunks / (e2e_ms / 1e3),
                     "ms_per_step": e2e_ms,
                     "timing": "host perf_counter around K software-pipelined host builds (uw_build_async k+1, uw_batch_wait k; "

@@ -371,6 +371,31 @@ def test_two_async_batches_overlap(uw, builder12):
     assert builder12.build(regions[0]).n_inds == want[0].n_inds
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(ordered=True), dict(staged=True)], ids=["fused", "ordered", "staged"])
+def test_output_arena_overflow_grows_and_reruns(uw, builder12, kw):
+    """A fresh context sizes its output arenas from a per-chunk guess (192 vertices / 640 indices); a batch of
+    nothing but surface-heavy chunks (z = -1: ~900 vertices each) overflows it, so the library must notice (totals /
+    bump allocator), grow and re-run the emitting stage -- also with two such batches in flight."""
+    pos = uw.region.box_region((-8, 8), (-8, 8), (-1, 0))          # 256 chunks, all on the surface layer
+    want = builder12.build(pos)
+    assert want.n_verts > 256 * 192 + 4096 and want.n_inds > 256 * 640 + 16384     # the guess really is too small
+    with uw.ChunkBuilder(uw.Perlin(0), **kw) as fresh:
+        got = fresh.build(pos)
+        assert got.n_verts == want.n_verts and got.n_inds == want.n_inds
+        for i in range(0, len(pos), 5):
+            a, b = want.chunk(i), got.chunk(i)
+            assert np.array_equal(a.inds, b.inds) and a.verts.tobytes() == b.verts.tobytes()
+    if not kw:
+        with uw.ChunkBuilder(uw.Perlin(0)) as fresh:                # both buffer sets start small
+            h0 = fresh.build_async(pos[:128])
+            h1 = fresh.build_async(pos[128:])
+            b0, b1 = fresh.wait(h0), fresh.wait(h1)
+            assert b0.n_inds + b1.n_inds == want.n_inds
+            for i in range(0, 128, 9):
+                assert np.array_equal(b0.chunk(i).inds, want.chunk(i).inds)
+                assert b1.chunk(i).verts.tobytes() == want.chunk(128 + i).verts.tobytes()
+
+
 def test_large_batch_properties(uw, builder12):
     """Config-3-sized slab properties that need no oracle: index range, packing, determinism,
     triangle soup equality between FP32 and exact-f64 topology."""

@@ -56,6 +56,9 @@ typedef enum uw_status {
                                      answered without evaluating the noise: blank-early above, solid below.  The
                                      reference encodes the same fact as world::MIN_Z / MAX_Z (world.rs:11-12,161).
                                      Outputs are identical; off by default so that benchmarks evaluate every sample. */
+#define UW_FLAG_EXPORTABLE  0x80u /* the packed vertex / index arenas are CUDA VMM allocations that can be handed to
+                                     another API or process as POSIX file descriptors: uw_export_arena_fd()
+                                     (mesh hand-off to the renderer without the host round trip)  */
 #define UW_FLAG_TRIS        0x8u  /* also emit the per-cell collision triangle lists (chunk.rs:167-174,
                                      245-250) -- SURVEY §8f-1                                       */
 
@@ -196,6 +199,17 @@ uw_status   uw_build_from_densities(uw_ctx* ctx, const int32_t* chunk_pos_xyz, c
 /* Batched density point queries: perlin_util::iso_at (perlin_util.rs:24-29) on n points
  * (x,y,z f64 triples, HOST) -> n floats (HOST).  SURVEY §8f-3. */
 uw_status   uw_iso_at(uw_ctx* ctx, const double* points_xyz, uint32_t n, float* out);
+
+/* ---- renderer hand-off without the host round trip (replaces the create_buffer_init copies of
+ * chunk.rs:291-305 for a renderer that can import external memory) ------------------------------------------
+ * Context created with UW_FLAG_EXPORTABLE, after uw_build_device() + uw_sync(): exports the arena that
+ * uw_device_view_get() describes (which: 0 = vertices, 1 = indices) as a POSIX file descriptor
+ * (cuMemExportToShareableHandle).  Importers: Vulkan VK_KHR_external_memory_fd (VkImportMemoryFdInfoKHR with
+ * VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT, allocationSize = *bytes), OpenGL EXT_memory_object_fd, or another
+ * CUDA context / process (cuMemImportFromShareableHandle).  The caller owns the fd.  *bytes is the size of the whole
+ * allocation (>= the used part); offsets inside it are the descriptor's vert_offset / index_offset.  A later
+ * build that has to GROW the arena replaces the allocation: export again when the capacity (bytes) changed. */
+uw_status   uw_export_arena_fd(uw_ctx* ctx, int which, int* fd, uint64_t* bytes);
 
 /* ---- plumbing ------------------------------------------------------------------------- */
 /* Run on an existing CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */

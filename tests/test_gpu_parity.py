@@ -487,6 +487,52 @@ def test_config3_full_region_invariants_on_device(uw):
         assert bool((a[k] == e[k]).all()), k
 
 
+def test_exportable_arenas_round_trip_through_a_file_descriptor(uw, builder12):
+    """SURVEY 8f-4 (renderer hand-off without the host round trip): with UW_FLAG_EXPORTABLE the packed arenas are
+    VMM allocations; uw_export_arena_fd hands out POSIX fds.  A consumer that only holds the fd (here: the CUDA
+    driver API through cuda-python, standing in for Vulkan's VK_KHR_external_memory_fd) maps the memory and
+    sees exactly the bytes the host path returns."""
+    import torch
+    try:
+        from cuda.bindings import driver as cu
+    except ImportError:
+        from cuda import cuda as cu
+    pos = uw.region.box_region((-3, 3), (-3, 3), (-2, 1))
+    want = builder12.build(pos)                                        # request-order packing
+    t = torch.from_numpy(pos).cuda()
+    with uw.ChunkBuilder(uw.Perlin(0), exportable=True, ordered=True) as b:
+        b.build_device(t.data_ptr(), len(pos))
+        b.sync()
+        v = b.device_view()
+        assert v.n_verts == want.n_verts and v.n_inds == want.n_inds
+        for which, nbytes, ref in ((0, v.n_verts * 24, want.verts.tobytes()), (1, v.n_inds * 2, want.inds.tobytes())):
+            fd, size = b.export_arena_fd(which)
+            assert fd >= 0 and size >= nbytes
+            err, handle = cu.cuMemImportFromShareableHandle(fd, cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR)
+            assert err == cu.CUresult.CUDA_SUCCESS, err
+            os.close(fd)                                               # the import holds its own reference
+            err, ptr = cu.cuMemAddressReserve(size, 0, 0, 0)
+            assert err == cu.CUresult.CUDA_SUCCESS, err
+            (err,) = cu.cuMemMap(ptr, size, 0, handle, 0)
+            assert err == cu.CUresult.CUDA_SUCCESS, err
+            acc = cu.CUmemAccessDesc()
+            acc.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+            acc.location.id = torch.cuda.current_device()
+            acc.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READ
+            (err,) = cu.cuMemSetAccess(ptr, size, [acc], 1)
+            assert err == cu.CUresult.CUDA_SUCCESS, err
+            got = np.empty(nbytes, dtype=np.uint8)
+            (err,) = cu.cuMemcpyDtoH(got.ctypes.data, ptr, nbytes)
+            assert err == cu.CUresult.CUDA_SUCCESS, err
+            assert got.tobytes() == ref
+            cu.cuMemUnmap(ptr, size); cu.cuMemAddressFree(ptr, size); cu.cuMemRelease(handle)
+        # host path of the same context still works (its arenas are exportable allocations too)
+        again = b.build(pos)
+        assert again.inds.tobytes() == want.inds.tobytes()
+    with pytest.raises(uw.UwError):
+        builder12.export_arena_fd(0)                                   # not created with the flag
+
+
 def test_device_resident_build_matches_host_build(uw, builder12):
     import torch
     pos = uw.region.box_region((-2, 2), (-2, 2), (-2, 1))

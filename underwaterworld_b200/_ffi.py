@@ -19,6 +19,7 @@ FLAG_TRIS = 0x8
 FLAG_STAGED = 0x10
 FLAG_ORDERED = 0x20
 FLAG_ANALYTIC_SKIP = 0x40
+FLAG_EXPORTABLE = 0x80
 
 CHUNK_BLANK_EARLY = 0x1
 CHUNK_HAS_MESH = 0x2
@@ -71,7 +72,7 @@ EXPORTS = [
     "uw_build", "uw_build_async", "uw_batch_wait", "uw_batch_view_get", "uw_batch_free",
     "uw_build_device", "uw_sync", "uw_device_view_get",
     "uw_debug_densities", "uw_debug_cases", "uw_build_from_densities", "uw_iso_at",
-    "uw_set_stream", "uw_get_stage_times", "uw_set_profiling", "uw_get_guard_count", "uw_debug_ffma_peak",
+    "uw_set_stream", "uw_get_stage_times", "uw_set_profiling", "uw_get_guard_count", "uw_debug_ffma_peak", "uw_export_arena_fd",
 ]
 
 _lib = None
@@ -122,5 +123,6 @@ def load_library() -> C.CDLL:
     lib.uw_set_profiling.argtypes = [vp, C.c_int]
     lib.uw_get_guard_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.uw_debug_ffma_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.uw_export_arena_fd.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib

@@ -116,7 +116,8 @@ class ChunkBuilder:
 
     def __init__(self, perlin: Optional[Perlin] = None, *, internal_size: int = INTERNAL_SIZE, device: int = -1,
                  exact_f64: bool = False, index32: bool = False, keep_densities: bool = False,
-                 staged: bool = False, ordered: bool = False, tris: bool = False, analytic_skip: bool = False, guard_eps: float = 0.0, **consts):
+                 staged: bool = False, ordered: bool = False, tris: bool = False, analytic_skip: bool = False, exportable: bool = False,
+                 guard_eps: float = 0.0, **consts):
         self._lib = _ffi.load_library()
         cfg = _ffi.UwConfig()
         self._lib.uw_config_default(C.byref(cfg))
@@ -127,7 +128,7 @@ class ChunkBuilder:
         cfg.flags = ((_ffi.FLAG_EXACT_F64 if exact_f64 else 0) | (_ffi.FLAG_INDEX32 if index32 else 0)
                      | (_ffi.FLAG_KEEP_DENSITIES if keep_densities else 0) | (_ffi.FLAG_STAGED if staged else 0)
                      | (_ffi.FLAG_ORDERED if ordered else 0) | (_ffi.FLAG_TRIS if tris else 0)
-                     | (_ffi.FLAG_ANALYTIC_SKIP if analytic_skip else 0))
+                     | (_ffi.FLAG_ANALYTIC_SKIP if analytic_skip else 0) | (_ffi.FLAG_EXPORTABLE if exportable else 0))
         for k, v in consts.items():
             if not hasattr(cfg, k):
                 raise TypeError(f"unknown config field {k!r}")
@@ -251,6 +252,13 @@ class ChunkBuilder:
     def build_device(self, d_positions_ptr: int, n: int):
         """Device-resident build: positions at a device pointer (n x 3 int32); no sync."""
         self._check(self._lib.uw_build_device(self._ctx, C.c_void_p(d_positions_ptr), n))
+
+    def export_arena_fd(self, which: int):
+        """(fd, allocation bytes) of the packed vertex (0) / index (1) arena of the last device-resident build:
+        a POSIX file descriptor a renderer can import (builder created with exportable=True)."""
+        fd, nbytes = C.c_int(-1), C.c_uint64(0)
+        self._check(self._lib.uw_export_arena_fd(self._ctx, which, C.byref(fd), C.byref(nbytes)))
+        return fd.value, nbytes.value
 
     def sync(self):
         self._check(self._lib.uw_sync(self._ctx))

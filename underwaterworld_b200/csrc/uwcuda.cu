@@ -1,6 +1,7 @@
 // uwcuda.cu -- host side of libuwcuda.so: context, buffers, launch sequence, C ABI.
 // Declared in include/uwcuda.h.  No CPU fallback: every entry point that computes needs a
 // CUDA device.  Nothing here includes, links or calls anything under oracle/.
+#include <cuda.h>            // driver API TYPES only (VMM arenas); entry points come from cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -19,6 +20,8 @@
 static thread_local std::string g_create_error;
 
 struct PinnedBlock { void* ptr; size_t bytes; };
+struct VmmArena { void* ptr = nullptr; size_t bytes = 0; CUmemGenericAllocationHandle handle = 0; };
+static void vmm_free(VmmArena* a);
 
 struct uw_ctx {
     uw_config cfg;
@@ -39,6 +42,7 @@ struct uw_ctx {
     McTables* d_mc = nullptr;
 
     bool tris = false;              // UW_FLAG_TRIS: per-cell collision triangles
+    bool exportable = false;        // UW_FLAG_EXPORTABLE: output arenas are VMM allocations with fd handles
     // grow-only per-batch buffers: TWO sets, so that a host build's D2H copies (set A, copy stream) overlap the
     // next batch's kernel (set B, compute stream).  B() is the set of the build being enqueued / last enqueued.
     struct BufSet {
@@ -56,6 +60,7 @@ struct uw_ctx {
         unsigned long long vcap = 0, icap = 0;
         uw_vert* d_verts = nullptr;
         void* d_inds = nullptr;
+        VmmArena vmm_verts, vmm_inds;   // UW_FLAG_EXPORTABLE: d_verts / d_inds alias these
         uw_tri* d_tris = nullptr;       // [icap / 3]
         uint16_t* d_tri_cell = nullptr; // [cap_chunks][S^3 + 1]
         int32_t* h_pos = nullptr; size_t h_pos_cap = 0;   // pinned staging of the request
@@ -331,7 +336,9 @@ extern "C" void uw_destroy(uw_ctx* c) {
     cudaFree(c->d_scan_part); cudaFree(c->d_scan_flag); cudaFree(c->d_scan_ctl);
     for (auto& b : c->sets) {
         cudaFree(b.d_pos); cudaFree(b.d_dens); cudaFree(b.d_counts); cudaFree(b.d_quarters); cudaFree(b.d_descs); cudaFree(b.d_active);
-        cudaFree(b.d_cases); cudaFree(b.d_verts); cudaFree(b.d_inds); cudaFree(b.d_tris); cudaFree(b.d_tri_cell);
+        cudaFree(b.d_cases);
+        if (c->exportable) { vmm_free(&b.vmm_verts); vmm_free(&b.vmm_inds); }
+        else { cudaFree(b.d_verts); cudaFree(b.d_inds); } cudaFree(b.d_tris); cudaFree(b.d_tri_cell);
         cudaFree(b.d_scan); cudaFree(b.d_order);
         if (b.h_pos) cudaFreeHost(b.h_pos);
         if (b.h_sum) cudaFreeHost(b.h_sum);
@@ -380,6 +387,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     // FP32 factorisation needs chunk-independent fractional parts: chunk_size a power of two
     c->big_path = cfg->internal_size > UW_SMALL_MAX_L - 1;
     c->tris = (cfg->flags & UW_FLAG_TRIS) != 0;
+    c->exportable = (cfg->flags & UW_FLAG_EXPORTABLE) != 0;
     if (c->tris && c->big_path) { c->err = "uw_create: UW_FLAG_TRIS is not available for internal_size > 15"; return bail(UW_ERR_UNSUPPORTED); }
     // FP32 factorised noise needs chunk-independent fractional parts: chunk_size a power of two.  Large chunks
     // have an FP32 kernel for internal_size 64 (BASELINE config 4); other large sizes use the exact f64 kernel.
@@ -537,6 +545,82 @@ extern "C" uw_status uw_set_profiling(uw_ctx* c, int enabled) {
 }
 
 // ---------------------------------------------------------------------------------------
+// exportable arenas (UW_FLAG_EXPORTABLE): CUDA virtual-memory-management allocations with a POSIX-fd handle
+// type.  The driver entry points are fetched through the runtime, so the library does not link libcuda.
+// ---------------------------------------------------------------------------------------
+struct DriverApi {
+    CUresult (*memCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*memRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*memAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*memAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*memMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*memUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*memSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*memGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*memExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    bool ok = false;
+};
+
+static const DriverApi& driver_api() {
+    static DriverApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    auto get = [](const char* name, void** fn) {
+        cudaDriverEntryPointQueryResult q;
+        return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    api.ok = get("cuMemCreate", (void**)&api.memCreate) && get("cuMemRelease", (void**)&api.memRelease) &&
+             get("cuMemAddressReserve", (void**)&api.memAddressReserve) && get("cuMemAddressFree", (void**)&api.memAddressFree) &&
+             get("cuMemMap", (void**)&api.memMap) && get("cuMemUnmap", (void**)&api.memUnmap) &&
+             get("cuMemSetAccess", (void**)&api.memSetAccess) &&
+             get("cuMemGetAllocationGranularity", (void**)&api.memGetAllocationGranularity) &&
+             get("cuMemExportToShareableHandle", (void**)&api.memExportToShareableHandle);
+    return api;
+}
+
+static void vmm_free(VmmArena* a) {
+    if (!a->ptr) return;
+    const DriverApi& d = driver_api();
+    d.memUnmap((CUdeviceptr)a->ptr, a->bytes);
+    d.memAddressFree((CUdeviceptr)a->ptr, a->bytes);
+    d.memRelease(a->handle);
+    a->ptr = nullptr; a->bytes = 0; a->handle = 0;
+}
+
+static uw_status vmm_alloc(uw_ctx* c, VmmArena* a, size_t bytes) {
+    const DriverApi& d = driver_api();
+    if (!d.ok) return fail(c, UW_ERR_UNSUPPORTED, "UW_FLAG_EXPORTABLE: the CUDA driver does not expose the virtual memory management API");
+    vmm_free(a);
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = c->device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    if (d.memGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0)
+        return fail(c, UW_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    CUmemGenericAllocationHandle h = 0;
+    CUresult r = d.memCreate(&h, size, &prop, 0);
+    if (r != CUDA_SUCCESS) return fail(c, r == CUDA_ERROR_OUT_OF_MEMORY ? UW_ERR_OOM : UW_ERR_CUDA, "cuMemCreate failed (exportable arena)");
+    CUdeviceptr p = 0;
+    if (d.memAddressReserve(&p, size, 0, 0, 0) != CUDA_SUCCESS) { d.memRelease(h); return fail(c, UW_ERR_CUDA, "cuMemAddressReserve failed"); }
+    if (d.memMap(p, size, 0, h, 0) != CUDA_SUCCESS) { d.memAddressFree(p, size); d.memRelease(h); return fail(c, UW_ERR_CUDA, "cuMemMap failed"); }
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof acc);
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE; acc.location.id = c->device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (d.memSetAccess(p, size, &acc, 1) != CUDA_SUCCESS) {
+        d.memUnmap(p, size); d.memAddressFree(p, size); d.memRelease(h);
+        return fail(c, UW_ERR_CUDA, "cuMemSetAccess failed");
+    }
+    a->ptr = (void*)p; a->bytes = size; a->handle = h;
+    return UW_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // buffers
 // ---------------------------------------------------------------------------------------
 template <typename T>
@@ -580,15 +664,29 @@ static uw_status ensure_outputs(uw_ctx* c, unsigned long long nv, unsigned long 
         unsigned long long cap = c->B().vcap ? c->B().vcap : 4096;
         while (cap < nv) cap *= 2;
         CU_TRY(c, cudaStreamSynchronize(c->stream));
-        CU_TRY(c, regrow(&c->B().d_verts, (size_t)cap));
+        if (c->exportable) {
+            CU_TRY(c, cudaDeviceSynchronize());
+            uw_status vst = vmm_alloc(c, &c->B().vmm_verts, (size_t)cap * sizeof(uw_vert));
+            if (vst != UW_OK) return vst;
+            c->B().d_verts = (uw_vert*)c->B().vmm_verts.ptr;
+        } else {
+            CU_TRY(c, regrow(&c->B().d_verts, (size_t)cap));
+        }
         c->B().vcap = cap;
     }
     if (ni > c->B().icap) {
         unsigned long long cap = c->B().icap ? c->B().icap : 16384;
         while (cap < ni) cap *= 2;
         CU_TRY(c, cudaStreamSynchronize(c->stream));
-        if (c->B().d_inds) { cudaFree(c->B().d_inds); c->B().d_inds = nullptr; }
-        CU_TRY(c, cudaMalloc(&c->B().d_inds, (size_t)cap * isz));
+        if (c->exportable) {
+            CU_TRY(c, cudaDeviceSynchronize());
+            uw_status ist = vmm_alloc(c, &c->B().vmm_inds, (size_t)cap * isz);
+            if (ist != UW_OK) return ist;
+            c->B().d_inds = c->B().vmm_inds.ptr;
+        } else {
+            if (c->B().d_inds) { cudaFree(c->B().d_inds); c->B().d_inds = nullptr; }
+            CU_TRY(c, cudaMalloc(&c->B().d_inds, (size_t)cap * isz));
+        }
         if (c->tris) CU_TRY(c, regrow(&c->B().d_tris, (size_t)cap / 3 + 1));
         c->B().icap = cap;
     }
@@ -1002,6 +1100,21 @@ extern "C" uw_status uw_device_view_get(uw_ctx* c, uw_device_view* out) {
     out->d_descs = c->B().d_descs; out->d_verts = c->B().d_verts;
     if (c->index32) out->d_inds32 = c->B().d_inds; else out->d_inds16 = c->B().d_inds;
     out->d_densities = c->B().d_dens; out->density_stride = c->dcfg.dens_stride;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_export_arena_fd(uw_ctx* c, int which, int* fd, uint64_t* bytes) {
+    if (!c) return UW_ERR_INVALID;
+    if (!fd || !bytes || (which != 0 && which != 1)) return fail(c, UW_ERR_INVALID, "uw_export_arena_fd: bad argument");
+    if (!c->exportable) return fail(c, UW_ERR_UNSUPPORTED, "uw_export_arena_fd: the context was not created with UW_FLAG_EXPORTABLE");
+    if (c->B().pending) return fail(c, UW_ERR_NOT_READY, "uw_export_arena_fd: call uw_sync first");
+    const VmmArena& a = which == 0 ? c->B().vmm_verts : c->B().vmm_inds;
+    if (!a.ptr) return fail(c, UW_ERR_NOT_READY, "uw_export_arena_fd: nothing has been built yet");
+    CU_TRY(c, cudaSetDevice(c->device));
+    int out = -1;
+    if (driver_api().memExportToShareableHandle(&out, a.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS || out < 0)
+        return fail(c, UW_ERR_CUDA, "cuMemExportToShareableHandle failed");
+    *fd = out; *bytes = a.bytes;
     return UW_OK;
 }
 

@@ -141,7 +141,9 @@ typedef struct uw_device_view {
     const void* d_verts;     /* uw_vert[n_verts]                                               */
     const void* d_inds16;    /* uint16_t[n_inds] or NULL                                       */
     const void* d_inds32;    /* uint32_t[n_inds] or NULL                                       */
-    const void* d_densities; /* float[n_chunks][density_stride], idx = x*L*L + y*L + z (chunk.rs:351-353) */
+    const void* d_densities; /* float[n_chunks][density_stride], idx = x*L*L + y*L + z (chunk.rs:351-353); NULL on the
+                                default (fused) path, which never materialises them -- set UW_FLAG_KEEP_DENSITIES
+                                (or use the staged / large-chunk paths)                                      */
     uint32_t    density_stride; /* floats per chunk (>= L^3, padded to 16 B)                   */
 } uw_device_view;
 

@@ -533,6 +533,26 @@ def test_exportable_arenas_round_trip_through_a_file_descriptor(uw, builder12):
         builder12.export_arena_fd(0)                                   # not created with the flag
 
 
+def test_keep_densities_tap_of_the_fused_kernel(uw):
+    """UW_FLAG_KEEP_DENSITIES: the fused kernel also writes its shared-memory density field to HBM (the default
+    path never materialises it and reports a NULL pointer); it equals the stand-alone noise kernel's output."""
+    import torch
+    from underwaterworld_b200.gather import _DevMem
+    pos = uw.region.box_region((-2, 2), (-2, 2), (-2, 1))
+    t = torch.from_numpy(pos).cuda()
+    with uw.ChunkBuilder(uw.Perlin(0)) as plain:
+        plain.build_device(t.data_ptr(), len(pos)); plain.sync()
+        assert not plain.device_view().d_densities
+        want = plain.debug_densities(pos)                          # k_noise_spec, host copy, n x L^3
+    with uw.ChunkBuilder(uw.Perlin(0), keep_densities=True) as keep:
+        keep.build_device(t.data_ptr(), len(pos)); keep.sync()
+        v = keep.device_view()
+        assert v.d_densities and v.density_stride >= 13 ** 3
+        d = torch.as_tensor(_DevMem(v.d_densities, len(pos) * v.density_stride * 4), device="cuda").view(torch.float32)
+        got = d.reshape(len(pos), v.density_stride)[:, :13 ** 3].cpu().numpy()
+    assert got.tobytes() == np.ascontiguousarray(want, dtype=np.float32).reshape(len(pos), -1).tobytes()
+
+
 def test_device_resident_build_matches_host_build(uw, builder12):
     import torch
     pos = uw.region.box_region((-2, 2), (-2, 2), (-2, 1))

@@ -164,7 +164,7 @@ typedef struct uw_batch uw_batch;
 uint32_t    uw_abi_version(void);
 void        uw_config_default(uw_config* cfg);                      /* chunk.rs:5-17 defaults, seed 0 */
 uw_status   uw_create(const uw_config* cfg, uw_ctx** out);          /* replaces noise::Perlin::new (state.rs:359) + consts */
-void        uw_destroy(uw_ctx* ctx);
+void        uw_destroy(uw_ctx* ctx);                                /* free every uw_batch of the context first: a batch's views live in the context's pinned pool */
 const char* uw_last_error(const uw_ctx* ctx);                       /* ctx may be NULL: last create error */
 
 /* The permutation table of noise::Perlin::new(cfg.seed) (noise-0.8.2). */

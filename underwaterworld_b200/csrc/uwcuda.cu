@@ -67,6 +67,8 @@ struct uw_ctx {
         FusedSummary* h_sum = nullptr;  // pinned + mapped: the last CTA of the fused kernel writes it over PCIe
         cudaEvent_t done = nullptr;     // recorded after the set's kernels
         bool busy = false;              // an async batch that has not been collected owns this set
+        uw_batch* owner = nullptr;      // that batch
+        cudaEvent_t copied = nullptr;   // recorded on the copy stream after the owner's D2H copies
         // state of the set's last build
         uint32_t last_n = 0;
         const int32_t* last_pos_dev = nullptr;
@@ -140,6 +142,7 @@ struct uw_batch {
     uint32_t n;
     int set;            // buffer set the batch's kernels write (-1: empty batch)
     bool ready;
+    bool copying;       // the D2H copies into `arena` have been issued on the copy stream (views are set)
     PinnedBlock arena;
     uw_batch_view view;
 };
@@ -343,6 +346,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
         if (b.h_pos) cudaFreeHost(b.h_pos);
         if (b.h_sum) cudaFreeHost(b.h_sum);
         if (b.done) cudaEventDestroy(b.done);
+        if (b.copied) cudaEventDestroy(b.copied);
     }
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_guard) cudaFreeHost(c->h_guard);
@@ -406,6 +410,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     if (!cu(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate copy")) return bail(UW_ERR_CUDA);
     for (auto& b : c->sets) {
         if (!cu(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming), "cudaEventCreate done")) return bail(UW_ERR_CUDA);
+        if (!cu(cudaEventCreateWithFlags(&b.copied, cudaEventDisableTiming), "cudaEventCreate copied")) return bail(UW_ERR_CUDA);
         if (!cu(cudaHostAlloc(&b.h_sum, sizeof(FusedSummary), cudaHostAllocMapped | cudaHostAllocPortable), "cudaHostAlloc summary")) return bail(UW_ERR_OOM);
     }
     if (!cu(cudaMalloc(&c->d_ctl, 2 * sizeof(FusedControl)), "cudaMalloc control")) return bail(UW_ERR_OOM);
@@ -945,8 +950,11 @@ static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n) {
     return UW_OK;
 }
 
-// Copy batch b's result (it owns buffer set b->set) into a pinned arena, on the copy stream.
-static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
+// Collecting batch b (it owns buffer set b->set) has two halves, so that the copy engine never idles when two
+// batches are in flight: collect_start waits for the set's kernels, validates the totals, and ISSUES the sized
+// D2H copies into a pinned arena on the copy stream; collect_finish waits for them and releases the set.
+static uw_status collect_start(uw_ctx* c, uw_batch* b) {
+    if (b->copying) return UW_OK;
     const int saved = c->cur;
     c->cur = b->set;
     uw_ctx::BufSet& B = c->B();
@@ -973,8 +981,8 @@ static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
         if (t.n_inds) e = cudaMemcpyAsync(base + off_tri, B.d_tris, sizeof(uw_tri) * (size_t)(t.n_inds / 3), cudaMemcpyDeviceToHost, cs);
         if (e == cudaSuccess) e = cudaMemcpyAsync(base + off_tcs, B.d_tri_cell, ncell1 * 2 * (size_t)b->n, cudaMemcpyDeviceToHost, cs);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
-    if (e != cudaSuccess) return done(fail(c, UW_ERR_CUDA, std::string("collect_batch: ") + cudaGetErrorString(e)));
+    if (e == cudaSuccess) e = cudaEventRecord(B.copied, cs);
+    if (e != cudaSuccess) return done(fail(c, UW_ERR_CUDA, std::string("collect_start: ") + cudaGetErrorString(e)));
     memset(&b->view, 0, sizeof b->view);
     if (c->tris) { b->view.tris = (const uw_tri*)(base + off_tri); b->view.tri_cell_start = (const uint16_t*)(base + off_tcs); }
     b->view.n_chunks = b->n; b->view.n_verts = t.n_verts; b->view.n_inds = t.n_inds;
@@ -982,9 +990,41 @@ static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
     b->view.verts = (const uw_vert*)(base + off_vert);
     if (c->index32) b->view.inds32 = (const uint32_t*)(base + off_ind);
     else b->view.inds16 = (const uint16_t*)(base + off_ind);
-    b->ready = true;
-    B.busy = false;
+    b->copying = true;
     return done(UW_OK);
+}
+
+static uw_status collect_finish(uw_ctx* c, uw_batch* b) {
+    uw_ctx::BufSet& B = c->sets[b->set];
+    CU_TRY(c, cudaEventSynchronize(B.copied));
+    b->ready = true;
+    B.busy = false; B.owner = nullptr;
+    return UW_OK;
+}
+
+static uw_status collect_batch(uw_ctx* c, uw_batch* b) {
+    uw_status st = collect_start(c, b);
+    if (st != UW_OK) return st;
+    // Keep the copy engine busy: while b's copies drain, watch the OTHER in-flight batch; the moment its kernels
+    // are done (they run underneath these copies) its own copies are queued right behind b's, instead of at its
+    // uw_batch_wait -- no gap on the PCIe link, and the caller's next submit overlaps them.
+    uw_ctx::BufSet& B = c->sets[b->set];
+    uw_ctx::BufSet& O = c->sets[b->set ^ 1];
+    for (;;) {
+        const bool other_waiting = O.busy && O.owner && !O.owner->copying;
+        if (!other_waiting) break;                               // nothing to watch: block in collect_finish
+        const cudaError_t q = cudaEventQuery(B.copied);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) return fail(c, UW_ERR_CUDA, std::string("collect_batch: ") + cudaGetErrorString(q));
+        if (cudaEventQuery(O.done) == cudaSuccess) {
+            st = collect_start(c, O.owner);
+            if (st != UW_OK) return st;
+        }
+    }
+    st = collect_finish(c, b);
+    if (st != UW_OK) return st;
+    if (O.busy && O.owner && !O.owner->copying && cudaEventQuery(O.done) == cudaSuccess) st = collect_start(c, O.owner);
+    return st;
 }
 
 // Batches in flight: the fused small-chunk path keeps all per-batch state in its buffer set, so two batches may
@@ -1005,7 +1045,7 @@ static uw_status build_common(uw_ctx* c, const int32_t* pos, const float* dens, 
     if (set < 0) return fail(c, UW_ERR_NOT_READY, "uw_build: too many async batches in flight; wait on (or free) an earlier one");
     CU_TRY(c, cudaSetDevice(c->device));
     uw_batch* b = new uw_batch();
-    b->ctx = c; b->n = n; b->set = -1; b->ready = false; b->arena.ptr = nullptr; b->arena.bytes = 0;
+    b->ctx = c; b->n = n; b->set = -1; b->ready = false; b->copying = false; b->arena.ptr = nullptr; b->arena.bytes = 0;
     memset(&b->view, 0, sizeof b->view);
     if (n == 0) { b->ready = true; *out = b; return UW_OK; }
     c->cur = set;
@@ -1021,12 +1061,13 @@ static uw_status build_common(uw_ctx* c, const int32_t* pos, const float* dens, 
     }
     if (st == UW_OK) st = enqueue_build(c, c->B().d_pos, n, dens != nullptr);
     if (st == UW_OK) {
-        c->B().busy = true;
+        c->B().busy = true; c->B().owner = b;
         if (!async) st = collect_batch(c, b);
     }
     if (st != UW_OK) {
         cudaStreamSynchronize(c->stream);
-        c->sets[set].busy = false; c->sets[set].pending = false;
+        cudaStreamSynchronize(c->copy_stream);
+        c->sets[set].busy = false; c->sets[set].pending = false; c->sets[set].owner = nullptr;
         if (b->arena.ptr) c->pool.push_back(b->arena);
         delete b;
         return st;
@@ -1062,10 +1103,12 @@ extern "C" uw_status uw_batch_view_get(const uw_batch* b, uw_batch_view* out) {
 
 extern "C" void uw_batch_free(uw_batch* b) {
     if (!b) return;
-    if (!b->ready && b->ctx && b->set >= 0) {      // abandoned async batch: let its kernels drain, release the set
+    if (!b->ready && b->ctx && b->set >= 0) {      // abandoned async batch: let its kernels and copies drain, release the set
         cudaSetDevice(b->ctx->device);
         cudaStreamSynchronize(b->ctx->stream);
-        b->ctx->sets[b->set].busy = false; b->ctx->sets[b->set].pending = false;
+        if (b->copying) cudaStreamSynchronize(b->ctx->copy_stream);
+        uw_ctx::BufSet& B = b->ctx->sets[b->set];
+        B.busy = false; B.pending = false; B.owner = nullptr;
     }
     if (b->arena.ptr) b->ctx->pool.push_back(b->arena);
     delete b;

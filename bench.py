@@ -198,7 +198,7 @@ def run_ours(args):
     # production launcher would -- on a two-socket box a remote pinned arena halves the D2H rate of the host path.
     numa = "unpinned (single rank: the CPU baseline of this run uses every host core)"
     try:
-        if world == 1:
+        if world == 1 or os.environ.get("UW_BENCH_NO_PIN"):
             raise RuntimeError("single rank")
         import pynvml
         pynvml.nvmlInit()

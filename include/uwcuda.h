@@ -48,8 +48,8 @@ typedef enum uw_status {
                                      kernel.  Results are identical.                                  */
 #define UW_FLAG_ORDERED     0x20u /* packed arenas in REQUEST order (decoupled look-back over per-chunk
                                      aggregates; deterministic layout, chunk i+1 follows chunk i).  Default:
-                                     completion order (one atomic bump allocation per chunk, ~17 % faster,
-                                     no inter-CTA dependency).  Every chunk's OWN buffers are identical in
+                                     completion order (one atomic bump allocation per chunk, no inter-CTA
+                                     dependency, cost-ordered hand-out: 52 us against 116 us for 2048 chunks).  Every chunk's OWN buffers are identical in
                                      both modes; only vert_offset / index_offset differ.              */
 #define UW_FLAG_ANALYTIC_SKIP 0x40u /* chunks whose z layer provably holds no surface (every octave of the noise is
                                      clamped to [-1, 1], so iso = terrace(z) + p cannot reach iso_level there) are

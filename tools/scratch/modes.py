@@ -5,7 +5,7 @@ pos = uw.region.config_positions('spawn')
 d_pos = torch.from_numpy(pos).cuda()
 flush = torch.empty(256<<20, dtype=torch.uint8, device='cuda')
 ref=None
-for name,kw in [('ordered',{}),('unordered',dict(ordered=True)),('staged',dict(staged=True))]:
+for name,kw in [('default(completion order)',{}),('ordered',dict(ordered=True)),('staged',dict(staged=True)),('tris',dict(tris=True)),('exportable',dict(exportable=True))]:
     b = uw.ChunkBuilder(uw.Perlin(0), **kw)
     st = torch.cuda.current_stream(); b.set_stream(st.cuda_stream)
     for flushit in (True, False):

@@ -1519,9 +1519,11 @@ __device__ __forceinline__ void emit_indices(const DevCfg& cfg, const McTables* 
     }
 }
 
-// F (UW_FLAG_TRIS): the reference's collision triangles, one thread per surface cell; triangle t of the
-// chunk is (indices 3t..3t+2), its corners recomputed from the cell's own edges (same ordered corner
-// pairs and densities as the vertex buffer -> bit-identical positions)
+// F (UW_FLAG_TRIS): the reference's collision triangles, one thread per TRIANGLE (a thread per surface cell would
+// run every warp for its busiest cell's 5 triangles while the average cell has 1.5).  Triangle j of the chunk is
+// (indices 3j..3j+2); its cell is found by a binary search over the surface cells' index bases, its corners are
+// recomputed from the cell's own edges (same ordered corner pairs and densities as the vertex buffer ->
+// bit-identical positions).
 template <int ST>
 __device__ __forceinline__ void emit_tris(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
                                           const ChunkShape sh, int px, int py, int pz, uw_tri* __restrict__ tout) {
@@ -1530,26 +1532,27 @@ __device__ __forceinline__ void emit_tris(const DevCfg& cfg, const McTables* __r
     const int offx = px * cfg.chunk_size, offy = py * cfg.chunk_size, offz = pz * cfg.chunk_size;
     const float* dens = s.dens;
     auto dens_at = [=](int ax, int ay, int az) { return dens[(ax * L + ay) * L + az]; };
-    for (uint32_t a = tid; a < sh.n_act; a += NT) {
-        const int cell = s.alist[a];
+    const uint32_t ntri = sh.n_ind / 3u;
+    for (uint32_t j = tid; j < ntri; j += NT) {
+        uint32_t lo = 0, hi = sh.n_act;                    // largest a with ibase[a] <= 3j (ibase is ascending; every surface cell has >= 1 triangle)
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ((uint32_t)s.ibase[mid] <= 3u * j) lo = mid; else hi = mid;
+        }
+        const int cell = s.alist[lo];
+        const int t = (int)((3u * j - s.ibase[lo]) / 3u);
         const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
         const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
-        float* dst = reinterpret_cast<float*>(tout + s.ibase[a] / 3u);
-#pragma unroll 1
-        for (int t = 0; t < 5; ++t) {
-            const int e0 = (int)((row >> (12 * t)) & 0xFull);
-            if (e0 == 15) break;
-            const int e1 = (int)((row >> (12 * t + 4)) & 0xFull), e2 = (int)((row >> (12 * t + 8)) & 0xFull);
-            float v[12];
-            edge_position(cfg, dens_at, x, y, z, e0, offx, offy, offz, v);
-            edge_position(cfg, dens_at, x, y, z, e1, offx, offy, offz, v + 3);
-            edge_position(cfg, dens_at, x, y, z, e2, offx, offy, offz, v + 6);
-            tri_normal(v, v + 3, v + 6, v + 9);
-            float4* d4 = reinterpret_cast<float4*>(dst + 12 * t);       // uw_tri is 48 B; the array base is 16-B aligned
-            d4[0] = make_float4(v[0], v[1], v[2], v[3]);
-            d4[1] = make_float4(v[4], v[5], v[6], v[7]);
-            d4[2] = make_float4(v[8], v[9], v[10], v[11]);
-        }
+        const int e0 = (int)((row >> (12 * t)) & 0xFull), e1 = (int)((row >> (12 * t + 4)) & 0xFull), e2 = (int)((row >> (12 * t + 8)) & 0xFull);
+        float v[12];
+        edge_position(cfg, dens_at, x, y, z, e0, offx, offy, offz, v);
+        edge_position(cfg, dens_at, x, y, z, e1, offx, offy, offz, v + 3);
+        edge_position(cfg, dens_at, x, y, z, e2, offx, offy, offz, v + 6);
+        tri_normal(v, v + 3, v + 6, v + 9);
+        float4* d4 = reinterpret_cast<float4*>(tout + j);                   // uw_tri is 48 B; the array base is 16-B aligned
+        d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+        d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+        d4[2] = make_float4(v[8], v[9], v[10], v[11]);
     }
 }
 

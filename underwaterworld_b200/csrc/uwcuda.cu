@@ -43,6 +43,7 @@ struct uw_ctx {
 
     bool tris = false;              // UW_FLAG_TRIS: per-cell collision triangles
     bool exportable = false;        // UW_FLAG_EXPORTABLE: output arenas are VMM allocations with fd handles
+    bool host_ptr_ok = false;       // the device can read pinned host allocations through their host address
     // grow-only per-batch buffers: TWO sets, so that a host build's D2H copies (set A, copy stream) overlap the
     // next batch's kernel (set B, compute stream).  B() is the set of the build being enqueued / last enqueued.
     struct BufSet {
@@ -387,6 +388,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         c->err = b; return bail(UW_ERR_NO_DEVICE);
     }
     c->num_sms = prop.multiProcessorCount;
+    c->host_ptr_ok = prop.unifiedAddressing && prop.canMapHostMemory;
     c->index32 = (cfg->flags & UW_FLAG_INDEX32) != 0 || cfg->internal_size > 22;
     // FP32 factorisation needs chunk-independent fractional parts: chunk_size a power of two
     c->big_path = cfg->internal_size > UW_SMALL_MAX_L - 1;
@@ -930,7 +932,11 @@ static uw_status finish_build(uw_ctx* c) {
     return UW_OK;
 }
 
-static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n) {
+// Returns (in *dev_pos) the pointer the kernels should read the positions from: normally the device copy; for a
+// batch of the fused path that is small enough to be latency-bound, the pinned staging buffer itself -- it is
+// mapped into the device's address space (UVA), every position is read exactly once (by the hand-out), and the
+// H2D copy's issue + completion latency would sit in front of the kernel.
+static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n, const int32_t** dev_pos = nullptr, bool zero_copy_ok = false) {
     for (uint32_t i = 0; i < 3 * n; ++i) {
         // fast path validity: |16*pos| must stay exactly representable next to
         // the 2^-23-granular lattice offsets; also keeps pos*chunk_size inside i32 (chunk.rs:90-94)
@@ -946,6 +952,17 @@ static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n) {
         c->B().h_pos_cap = cap;
     }
     memcpy(c->B().h_pos, pos, (size_t)n * 3 * sizeof(int32_t));
+    if (dev_pos) *dev_pos = c->B().d_pos;
+    // (only in the cost-ordered range: there a few CTAs read all positions in parallel while filing the request;
+    // below it every CTA would fetch its own first position over PCIe on its critical path -- measured slower)
+#ifdef UW_NO_ZC_POS
+    zero_copy_ok = false;
+#endif
+    if (zero_copy_ok && dev_pos && c->use_fused && c->host_ptr_ok && !c->ordered && c->z_hi >= c->z_lo &&
+        n > (uint32_t)(c->num_sms * c->fused_blocks_per_sm) && n <= c->order_cap) {
+        *dev_pos = c->B().h_pos;
+        return UW_OK;
+    }
     CU_TRY(c, cudaMemcpyAsync(c->B().d_pos, c->B().h_pos, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     return UW_OK;
 }
@@ -1050,8 +1067,9 @@ static uw_status build_common(uw_ctx* c, const int32_t* pos, const float* dens, 
     if (n == 0) { b->ready = true; *out = b; return UW_OK; }
     c->cur = set;
     b->set = set;
+    const int32_t* dev_pos = nullptr;
     uw_status st = ensure_chunks(c, n);
-    if (st == UW_OK) st = stage_positions(c, pos, n);
+    if (st == UW_OK) st = stage_positions(c, pos, n, &dev_pos, dens == nullptr);
     if (st == UW_OK && dens) {
         st = ensure_dens(c);
         const DevCfg& d = c->dcfg;
@@ -1059,7 +1077,7 @@ static uw_status build_common(uw_ctx* c, const int32_t* pos, const float* dens, 
                                                         cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
         if (e != cudaSuccess) st = fail(c, UW_ERR_CUDA, std::string("cudaMemcpy2DAsync densities: ") + cudaGetErrorString(e));
     }
-    if (st == UW_OK) st = enqueue_build(c, c->B().d_pos, n, dens != nullptr);
+    if (st == UW_OK) st = enqueue_build(c, dev_pos, n, dens != nullptr);
     if (st == UW_OK) {
         c->B().busy = true; c->B().owner = b;
         if (!async) st = collect_batch(c, b);

@@ -396,6 +396,18 @@ def test_output_arena_overflow_grows_and_reruns(uw, builder12, kw):
                 assert b1.chunk(i).verts.tobytes() == want.chunk(128 + i).verts.tobytes()
 
 
+def test_build_stream_matches_blocking_builds(uw, builder12):
+    slices = [uw.region.box_region((4 * k - 8, 4 * k - 4), (-4, 4), (-3, 2)) for k in range(4)]
+    got = list(builder12.build_stream(iter(slices)))
+    assert len(got) == len(slices)
+    for sl, g in zip(slices, got):
+        w = builder12.build(sl)
+        assert np.array_equal(g.descs["pos"], sl) and g.n_inds == w.n_inds and g.n_verts == w.n_verts
+        for i in range(0, len(sl), 11):
+            assert np.array_equal(g.chunk(i).inds, w.chunk(i).inds) and g.chunk(i).verts.tobytes() == w.chunk(i).verts.tobytes()
+    assert list(builder12.build_stream([])) == []
+
+
 def test_large_batch_properties(uw, builder12):
     """Config-3-sized slab properties that need no oracle: index range, packing, determinism,
     triangle soup equality between FP32 and exact-f64 topology."""

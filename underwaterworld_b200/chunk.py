@@ -240,6 +240,20 @@ class ChunkBuilder:
         self._check(self._lib.uw_batch_wait(handle))
         return self._collect(handle)
 
+    def build_stream(self, batches):
+        """Generator over an iterable of position arrays: yields one Batch per input, in order, keeping TWO batches
+        in flight (uw_build_async for batch k+1 before uw_batch_wait for batch k), so that batch k's copy to the
+        host runs underneath batch k+1's kernel.  The streaming form of World::build_full_step for a loader that
+        hands over a whole region in slices."""
+        prev = None
+        for positions in batches:
+            nxt = self.build_async(positions)
+            if prev is not None:
+                yield self.wait(prev)
+            prev = nxt
+        if prev is not None:
+            yield self.wait(prev)
+
     def build_from_densities(self, positions, densities) -> Batch:
         p = _as_positions(positions)
         d = np.ascontiguousarray(densities, dtype=np.float32).reshape(p.shape[0], -1)

@@ -304,6 +304,33 @@ def test_golden_oracle_kats_s12(uw, golden_dir):
             np.testing.assert_allclose(m.verts["color"], g[f"verts_{ci}"][:, 3:], rtol=0, atol=COL_TOL)
 
 
+@pytest.mark.parametrize("seed", [7, 20260101])
+def test_random_far_positions_match_oracle(uw, oracle12, seed):
+    """Chunks scattered over the whole supported range (|pos| <= 2^24: offsets up to 2^28 world units, where the f32
+    world positions have a 32-unit ulp and the noise lattice wraps many times) on the surface layers: the default
+    path's index buffers / counts / flags equal the oracle's bit for bit, and the exact-f64 mode reproduces vertex
+    positions and densities bit for bit as well."""
+    rng = np.random.default_rng(seed)
+    n = 240
+    mag = rng.choice([3, 200, 70_000, 1 << 20, (1 << 24) - 2], size=(n, 2))
+    xy = (rng.integers(-1, 2, size=(n, 2)) * mag + rng.integers(-2, 3, size=(n, 2))).clip(-(1 << 24), 1 << 24)
+    z = rng.integers(-4, 4, size=(n, 1))
+    pos = np.ascontiguousarray(np.concatenate([xy, z], axis=1).astype(np.int32))
+    perm = oracle12.perm_table(seed)
+    refs = _oracle_batch(oracle12, perm, pos, MODE_FAST)
+    assert sum(len(r["inds"]) for r in refs) > 50_000
+    with uw.ChunkBuilder(uw.Perlin(seed)) as fast:
+        got = fast.build(pos)
+    for i, r in enumerate(refs):
+        m = got.chunk(i)
+        assert m.flags & 3 == r["flags"] & 3, pos[i]
+        assert np.array_equal(m.inds.astype(np.uint32), r["inds"]), f"indices of chunk {pos[i]}"
+        assert len(m.verts) == len(r["verts"])
+    with uw.ChunkBuilder(uw.Perlin(seed), exact_f64=True, ordered=True) as exact:
+        sub = pos[::4]
+        _check_batch(exact.build(sub), refs[::4], exact_positions=True)
+
+
 def test_edge_cases(uw, builder12, oracle12):
     # empty batch
     b0 = builder12.build(np.zeros((0, 3), dtype=np.int32))

@@ -1783,14 +1783,14 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
 // ---------------------------------------------------------------------------------------
 #define UW_BIG_VCAP 4096     // slab vertex-list tile (entries)
 struct BigSmem {
-    float* plane[2]; uint32_t* bits[2]; uint16_t* vb[2]; uint8_t* cs[2]; uint16_t* ib; uint16_t* alist; uint16_t* vlist;
+    float* plane[3]; uint32_t* bits[3]; uint16_t* vb[2]; uint8_t* cs[2]; uint16_t* ib; uint16_t* alist; uint16_t* vlist;   // planes / sign bits: ring of 3
     uint32_t* lut; uint64_t* rows; uint16_t* before; uint16_t* crossed; uint8_t* nind;
 };
 
 __host__ __device__ inline size_t big_smem_bytes(const DevCfg& cfg) {
     const size_t L2p = ((size_t)cfg.L2 + 3) & ~(size_t)3, nw = (((size_t)cfg.L2 + 31) / 32 + 3) & ~(size_t)1;
     const size_t cells2 = ((size_t)cfg.S * cfg.S + 7) & ~(size_t)7;
-    return 2 * L2p * 4 + 256 * 8 + 256 * 4 + 2 * nw * 4 + 256 * 12 * 2 + 256 * 2 + 256
+    return 3 * L2p * 4 + 256 * 8 + 256 * 4 + 3 * nw * 4 + 256 * 12 * 2 + 256 * 2 + 256
          + 4 * cells2 * 2 + UW_BIG_VCAP * 2 + 2 * ((cells2 + 15) & ~(size_t)15);
 }
 
@@ -1800,10 +1800,12 @@ __device__ __forceinline__ BigSmem big_smem_carve(const DevCfg& cfg, unsigned ch
     BigSmem s;
     s.plane[0] = (float*)base; base += L2p * 4;
     s.plane[1] = (float*)base; base += L2p * 4;
+    s.plane[2] = (float*)base; base += L2p * 4;
     s.rows = (uint64_t*)base; base += 256 * 8;
     s.lut = (uint32_t*)base; base += 256 * 4;
     s.bits[0] = (uint32_t*)base; base += nw * 4;
     s.bits[1] = (uint32_t*)base; base += nw * 4;
+    s.bits[2] = (uint32_t*)base; base += nw * 4;
     s.before = (uint16_t*)base; base += 256 * 12 * 2;
     s.crossed = (uint16_t*)base; base += 256 * 2;
     s.nind = (uint8_t*)base; base += 256;
@@ -2001,10 +2003,12 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
 #pragma unroll
             for (int q = 0; q < UW_BIG_NLD; ++q) { const int idx = q * UW_BIG_NT + tid; pre[q] = idx < L2 ? __ldg(src + idx) : 0.f; }
         };
-        // plane x -> buffer x & 1: floats and sign bits (warp ballots)
+        // plane x -> ring slot x % 3: floats and sign bits (warp ballots).  Three slots: the vertex pass of slab cx
+        // still reads planes cx and cx+1 while the next iteration already commits plane cx+2, so no barrier is
+        // needed at the end of a slab.
         auto commit = [&](int x) {
-            float* pl = s.plane[x & 1];
-            uint32_t* bt = s.bits[x & 1];
+            float* pl = s.plane[x % 3];
+            uint32_t* bt = s.bits[x % 3];
 #pragma unroll
             for (int q = 0; q < UW_BIG_NLD; ++q) {
                 const int base = q * UW_BIG_NT + tid - lane;
@@ -2024,8 +2028,8 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
             commit(cx + 1);
             if (cx + 2 <= x1) issue(cx + 2);               // in flight while this slab is classified and emitted
             __syncthreads();
-            const uint32_t* A = s.bits[cx & 1];            // plane x = cx
-            const uint32_t* B = s.bits[(cx + 1) & 1];      // plane x = cx + 1
+            const uint32_t* A = s.bits[cx % 3];            // plane x = cx
+            const uint32_t* B = s.bits[(cx + 1) % 3];      // plane x = cx + 1
             uint8_t* cs_cur = s.cs[cx & 1];
             uint16_t* vb_cur = s.vb[cx & 1];
             const uint8_t* cs_prev = s.cs[(cx + 1) & 1];
@@ -2108,8 +2112,8 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
                     }
                 }
                 __syncthreads();
-                const float* P0 = s.plane[cx & 1];
-                const float* P1 = s.plane[(cx + 1) & 1];
+                const float* P0 = s.plane[cx % 3];
+                const float* P1 = s.plane[(cx + 1) % 3];
                 auto dens_at = [=](int ax, int ay, int az) { return (ax == cx ? P0 : P1)[ay * L + az]; };
                 for (uint32_t v0 = 0; !warm && v0 < (slab_nv ? slab_nv : 1u); v0 += UW_BIG_VCAP) {
                     if (v0) __syncthreads();                // the previous tile's vertex threads are done with vlist
@@ -2158,8 +2162,10 @@ __global__ void __launch_bounds__(UW_BIG_NT, 2) k_emit_big(const __grid_constant
             }
             vrun_prev = vrun;
             vrun += slab_nv; irun += ti;
-            __syncthreads();                               // buffers (cx & 1) are overwritten by the next commit
+            // no barrier here: the next commit writes ring slot (cx + 2) % 3; case / vertex-base arrays, the surface-
+            // cell list and the vertex list are only rewritten behind the next iteration's first barriers
         }
+        __syncthreads();                                   // before the next work unit reuses every buffer
     }
 }
 

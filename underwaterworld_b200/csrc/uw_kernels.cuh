@@ -571,8 +571,11 @@ __device__ __forceinline__ Ticket ticket_fetch(const Handout& h, uint32_t t) {
 // Arithmetic per octave-sample (z stage): with (R0,S0) / (R1,S1) the y-lerped value/z-slope at
 // the low/high noise-lattice plane,  v = a0 + w (a1 - a0),  a0 = R0 + S0 d,  a1 = R1 + S1 (d-1)
 //   =>  v = fma(w, fma(d, D, C), fma(d, S0, R0)),   C = (R1 - R0) - S1,  D = S1 - S0
-// 3 FFMA + 2 FMNMX (the reference's clamp) + 1 FADD (octave sum).  The octave weight
-// 2/sqrt(3) * 2^-o / sum(2^-o) is folded into the x stage (everything downstream is linear).
+// The reference's clamp of every octave to [-1, 1] costs nothing: stage X carries the octave normalised to its
+// clamp range and shifted, u = v / sqrt(3) + 1/2 (the shift rides on the value component through the y and z
+// lerps, whose weights sum to 1), so the clamp is the .sat of the last FFMA, and the octave weight
+// 2^-o / sum(2^-o) is the multiplier of the FFMA that accumulates the octaves onto (terrace term - 1):
+// 3 FFMA (one .SAT) + 1 FFMA per octave-sample (it was 3 FFMA + 2 FMNMX + 1 FADD).
 // ---------------------------------------------------------------------------------------
 template <int ST, int NOCT>
 struct SpecDims {
@@ -645,7 +648,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     if (tid >= NT - 32 && tid - (NT - 32) < L) {   // terrace term perlin_util.rs:27-28 (last warp: it has idle lanes later)
         float adj, fm;
         terrace_terms(cfg, tid - (NT - 32), pz, adj, fm);
-        sm.terr[tid - (NT - 32)] = __fsub_rn(adj, fm);
+        // minus 1: every octave value is carried as u = v / (2 lim) + 1/2 in [0, 1] (see stage YZ) and
+        // sum_o lim_o = 1
+        sm.terr[tid - (NT - 32)] = __fsub_rn(__fsub_rn(adj, fm), 1.0f);
     }
     if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; }
     __syncthreads();
@@ -656,7 +661,10 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
 #pragma unroll
     for (int o = 0; o < NOCT; ++o) {
         const int G = D::G(o), lb = D::lat_base(o), xb = D::x_base(o);
-        const float sc = 1.1547005383792515f * inv_max / (float)(1 << o);
+        // the octave value is carried normalised to its clamp range and shifted: u = v * (2/sqrt(3)) / 2 + 1/2, so
+        // that the reference's clamp to [-1, 1] becomes the .sat of the last FFMA of stage YZ; the shift rides on
+        // the value component through the y and z lerps (weights sum to 1), the slopes are only scaled
+        const float sc = 1.1547005383792515f * 0.5f;
         for (int t = tid; t < L * G * G; t += NT) {
             const int i = t / (G * G), r = t - i * G * G;
             const int c = (i << o) / ST;
@@ -666,7 +674,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             const float d = ax.x, d1 = ax.y, w = ax.z;
             const float q0 = g0.x * d, q1 = g1.x * d1;
             float4 e;
-            e.x = fmaf(w, q1 - q0, q0) * sc;
+            e.x = fmaf(fmaf(w, q1 - q0, q0), sc, 0.5f);
             e.y = fmaf(w, g1.y - g0.y, g0.y) * sc;
             e.z = fmaf(w, g1.z - g0.z, g0.z) * sc;
             e.w = 0.f;
@@ -703,10 +711,10 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         float* out = sm.dens + tid * L;
         const float isl = cfg.iso_level, eps = cfg.guard_eps;
         uint32_t signs = 0;                       // bit (L-1-k) <- (iso_k < iso_level), shifted in MSB-first
-        uint32_t near = 0;                        // bit k <- sample k fell inside the guard band
+        float nearest = 3.0e38f;                  // min |iso - iso_level| of the column: one FMNMX per sample
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            float total = 0.f;
+            float total = sm.terr[k];                                    // terrace term - 1
 #pragma unroll
             for (int o = 0; o < NOCT; ++o) {
                 const int c = D::cell(o, k);
@@ -715,19 +723,24 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
                 else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; ystage(o, c + 1, R1[o], S1[o]); }
                 if (first || step) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
                 const float d = D::tab_d(o, k), w = D::tab_w(o, k);      // immediates after unrolling
-                float v = fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o]));
-                const float lim = inv_max / (float)(1 << o);            // the reference's clamp to [-1, 1], scaled
-                v = fminf(fmaxf(v, -lim), lim);
-                total += v;
+                // FFMA.SAT = the reference's clamp to [-1, 1] in the normalised, shifted scale
+                const float u = __saturatef(fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o])));
+                total = fmaf(u, 2.0f * inv_max / (float)(1 << o), total);   // octave weight 2^-o / sum(2^-o), times 2 lim
             }
-            const float iso = total + sm.terr[k];
+            const float iso = total;
             const float diff = iso - isl;
             out[k] = iso;
-            if (fabsf(diff) < eps) near |= 1u << k;
+            nearest = fminf(nearest, fabsf(diff));
             signs = __funnelshift_l(__float_as_uint(diff), signs, 1);   // (signs << 1) | sign bit of diff
         }
         uint32_t inside = __brev(signs) >> (32 - L);                     // bit k <- (iso_k < iso_level)
         bool any_eq = false;
+        uint32_t near = 0;                        // bit k <- sample k fell inside the guard band
+        if (nearest < eps) {                      // rare: find which samples (the column is still in shared memory)
+#pragma unroll 1
+            for (int k = 0; k < L; ++k)
+                if (fabsf(out[k] - isl) < eps) near |= 1u << k;
+        }
         while (near) {                                                   // rare: exact f64 re-evaluation
             const int k = __ffs(near) - 1;
             near &= near - 1;
@@ -1671,7 +1684,7 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
         if (tid < L) {
             float adj, fm;
             terrace_terms(cfg, tid, pz, adj, fm);
-            sm.terr[tid] = __fsub_rn(adj, fm);
+            sm.terr[tid] = __fsub_rn(__fsub_rn(adj, fm), 1.0f);       // minus 1: octave values are carried shifted, see noise_chunk_spec
         }
         __syncthreads();
         // ---- stage X (only the planes this unit touches) ------------------------------------------
@@ -1680,7 +1693,7 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
 #pragma unroll
             for (int o = 0; o < NOCT; ++o) {
                 const int G = D::G(o), lb = D::lat_base(o);
-                const float sc = 1.1547005383792515f * inv_max / (float)(1 << o);
+                const float sc = 1.1547005383792515f * 0.5f;         // normalised to the clamp range, see noise_chunk_spec
                 for (int t = tid; t < npl * G * G; t += NT) {
                     const int pl = t / (G * G), r = t - pl * G * G;
                     const int i = i_min + pl, c = (i << o) / ST;
@@ -1688,7 +1701,7 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
                     const float4 ax = sm.axis[o][i];
                     const float q0 = g0.x * ax.x, q1 = g1.x * ax.y;
                     float4 e;
-                    e.x = fmaf(ax.z, q1 - q0, q0) * sc;
+                    e.x = fmaf(fmaf(ax.z, q1 - q0, q0), sc, 0.5f);
                     e.y = fmaf(ax.z, g1.y - g0.y, g0.y) * sc;
                     e.z = fmaf(ax.z, g1.z - g0.z, g0.z) * sc;
                     e.w = 0.f;
@@ -1747,7 +1760,7 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
         };
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            float total = 0.f;
+            float total = sm.terr[k];
 #pragma unroll
             for (int o = 0; o < NOCT; ++o) {
                 const int c = D::cell(o, k);
@@ -1756,12 +1769,10 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
                 else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; ystage(o, c + 1, R1[o], S1[o]); }
                 if (first || step) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
                 const float d = D::tab_d(o, k), w = D::tab_w(o, k);
-                float v = fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o]));
-                const float lim = inv_max / (float)(1 << o);
-                v = fminf(fmaxf(v, -lim), lim);
-                total += v;
+                const float u = __saturatef(fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o])));   // FFMA.SAT = the clamp
+                total = fmaf(u, 2.0f * inv_max / (float)(1 << o), total);
             }
-            const float iso = total + sm.terr[k];
+            const float iso = total;
             const int kk = k < HALF ? k : k - HALF;
             trow[kk] = iso;
             if (live && fabsf(iso - isl) < eps) near |= 1ull << kk;

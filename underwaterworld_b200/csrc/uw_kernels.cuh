@@ -580,10 +580,22 @@ __device__ __forceinline__ Ticket ticket_fetch(const Handout& h, uint32_t t) {
 template <int ST, int NOCT>
 struct SpecDims {
     static constexpr int S = ST, L = ST + 1;
-    __host__ __device__ static constexpr int G(int o) { return (1 << o) + 2; }
-    __host__ __device__ static constexpr int lat_base(int o) { return o == 0 ? 0 : o == 1 ? 27 : o == 2 ? 91 : o == 3 ? 307 : 1307; }   // prefix of G^3
-    __host__ __device__ static constexpr int x_base(int o) { return L * (o == 0 ? 0 : o == 1 ? 9 : o == 2 ? 25 : o == 3 ? 61 : 161); }  // L * prefix of G^2
-    static constexpr int LAT = lat_base(NOCT), XN = x_base(NOCT);
+    // Noise-lattice planes per axis and octave.  The chunk spans 2^o noise cells -> 2^o + 1 lattice planes, plus
+    // one more ONLY for the chunk's last sample (k = S), which sits a hair (2^o * 3e-8) inside the next cell when
+    // SIZE_SCALE = f32(16/S) rounds up (chunk.rs:7).  Its weight on that extra plane is fade(3e-8) ~ 1e-22 -- far
+    // below half an ulp of anything it is added to -- so when that holds for every octave (PRUNE; true for
+    // S = 10, 12 and, with weight exactly 0, 64) the plane is never hashed, lerped or read: 160 instead of 307
+    // hash chains and 494 instead of 793 x-lerps per 13^3 chunk.  (The exact f64 guard-band path keeps the term.)
+    __host__ __device__ static constexpr bool prune() {
+        for (int o = 0; o < NOCT; ++o) {
+            if (!(tab_w(o, ST) < 1e-15f) || cell(o, ST) != (1 << o) || cell(o, ST - 1) >= (1 << o)) return false;
+        }
+        return true;
+    }
+    static constexpr bool PRUNE = prune();
+    __host__ __device__ static constexpr int G(int o) { return (1 << o) + (PRUNE ? 1 : 2); }
+    __host__ __device__ static constexpr int lat_base(int o) { int b = 0; for (int q = 0; q < o; ++q) b += G(q) * G(q) * G(q); return b; }   // prefix of G^3
+    __host__ __device__ static constexpr int x_base(int o) { int b = 0; for (int q = 0; q < o; ++q) b += G(q) * G(q); return L * b; }       // L * prefix of G^2
     static constexpr int DSTRIDE = (L * L * L + 3) & ~3;
     static constexpr int NT = ((L * L + 31) / 32) * 32;
     __host__ __device__ static constexpr int cell(int o, int k) { return (k << o) / ST; }
@@ -599,6 +611,7 @@ struct SpecDims {
     __host__ __device__ static constexpr float tab_d(int o, int k) { return (float)axis_frac(o, k); }
     __host__ __device__ static constexpr float tab_w(int o, int k) { return (float)cfade(axis_frac(o, k)); }
     __host__ __device__ static constexpr int tab_c(int o, int k) { return (int)cfloor(axis_p(o, k)); }
+    static constexpr int LAT = lat_base(NOCT), XN = x_base(NOCT), GTOP = G(NOCT - 1);
 };
 
 template <int ST, int NOCT>
@@ -609,7 +622,8 @@ struct SpecSmem {
     // lat + X (+ this pad) are dead after the noise stages; the fused kernel reuses the region for the
     // vertex-id table of K4 (L^3 * 5 u16)
     static constexpr int VID_BYTES = D::L * D::L * D::L * 5 * 2;
-    static constexpr int PAD = VID_BYTES > (D::LAT + D::XN) * 16 ? ((VID_BYTES - (D::LAT + D::XN) * 16 + 15) / 16) * 16 : 16;
+    static constexpr int PAD0 = VID_BYTES > (D::LAT + D::XN) * 16 ? ((VID_BYTES - (D::LAT + D::XN) * 16 + 15) / 16) * 16 : 16;
+    static constexpr int PAD = PAD0 > D::GTOP * 16 ? PAD0 : D::GTOP * 16;   // >= one X row: see stage X (PRUNE)
     unsigned char xpad[PAD];
     float dens[D::DSTRIDE];
     float4 grad[16];
@@ -668,8 +682,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         for (int t = tid; t < L * G * G; t += NT) {
             const int i = t / (G * G), r = t - i * G * G;
             const int c = (i << o) / ST;
+            const int c1 = D::PRUNE ? min(c + 1, G - 1) : c + 1;         // i = S: weight ~ 1e-22 on a plane that is not kept
             const float4 g0 = sm.lat[lb + c * G * G + r];
-            const float4 g1 = sm.lat[lb + (c + 1) * G * G + r];
+            const float4 g1 = sm.lat[lb + c1 * G * G + r];
             const float4 ax = sm.axis[o][i];
             const float d = ax.x, d1 = ax.y, w = ax.z;
             const float q0 = g0.x * d, q1 = g1.x * d1;
@@ -681,6 +696,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             sm.X[xb + t] = e;
         }
     }
+    // PRUNE: a column with j = S reads the X row "one past" its last kept row with weight ~ 1e-22; that is row 0 of
+    // the next x-plane / the next octave (finite values) or, for the very last one, this pad row: keep it finite
+    if (D::PRUNE && tid < D::GTOP) sm.X[D::XN + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     PHASE_MARK(12);
     if (hand && tid == NT - 1) *tk_out = ticket_fetch(*hand, tk_t);
@@ -719,12 +737,15 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             for (int o = 0; o < NOCT; ++o) {
                 const int c = D::cell(o, k);
                 const bool first = (k == 0), step = (k > 0) && (c != D::cell(o, k > 0 ? k - 1 : 0));
+                // PRUNE: the last sample's weight on the far plane is ~ 1e-22 (or 0): v = a0, from the plane already held
+                const bool top = D::PRUNE && k == L - 1;
                 if (first) { ystage(o, c, R0[o], S0[o]); ystage(o, c + 1, R1[o], S1[o]); }
-                else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; ystage(o, c + 1, R1[o], S1[o]); }
-                if (first || step) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
+                else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; if (!top) ystage(o, c + 1, R1[o], S1[o]); }
+                if ((first || step) && !top) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
                 const float d = D::tab_d(o, k), w = D::tab_w(o, k);      // immediates after unrolling
                 // FFMA.SAT = the reference's clamp to [-1, 1] in the normalised, shifted scale
-                const float u = __saturatef(fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o])));
+                const float u = top ? __saturatef(fmaf(d, S0[o], R0[o]))
+                                    : __saturatef(fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o])));
                 total = fmaf(u, 2.0f * inv_max / (float)(1 << o), total);   // octave weight 2^-o / sum(2^-o), times 2 lim
             }
             const float iso = total;
@@ -1633,7 +1654,7 @@ struct BigNoiseSmem {
     using D = SpecDims<ST, NOCT>;
     static constexpr int NT = 256, NW = NT / 32;
     static constexpr int PLMAX = (NT + D::L - 2) / D::L + 1;           // x-planes 256 consecutive columns can touch
-    static constexpr int G2SUM = (NOCT >= 1 ? 9 : 0) + (NOCT >= 2 ? 16 : 0) + (NOCT >= 3 ? 36 : 0) + (NOCT >= 4 ? 100 : 0);
+    static constexpr int G2SUM = D::x_base(NOCT) / D::L;                 // sum over octaves of G^2
     static constexpr int HALF = (D::L + 1) / 2;                         // z samples per tile flush
     float4 lat[D::LAT];
     float4 X[PLMAX * G2SUM];
@@ -1660,6 +1681,9 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
     for (int t = tid; t < 256; t += NT) sm.perm[t] = g_perm[t];
     if (tid < 16) sm.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
     for (int t = tid; t < NOCT * L; t += NT) sm.axis[t / L][t % L] = g_axis[t];
+    // PRUNE: columns with j = S read one X row past their last kept row (weight ~ 0): that row must hold finite
+    // values from the first unit on -- X only ever holds finite values afterwards, and `axis` follows it
+    for (int t = tid; t < SM::PLMAX * SM::G2SUM; t += NT) sm.X[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     constexpr float inv_max = 1.0f / (2.0f - 1.0f / (float)(1 << (NOCT - 1)));
@@ -1697,7 +1721,8 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
                 for (int t = tid; t < npl * G * G; t += NT) {
                     const int pl = t / (G * G), r = t - pl * G * G;
                     const int i = i_min + pl, c = (i << o) / ST;
-                    const float4 g0 = sm.lat[lb + c * G * G + r], g1 = sm.lat[lb + (c + 1) * G * G + r];
+                    const int c1 = D::PRUNE ? min(c + 1, G - 1) : c + 1;  // see SpecDims::prune
+                    const float4 g0 = sm.lat[lb + c * G * G + r], g1 = sm.lat[lb + c1 * G * G + r];
                     const float4 ax = sm.axis[o][i];
                     const float q0 = g0.x * ax.x, q1 = g1.x * ax.y;
                     float4 e;
@@ -1765,11 +1790,14 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
             for (int o = 0; o < NOCT; ++o) {
                 const int c = D::cell(o, k);
                 const bool first = (k == 0), step = (k > 0) && (c != D::cell(o, k > 0 ? k - 1 : 0));
+                // PRUNE: the last sample's weight on the far plane is ~ 1e-22 (or 0): v = a0, from the plane already held
+                const bool top = D::PRUNE && k == L - 1;
                 if (first) { ystage(o, c, R0[o], S0[o]); ystage(o, c + 1, R1[o], S1[o]); }
-                else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; ystage(o, c + 1, R1[o], S1[o]); }
-                if (first || step) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
+                else if (step) { R0[o] = R1[o]; S0[o] = S1[o]; if (!top) ystage(o, c + 1, R1[o], S1[o]); }
+                if ((first || step) && !top) { Cc[o] = (R1[o] - R0[o]) - S1[o]; Dd[o] = S1[o] - S0[o]; }
                 const float d = D::tab_d(o, k), w = D::tab_w(o, k);
-                const float u = __saturatef(fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o])));   // FFMA.SAT = the clamp
+                const float u = top ? __saturatef(fmaf(d, S0[o], R0[o]))
+                                    : __saturatef(fmaf(w, fmaf(d, Dd[o], Cc[o]), fmaf(d, S0[o], R0[o])));   // FFMA.SAT = the clamp
                 total = fmaf(u, 2.0f * inv_max / (float)(1 << o), total);
             }
             const float iso = total;

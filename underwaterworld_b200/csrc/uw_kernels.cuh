@@ -1267,8 +1267,13 @@ __device__ __forceinline__ float srgb_of(float ch_plus_m) {
 }
 
 __device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, int vi, float out[3]) {
-    const float ratio = __fdiv_rn(world_z, (float)cfg.chunk_size);
-    const float mix = __fdiv_rn(__fsub_rn(ratio, cfg.min_z), __fsub_rn(cfg.max_z, cfg.min_z));
+    // x / 2^n == x * 2^-n exactly (no subnormals in reach): the two power-of-two divisions of the reference's
+    // constants (CHUNK_SIZE = 16, MAX_Z - MIN_Z = 4) are multiplies; anything else divides
+    const float ratio = cfg.cs_pow2 ? __fmul_rn(world_z, (float)cfg.inv_chunk_size) : __fdiv_rn(world_z, (float)cfg.chunk_size);
+    const float zr = __fsub_rn(cfg.max_z, cfg.min_z);
+    const bool zr_pow2 = (__float_as_uint(zr) & 0x807FFFFFu) == 0u && zr >= 1.0f / 1024.0f && zr <= 1024.0f;
+    const float num = __fsub_rn(ratio, cfg.min_z);
+    const float mix = zr_pow2 ? __fmul_rn(num, __uint_as_float(0x7F000000u - __float_as_uint(zr))) : __fdiv_rn(num, zr);
     float hue = __fadd_rn(cfg.min_hue, __fmul_rn(__fsub_rn(cfg.max_hue, cfg.min_hue), mix));
     float r = fabsf(hue) < 360.0f ? hue : fmodf(hue, 360.0f);   // f32::rem_euclid, util.rs:123 (fmod is exact)
     if (r < 0.0f) r = __fadd_rn(r, 360.0f);
@@ -1544,11 +1549,16 @@ __device__ __forceinline__ void emit_indices(const DevCfg& cfg, const McTables* 
         const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
         const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
         IndexT* dst = iout + s.ibase[a];
+        const uint16_t* vid = s.vid + lbase;
 #pragma unroll
-        for (int k = 0; k < 15; ++k) {
-            const uint32_t e = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
-            if (e == 15u) break;
-            dst[k] = (IndexT)s.vid[lbase + s.eoff[e]];                 // `ind as u16`, chunk.rs:243
+        for (int k = 0; k < 15; k += 3) {                              // a triangle at a time: three independent lookups in flight
+            const uint32_t e0 = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
+            if (e0 == 15u) break;
+            const uint32_t e1 = ((k + 1 < 8 ? rlo : rhi) >> (4 * ((k + 1) & 7))) & 15u;
+            const uint32_t e2 = ((k + 2 < 8 ? rlo : rhi) >> (4 * ((k + 2) & 7))) & 15u;
+            const uint32_t o0 = s.eoff[e0], o1 = s.eoff[e1], o2 = s.eoff[e2];
+            const IndexT i0 = (IndexT)vid[o0], i1 = (IndexT)vid[o1], i2 = (IndexT)vid[o2];   // `ind as u16`, chunk.rs:243
+            dst[k] = i0; dst[k + 1] = i1; dst[k + 2] = i2;
         }
     }
 }

@@ -1366,13 +1366,14 @@ __device__ __forceinline__ void owner_of(int e, int x, int y, int z, int& ox, in
 // ---------------------------------------------------------------------------------------
 #define UW_SMALL_MAX_CELLS ((UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1))
 #ifndef UW_VLIST_CAP
-#define UW_VLIST_CAP 4096
+#define UW_VLIST_CAP 3072
 #endif
 #define UW_EDGE_KINDS 5      // +x, -x, +y, +z, -z  (-y never occurs: edges 8..11 all run +y)
 
 struct EmitSmem {
     float* dens; uint32_t* bits; uint32_t* mask; uint16_t* vbase; uint16_t* ibase; uint16_t* alist;
     uint16_t* vlist; uint16_t* vid; uint8_t* cs; uint32_t* lut; uint16_t* eoff;
+    const uint64_t* rows;           // McTables::rows in shared memory (the L1 left beside 4 x 55 KB of shared memory does not keep it)
 };
 
 // per edge: (corner_a lattice offset) * 5 + direction kind, for lattice size L
@@ -1395,6 +1396,7 @@ __host__ __device__ inline size_t emit_smem_bytes(const DevCfg& cfg) {
     b += UW_VLIST_CAP * 2;
     b += (((size_t)cfg.L3 * UW_EDGE_KINDS + 7) & ~(size_t)7) * 2;
     b += 256 * 4 + 16 * 2;
+    b += 256 * 8;
     b += (cells + 15) & ~(size_t)15;
     return b;
 }
@@ -1402,7 +1404,8 @@ __host__ __device__ inline size_t emit_smem_bytes(const DevCfg& cfg) {
 __device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned char* base) {
     const size_t cells = (size_t)cfg.S * cfg.S * cfg.S, cells2 = (cells + 7) & ~(size_t)7;
     EmitSmem s;
-    s.dens = (float*)base;        base += (size_t)cfg.dens_stride * 4;
+    s.dens = (float*)base;        base += (size_t)cfg.dens_stride * 4;       // multiple of 16 bytes
+    s.rows = (const uint64_t*)base; base += 256 * 8;
     s.bits = (uint32_t*)base;     base += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
     s.mask = (uint32_t*)base;     base += ((size_t)cfg.L2 + 3) / 4 * 16;
     s.vbase = (uint16_t*)base;    base += cells2 * 2;
@@ -1498,7 +1501,7 @@ __device__ __forceinline__ void emit_fill(const DevCfg& cfg, const McTables* __r
         const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
         const uint32_t own = 0x4F0u | (y == 0 ? 0x00Fu : 0u) | (x == 0 ? 0x800u : 0u)
                            | (z == 0 ? (0x200u | (x == 0 ? 0x100u : 0u)) : 0u);
-        const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
+        const uint64_t row = s.rows[s.cs[cell]];
         const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
         const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
         uint32_t vnext = s.vbase[a], todo = own;        // owned edges not yet numbered
@@ -1545,7 +1548,7 @@ __device__ __forceinline__ void emit_indices(const DevCfg& cfg, const McTables* 
     for (uint32_t a = tid; a < sh.n_act; a += NT) {
         const int cell = s.alist[a];
         const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
-        const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
+        const uint64_t row = s.rows[s.cs[cell]];
         const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
         const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
         IndexT* dst = iout + s.ibase[a];
@@ -1586,7 +1589,7 @@ __device__ __forceinline__ void emit_tris(const DevCfg& cfg, const McTables* __r
         const int cell = s.alist[lo];
         const int t = (int)((3u * j - s.ibase[lo]) / 3u);
         const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
-        const uint64_t row = __ldg(&mc->rows[s.cs[cell]]);
+        const uint64_t row = s.rows[s.cs[cell]];
         const int e0 = (int)((row >> (12 * t)) & 0xFull), e1 = (int)((row >> (12 * t + 4)) & 0xFull), e2 = (int)((row >> (12 * t + 8)) & 0xFull);
         float v[12];
         edge_position(cfg, dens_at, x, y, z, e0, offx, offy, offz, v);
@@ -1632,7 +1635,7 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
     const int L = (ST > 0 ? ST : cfg.S) + 1;
     const uint32_t n_active = totals->n_active;
     if (totals->overflow) return;                       // host grows the arenas and relaunches
-    for (int t = tid; t < 256; t += NT) s.lut[t] = mc->lut[t];
+    for (int t = tid; t < 256; t += NT) { s.lut[t] = mc->lut[t]; const_cast<uint64_t*>(s.rows)[t] = mc->rows[t]; }
     fill_edge_offsets(s.eoff, L);
 
     for (uint32_t a = blockIdx.x; a < n_active; a += gridDim.x) {
@@ -2243,6 +2246,7 @@ struct FusedSmem {
     uint16_t vbase[ST * ST * ST + 8];                 // vbase / ibase / alist: one entry per SURFACE cell (worst case: all)
     uint16_t ibase[ST * ST * ST + 8];
     uint16_t alist[ST * ST * ST + 8];
+    uint64_t rows[256];
     uint32_t lut[256];
     uint16_t eoff[16];
     uint8_t cs[((ST * ST * ST + 15) / 16) * 16];
@@ -2332,7 +2336,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     es.dens = sm.n.dens; es.bits = nullptr; es.mask = sm.n.mask;
     es.vid = reinterpret_cast<uint16_t*>(sm.n.lat);
     es.vlist = sm.vlist; es.vbase = sm.vbase; es.ibase = sm.ibase; es.alist = sm.alist;
-    es.cs = sm.cs; es.lut = sm.lut; es.eoff = sm.eoff;
+    es.cs = sm.cs; es.lut = sm.lut; es.eoff = sm.eoff; es.rows = sm.rows;
     using NS = SpecSmem<ST, NOCT>;
     static_assert(offsetof(NS, X) == offsetof(NS, lat) + sizeof(sm.n.lat), "lat and X must be adjacent");
     static_assert(offsetof(NS, xpad) == offsetof(NS, X) + sizeof(sm.n.X), "X and xpad must be adjacent");
@@ -2363,7 +2367,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         const int o = t / L, i = t - o * L;
         sm.n.axis[o][i] = make_float4(tab.d[o][i], tab.d1[o][i], tab.w[o][i], 0.f);
     }
-    for (int t = tid; t < 256; t += D::NT) sm.lut[t] = mc->lut[t];
+    for (int t = tid; t < 256; t += D::NT) { sm.lut[t] = mc->lut[t]; sm.rows[t] = mc->rows[t]; }
     fill_edge_offsets(sm.eoff, L);
 
     if (tid == D::NT - 1) {

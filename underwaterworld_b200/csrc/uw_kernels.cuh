@@ -1298,7 +1298,9 @@ __device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, i
 template <class DensAt>
 __device__ __forceinline__ int edge_position(const DevCfg& cfg, DensAt dens_at, int x, int y, int z, int e,
                                              int offx, int offy, int offz, float p[3]) {
-    const int ca = c_edge_a[e], cb = c_edge_b[e];
+    // EDGE_VERTEX_INDICES (marching_table.rs:1-14) as nibble-packed immediates: a per-lane index into constant
+    // memory would replay once per distinct edge in the warp
+    const int ca = (int)((0x321076543210ull >> (4 * e)) & 15ull), cb = (int)((0x765447650321ull >> (4 * e)) & 15ull);
     int ax, ay, az, bx, by, bz;
     corner_off(ca, ax, ay, az); corner_off(cb, bx, by, bz);
     ax += x; ay += y; az += z; bx += x; by += y; bz += z;

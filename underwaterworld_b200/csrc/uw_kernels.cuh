@@ -269,6 +269,7 @@ __device__ __forceinline__ NoiseSmem noise_smem_carve(const DevCfg& cfg, unsigne
 // per-chunk flags written by K1/K2
 #define CF_ALL_GT   1u   // every sample >  iso_level  -> early blank (chunk.rs:131-133)
 #define CF_ANY_LT   2u   // some sample  <  iso_level  -> mesh stage may emit
+#define CF_ALL_LT   4u   // every sample <  iso_level  -> all-solid: every case is 255, nothing to emit (fused kernel only)
 
 template <int LT, int NOCT>
 __global__ void __launch_bounds__(256) k_noise_small(const __grid_constant__ DevCfg cfg,
@@ -666,7 +667,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         // sum_o lim_o = 1
         sm.terr[tid - (NT - 32)] = __fsub_rn(__fsub_rn(adj, fm), 1.0f);
     }
-    if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; }
+    if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; sm.red[2] = 1; }
     __syncthreads();
     PHASE_MARK(11);
 
@@ -775,13 +776,15 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         // outside the guard band |iso - isl| >= eps > 0, so "all > isl" <=> no inside bit and no exact tie
         const bool all_gt = (inside == 0u) && !any_eq, any_lt = inside != 0u;
         const bool w_all = __all_sync(__activemask(), all_gt), w_any = __any_sync(__activemask(), any_lt);
+        const bool w_solid = __all_sync(__activemask(), inside == (1u << L) - 1u);      // the all-full vote
         if ((tid & 31) == 0 || tid == (L * L / 32) * 32) {
             if (!w_all) sm.red[0] = 0;
             if (w_any) sm.red[1] = 1;
+            if (!w_solid) sm.red[2] = 0;
         }
     }
     __syncthreads();
-    return (sm.red[0] ? CF_ALL_GT : 0u) | (sm.red[1] ? CF_ANY_LT : 0u);
+    return (sm.red[0] ? CF_ALL_GT : 0u) | (sm.red[1] ? CF_ANY_LT : 0u) | (sm.red[2] ? CF_ALL_LT : 0u);
 }
 
 template <int ST, int NOCT>
@@ -2404,7 +2407,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         ChunkShape sh;
         sh.n_vert = 0; sh.n_ind = 0; sh.n_act = 0;
         unsigned long long packed = 0;
-        if (fl & CF_ANY_LT)
+        if ((fl & (CF_ANY_LT | CF_ALL_LT)) == CF_ANY_LT)   // all-empty and all-full chunks skip K2..K4 (north_star's ballot skip)
             sh = emit_prepare<ST>(cfg, es, sm.w, tri_cell ? tri_cell + (size_t)chunk * (ST * ST * ST + 1) : nullptr,
                                   ordered ? nullptr : &ctr->alloc, &packed);
         const uint32_t nv = sh.n_vert, ni = sh.n_ind;

@@ -158,3 +158,22 @@ def test_tri_lists_cover_every_triangle(oracle12):
     assert np.array_equal(v.view(np.uint32), r["tris"]["verts"].view(np.uint32))
     n = np.linalg.norm(r["tris"]["normal"], axis=1)
     assert np.all((np.abs(n - 1) < 1e-5) | (n == 0))
+
+
+@pytest.mark.parametrize("S", [10, 12, 64])
+def test_far_lattice_plane_carries_no_weight(S):
+    """The argument behind SpecDims::prune() (uw_kernels.cuh): the chunk's last sample (k = S) is the only one that
+    reaches the (2^o + 1)-th noise-lattice plane of an axis, and its fade weight on that plane is far below half an
+    ulp of anything it is added to (exactly 0 when SIZE_SCALE is exact), so the FP32 kernels never touch the plane.
+    f64 arithmetic of chunk.rs:107-116 / the noise crate's quintic fade, as the host builds its axis tables."""
+    scale = float(np.float32(16.0) / np.float32(S))                  # SIZE_SCALE (f32), chunk.rs:7
+    for o in range(3):
+        cells = [int(np.floor(((k * scale) / 16.0) * (1 << o))) for k in range(S + 1)]
+        assert max(cells[:-1]) == (1 << o) - 1 and cells[-1] == (1 << o)
+        p = ((S * scale) / 16.0) * (1 << o)
+        d = p - np.floor(p)
+        w = (d * d * d) * (d * (d * 6.0 - 15.0) + 10.0)
+        assert 0.0 <= w < 1e-15
+        # dropped term <= w * |a1 - a0| <= 1e-15 * 4: nothing next to the FP32 path's 2e-6 density tolerance, and
+        # samples inside the guard band are re-evaluated in f64 with the term in place
+        assert w * 4.0 < 0.5 * float(np.spacing(np.float32(1e-6)))

@@ -202,6 +202,11 @@ uw_status   uw_build_from_densities(uw_ctx* ctx, const int32_t* chunk_pos_xyz, c
  * (x,y,z f64 triples, HOST) -> n floats (HOST).  SURVEY §8f-3. */
 uw_status   uw_iso_at(uw_ctx* ctx, const double* points_xyz, uint32_t n, float* out);
 
+/* Vertex colour of chunk.rs:215-222 (util.rs:93-95 create_mix_ratio, :122-153 hsv_to_rgb, :106-112 to_srgb) for n
+ * (world z, value level = corner_b index % 3) pairs (HOST) -> n RGB triples (HOST): the kernels' own colour code,
+ * so the tests can sweep the whole hue range instead of the z values a mesh happens to hold. */
+uw_status   uw_debug_vertex_colors(uw_ctx* ctx, const float* world_z, const uint32_t* level, uint32_t n, float* out_rgb);
+
 /* ---- renderer hand-off without the host round trip (replaces the create_buffer_init copies of
  * chunk.rs:291-305 for a renderer that can import external memory) ------------------------------------------
  * Context created with UW_FLAG_EXPORTABLE, after uw_build_device() + uw_sync(): exports the arena that

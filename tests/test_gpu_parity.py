@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 from oracle import MODE_FAITHFUL, MODE_FAST, FLAG_BLANK_EARLY, FLAG_HAS_MESH  # noqa: E402
 
 DENS_TOL = 2e-6       # FP32 factorised noise vs f64 reference (measured max ~3e-7)
-COL_TOL = 1e-6        # one powf per vertex: CUDA powf (<= 2 ulp here) vs glibc powf
+COL_TOL = 1e-6        # one pow(x, 2.4f) per vertex: the kernels' pow24_tab (<= 2 ulp) vs glibc powf
 GUARD_EPS = 1e-5      # default guard band of the library
 
 
@@ -329,6 +329,25 @@ def test_random_far_positions_match_oracle(uw, oracle12, seed):
     with uw.ChunkBuilder(uw.Perlin(seed), exact_f64=True, ordered=True) as exact:
         sub = pos[::4]
         _check_batch(exact.build(sub), refs[::4], exact_positions=True)
+
+
+def test_vertex_colour_function_over_the_whole_hue_range(builder12, oracle12):
+    """chunk.rs:215-222 through the colour parity tap: world z swept far beyond what a mesh holds (the hue wraps),
+    all three value levels.  Two channels are host constants (bit-exact); the third is one pow(x, 2.4f) per vertex,
+    evaluated by the kernels' table-driven FP32 pow24_tab: <= 3 ulp of the oracle's glibc powf (measured 2)."""
+    rng = np.random.default_rng(5)
+    z = np.concatenate([np.linspace(-80.0, 80.0, 40001), rng.uniform(-48.0, 48.0, 20000),
+                        np.arange(-64, 65, dtype=np.float64) * (16.0 / 12.0)]).astype(np.float32)
+    worst = 0.0
+    for level in range(3):
+        got = builder12.debug_vertex_colors(z, level)
+        want = np.stack([oracle12.vertex_color(float(v), level) for v in z])
+        np.testing.assert_allclose(got, want, rtol=0, atol=COL_TOL)
+        ulp = np.abs(got.astype(np.float64) - want.astype(np.float64)) / np.spacing(np.abs(want)).astype(np.float64)
+        worst = max(worst, float(ulp.max()))
+        assert (np.sort(ulp, axis=1)[:, :2] == 0).all(), "two of the three channels are exact constants"
+    assert worst <= 3.0, worst
+    print(f"vertex colour: worst error {worst:.2f} ulp over {3 * len(z)} (z, level) pairs")
 
 
 def test_edge_cases(uw, builder12, oracle12):

@@ -72,7 +72,7 @@ EXPORTS = [
     "uw_build", "uw_build_async", "uw_batch_wait", "uw_batch_view_get", "uw_batch_free",
     "uw_build_device", "uw_sync", "uw_device_view_get",
     "uw_debug_densities", "uw_debug_cases", "uw_build_from_densities", "uw_iso_at",
-    "uw_set_stream", "uw_get_stage_times", "uw_set_profiling", "uw_get_guard_count", "uw_debug_ffma_peak", "uw_export_arena_fd",
+    "uw_set_stream", "uw_get_stage_times", "uw_set_profiling", "uw_get_guard_count", "uw_debug_ffma_peak", "uw_export_arena_fd", "uw_debug_vertex_colors",
 ]
 
 _lib = None
@@ -123,6 +123,7 @@ def load_library() -> C.CDLL:
     lib.uw_set_profiling.argtypes = [vp, C.c_int]
     lib.uw_get_guard_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.uw_debug_ffma_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.uw_debug_vertex_colors.argtypes = [vp, vp, vp, u32, vp]
     lib.uw_export_arena_fd.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib

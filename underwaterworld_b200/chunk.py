@@ -289,6 +289,14 @@ class ChunkBuilder:
         self._check(self._lib.uw_debug_densities(self._ctx, p.ctypes.data, p.shape[0], out.ctypes.data))
         return out
 
+    def debug_vertex_colors(self, world_z, level) -> np.ndarray:
+        """The kernels' vertex colour (chunk.rs:215-222) for (world z, corner_b index % 3) pairs -> (n, 3) float32."""
+        z = np.ascontiguousarray(world_z, dtype=np.float32).reshape(-1)
+        lv = np.ascontiguousarray(np.broadcast_to(np.asarray(level, dtype=np.uint32), z.shape))
+        out = np.empty((z.shape[0], 3), dtype=np.float32)
+        self._check(self._lib.uw_debug_vertex_colors(self._ctx, z.ctypes.data, lv.ctypes.data, z.shape[0], out.ctypes.data))
+        return out
+
     def debug_cases(self, positions) -> np.ndarray:
         p = _as_positions(positions)
         out = np.empty((p.shape[0], self.S ** 3), dtype=np.uint8)

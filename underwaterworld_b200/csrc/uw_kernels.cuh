@@ -66,6 +66,7 @@ struct McTables {
     uint16_t before[256][12];  // edges first-appearing before edge e in the row
     uint8_t  ninds[256];       // indices per case
     uint32_t lut[256];         // by "natural" corner pattern (natural_of): case | ninds << 8 | crossed << 12
+    float powtab[48];          // pow24_tab: [i] = 1/c_i, [16+i] = hi(log2 c_i), [32+i] = lo(log2 c_i), c_i ~ 1 + (i + 1/2)/16
 };
 
 __device__ __constant__ uint8_t c_edge_a[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3};
@@ -1263,13 +1264,42 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restr
 // Two of the three channels only depend on the value level -> host-precomputed constants
 // (identical to the oracle's); the hue-dependent channel needs one powf.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ float srgb_of(float ch_plus_m) {
+// powf(x, 2.4f) (util.rs:110) in 36 FP32 instructions, no branches: x = 2^e m, m in [1, 2) falls into one of 16
+// intervals with midpoint c_i; r = m / c_i - 1 exactly (one FMA against the tabulated 1/c_i, |r| < 1/32),
+// log2 x = (e + hi_i) + (lo_i + r P4(r)) as a two-float sum, times 2.4f with the rounding error of the product
+// recovered by FMA, 2^f by a degree-6 polynomial on [-1/2, 1/2], 2^n through the exponent field.  Measured over every
+// f32 in the colour's range against f64 pow (tests/test_gpu_parity.py): <= 2 ulp, as CUDA's powf here (which costs ~100
+// instructions with branches).  tab = McTables::powtab in shared memory.  Domain: x in [2^-20, 2^20]; else powf.
+__device__ __forceinline__ float pow24_tab(float x, const float* __restrict__ tab) {
+    const uint32_t bits = __float_as_uint(x);
+    const int e = (int)(bits >> 23) - 127;
+    const float m = __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u);
+    const uint32_t i = (bits >> 19) & 15u;
+    const float r = fmaf(m, tab[i], -1.0f);
+    float p = fmaf(0.2888079881668091f, r, -0.3609875738620758f);
+    p = fmaf(p, r, 0.48089829087257385f); p = fmaf(p, r, -0.721347451210022f); p = fmaf(p, r, 1.4426950216293335f);
+    const float Lh = (float)e + tab[16 + i];                     // exact: hi_i has 16 fractional bits
+    const float Ll = fmaf(p, r, tab[32 + i]);
+    const float yh = 2.4f * Lh;
+    const float yl = fmaf(2.4f, Ll, fmaf(2.4f, Lh, -yh));
+    const float n = rintf(yh);
+    const float f = (yh - n) + yl;
+    float q = fmaf(0.00015461444854736328f, f, 0.0013400427997112274f);
+    q = fmaf(q, f, 0.009618056938052177f); q = fmaf(q, f, 0.05550327152013779f); q = fmaf(q, f, 0.24022650718688965f);
+    q = fmaf(q, f, 0.6931471824645996f);   q = fmaf(q, f, 1.0f);
+    return __uint_as_float(__float_as_uint(q) + ((uint32_t)(int)n << 23));
+}
+
+__device__ __forceinline__ float srgb_of(float ch_plus_m, const float* __restrict__ powtab) {
     const float c255 = __fmul_rn(ch_plus_m, 255.0f);
     const float b = __fdiv_rn(__fadd_rn(__fdiv_rn(c255, 255.0f), 0.055f), 1.055f);
+#ifndef UW_POWF_LIBM
+    if (powtab != nullptr && b >= 9.5367431640625e-07f && b <= 1048576.0f) return pow24_tab(b, powtab);
+#endif
     return powf(b, 2.4f);
 }
 
-__device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, int vi, float out[3]) {
+__device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, int vi, float out[3], const float* __restrict__ powtab = nullptr) {
     // x / 2^n == x * 2^-n exactly (no subnormals in reach): the two power-of-two divisions of the reference's
     // constants (CHUNK_SIZE = 16, MAX_Z - MIN_Z = 4) are multiplies; anything else divides
     const float ratio = cfg.cs_pow2 ? __fmul_rn(world_z, (float)cfg.inv_chunk_size) : __fdiv_rn(world_z, (float)cfg.chunk_size);
@@ -1286,7 +1316,7 @@ __device__ __forceinline__ void vertex_color(const DevCfg& cfg, float world_z, i
     // h in [0, 6]: fmod(h, 2) == h - 2*floor(h/2) exactly (every step is exact in f32)
     const float hm2 = (h >= 0.0f && h < 16.0f) ? __fsub_rn(h, __fmul_rn(2.0f, floorf(__fmul_rn(h, 0.5f)))) : fmodf(h, 2.0f);
     const float x = __fmul_rn(c, __fsub_rn(1.0f, fabsf(__fsub_rn(hm2, 1.0f))));
-    const float X = srgb_of(__fadd_rn(x, m));
+    const float X = srgb_of(__fadd_rn(x, m), powtab);
     const float HI = cfg.srgb_hi[vi], LO = cfg.srgb_lo[vi];
     if      (0.0f <= h && h < 1.0f) { out[0] = HI; out[1] = X;  out[2] = LO; }
     else if (1.0f <= h && h < 2.0f) { out[0] = X;  out[1] = HI; out[2] = LO; }
@@ -1321,9 +1351,23 @@ __device__ __forceinline__ int edge_position(const DevCfg& cfg, DensAt dens_at, 
 // vertex (position + colour) of the directed edge `e` of cell (x,y,z): chunk.rs:178-231
 template <class DensAt>
 __device__ __forceinline__ void make_vertex_from(const DevCfg& cfg, DensAt dens_at, int x, int y, int z, int e,
-                                                 int offx, int offy, int offz, float v[6]) {
+                                                 int offx, int offy, int offz, float v[6], const float* __restrict__ powtab = nullptr) {
     const int cb = edge_position(cfg, dens_at, x, y, z, e, offx, offy, offz, v);
-    vertex_color(cfg, v[2], cb % 3, v + 3);
+    vertex_color(cfg, v[2], cb % 3, v + 3, powtab);
+}
+
+// parity tap: the product's vertex colour (table-driven pow included) on arbitrary (world z, value level) pairs
+__global__ void __launch_bounds__(256) k_vertex_colors(const __grid_constant__ DevCfg cfg, const McTables* __restrict__ mc,
+                                                       const float* __restrict__ world_z, const uint32_t* __restrict__ level,
+                                                       uint32_t n, float* __restrict__ rgb) {
+    __shared__ float s_powtab[48];
+    if (threadIdx.x < 48) s_powtab[threadIdx.x] = mc->powtab[threadIdx.x];
+    __syncthreads();
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        float c[3];
+        vertex_color(cfg, world_z[t], (int)(level[t] % 3u), c, s_powtab);
+        rgb[3 * t] = c[0]; rgb[3 * t + 1] = c[1]; rgb[3 * t + 2] = c[2];
+    }
 }
 
 // util::Tri::new (util.rs:12-21) with cgmath's cross / magnitude / div and safe_normalize (util.rs:61-64); f32, unfused
@@ -1339,9 +1383,9 @@ __device__ __forceinline__ void tri_normal(const float a[3], const float b[3], c
 }
 
 __device__ __forceinline__ void make_vertex(const DevCfg& cfg, const float* s_dens, int x, int y, int z, int e,
-                                            int offx, int offy, int offz, float v[6]) {
+                                            int offx, int offy, int offz, float v[6], const float* __restrict__ powtab = nullptr) {
     const int L = cfg.L;
-    make_vertex_from(cfg, [=](int ax, int ay, int az) { return s_dens[(ax * L + ay) * L + az]; }, x, y, z, e, offx, offy, offz, v);
+    make_vertex_from(cfg, [=](int ax, int ay, int az) { return s_dens[(ax * L + ay) * L + az]; }, x, y, z, e, offx, offy, offz, v, powtab);
 }
 
 // owner (first cell in scan order holding the same ORDERED corner pair), SURVEY App. B.4
@@ -1378,6 +1422,7 @@ __device__ __forceinline__ void owner_of(int e, int x, int y, int z, int& ox, in
 struct EmitSmem {
     float* dens; uint32_t* bits; uint32_t* mask; uint16_t* vbase; uint16_t* ibase; uint16_t* alist;
     uint16_t* vlist; uint16_t* vid; uint8_t* cs; uint32_t* lut; uint16_t* eoff;
+    const float* powtab;            // McTables::powtab in shared memory
     const uint64_t* rows;           // McTables::rows in shared memory (the L1 left beside 4 x 55 KB of shared memory does not keep it)
 };
 
@@ -1401,7 +1446,7 @@ __host__ __device__ inline size_t emit_smem_bytes(const DevCfg& cfg) {
     b += UW_VLIST_CAP * 2;
     b += (((size_t)cfg.L3 * UW_EDGE_KINDS + 7) & ~(size_t)7) * 2;
     b += 256 * 4 + 16 * 2;
-    b += 256 * 8;
+    b += 256 * 8 + 48 * 4;
     b += (cells + 15) & ~(size_t)15;
     return b;
 }
@@ -1411,6 +1456,7 @@ __device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned 
     EmitSmem s;
     s.dens = (float*)base;        base += (size_t)cfg.dens_stride * 4;       // multiple of 16 bytes
     s.rows = (const uint64_t*)base; base += 256 * 8;
+    s.powtab = (const float*)base;  base += 48 * 4;
     s.bits = (uint32_t*)base;     base += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
     s.mask = (uint32_t*)base;     base += ((size_t)cfg.L2 + 3) / 4 * 16;
     s.vbase = (uint16_t*)base;    base += cells2 * 2;
@@ -1538,7 +1584,7 @@ __device__ __forceinline__ void emit_verts(const DevCfg& cfg, const EmitSmem& s,
         const int cell = ent & 0xFFF, e = ent >> 12;
         const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
         float v[6];
-        make_vertex(cfg, s.dens, x, y, z, e, offx, offy, offz, v);
+        make_vertex(cfg, s.dens, x, y, z, e, offx, offy, offz, v, s.powtab);
         float2* dst = reinterpret_cast<float2*>(vout + v0 + t);
         dst[0] = make_float2(v[0], v[1]); dst[1] = make_float2(v[2], v[3]); dst[2] = make_float2(v[4], v[5]);
     }
@@ -1641,6 +1687,7 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
     const uint32_t n_active = totals->n_active;
     if (totals->overflow) return;                       // host grows the arenas and relaunches
     for (int t = tid; t < 256; t += NT) { s.lut[t] = mc->lut[t]; const_cast<uint64_t*>(s.rows)[t] = mc->rows[t]; }
+    if (tid < 48) const_cast<float*>(s.powtab)[tid] = mc->powtab[tid];
     fill_edge_offsets(s.eoff, L);
 
     for (uint32_t a = blockIdx.x; a < n_active; a += gridDim.x) {
@@ -2252,6 +2299,7 @@ struct FusedSmem {
     uint16_t ibase[ST * ST * ST + 8];
     uint16_t alist[ST * ST * ST + 8];
     uint64_t rows[256];
+    float powtab[48];
     uint32_t lut[256];
     uint16_t eoff[16];
     uint8_t cs[((ST * ST * ST + 15) / 16) * 16];
@@ -2341,7 +2389,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     es.dens = sm.n.dens; es.bits = nullptr; es.mask = sm.n.mask;
     es.vid = reinterpret_cast<uint16_t*>(sm.n.lat);
     es.vlist = sm.vlist; es.vbase = sm.vbase; es.ibase = sm.ibase; es.alist = sm.alist;
-    es.cs = sm.cs; es.lut = sm.lut; es.eoff = sm.eoff; es.rows = sm.rows;
+    es.cs = sm.cs; es.lut = sm.lut; es.eoff = sm.eoff; es.rows = sm.rows; es.powtab = sm.powtab;
     using NS = SpecSmem<ST, NOCT>;
     static_assert(offsetof(NS, X) == offsetof(NS, lat) + sizeof(sm.n.lat), "lat and X must be adjacent");
     static_assert(offsetof(NS, xpad) == offsetof(NS, X) + sizeof(sm.n.X), "X and xpad must be adjacent");
@@ -2373,6 +2421,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         sm.n.axis[o][i] = make_float4(tab.d[o][i], tab.d1[o][i], tab.w[o][i], 0.f);
     }
     for (int t = tid; t < 256; t += D::NT) { sm.lut[t] = mc->lut[t]; sm.rows[t] = mc->rows[t]; }
+    if (tid < 48) sm.powtab[tid] = mc->powtab[tid];
     fill_edge_offsets(sm.eoff, L);
 
     if (tid == D::NT - 1) {

@@ -435,6 +435,12 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
             for (int b = 0; b < 8; ++b) if ((nat >> b) & 1) cs |= 1u << corner_of_bit[b];
             h->lut[nat] = cs | ((uint32_t)ninds[cs] << 8) | ((uint32_t)crossed[cs] << 12);
         }
+        for (int i = 0; i < 16; ++i) {                       // pow24_tab (uw_kernels.cuh)
+            const float ic = (float)(1.0 / (1.0 + (i + 0.5) / 16.0));
+            const double l2 = -log2((double)ic);               // log2 of the c_i that 1/c_i = ic stands for
+            const double hi = nearbyint(l2 * 65536.0) / 65536.0;
+            h->powtab[i] = ic; h->powtab[16 + i] = (float)hi; h->powtab[32 + i] = (float)(l2 - hi);
+        }
         bool ok = cu(cudaMalloc(&c->d_mc, sizeof(McTables)), "cudaMalloc mc") &&
                   cu(cudaMemcpy(c->d_mc, h, sizeof(McTables), cudaMemcpyHostToDevice), "memcpy mc");
         delete h;
@@ -1261,6 +1267,31 @@ extern "C" uw_status uw_iso_at(uw_ctx* c, const double* pts, uint32_t n, float* 
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_pts); cudaFree(d_out);
     if (e != cudaSuccess) return fail(c, UW_ERR_CUDA, std::string("uw_iso_at: ") + cudaGetErrorString(e));
+    return UW_OK;
+}
+
+extern "C" uw_status uw_debug_vertex_colors(uw_ctx* c, const float* world_z, const uint32_t* level, uint32_t n, float* out_rgb) {
+    if (!c) return UW_ERR_INVALID;
+    if ((!world_z || !level || !out_rgb) && n) return fail(c, UW_ERR_INVALID, "uw_debug_vertex_colors: null argument");
+    if (n == 0) return UW_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    float* d_z = nullptr; uint32_t* d_l = nullptr; float* d_o = nullptr;
+    cudaError_t e = cudaMalloc(&d_z, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_l, (size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, (size_t)n * 12);
+    if (e != cudaSuccess) { cudaFree(d_z); cudaFree(d_l); cudaFree(d_o); return fail(c, UW_ERR_OOM, "uw_debug_vertex_colors: cudaMalloc failed"); }
+    e = cudaMemcpyAsync(d_z, world_z, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_l, level, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        unsigned blocks = (n + 255) / 256;
+        if (blocks > (unsigned)c->num_sms * 8) blocks = c->num_sms * 8;
+        k_vertex_colors<<<blocks, 256, 0, c->stream>>>(c->dcfg, c->d_mc, d_z, d_l, n, d_o);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_z); cudaFree(d_l); cudaFree(d_o);
+    if (e != cudaSuccess) return fail(c, UW_ERR_CUDA, std::string("uw_debug_vertex_colors: ") + cudaGetErrorString(e));
     return UW_OK;
 }
 

@@ -599,7 +599,16 @@ struct SpecDims {
     __host__ __device__ static constexpr int lat_base(int o) { int b = 0; for (int q = 0; q < o; ++q) b += G(q) * G(q) * G(q); return b; }   // prefix of G^3
     __host__ __device__ static constexpr int x_base(int o) { int b = 0; for (int q = 0; q < o; ++q) b += G(q) * G(q); return L * b; }       // L * prefix of G^2
     static constexpr int DSTRIDE = (L * L * L + 3) & ~3;
-    static constexpr int NT = ((L * L + 31) / 32) * 32;
+    static constexpr int NT = ((L * L + 31) / 32) * 32;          // one thread per (x, y) column: the stand-alone noise kernel
+    // The fused kernel runs one warp more than the columns need (7 instead of 6 at L = 13): stage YZ leaves it idle,
+    // but the stages whose item counts are not tied to the columns (H, X, the K4 passes) and the latency hiding of
+    // every stage gain more than 72 instead of 80 registers cost: -1.8 % at 2048 chunks, -2.6 % at 524 288 (it was
+    // -4 % / +3 % before the K1 rework); an eighth warp (64 registers) gives it back.  The stand-alone noise kernel
+    // is faster with 5 x 6 warps than with 4 x 7 (209 vs 222 us at 32 768 chunks).
+#ifndef UW_FUSED_EXTRA_WARPS
+#define UW_FUSED_EXTRA_WARPS 1
+#endif
+    static constexpr int NTF = NT + 32 * UW_FUSED_EXTRA_WARPS;
     __host__ __device__ static constexpr int cell(int o, int k) { return (k << o) / ST; }
     // compile-time axis tables for CHUNK_SIZE = 16 (chunk.rs:5): same f64 arithmetic as setup_tables();
     // the host selects this kernel only if its runtime tables match these bit for bit.
@@ -638,14 +647,13 @@ struct SpecSmem {
 
 // stages H, X, YZ for one chunk; leaves densities in sm.dens and column sign masks in sm.mask.
 // Returns (block-uniform) CF_ALL_GT | CF_ANY_LT.  All threads must call; ends with a barrier.
-template <int ST, int NOCT>
+template <int ST, int NOCT, int NT /*threads of the CTA: SpecDims::NT or ::NTF*/>
 __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const AxisTables& tab, SpecSmem<ST, NOCT>& sm,
                                                      int px, int py, int pz, unsigned long long* guard_count PHASE_ARG,
                                                      const Handout* hand = nullptr, Ticket* tk_out = nullptr) {
     using D = SpecDims<ST, NOCT>;
     constexpr int L = D::L;
     const int tid = threadIdx.x;
-    constexpr int NT = D::NT;
     // the NEXT chunk's ticket: atomic issued here, (chunk, position) loads after stage X, values first touched by
     // the caller at the end of the iteration -- see ticket_begin / ticket_fetch
     uint32_t tk_t = 0;
@@ -809,7 +817,7 @@ k_noise_spec(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTab
 #ifdef UW_PHASE_TIMING
         long long t_phase = 0;
 #endif
-        noise_chunk_spec<ST, NOCT>(cfg, tab, sm, px, py, pz, guard_count PHASE_PASS);
+        noise_chunk_spec<ST, NOCT, D::NT>(cfg, tab, sm, px, py, pz, guard_count PHASE_PASS);
         float4* dst = reinterpret_cast<float4*>(dens + (size_t)chunk * D::DSTRIDE);
         const float4* src = reinterpret_cast<const float4*>(sm.dens);
         for (int t = tid; t < D::DSTRIDE / 4; t += D::NT) dst[t] = src[t];
@@ -2363,7 +2371,7 @@ __device__ __forceinline__ void lookback_block(ScanSlot* st, uint32_t c, unsigne
 #define UW_FUSED_MINB 4
 #endif
 template <int ST, int NOCT, typename IndexT>
-__global__ void __launch_bounds__(SpecDims<ST, NOCT>::NT, UW_FUSED_MINB)
+__global__ void __launch_bounds__(SpecDims<ST, NOCT>::NTF, UW_FUSED_MINB)
 k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTables tab,
               const uint8_t* __restrict__ g_perm, const McTables* __restrict__ mc,
               const int32_t* __restrict__ pos, uint32_t n,
@@ -2411,20 +2419,20 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // start-up order matters at 2048 chunks (the prologue is ~10 % of the kernel): first the global round trips of
     // the hand-out (filing the request / the first ticket's atomic), then the table loads underneath them
     uint32_t t_first = 0;
-    if (tid == D::NT - 1) t_first = ticket_begin(hand);
+    if (tid == D::NTF - 1) t_first = ticket_begin(hand);
     if (order) handout_classify(hand);
 
-    for (int t = tid; t < 256; t += D::NT) sm.n.perm[t] = g_perm[t];
+    for (int t = tid; t < 256; t += D::NTF) sm.n.perm[t] = g_perm[t];
     if (tid < 16) sm.n.grad[tid] = make_float4(c_grad_vec[tid][0], c_grad_vec[tid][1], c_grad_vec[tid][2], 0.f);
-    for (int t = tid; t < NOCT * L; t += D::NT) {
+    for (int t = tid; t < NOCT * L; t += D::NTF) {
         const int o = t / L, i = t - o * L;
         sm.n.axis[o][i] = make_float4(tab.d[o][i], tab.d1[o][i], tab.w[o][i], 0.f);
     }
-    for (int t = tid; t < 256; t += D::NT) { sm.lut[t] = mc->lut[t]; sm.rows[t] = mc->rows[t]; }
+    for (int t = tid; t < 256; t += D::NTF) { sm.lut[t] = mc->lut[t]; sm.rows[t] = mc->rows[t]; }
     if (tid < 48) sm.powtab[tid] = mc->powtab[tid];
     fill_edge_offsets(sm.eoff, L);
 
-    if (tid == D::NT - 1) {
+    if (tid == D::NTF - 1) {
         if (order) handout_ready(hand);
         const Ticket t0 = ticket_fetch(hand, t_first);
         sm.cur[0] = (int)t0.chunk; sm.cur[1] = t0.px; sm.cur[2] = t0.py; sm.cur[3] = t0.pz;
@@ -2443,13 +2451,13 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         nxt.chunk = TICKET_DONE; nxt.px = nxt.py = nxt.pz = 0;
 
         // ---- K1 ---------------------------------------------------------------------------------
-        const uint32_t fl = noise_chunk_spec<ST, NOCT>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS,
+        const uint32_t fl = noise_chunk_spec<ST, NOCT, D::NTF>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS,
                                                        &hand, &nxt);
         PHASE_MARK(1);                                     // K1 noise
         if (dens_out) {
             float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);
             const float4* src = reinterpret_cast<const float4*>(sm.n.dens);
-            for (int t = tid; t < D::DSTRIDE / 4; t += D::NT) dst[t] = src[t];
+            for (int t = tid; t < D::DSTRIDE / 4; t += D::NTF) dst[t] = src[t];
         }
 
         // ---- K2: cases, counts, per-cell bases (block-uniform skip when no sample is inside) -------------
@@ -2514,7 +2522,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             }
             if (!ordered && ni > 0 && (ev + nv > vcap || ei + ni > icap)) totals->overflow = 1u;
         }
-        if (tid == D::NT - 1) { sm.cur[0] = (int)nxt.chunk; sm.cur[1] = nxt.px; sm.cur[2] = nxt.py; sm.cur[3] = nxt.pz; }
+        if (tid == D::NTF - 1) { sm.cur[0] = (int)nxt.chunk; sm.cur[1] = nxt.px; sm.cur[2] = nxt.py; sm.cur[3] = nxt.pz; }
         __syncthreads();                                   // chunk fully emitted, smem reusable, next ticket visible
         PHASE_MARK(6);                                     // tail: descriptor + waiting for the other warps
 #ifdef UW_PHASE_TIMING

@@ -126,7 +126,7 @@ struct uw_ctx {
     emit16_fn_t emit16_fn = nullptr;
     emit32_fn_t emit32_fn = nullptr;
     bool spec_noise = false;        // compile-time specialised noise kernel in use
-    int noise_threads = 192, noise_blocks_per_sm = 1; size_t noise_smem = 0;
+    int noise_threads = 192, fused_threads = 224, noise_blocks_per_sm = 1; size_t noise_smem = 0;
     int emit_blocks_per_sm = 1; size_t emit_smem = 0;
     int classify_blocks_per_sm = 1;
 
@@ -492,12 +492,12 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         c->noise_fn = k_noise_small<0, 0>;
         if (spec_ok(SpecDims<12, 3>())) {
             c->noise_fn = k_noise_spec<12, 3>; c->spec_noise = true;
-            c->noise_threads = SpecDims<12, 3>::NT; c->noise_smem = sizeof(SpecSmem<12, 3>);
+            c->noise_threads = SpecDims<12, 3>::NT; c->fused_threads = SpecDims<12, 3>::NTF; c->noise_smem = sizeof(SpecSmem<12, 3>);
             c->fused16_fn = k_build_fused<12, 3, uint16_t>; c->fused32_fn = k_build_fused<12, 3, uint32_t>;
             c->fused_smem = sizeof(FusedSmem<12, 3>);
         } else if (spec_ok(SpecDims<10, 3>())) {
             c->noise_fn = k_noise_spec<10, 3>; c->spec_noise = true;
-            c->noise_threads = SpecDims<10, 3>::NT; c->noise_smem = sizeof(SpecSmem<10, 3>);
+            c->noise_threads = SpecDims<10, 3>::NT; c->fused_threads = SpecDims<10, 3>::NTF; c->noise_smem = sizeof(SpecSmem<10, 3>);
             c->fused16_fn = k_build_fused<10, 3, uint16_t>; c->fused32_fn = k_build_fused<10, 3, uint32_t>;
             c->fused_smem = sizeof(FusedSmem<10, 3>);
         }
@@ -518,7 +518,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
                  cu(set_attr((const void*)c->fused32_fn, c->fused_smem), "attr fused32");
         if (!ok) return bail(UW_ERR_CUDA);
         int nb = 1;
-        if (c->fused16_fn && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->fused16_fn, c->noise_threads, c->fused_smem) == cudaSuccess && nb > 0)
+        if (c->fused16_fn && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->fused16_fn, c->fused_threads, c->fused_smem) == cudaSuccess && nb > 0)
             c->fused_blocks_per_sm = nb;
         c->order_cap = (size_t)16 * c->num_sms * c->fused_blocks_per_sm;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->noise_fn, c->noise_threads, c->noise_smem) == cudaSuccess && nb > 0)
@@ -831,10 +831,10 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     // ordered-packing mode needs tickets == request order.  Only worth it when CTAs get just a few chunks each.
     uint4* d_order = (!c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= c->order_cap) ? c->B().d_order : nullptr;
     if (c->index32)
-        c->fused32_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
+        c->fused32_fn<<<grid, c->fused_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
             c->B().d_descs, c->B().d_verts, (uint32_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
     else
-        c->fused16_fn<<<grid, c->noise_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
+        c->fused16_fn<<<grid, c->fused_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
             c->B().d_descs, c->B().d_verts, (uint16_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
     c->launches++;
     CU_TRY(c, cudaGetLastError());

@@ -1499,15 +1499,10 @@ __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const Emit
         const bool col_empty = any == 0u, col_full = (all & (all >> 16) & full) == full;
         ownn = 0x4F0u | (y == 0 ? 0x00Fu : 0u) | (x == 0 ? 0x800u : 0u);      // SURVEY App. B.4 ownership, z > 0
         own0 = ownn | 0x200u | (x == 0 ? 0x100u : 0u);                          // z == 0 also owns 9 (and 8 if x == 0)
-        if (col_empty || col_full) {
-            const uint8_t fill = col_full ? 255 : 0;
-#pragma unroll 4
-            for (int z = 0; z < S; ++z) s.cs[col * S + z] = fill;
-        } else {
+        if (!(col_empty || col_full)) {        // the case bytes are only ever read at surface cells: phase C files them
 #pragma unroll 4
             for (int z = 0; z < S; ++z) {
                 const uint32_t t = s.lut[natural_of(q0, q1, z)];            // case | ninds << 8 | crossed << 12
-                s.cs[col * S + z] = (uint8_t)t;
                 if (t >> 8) {
                     ni += (t >> 8) & 15u;
                     nva += __popc((t >> 12) & (z == 0 ? own0 : ownn)) + 0x10000u;
@@ -1539,6 +1534,7 @@ __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const Emit
         const uint32_t t = s.lut[natural_of(q0, q1, z)];
         s.vbase[ra] = (uint16_t)rv; s.ibase[ra] = (uint16_t)ri;        // indexed by surface-cell rank, like alist
         s.alist[ra++] = (uint16_t)cell;
+        s.cs[cell] = (uint8_t)t;                                       // case index, chunk.rs:155-162
         ri += (t >> 8) & 15u;
         rv += __popc((t >> 12) & (z == 0 ? own0 : ownn));
     }

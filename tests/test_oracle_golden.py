@@ -177,3 +177,50 @@ def test_far_lattice_plane_carries_no_weight(S):
         # dropped term <= w * |a1 - a0| <= 1e-15 * 4: nothing next to the FP32 path's 2e-6 density tolerance, and
         # samples inside the guard band are re-evaluated in f64 with the term in place
         assert w * 4.0 < 0.5 * float(np.spacing(np.float32(1e-6)))
+
+
+def test_table_driven_pow24_scheme_is_within_two_ulp():
+    """The arithmetic of pow24_tab (uw_kernels.cuh: 16-interval table of 1/c_i and a two-float log2 c_i, degree-4 and
+    degree-6 polynomials, the product with 2.4f carried as a two-float sum) restated in numpy float32 (FMA emulated
+    through float64, whose product of two floats is exact): <= 2.5 ulp against the unrounded f64 pow over the colour's
+    input range, i.e. at most 2 ulp from the correctly rounded f32 result.
+    The device code itself is checked on the GPU (test_vertex_colour_function_over_the_whole_hue_range)."""
+    f32 = np.float32
+
+    def fma(a, b, c):
+        return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(f32)
+
+    i = np.arange(16)
+    inv_c = (1.0 / (1.0 + (i + 0.5) / 16.0)).astype(f32)
+    l2 = -np.log2(inv_c.astype(np.float64))
+    hi = np.rint(l2 * 65536.0) / 65536.0
+    lh, ll = hi.astype(f32), (l2 - hi).astype(f32)
+    assert (lh.astype(np.float64) == hi).all()                       # 16 fractional bits: exact in f32
+    P = [f32(v) for v in (1.4426950216293335, -0.721347451210022, 0.48089829087257385, -0.3609875738620758, 0.2888079881668091)]
+    Q = [f32(v) for v in (1.0, 0.6931471824645996, 0.24022650718688965, 0.05550327152013779, 0.009618056938052177,
+                          0.0013400427997112274, 0.00015461444854736328)]
+    rng = np.random.default_rng(3)
+    b = np.concatenate([rng.uniform(0.04, 1.1, 300000), np.linspace(0.05, 1.0, 100001)]).astype(f32)
+    bits = b.view(np.uint32)
+    e = (bits >> 23).astype(np.int32) - 127
+    m = ((bits & 0x7FFFFF) | 0x3F800000).view(f32)
+    k = ((bits >> 19) & 15).astype(np.int64)
+    r = fma(m, inv_c[k], f32(-1.0))
+    p = fma(P[4], r, P[3])
+    for c in (P[2], P[1], P[0]):
+        p = fma(p, r, c)
+    Lh = e.astype(f32) + lh[k]
+    Ll = fma(p, r, ll[k])
+    pw = f32(2.4)
+    yh = (pw * Lh).astype(f32)
+    yl = fma(pw, Ll, fma(pw, Lh, -yh))
+    n = np.rint(yh)
+    f = ((yh - n).astype(f32) + yl).astype(f32)
+    q = fma(Q[6], f, Q[5])
+    for c in (Q[4], Q[3], Q[2], Q[1], Q[0]):
+        q = fma(q, f, c)
+    got = np.ldexp(q, n.astype(np.int32)).astype(f32)
+    want = np.power(b.astype(np.float64), float(pw))
+    ulp = np.abs(got.astype(np.float64) - want) / np.spacing(want.astype(f32)).astype(np.float64)
+    assert ulp.max() <= 2.5, ulp.max()
+    assert (ulp > 1.0).mean() < 0.01

@@ -3,21 +3,29 @@
 
 Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W
 prints ONE JSON line on rank 0.  A "step" is one pass of the whole hot path (K1 noise ->
-K2 classify -> K3 scan -> K4 emit) over one batch of chunk positions:
+K2 classify -> K3 scan -> K4 emit, one fused kernel) over one region of chunk positions.
 
-  N = 1   BASELINE.json configs[1]: the 16x16x8 spawn neighbourhood, 2048 chunks of 12^3
-          cells, one batched call.
-  N > 1   every rank owns its own 16x16x8 x-slab of a region that grows along x with N
-          (weak scaling, no collective on the compute path -- chunks are independent).
+Workload at EVERY N: BASELINE.json configs[2], the configuration its metric ("... at 1/2/4/8 B200") is quoted on:
+the 128x128x32 region = 524 288 chunks of 12^3 cells, cut into N contiguous x-slabs (strong scaling; one process
+per GPU; no collective on the compute path -- chunks are independent, chunk.rs:89-129).
 
-value  = voxels/s (cells/s) device-resident: positions already in HBM, outputs stay in HBM,
-         timed with CUDA events on the launching stream, L2 flushed between steps.
-e2e    = the same metric through the C ABI with HOST buffers (pinned H2D of the positions, the kernel, D2H of
-         descriptors + vertices + indices into pinned host memory), K builds software-pipelined two deep
-         (uw_build_async / uw_batch_wait); the blocking single-call latency is reported beside it.
---impl reference  times the CPU oracle (oracle/, faithful mode = the reference's algorithm,
-         all host threads) on a bounded sample of the same workload.  The reference itself is
-         Rust and cannot be compiled in this image (no cargo/rustc) -- see DESIGN.md.
+  value     voxels/s (cells/s), device-resident: every rank's slab positions are already in its HBM, outputs stay in
+            its own HBM; CUDA events on the launching stream around every step's launch, L2 flushed between steps,
+            MAX over ranks.
+  e2e       the same metric through the C ABI from HOST positions to meshes the renderer can draw: pinned H2D of
+            every rank's slab, the fused kernels writing vertices / indices / descriptors straight into the
+            RENDERING GPU's arenas (rank 0; NVLink peer stores from the other ranks -- uw_gather_*), the head flags,
+            and the D2H of the draw list (descriptors of the meshed chunks) + heads on rank 0.  The reference's build_full ends the same
+            way: in GPU buffers (wgpu, chunk.rs:291-305) plus host-side counts.  Host wall clock per step, barrier
+            before every step, MAX over ranks.
+  e2e_host  beside it: every rank streams its slab's full meshes into pinned HOST memory (uw_build_async /
+            uw_batch_wait, slices of 8192 chunks, two in flight) -- PCIe-bound; `d2h_ceiling_gbs` is a bare pinned
+            D2H copy of the same bytes by all ranks at once, measured in this run.
+  configs   (N = 1 only) BASELINE configs[1] (2048 chunks: burst latency, pipelined host path, per-stage rooflines
+            of the staged pipeline at 32 768 chunks), configs[3] (64^3) and configs[4] (flythrough).
+
+--impl reference  times the CPU oracle (oracle/, faithful mode = the reference's algorithm, all host threads) on a
+bounded sample of the same region.  The reference is Rust and cannot be compiled in this image -- see DESIGN.md.
 """
 from __future__ import annotations
 
@@ -33,6 +41,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 S = 12
 L3 = (S + 1) ** 3
@@ -40,6 +49,12 @@ CELLS = S ** 3
 SEED = 0
 FLOP_PER_SAMPLE = 285          # algorithmic op count of the reference's density function
 FP32_NOMINAL_TFLOPS = 74.4     # 148 SM x 128 lanes x 2 x 1.965 GHz
+ISSUE_SLOTS_PER_CYCLE = 148 * 4
+
+REGION = ((-64, 64), (-64, 64), (-16, 16))      # BASELINE configs[2]
+WORKLOAD = ("large region 128x128x32 = 524288 chunks of 12^3 (BASELINE configs[2]) cut into N contiguous x-slabs, "
+            "seed 0, octaves 3, iso -0.1")
+HOST_SLICE = 8192
 
 
 def env_int(name, default):
@@ -58,6 +73,15 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tracked_profile(name):
+    """A tracked ncu summary under profiles/ (JSON written by tools/ncu_json.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", name)
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -116,22 +140,21 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def rank_positions(rank: int) -> np.ndarray:
+def region_positions() -> np.ndarray:
     from underwaterworld_b200 import region
-    # rank r owns x in [-8 + 16 r, 8 + 16 r): config 2 for rank 0, the next x-slabs for the others
-    return region.box_region((-8 + 16 * rank, 8 + 16 * rank), (-8, 8), (-4, 4))
+    return region.box_region(*REGION)
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU oracle timing (cpu_baseline leg and --impl reference)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample(pos: np.ndarray, n: int) -> np.ndarray:
-    """Bounded sample that keeps the z-layer mix of the workload (z is the fastest index, 8 layers:
-    an odd stride visits every layer equally)."""
-    if n >= len(pos):
-        return pos
-    stride = max(1, len(pos) // n) | 1
-    return np.ascontiguousarray(pos[::stride][:n])
+def cpu_sample(x_columns: int) -> np.ndarray:
+    """Bounded sample of the region that keeps its composition: `x_columns` full x-planes (all 128 y, all 32 z
+    layers) from the middle of the region -- 4096 chunks each, 5 of the 32 z layers can hold surface, as in the
+    whole region."""
+    from underwaterworld_b200 import region
+    x0 = -(x_columns // 2)
+    return region.box_region((x0, x0 + x_columns), REGION[1], REGION[2])
 
 
 def time_cpu(pos: np.ndarray, threads: int, repeats: int = 1):
@@ -146,18 +169,26 @@ def time_cpu(pos: np.ndarray, threads: int, repeats: int = 1):
     return best
 
 
+def base_line(args, world):
+    return {
+        "metric": "voxels/s (Perlin + MC mesh build)", "unit": "voxels/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "data": "synthetic",
+        "config": {"workload": WORKLOAD, "region_chunks": 524288, "cells_per_chunk": CELLS, "samples_per_chunk": L3},
+    }
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    pos = rank_positions(0)
     threads = os.cpu_count() or 1
-    # calibrate on a small sample, then size the per-step sample so the run stays within ~2 minutes
-    cal = time_cpu(cpu_sample(pos, 128), threads)
-    rate = 128 / max(cal["seconds"], 1e-6)
-    budget_s = 90.0
-    n = int(min(len(pos), max(64, rate * budget_s / max(1, args.steps + args.warmup))))
-    sample = cpu_sample(pos, n)
+    # calibrate on one x-plane, then size the per-step sample so the whole run stays within ~2 minutes
+    cal = time_cpu(cpu_sample(1), threads)
+    rate = 4096 / max(cal["seconds"], 1e-6)
+    budget_s = 100.0
+    cols = int(max(1, min(128, rate * budget_s / max(1, args.steps + args.warmup) / 4096)))
+    sample = cpu_sample(cols)
     for _ in range(args.warmup):
         time_cpu(sample, threads)
     t = 0.0
@@ -165,21 +196,18 @@ def run_reference(args):
         t += time_cpu(sample, threads)["seconds"]
     ms = 1e3 * t / args.steps
     value = len(sample) * CELLS / (ms / 1e3)
-    line = {
-        "impl": "reference", "metric": "voxels/s (Perlin + MC mesh build)", "value": value, "unit": "voxels/s",
-        "chunks_per_s": len(sample) / (ms / 1e3),
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 noise / f32 mesh",
-        "data": "synthetic",
-        "config": {"workload": "spawn-neighbourhood 16x16x8 chunks of 12^3 (BASELINE configs[1]), seed 0",
-                   "sample_chunks_per_step": len(sample)},
+    line = base_line(args, args.gpus)
+    line.update({
+        "impl": "reference", "value": value, "chunks_per_s": len(sample) / (ms / 1e3), "ms_per_step": ms,
+        "dtype": "f64 noise / f32 mesh",
         "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": threads, "kind": "port",
-                         "sample": f"{len(sample)} of 2048 chunks per step (odd-stride subsample keeping the z-layer mix), "
-                                   "oracle faithful mode (linear-search dedup, per-index colour, per-cell Tri map)"},
+                         "sample": f"{cols} of the region's 128 x-planes per step ({len(sample)} chunks: every y, every z layer), "
+                                   "oracle faithful mode (linear-search dedup, per-index colour, per-cell Tri map), -O3"},
         "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference is Rust; no cargo/rustc in this image -> CPU restatement (oracle/) timed instead",
-    }
+    })
+    line["config"]["sample_chunks_per_step"] = len(sample)
     emit(line)
     return 0
 
@@ -216,26 +244,32 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce(x, op):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        t = torch.tensor(np.atleast_1d(np.asarray(x, dtype=np.float64)), device="cuda")
+        dist.all_reduce(t, op=op)
+        r = t.cpu().numpy()
+        return float(r[0]) if np.ndim(x) == 0 else r
 
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def rmax(x):
+        return reduce(x, dist.ReduceOp.MAX) if world > 1 else x
+
+    def rsum(x):
+        return reduce(x, dist.ReduceOp.SUM) if world > 1 else x
 
     import underwaterworld_b200 as uw
-    from underwaterworld_b200 import _ffi
+    from underwaterworld_b200 import _ffi, gather as G
     lib = uw.load_library()
 
-    pos = rank_positions(rank)
-    n = len(pos)
+    whole = region_positions()
+    n_total = len(whole)
+    first, n = G.slab_bounds(n_total, world, rank)
+    # the request lives in PINNED host memory (the contract's "host->device copy from pinned host memory"): the library
+    # then copies it to the device straight from this buffer
+    pos_pin = torch.from_numpy(np.ascontiguousarray(whole[first:first + n])).pin_memory()
+    pos = pos_pin.numpy()
+    del whole
     builder = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local)
     stream = torch.cuda.current_stream()
     builder.set_stream(stream.cuda_stream)
@@ -243,15 +277,15 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
 
     K, W = args.steps, max(args.warmup, 3)
+    sampler = ClockSampler(local)
 
-    # ---- device-resident value ------------------------------------------------------------
+    # ---- value: device-resident, every rank its slab --------------------------------------------------
     for i in range(W):
         flush.fill_(i & 0xFF)
         builder.build_device(d_pos.data_ptr(), n)
     builder.sync()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    sampler = ClockSampler(local)
     barrier()
     with sampler:
         for i in range(K):
@@ -262,265 +296,391 @@ def run_ours(args):
         builder.sync()
         barrier()
         step_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
-        # keep sampling clocks through the e2e loop as well (the device loop alone is milliseconds)
-        # ---- e2e through the C ABI with host buffers ---------------------------------------
-        ctx = builder._ctx
-        view = _ffi.UwBatchView()
-        h = C.c_void_p()
+        launches_per_step = builder.stage_times()["launches"]
+        dv = builder.device_view()
+        my_verts, my_inds = int(dv.n_verts), int(dv.n_inds)
 
-        def e2e_step():
-            st = lib.uw_build(ctx, pos.ctypes.data, n, C.byref(h))
-            if st != 0:
-                raise RuntimeError(lib.uw_last_error(ctx).decode())
-            lib.uw_batch_view_get(h, C.byref(view))
-            nv, ni = view.n_verts, view.n_inds
-            lib.uw_batch_free(h)
-            return nv, ni
-
+        # ---- e2e: host positions -> meshes in the rendering GPU's arenas (rank 0) + draw list on the host ----------
+        rg = G.RegionGather(builder, rank, world, n_total, dst=0, bcast_device="cuda" if world > 1 else None)
+        res = None
         for i in range(W):
             flush.fill_(i & 0xFF)
-            torch.cuda.synchronize()
-            e2e_step()
-        barrier()
+            barrier()
+            rg.build(pos, first)
+            if rank == 0:
+                res = rg.wait(draw_to_host=True)
+            builder.sync()
         e2e_t = []
-        nv = ni = 0
         for i in range(K):
             flush.fill_(i & 0xFF)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            nv, ni = e2e_step()
-            e2e_t.append(time.perf_counter() - t0)
-        barrier()
-        # host-timed: the median is robust against the clock-sampling thread and other host noise
-        single_ms = 1e3 * float(np.median(e2e_t))
-        e2e_mean_ms = 1e3 * float(np.mean(e2e_t))
-
-        # The same K host builds, software-pipelined the way a streaming caller uses the ABI: submit batch k+1
-        # (uw_build_async), then collect batch k (uw_batch_wait) -- batch k's D2H runs on the library's copy
-        # stream underneath batch k+1's kernel.  One wall-clock region around all K steps, nothing in flight at
-        # either end; every step's H2D and D2H is inside it.
-        def pipelined(steps):
-            prev = C.c_void_p()
-            if lib.uw_build_async(ctx, pos.ctypes.data, n, C.byref(prev)) != 0:
-                raise RuntimeError(lib.uw_last_error(ctx).decode())
-            for _ in range(1, steps):
-                nxt = C.c_void_p()
-                if lib.uw_build_async(ctx, pos.ctypes.data, n, C.byref(nxt)) != 0:
-                    raise RuntimeError(lib.uw_last_error(ctx).decode())
-                if lib.uw_batch_wait(prev) != 0:
-                    raise RuntimeError(lib.uw_last_error(ctx).decode())
-                lib.uw_batch_view_get(prev, C.byref(view))
-                lib.uw_batch_free(prev)
-                prev = nxt
-            if lib.uw_batch_wait(prev) != 0:
-                raise RuntimeError(lib.uw_last_error(ctx).decode())
-            lib.uw_batch_view_get(prev, C.byref(view))
-            lib.uw_batch_free(prev)
-
-        pipelined(max(W, 3))
-        pipe_t = []
-        for _ in range(3):
-            flush.fill_(1)
-            torch.cuda.synchronize()
             barrier()
             t0 = time.perf_counter()
-            pipelined(K)
-            pipe_t.append(time.perf_counter() - t0)
+            rg.build(pos, first)
+            if rank == 0:
+                res = rg.wait(draw_to_host=True)
+            builder.sync()
+            e2e_t.append(time.perf_counter() - t0)
         barrier()
-        e2e_s = float(np.median(pipe_t))
-    ms_per_step = max_over_ranks(sum(step_ms) / K)
-    e2e_ms = max_over_ranks(1e3 * e2e_s / K)
-    single_ms = max_over_ranks(single_ms)
-    total_chunks = n * world
-    value = total_chunks * CELLS / (ms_per_step / 1e3)
-    e2e_value = total_chunks * CELLS / (e2e_ms / 1e3)
-    h2d = n * 12
-    d2h = n * 32 + nv * 24 + ni * 2 + 32 + 8
-    launches_per_step = builder.stage_times()["launches"]
+        e2e_steps = rmax(np.array(e2e_t))                    # per step: the slowest rank (rank 0 waits for all)
+        if rank == 0:
+            g_verts, g_inds = int(res.n_verts), int(res.n_inds)
+            g_mesh = sum(s["n_mesh"] for s in res.segments)
+            g_blank = sum(s["n_blank"] for s in res.segments)
+            g_guard = sum(s["guard"] for s in res.segments)
+            assert res.n_chunks == n_total
+        rg.close()
 
-    # ---- kernel times for the roofline (separate passes, CUDA events inside the library) -----------
-    def stage_profile(bld, reps=20):
-        bld.set_stream(stream.cuda_stream)
-        bld.set_profiling(True)
-        acc = {"noise_ms": 0.0, "classify_ms": 0.0, "scan_ms": 0.0, "emit_ms": 0.0, "total_ms": 0.0}
-        for i in range(reps + 2):
-            flush.fill_(i & 0xFF)
-            bld.build_device(d_pos.data_ptr(), n)
-            bld.sync()
-            if i >= 2:
-                t = bld.stage_times()
-                for k in acc:
-                    acc[k] += t[k] / reps
-        bld.set_profiling(False)
-        return acc
+        # ---- e2e_host: every rank streams its slab's meshes into pinned host memory ----------------------------
+        ctx = builder._ctx
+        view = _ffi.UwBatchView()
+        slices = [pos[a:a + HOST_SLICE] for a in range(0, n, HOST_SLICE)]
 
-    fused_ms = stage_profile(builder)["total_ms"]            # default path: (order kernel +) the fused kernel
-    dv = builder.device_view()
-    n_verts, n_inds = int(dv.n_verts), int(dv.n_inds)
-    staged = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local, staged=True)
-    acc = stage_profile(staged)                              # the same stages as four kernels, for attribution
-    staged.close()
-    skipper = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local, analytic_skip=True)
-    skip_ms = stage_profile(skipper)["total_ms"]             # reported beside the headline, never as the headline
-    skipper.close()
-    hb = builder.build(pos)                                  # host path once, for the mesh statistics
-    n_active = int((hb.descs["index_count"] > 0).sum())
-    n_blank = int((hb.descs["flags"] & 1).sum())
-    assert hb.n_verts == n_verts and hb.n_inds == n_inds
-    guards = builder.guard_count()
+        def host_pass():
+            """uw_build_async(k+1) before uw_batch_wait(k): batch k's D2H runs under batch k+1's kernel."""
+            nv = ni = 0
+            prev = None
+            for sl in slices:
+                h = C.c_void_p()
+                if lib.uw_build_async(ctx, sl.ctypes.data, len(sl), C.byref(h)) != 0:
+                    raise RuntimeError(lib.uw_last_error(ctx).decode())
+                if prev is not None:
+                    if lib.uw_batch_wait(prev) != 0:
+                        raise RuntimeError(lib.uw_last_error(ctx).decode())
+                    lib.uw_batch_view_get(prev, C.byref(view)); nv += view.n_verts; ni += view.n_inds
+                    lib.uw_batch_free(prev)
+                prev = h
+            if lib.uw_batch_wait(prev) != 0:
+                raise RuntimeError(lib.uw_last_error(ctx).decode())
+            lib.uw_batch_view_get(prev, C.byref(view)); nv += view.n_verts; ni += view.n_inds
+            lib.uw_batch_free(prev)
+            return nv, ni
 
-    peak, peak_src = measured_peaks()
-    ffma_tflops = builder.ffma_peak_tflops()                 # measured FP32 peak (FFMA chains), beside the nominal one
-    out_bytes = n * 32 + 24 * n_verts + 2 * n_inds
-    alg_bytes = {
-        "fused": n * 12 + out_bytes,                                    # positions in, descriptors + mesh out
-        "noise": n * 4 * L3 + n * 12,                                   # staged: write densities (+ read positions)
-        "classify": n * 4 * L3 + n * 16,                                # staged: read densities, write counts
-        "scan": n * (16 + 12 + 32 + 4),
-        "emit": n_active * (4 * L3 + 32) + 24 * n_verts + 2 * n_inds,   # staged: read active densities, write mesh
-    }
-    stage_ms = {"noise": acc["noise_ms"], "classify": acc["classify_ms"], "scan": acc["scan_ms"], "emit": acc["emit_ms"]}
-    achieved = alg_bytes["fused"] / (fused_ms / 1e3) / 1e9 if fused_ms > 0 else 0.0
-    noise_flops = n * L3 * FLOP_PER_SAMPLE
-    fused_tflops = noise_flops / (fused_ms / 1e3) / 1e12 if fused_ms > 0 else 0.0
-    # The dominant kernel is bound by FP32 issue, not by HBM or the tensor cores (SURVEY 8d names the FP32-ALU roofline
-    # for the noise stage, 57 % of this kernel's cycles); its HBM view is reported beside it.
-    roofline = {"kernel": "k_build_fused<12,3,u16> (noise + classify + scan + emit in one persistent kernel)",
-                "bound": "fp32", "achieved": fused_tflops, "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s",
-                "frac": fused_tflops / FP32_NOMINAL_TFLOPS,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from profiles/r01_ncu_fused_full.txt
-                # (ncu --set full): reads only; the mesh writes are still resident in the 126 MB L2 when the kernel ends
-                "traffic": 139520,
-                "peak_source": "nominal FP32 FMA peak, 148 SMs x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json holds HBM and bf16 "
-                               "only); the FFMA-chain rate measured in this run is in measured_ffma_peak_tflops",
-                "measured_ffma_peak_tflops": ffma_tflops,
-                "frac_of_measured_ffma": fused_tflops / ffma_tflops if ffma_tflops > 0 else None,
-                "algorithmic_flop_per_launch": noise_flops, "avg_launch_ms": fused_ms,
-                "note": "achieved = the reference's op count for the noise (285 FLOP/sample x 2197 samples x 2048 chunks, SURVEY 8d) "
-                        "over the WHOLE fused kernel time, extraction included; the tensor-product factorisation executes ~3x "
-                        "fewer instructions than that count. At 2048 chunks (3.5 chunks per CTA) the kernel is latency / tail-"
-                        "bound; the same kernel reaches 2x this fraction at 32768 chunks (north_star.fused_kernel)",
-                "hbm_view": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": alg_bytes["fused"],
-                             "note": "densities never leave the SM: compulsory HBM traffic is positions in and mesh out only"},
-                "staged_pipeline": {
-                    "stages_ms": stage_ms,
-                    "stages_gbs": {k: (alg_bytes[k] / (stage_ms[k] / 1e3) / 1e9 if stage_ms[k] > 0 else None) for k in stage_ms},
-                    "noise_algorithmic_tflops": noise_flops / (stage_ms["noise"] / 1e3) / 1e12 if stage_ms["noise"] > 0 else None,
-                    "note": "UW_FLAG_STAGED: same stages as four kernels with densities materialised in HBM"}}
+        KH = max(3, min(K, 10))
+        for _ in range(2):
+            host_pass()
+        host_t = []
+        hv = hi = 0
+        for _ in range(KH):
+            barrier()
+            t0 = time.perf_counter()
+            hv, hi = host_pass()
+            host_t.append(time.perf_counter() - t0)
+        barrier()
+        host_steps = rmax(np.array(host_t))
+        host_bytes = n * 32 + hv * 24 + hi * 2
 
-    # ---- north_star targets, measured where they are defined (rank 0 only; a few extra milliseconds) ----------
-    north_star = None
-    if rank == 0:
-        from underwaterworld_b200 import region as _region
-        big = _region.box_region((-32, 32), (-32, 32), (-4, 4))            # 32768 chunks: enough waves to amortise latency
-        d_big = torch.from_numpy(big).cuda()
-        stg = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local, staged=True)
-        stg.set_stream(stream.cuda_stream)
-        stg.set_profiling(True)
-        t_big = {"noise_ms": 0.0, "classify_ms": 0.0, "scan_ms": 0.0, "emit_ms": 0.0}
+        # bare pinned D2H of the same bytes by all ranks at once: the ceiling of the host path on this box
+        pin = torch.empty(max(host_bytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        devbuf = torch.empty_like(pin, device="cuda")
+        d2h_t = []
         for i in range(5):
-            stg.build_device(d_big.data_ptr(), len(big)); stg.sync()
-            if i >= 2:
-                tt = stg.stage_times()
-                for k in t_big:
-                    t_big[k] += tt[k] / 3
-        vb = stg.device_view()
-        nb_act = None
-        stg.close()
+            barrier()
+            t0 = time.perf_counter()
+            pin.copy_(devbuf, non_blocking=True)
+            torch.cuda.synchronize()
+            d2h_t.append(time.perf_counter() - t0)
+        barrier()
+        d2h_steps = rmax(np.array(d2h_t[1:]))
+        del pin, devbuf
+
+    ms_per_step = rmax(sum(step_ms) / K)
+    tot_verts, tot_inds = int(rsum(my_verts)), int(rsum(my_inds))
+    tot_host_bytes = rsum(float(host_bytes))
+    e2e_ms = 1e3 * float(np.mean(e2e_steps))
+    host_ms = 1e3 * float(np.median(host_steps))
+    d2h_ms = 1e3 * float(np.median(d2h_steps))
+    value = n_total * CELLS / (ms_per_step / 1e3)
+
+    # ---- sustained leg (N = 1): >= 2 s of back-to-back launches, clocks sampled ------------------------------
+    sustained = None
+    if rank == 0 and world == 1 and not args.quick:
+        s2 = ClockSampler(local)
+        reps = int(max(50, 2200.0 / max(ms_per_step, 0.05)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for i in range(2):
-            builder.build_device(d_big.data_ptr(), len(big)); builder.sync()
-        e0.record(stream)
-        for i in range(5):
-            builder.build_device(d_big.data_ptr(), len(big))
-        e1.record(stream); builder.sync()
-        fused_big_ms = e0.elapsed_time(e1) / 5
-        # densities read once (K1 and K2 are separate kernels here) + mesh + descriptor + position;
-        # the emit stage's second read of the surface chunks' densities is implementation traffic, not counted
-        ext_bytes = len(big) * (4 * L3 + 44) + 24 * int(vb.n_verts) + 2 * int(vb.n_inds)
-        ext_ms = t_big["classify_ms"] + t_big["scan_ms"] + t_big["emit_ms"]
-        north_star = {
-            "batch_chunks": len(big),
-            "noise_stage": {"kernel": "k_noise_spec<12,3> (staged pipeline)", "ms": t_big["noise_ms"],
-                            "algorithmic_tflops": len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12,
-                            "frac_of_nominal_fp32_peak": len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12 / FP32_NOMINAL_TFLOPS,
-                            "frac_of_measured_ffma_peak": len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12 / ffma_tflops,
-                            "density_write_gbs": len(big) * 4 * L3 / (t_big["noise_ms"] / 1e3) / 1e9},
-            "extraction_stages": {"kernels": "k_classify_spec<12> + k_scan_chunks + k_emit_small<12,u16> (staged pipeline)",
-                                  "ms": ext_ms,
-                                  "stages_ms": {"classify": t_big["classify_ms"], "scan": t_big["scan_ms"], "emit": t_big["emit_ms"]},
-                                  "algorithmic_bytes": ext_bytes,
-                                  "algorithmic_gbs": ext_bytes / (ext_ms / 1e3) / 1e9,
-                                  "frac_of_measured_hbm": ext_bytes / (ext_ms / 1e3) / 1e9 / peak,
-                                  "classify_gbs": len(big) * (4 * L3 + 16) / (t_big["classify_ms"] / 1e3) / 1e9,
-                                  "classify_frac_of_measured_hbm": len(big) * (4 * L3 + 16) / (t_big["classify_ms"] / 1e3) / 1e9 / peak,
-                                  "note": "classify is the HBM-shaped stage; emit (edge lerp, per-vertex powf colour, index tables) is "
-                                          "instruction-issue-bound, see profiles/ and DESIGN.md"},
-            "fused_kernel": {"ms": fused_big_ms, "chunks_per_s": len(big) / (fused_big_ms / 1e3),
-                             "voxels_per_s": len(big) * CELLS / (fused_big_ms / 1e3),
-                             "algorithmic_tflops": len(big) * L3 * FLOP_PER_SAMPLE / (fused_big_ms / 1e3) / 1e12,
-                             "frac_of_nominal_fp32_peak": len(big) * L3 * FLOP_PER_SAMPLE / (fused_big_ms / 1e3) / 1e12 / FP32_NOMINAL_TFLOPS},
-            "note": "targets: >= 60 % of peak FP32 in the noise stage, >= 50 % of peak HBM in the extraction stages. "
-                    "FLOPs are the reference's algorithmic count (285 per sample); the kernels execute ~3x fewer instructions."}
-        del d_big
+        with s2:
+            e0.record(stream)
+            for _ in range(reps):
+                builder.build_device(d_pos.data_ptr(), n)
+            e1.record(stream)
+            builder.sync()
+        sms = e0.elapsed_time(e1) / reps
+        sustained = {"launches": reps, "seconds": e0.elapsed_time(e1) / 1e3, "ms_per_step": sms,
+                     "voxels_per_s": n_total * CELLS / (sms / 1e3), "clocks": s2.summary(),
+                     "note": "back-to-back launches of the same region, no L2 flush in between, CUDA events around the whole run"}
 
-    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------
+    # ---- roofline of the dominant kernel, from the SAME timing as ms_per_step ------------------------------
+    peak, peak_src = measured_peaks()
+    ffma_tflops = builder.ffma_peak_tflops() if rank == 0 else 0.0
+    slab_flops = n * L3 * FLOP_PER_SAMPLE                        # this launch's algorithmic work (rank 0's slab)
+    my_ms = sum(step_ms) / K
+    out_bytes = n * 12 + n * 32 + 24 * my_verts + 2 * my_inds
+    prof = tracked_profile("r02_ncu_fused_config3.json")        # ncu --set full of this kernel on the N = 1 launch
+    roofline = None
+    if rank == 0:
+        ach = slab_flops / (my_ms / 1e3) / 1e12
+        roofline = {
+            "kernel": "k_build_fused<12,3,u16> (noise + classify + scan + emit in one persistent kernel; one launch per step)",
+            "bound": "fp32", "achieved": ach, "peak": FP32_NOMINAL_TFLOPS, "unit": "TFLOP/s", "frac": ach / FP32_NOMINAL_TFLOPS,
+            "algorithmic_flop_per_launch": slab_flops, "avg_launch_ms": my_ms,
+            "timing": "CUDA events around each of the K timed launches on the launching stream (the same events ms_per_step is "
+                      "computed from; this rank's mean)",
+            "peak_source": "nominal FP32 FMA peak, 148 SMs x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json holds HBM and bf16 only); "
+                           "the FFMA-chain rate measured in this run is measured_ffma_peak_tflops",
+            "measured_ffma_peak_tflops": ffma_tflops,
+            "frac_of_measured_ffma": ach / ffma_tflops if ffma_tflops > 0 else None,
+            "traffic": (prof or {}).get("dram_bytes") if world == 1 else None,
+            "traffic_source": "profiles/r02_ncu_fused_config3.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch "
+                              "(ncu --set full, N = 1 region launch)" if (prof and world == 1) else None,
+            "note": "achieved = SURVEY 8d's algorithmic count (285 FLOP per density sample x 2197 samples x chunks of this launch) over "
+                    "the WHOLE fused kernel (extraction included).  The tensor-product factorisation executes several times fewer "
+                    "instructions than that count, so this can exceed 1; `hardware_view` is the honest utilisation figure.",
+            "hbm_view": {"achieved": out_bytes / (my_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": out_bytes / (my_ms / 1e3) / 1e9 / peak, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": out_bytes,
+                         "note": "densities never leave the SM: compulsory HBM traffic is positions in and mesh out only"},
+        }
+        if prof and world == 1 and prof.get("warp_inst"):
+            clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+            roofline["hardware_view"] = {
+                "warp_instructions_per_launch": prof["warp_inst"],
+                "issue_slot_frac": prof["warp_inst"] / (ISSUE_SLOTS_PER_CYCLE * clk * my_ms / 1e3),
+                "ncu_issue_active_pct": prof.get("issue_active_pct"), "ncu_fma_pipe_pct": prof.get("fma_pipe_pct"),
+                "source": "instruction count from profiles/r02_ncu_fused_config3.json over this run's launch time and sampled SM clock; "
+                          "148 SMs x 4 issue slots per cycle"}
+
+    # ---- the other BASELINE configs, rank 0 at N = 1 -----------------------------------------------------------
+    configs = None
+    if rank == 0 and world == 1 and not args.quick:
+        configs = other_configs(uw, torch, builder, stream, flush, local, peak, ffma_tflops, K, W)
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same region -----------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        one = time_cpu(pos, 1)                      # the reference is single-threaded (README.md:19)
-        allc = time_cpu(pos, threads)
+        cols = 2
+        sample = cpu_sample(cols)
+        allc = time_cpu(sample, threads)
+        if allc["seconds"] < 5.0:                   # fast host: take a bigger bite (10-30 s of CPU work in total)
+            cols = int(min(16, max(2, 12.0 / max(allc["seconds"], 1e-3))))
+            sample = cpu_sample(cols)
+            allc = time_cpu(sample, threads)
+        one = time_cpu(cpu_sample(1), 1)            # the reference is single-threaded (README.md:19)
         cpu_baseline = {
-            "value": n * CELLS / allc["seconds"], "unit": "voxels/s", "cores": threads, "kind": "port",
-            "sample": "the full 2048-chunk workload, once per thread count; oracle faithful mode "
-                      "(linear-search dedup, per-index colour, per-cell Tri map)",
-            "chunks_per_s": n / allc["seconds"],
-            "single_thread": {"value": n * CELLS / one["seconds"], "chunks_per_s": n / one["seconds"], "cores": 1},
+            "value": len(sample) * CELLS / allc["seconds"], "unit": "voxels/s", "cores": threads, "kind": "port",
+            "sample": f"{cols} of the region's 128 x-planes ({len(sample)} chunks: every y, every z layer), once; oracle faithful "
+                      "mode (linear-search dedup, per-index colour, per-cell Tri map), g++ -O3",
+            "chunks_per_s": len(sample) / allc["seconds"],
+            "single_thread": {"value": 4096 * CELLS / one["seconds"], "chunks_per_s": 4096 / one["seconds"], "cores": 1,
+                              "sample": "1 x-plane (4096 chunks)"},
         }
 
     if rank == 0:
-        line = {
-            "metric": "voxels/s (Perlin + MC mesh build)", "value": value, "unit": "voxels/s",
-            "chunks_per_s": total_chunks / (ms_per_step / 1e3),
-            "nontrivial": {"chunks_with_mesh_per_s": n_active * world / (ms_per_step / 1e3),
-                           "voxels_per_s": n_active * world * CELLS / (ms_per_step / 1e3),
-                           "note": "same time, counting only chunks that end with a mesh (rank 0's share x N)"},
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 noise + f64 guard band / f32 mesh / u16 indices", "data": "synthetic",
-            "config": {"workload": "spawn-neighbourhood 16x16x8 = 2048 chunks of 12^3 per GPU (BASELINE configs[1]; "
-                                   "rank r owns x in [-8+16r, 8+16r)), seed 0, octaves 3, iso -0.1",
-                       "chunks_per_gpu": n, "cells_per_chunk": CELLS, "samples_per_chunk": L3,
-                       "l2": "flushed between timed steps (256 MB write)", "parallelism": f"chunk-slabs x{world}",
-                       "host_affinity": numa},
-            "e2e": {"value": e2e_value, "unit": "voxels/s", "chunks_per_s": total_chunks / (e2e_ms / 1e3),
-                    "ms_per_step": e2e_ms,
-                    "timing": "host perf_counter around K software-pipelined host builds (uw_build_async k+1, uw_batch_wait k; "
-                              "two batches in flight, D2H of batch k under the kernel of batch k+1), median of 3 runs",
-                    "single_call": {"ms_per_step": single_ms, "ms_per_step_mean": e2e_mean_ms,
-                                    "chunks_per_s": total_chunks / (single_ms / 1e3),
-                                    "timing": "blocking uw_build, host perf_counter, median of K steps, L2 flushed between steps"},
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        h2d = n_total * 12
+        d2h = g_mesh * 32 + 64 * world + 4
+        line = base_line(args, world)
+        line["steps"], line["warmup"] = K, W
+        line.update({
+            "value": value, "chunks_per_s": n_total / (ms_per_step / 1e3), "ms_per_step": ms_per_step,
+            "dtype": "f32 noise + f64 guard band / f32 mesh / u16 indices",
+            "nontrivial": {"chunks_with_mesh": g_mesh, "chunks_with_mesh_per_s": g_mesh / (ms_per_step / 1e3),
+                           "voxels_per_s": g_mesh * CELLS / (ms_per_step / 1e3),
+                           "note": "same time, counting only chunks that end with a mesh"},
+            "e2e": {"value": n_total * CELLS / (e2e_ms / 1e3), "unit": "voxels/s", "chunks_per_s": n_total / (e2e_ms / 1e3),
+                    "ms_per_step": e2e_ms, "ms_per_step_median": 1e3 * float(np.median(e2e_steps)),
+                    "path": "host positions -> pinned H2D per rank -> fused kernels store meshes + descriptors straight into rank 0's "
+                            "arenas (NVLink peer stores from ranks > 0; uw_gather_build) -> head flags -> rank 0: uw_gather_wait + D2H "
+                            "of the draw list (descriptors of the chunks that ended with a mesh) and the heads into pinned host memory",
+                    "timing": "host perf_counter per step on every rank (barrier, build, wait/sync), MAX over ranks per step, mean over K",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "mesh_bytes_to_render_gpu": 24 * g_verts + 2 * g_inds,
+                    "nvlink_bytes_per_step": (24 * (g_verts - int(res.segments[0]["n_verts"])) + 2 * (g_inds - int(res.segments[0]["n_inds"]))
+                                              + 32 * (n_total - int(res.segments[0]["n_chunks"]))) if world > 1 else 0},
+            "e2e_host": {"value": n_total * CELLS / (host_ms / 1e3), "unit": "voxels/s", "chunks_per_s": n_total / (host_ms / 1e3),
+                         "ms_per_step": host_ms, "d2h_bytes_per_step": tot_host_bytes, "h2d_bytes_per_step": h2d,
+                         "achieved_d2h_gbs": tot_host_bytes / (host_ms / 1e3) / 1e9,
+                         "d2h_ceiling_gbs": tot_host_bytes / (d2h_ms / 1e3) / 1e9,
+                         "frac_of_d2h_ceiling": d2h_ms / host_ms,
+                         "path": f"every rank: uw_build_async / uw_batch_wait over slices of {HOST_SLICE} chunks, two in flight; full meshes "
+                                 "(descriptors + vertices + indices) into pinned host memory",
+                         "timing": f"host perf_counter around one pass over the rank's slab, barrier before, MAX over ranks, median of {KH} passes; "
+                                   "d2h_ceiling = bare pinned cudaMemcpy of the same bytes by all ranks simultaneously, same run"},
             "gpu_launches": int(launches_per_step) * K,
             "kernels_per_step": ["k_build_fused"],
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "analytic_skip_variant": {
-                "ms_per_step": skip_ms, "chunks_per_s": n / (skip_ms / 1e3) if skip_ms > 0 else None,
-                "note": "UW_FLAG_ANALYTIC_SKIP (off by default, NOT the headline): z layers that provably hold no surface "
-                        "(|noise| <= 1) are answered without evaluating the noise; outputs identical (tests), "
-                        "but their samples are not evaluated, so no noise FLOPs may be credited for them"},
-            "north_star": north_star,
+            "sustained": sustained,
+            "configs": configs,
             "clocks": sampler.summary(),
-            "mesh": {"n_verts": n_verts, "n_inds": n_inds, "chunks_with_mesh": n_active, "chunks_blank_early": n_blank,
-                     "guard_band_reevals": int(guards)},
-        }
+            "mesh": {"n_verts": tot_verts, "n_inds": tot_inds, "chunks_with_mesh": g_mesh, "chunks_blank_early": g_blank,
+                     "guard_band_reevals": int(g_guard)},
+        })
+        line["config"].update({"chunks_per_gpu": n, "parallelism": f"x-slabs x{world}", "host_affinity": numa,
+                               "l2": "flushed between timed steps (256 MB write)"})
         emit(line)
     builder.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def other_configs(uw, torch, builder, stream, flush, local, peak, ffma_tflops, K, W):
+    """BASELINE configs[1], [3], [4] and the north_star's per-stage targets (rank 0, N = 1)."""
+    from underwaterworld_b200 import _ffi, region
+    lib = uw.load_library()
+    out = {}
+
+    # ---- configs[1]: 2048 chunks, one batched launch (burst latency) ----------------------------------------------
+    pos = region.box_region((-8, 8), (-8, 8), (-4, 4))
+    n = len(pos)
+    d_pos = torch.from_numpy(pos).cuda()
+    for i in range(W):
+        flush.fill_(i & 0xFF)
+        builder.build_device(d_pos.data_ptr(), n)
+    builder.sync()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        ev0[i].record(stream)
+        builder.build_device(d_pos.data_ptr(), n)
+        ev1[i].record(stream)
+    builder.sync()
+    ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)) / K
+    dv = builder.device_view()
+    nv, ni = int(dv.n_verts), int(dv.n_inds)
+    ctx = builder._ctx
+    view = _ffi.UwBatchView()
+
+    def pipelined(steps):
+        prev = C.c_void_p()
+        if lib.uw_build_async(ctx, pos.ctypes.data, n, C.byref(prev)) != 0:
+            raise RuntimeError(lib.uw_last_error(ctx).decode())
+        for _ in range(1, steps):
+            nxt = C.c_void_p()
+            if lib.uw_build_async(ctx, pos.ctypes.data, n, C.byref(nxt)) != 0:
+                raise RuntimeError(lib.uw_last_error(ctx).decode())
+            if lib.uw_batch_wait(prev) != 0:
+                raise RuntimeError(lib.uw_last_error(ctx).decode())
+            lib.uw_batch_free(prev)
+            prev = nxt
+        if lib.uw_batch_wait(prev) != 0:
+            raise RuntimeError(lib.uw_last_error(ctx).decode())
+        lib.uw_batch_view_get(prev, C.byref(view))
+        lib.uw_batch_free(prev)
+
+    pipelined(max(W, 3))
+    pt = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pipelined(K)
+        pt.append(time.perf_counter() - t0)
+    pipe_ms = 1e3 * float(np.median(pt)) / K
+    single = []
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = C.c_void_p()
+        lib.uw_build(ctx, pos.ctypes.data, n, C.byref(h))
+        lib.uw_batch_free(h)
+        single.append(time.perf_counter() - t0)
+    flops = n * L3 * FLOP_PER_SAMPLE
+    out["config2_spawn_2048"] = {
+        "workload": "BASELINE configs[1]: 16x16x8 = 2048 chunks of 12^3 around the sub start, one batched launch",
+        "ms_per_step": ms, "voxels_per_s": n * CELLS / (ms / 1e3), "chunks_per_s": n / (ms / 1e3),
+        "timing": "CUDA events around each launch, L2 flushed between steps, mean of K",
+        "roofline_fp32": {"achieved_tflops": flops / (ms / 1e3) / 1e12, "frac_of_nominal": flops / (ms / 1e3) / 1e12 / FP32_NOMINAL_TFLOPS,
+                          "note": "latency / tail-bound at 3.5 chunks per resident CTA"},
+        "e2e_host_pipelined": {"ms_per_step": pipe_ms, "chunks_per_s": n / (pipe_ms / 1e3), "voxels_per_s": n * CELLS / (pipe_ms / 1e3),
+                               "d2h_bytes_per_step": n * 32 + nv * 24 + ni * 2, "h2d_bytes_per_step": n * 12},
+        "e2e_host_single_call_ms": 1e3 * float(np.median(single)),
+        "mesh": {"n_verts": nv, "n_inds": ni},
+    }
+
+    # ---- north_star per-stage targets: staged pipeline at 32 768 chunks -------------------------------------------
+    big = region.box_region((-32, 32), (-32, 32), (-4, 4))
+    d_big = torch.from_numpy(big).cuda()
+    stg = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local, staged=True)
+    stg.set_stream(stream.cuda_stream)
+    stg.set_profiling(True)
+    t_big = {"noise_ms": 0.0, "classify_ms": 0.0, "scan_ms": 0.0, "emit_ms": 0.0}
+    for i in range(5):
+        stg.build_device(d_big.data_ptr(), len(big)); stg.sync()
+        if i >= 2:
+            tt = stg.stage_times()
+            for k in t_big:
+                t_big[k] += tt[k] / 3
+    vb = stg.device_view()
+    stg.close()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(2):
+        builder.build_device(d_big.data_ptr(), len(big)); builder.sync()
+    e0.record(stream)
+    for i in range(5):
+        builder.build_device(d_big.data_ptr(), len(big))
+    e1.record(stream); builder.sync()
+    fused_big_ms = e0.elapsed_time(e1) / 5
+    ext_bytes = len(big) * (4 * L3 + 44) + 24 * int(vb.n_verts) + 2 * int(vb.n_inds)
+    ext_ms = t_big["classify_ms"] + t_big["scan_ms"] + t_big["emit_ms"]
+    nprof = tracked_profile("r02_ncu_noise_32768.json")
+    noise_tf = len(big) * L3 * FLOP_PER_SAMPLE / (t_big["noise_ms"] / 1e3) / 1e12
+    out["north_star_stages_32768"] = {
+        "batch_chunks": len(big),
+        "noise_stage": {"kernel": "k_noise_spec<12,3> (staged pipeline)", "ms": t_big["noise_ms"],
+                        "algorithmic_tflops": noise_tf, "frac_of_nominal_fp32_peak": noise_tf / FP32_NOMINAL_TFLOPS,
+                        "frac_of_measured_ffma_peak": noise_tf / ffma_tflops if ffma_tflops else None,
+                        "hardware_view": None if not nprof else {
+                            "warp_instructions": nprof.get("warp_inst"),
+                            "issue_slot_frac": nprof["warp_inst"] / (ISSUE_SLOTS_PER_CYCLE * 1.965e9 * t_big["noise_ms"] / 1e3),
+                            "ncu_issue_active_pct": nprof.get("issue_active_pct"), "ncu_fma_pipe_pct": nprof.get("fma_pipe_pct"),
+                            "ncu_lsu_pipe_pct": nprof.get("lsu_pipe_pct"),
+                            "source": "profiles/r02_ncu_noise_32768.json (ncu --set full of this kernel at this batch size)"},
+                        "density_write_gbs": len(big) * 4 * L3 / (t_big["noise_ms"] / 1e3) / 1e9},
+        "extraction_stages": {"kernels": "k_classify_spec<12> + k_scan_chunks + k_emit_small<12,u16> (staged pipeline)", "ms": ext_ms,
+                              "stages_ms": {"classify": t_big["classify_ms"], "scan": t_big["scan_ms"], "emit": t_big["emit_ms"]},
+                              "algorithmic_bytes": ext_bytes, "algorithmic_gbs": ext_bytes / (ext_ms / 1e3) / 1e9,
+                              "frac_of_measured_hbm": ext_bytes / (ext_ms / 1e3) / 1e9 / peak,
+                              "classify_frac_of_measured_hbm": len(big) * (4 * L3 + 16) / (t_big["classify_ms"] / 1e3) / 1e9 / peak},
+        "fused_kernel": {"ms": fused_big_ms, "chunks_per_s": len(big) / (fused_big_ms / 1e3),
+                         "voxels_per_s": len(big) * CELLS / (fused_big_ms / 1e3)},
+        "note": "targets: >= 60 % of peak FP32 in the noise stage (algorithmic FLOPs, SURVEY 8d), >= 50 % of peak HBM in the extraction stages",
+    }
+    del d_big
+
+    # ---- configs[3]: the 2048-chunk region at 64^3 cells per chunk ------------------------------------------------
+    try:
+        b64 = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=64, device=local)
+        b64.set_stream(stream.cuda_stream)
+        for i in range(2):
+            b64.build_device(d_pos.data_ptr(), n); b64.sync()
+        e0.record(stream)
+        for i in range(3):
+            b64.build_device(d_pos.data_ptr(), n)
+        e1.record(stream); b64.sync()
+        ms64 = e0.elapsed_time(e1) / 3
+        b64.set_profiling(True)
+        b64.build_device(d_pos.data_ptr(), n); b64.sync()
+        st64 = b64.stage_times()
+        v64 = b64.device_view()
+        out["config4_highres_64"] = {
+            "workload": "BASELINE configs[3]: the 16x16x8 region at 64^3 cells per chunk (u32 indices)",
+            "ms_per_step": ms64, "voxels_per_s": n * 64 ** 3 / (ms64 / 1e3), "chunks_per_s": n / (ms64 / 1e3),
+            "stages_ms": {k: st64[k] for k in ("noise_ms", "classify_ms", "scan_ms", "emit_ms")},
+            "mesh": {"n_verts": int(v64.n_verts), "n_inds": int(v64.n_inds)},
+            "hbm_frac_end_to_end": (n * 65 ** 3 * 4 * 3 + 24 * int(v64.n_verts) + 4 * int(v64.n_inds)) / (ms64 / 1e3) / 1e9 / peak,
+        }
+        b64.close()
+    except Exception as e:                                  # pragma: no cover
+        out["config4_highres_64"] = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- configs[4]: scripted flythrough, per-frame batches -------------------------------------------------------
+    try:
+        from bench_flythrough import flythrough
+        out["config5_flythrough"] = flythrough(builder)
+    except Exception as e:                                  # pragma: no cover
+        out["config5_flythrough"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 _JSON_FD = None
@@ -544,10 +704,11 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the other configs and the sustained leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

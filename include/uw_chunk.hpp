@@ -115,9 +115,14 @@ public:
         num_inds_ = d.index_count;
         verts_.clear();
         inds_.clear();
+        inds32_.clear();
+        index32_ = v.inds32 != nullptr;
         if (d.flags & UW_CHUNK_HAS_MESH) {
             verts_.assign(v.verts + d.vert_offset, v.verts + d.vert_offset + d.vert_count);
-            inds_.assign(v.inds16 + d.index_offset, v.inds16 + d.index_offset + d.index_count);
+            // a builder created with UW_FLAG_INDEX32 (or internal_size > 22, where `ind as u16` could wrap,
+            // chunk.rs:243) returns u32 indices only: inds16 is NULL then
+            if (index32_) inds32_.assign(v.inds32 + d.index_offset, v.inds32 + d.index_offset + d.index_count);
+            else          inds_.assign(v.inds16 + d.index_offset, v.inds16 + d.index_offset + d.index_count);
         }
         done_ = true;
     }
@@ -129,8 +134,16 @@ public:
     }
     const std::vector<uint16_t>& inds_buffer_slice() const {                 // chunk.rs:347
         if (!not_blank()) throw std::logic_error("called inds_buffer_slice() on a blank chunk");
+        if (index32_) throw std::logic_error("this builder emits u32 indices: use inds32_buffer_slice()");
         return inds_;
     }
+    // u32 variant (wgpu::IndexFormat::Uint32 instead of state.rs:506's Uint16) for UW_FLAG_INDEX32 builders
+    const std::vector<uint32_t>& inds32_buffer_slice() const {
+        if (!not_blank()) throw std::logic_error("called inds32_buffer_slice() on a blank chunk");
+        if (!index32_) throw std::logic_error("this builder emits u16 indices: use inds_buffer_slice()");
+        return inds32_;
+    }
+    bool index32() const { return index32_; }
     size_t num_inds() const { return num_inds_; }                            // chunk.rs:348
     bool blank_early() const { return flags_ & UW_CHUNK_BLANK_EARLY; }
     const std::array<int32_t, 3>& pos() const { return pos_; }
@@ -140,6 +153,8 @@ private:
     std::array<int32_t, 3> pos_, chunk_offset_;
     std::vector<VertColor> verts_;
     std::vector<uint16_t> inds_;
+    std::vector<uint32_t> inds32_;
+    bool index32_ = false;
     size_t num_inds_ = 0;
     uint32_t flags_ = 0;
     bool done_ = false;

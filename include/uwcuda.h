@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define UW_ABI_VERSION 1
+#define UW_ABI_VERSION 2
 
 typedef enum uw_status {
     UW_OK              = 0,
@@ -217,6 +217,99 @@ uw_status   uw_debug_vertex_colors(uw_ctx* ctx, const float* world_z, const uint
  * allocation (>= the used part); offsets inside it are the descriptor's vert_offset / index_offset.  A later
  * build that has to GROW the arena replaces the allocation: export again when the capacity (bytes) changed. */
 uw_status   uw_export_arena_fd(uw_ctx* ctx, int which, int* fd, uint64_t* bytes);
+
+/* ---- multi-GPU: one region, G GPUs of one box, finished meshes on the rendering GPU ---------------------------
+ * SURVEY §8e / BASELINE configs[2].  Chunks are independent (chunk.rs:89-129: a chunk's output is a function of
+ * pos, seed and constants only), so a region is cut into contiguous slabs of the position list -- x-slabs for the
+ * x-major window order of World::update_nearby (world.rs:164-170) -- one per GPU, with NO collective on the compute
+ * path.  The only cross-GPU traffic is the optional gather of the finished meshes to the GPU that draws
+ * (state.rs:500-508 consumes them there).  It is FUSED into the build: the rendering GPU owns one arena per buffer
+ * kind, cut into one segment per producer; a producer GPU's fused kernel stores its vertices, indices and
+ * descriptors straight into its segment through NVLink peer addresses while it computes (no staging copy, no
+ * second pass), and its last CTA publishes a per-segment head {totals, epoch} after a system-wide fence.  The
+ * consumer waits for the heads on its own stream (uw_gather_wait) -- one-sided, no rendezvous, no NCCL.
+ *
+ *   render process/GPU : uw_gather_create  -> uw_gather_info (plain bytes; hand it to the producers)
+ *   every producer     : uw_gather_attach(info, segment)          (same process: peer access; other process: CUDA IPC)
+ *                        uw_gather_build(pos, n, first_chunk)      async; outputs land in the render GPU's arenas
+ *   render process/GPU : uw_gather_wait    -> uw_gather_result     the k-th wait returns when every segment's k-th
+ *                                                                  build has landed
+ * Descriptor i of the arena belongs to request chunk i (first_chunk + local index); its vert_offset / index_offset
+ * are element offsets into the arena (segment s starts at s * seg_vcap / s * seg_icap), index VALUES stay
+ * chunk-local as everywhere else.  Fused path only (internal_size 10 / 12, no UW_FLAG_TRIS / STAGED /
+ * KEEP_DENSITIES); a segment that overflows its capacity fails the producer's uw_sync with UW_ERR_OOM.
+ * uw_multi_* below drives all of this from ONE process (what a Rust `World` would call). */
+#define UW_MAX_SEGMENTS 16
+#define UW_GATHER_DESCS_TO_HOST 0x1u   /* uw_gather_wait also copies ALL descriptors (request order) to pinned host memory      */
+#define UW_GATHER_DRAW_TO_HOST  0x2u   /* ... copies the DRAW LIST: the descriptors of the chunks that ended with a mesh only
+                                          (Chunk::not_blank, what World::build_full_step keeps for rendering, world.rs:117-121;
+                                          8 % of the chunks of a terrain region), per segment in completion order          */
+
+typedef struct uw_gather_info {
+    uint32_t abi_version, n_segments;
+    int32_t  device;            /* render device ordinal (as seen by the owner process)                     */
+    uint32_t index_bytes;       /* 2 or 4                                                                   */
+    uint64_t owner_pid;
+    uint64_t base, bytes;       /* the arena allocation: owner-process device address, size                 */
+    uint64_t off_head, off_descs, off_verts, off_inds, off_draw;   /* byte offsets of the five parts inside it */
+    uint64_t n_chunks;          /* descriptor capacity (chunks of the whole region)                         */
+    uint64_t seg_vcap, seg_icap;/* capacity of ONE segment, in vertices / indices                           */
+    uint8_t  ipc_handle[64];    /* cudaIpcMemHandle_t of the allocation                                     */
+} uw_gather_info;
+
+typedef struct uw_gather_segment {
+    uint64_t first_chunk;       /* request index of the segment's first chunk                               */
+    uint32_t n_chunks, n_mesh, n_blank, overflow;
+    uint64_t n_verts, n_inds;   /* elements used in the segment (vertex allocations are padded to even counts) */
+    uint64_t guard;             /* f64 guard-band re-evaluations                                            */
+} uw_gather_segment;
+
+typedef struct uw_gather_result {
+    uint32_t n_segments, epoch;
+    uint64_t n_chunks, n_verts, n_inds;                      /* sums over the segments                       */
+    const void* d_descs;        /* uw_chunk_desc[n_chunks capacity], render GPU                             */
+    const void* d_verts;        /* uw_vert[n_segments * seg_vcap]                                           */
+    const void* d_inds;         /* index_bytes * [n_segments * seg_icap]                                    */
+    uint64_t seg_vcap, seg_icap;
+    const uw_chunk_desc* h_descs; /* pinned host copy of the descriptors (UW_GATHER_DESCS_TO_HOST), else NULL;
+                                     valid until the next uw_gather_wait                                    */
+    const uw_chunk_desc* h_draw;  /* pinned host copy of the draw list (UW_GATHER_DRAW_TO_HOST), else NULL: segment 0's
+                                     n_mesh entries, then segment 1's, ...                                  */
+    const void* d_draw;           /* the draw list on the render GPU: uw_chunk_desc[n_segments][n_chunks capacity]      */
+    uint64_t n_draw;              /* sum of seg[].n_mesh                                                    */
+    uw_gather_segment seg[UW_MAX_SEGMENTS];
+} uw_gather_result;
+
+/* seg_vcap / seg_icap = 0: sized for ceil(n_chunks / n_segments) chunks per segment like the library's own arenas. */
+uw_status   uw_gather_create(uw_ctx* render_ctx, uint32_t n_segments, uint64_t n_chunks, uint64_t seg_vcap, uint64_t seg_icap,
+                             uw_gather_info* out);
+uw_status   uw_gather_destroy(uw_ctx* render_ctx);           /* producers detach first                        */
+uw_status   uw_gather_attach(uw_ctx* ctx, const uw_gather_info* info, uint32_t segment);
+uw_status   uw_gather_detach(uw_ctx* ctx);
+/* Chunk::new + build_full for n chunks (HOST positions; request indices first_chunk .. first_chunk + n) into the
+ * attached segment.  Returns once the pinned H2D copy and the kernel are enqueued; uw_sync() completes it locally.
+ * If chunk_pos_xyz is itself page-locked memory the copy reads it directly: keep it unchanged until then. */
+uw_status   uw_gather_build(uw_ctx* ctx, const int32_t* chunk_pos_xyz, uint32_t n, uint64_t first_chunk);
+/* Same with positions already on the producer's device. */
+uw_status   uw_gather_build_device(uw_ctx* ctx, const int32_t* d_chunk_pos_xyz, uint32_t n, uint64_t first_chunk);
+uw_status   uw_gather_wait(uw_ctx* render_ctx, uint32_t flags, uw_gather_result* out);
+
+/* Contiguous slab `part` of `parts` of a list of n chunks (remainder spread one per slab) -- the partition
+ * uw_multi_build and bench.py use. */
+void        uw_slab_bounds(uint32_t n, uint32_t parts, uint32_t part, uint32_t* first, uint32_t* count);
+
+/* One process, G GPUs: devices[0] renders.  uw_multi_build = World::build_full_step for a whole region
+ * (world.rs:113-123) -- slabs, G fused launches (each GPU's H2D + kernel on its own stream), meshes gathered into
+ * devices[0]'s arenas as they are produced, wait.  flags: UW_GATHER_DESCS_TO_HOST.  The result's pointers stay valid
+ * until the next uw_multi_build / uw_multi_destroy. */
+typedef struct uw_multi uw_multi;
+uw_status   uw_multi_create(const uw_config* cfg, const int32_t* devices, uint32_t n_devices, uw_multi** out);
+uw_status   uw_multi_build(uw_multi* m, const int32_t* chunk_pos_xyz, uint32_t n, uint32_t flags, uw_gather_result* out);
+void        uw_multi_destroy(uw_multi* m);
+const char* uw_multi_last_error(const uw_multi* m);           /* m may be NULL: last create error             */
+/* Verification aid: blocking copy of `bytes` of device memory (any device of the process: unified addressing) to the
+ * host -- how the tests read a gather arena back. */
+uw_status   uw_debug_copy_to_host(const void* d_src, uint64_t bytes, void* h_dst);
 
 /* ---- plumbing ------------------------------------------------------------------------- */
 /* Run on an existing CUDA stream (cudaStream_t as void*), e.g. torch's current stream. */

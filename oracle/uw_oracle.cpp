@@ -11,7 +11,7 @@
 // tests/golden/ (see oracle/gen_golden.py and DESIGN.md "Oracle pinning" for exactly which
 // functions are pinned that way and which are not).
 //
-// Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math -shared -fPIC  (see oracle/Makefile)
+// Build: g++ -O3 -std=c++17 -ffp-contract=off -fno-fast-math -shared -fPIC  (see oracle/Makefile)
 // -ffp-contract=off is REQUIRED: neither wasm nor default Rust codegen fuses mul+add.
 //
 // Everything here follows, by file:line,

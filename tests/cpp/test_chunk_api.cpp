@@ -54,6 +54,29 @@ int main(int argc, char** argv) {
             printf("pipelined batches=%zu bad=%zu\n", seen, bad);
             if (seen != stream.size() || bad) return 6;
         }
+        // a UW_FLAG_INDEX32 builder returns u32 indices only (inds16 == NULL): same values, wider type
+        {
+            uw_config cfg;
+            uw_config_default(&cfg);
+            cfg.seed = seed; cfg.flags |= UW_FLAG_INDEX32;
+            uw::ChunkBuilder b32{cfg};
+            size_t bad32 = 0, meshes32 = 0;
+            auto batch32 = uw::build_chunks(b32, positions);
+            for (size_t i = 0; i < positions.size(); ++i) {
+                if (batch32[i].num_inds() != batch[i].num_inds()) { ++bad32; continue; }
+                if (!batch32[i].not_blank()) continue;
+                ++meshes32;
+                if (!batch32[i].index32()) ++bad32;
+                const auto& a = batch32[i].inds32_buffer_slice();
+                const auto& r = batch[i].inds_buffer_slice();
+                for (size_t k = 0; k < a.size(); ++k) bad32 += a[k] != (uint32_t)r[k];
+                bool threw16 = false;
+                try { batch32[i].inds_buffer_slice(); } catch (const std::logic_error&) { threw16 = true; }
+                bad32 += !threw16;
+            }
+            printf("index32 meshes=%zu bad=%zu\n", meshes32, bad32);
+            if (bad32 || !meshes32) return 7;
+        }
         // the reference panics when slicing a blank chunk's buffers (chunk.rs:346): here it throws
         uw::Chunk blank({0, 0, 5});
         blank.build_full(builder);

@@ -29,7 +29,7 @@ def test_header_symbols_are_all_exported(lib):
     assert declared == set(_ffi.EXPORTS)
     for sym in declared:
         assert hasattr(lib, sym), f"libuwcuda.so does not export {sym}"
-    assert lib.uw_abi_version() == 1
+    assert lib.uw_abi_version() == 2
 
 
 def test_config_default_matches_reference_constants(lib):

@@ -48,6 +48,7 @@ def test_cpp_mirror_matches_oracle(exe, oracle12):
     p = subprocess.run([exe, "0"], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "OK" in p.stdout and "blank_slice_throws=1" in p.stdout
+    assert re.search(r"index32 meshes=[1-9]\d* bad=0", p.stdout)        # u32 builders: no NULL inds16 dereference
     perm = oracle12.perm_table(0)
     n = 0
     for line in p.stdout.splitlines():

@@ -1,0 +1,200 @@
+"""GPU tests of the multi-GPU path (include/uwcuda.h uw_gather_* / uw_multi_*; SURVEY §8e, BASELINE configs[2]).
+
+Chunks are independent (chunk.rs:89-129), so a region built as slabs -- by several producers, into segments of the
+rendering GPU's arenas, through local, peer or CUDA-IPC addresses -- must give every chunk exactly the buffers a
+plain single-context build gives it.  Everything below runs on ONE GPU too (several producers may share a device);
+with two or more GPUs visible the same tests also cross NVLink.
+"""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def uw():
+    import underwaterworld_b200 as m
+    m.load_library()
+    return m
+
+
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _assert_same_chunks(descs, verts, inds, ref_batch, first=0):
+    """Arena contents (descs/verts/inds addressed through the descriptors) == the reference batch, chunk by chunk,
+    bit for bit (same kernel, same arithmetic: only the placement differs)."""
+    for i in range(len(ref_batch)):
+        d, r = descs[first + i], ref_batch.chunk(i)
+        assert tuple(int(v) for v in d["pos"]) == r.pos
+        assert int(d["flags"]) == r.flags
+        assert int(d["vert_count"]) == len(r.verts) and int(d["index_count"]) == len(r.inds), f"counts of chunk {i}"
+        vo, io = int(d["vert_offset"]), int(d["index_offset"])
+        assert np.array_equal(verts[vo:vo + len(r.verts)].view(np.uint8), r.verts.view(np.uint8)), f"vertices of chunk {i}"
+        assert np.array_equal(inds[io:io + len(r.inds)], r.inds), f"indices of chunk {i}"
+
+
+def test_slab_bounds_match_the_library(uw):
+    import ctypes as C
+    lib = uw.load_library()
+    for n, parts in [(0, 3), (1, 4), (7, 3), (2048, 8), (524288, 8), (17 * 6 * 8, 5)]:
+        cover = 0
+        for p in range(parts):
+            f, c = C.c_uint32(), C.c_uint32()
+            lib.uw_slab_bounds(n, parts, p, C.byref(f), C.byref(c))
+            assert (f.value, c.value) == uw.gather.slab_bounds(n, parts, p)
+            assert f.value == cover
+            cover += c.value
+        assert cover == n
+
+
+def test_single_segment_gather_equals_plain_build(uw):
+    pos = uw.region.box_region((-3, 3), (-3, 3), (-3, 2))            # 180 chunks through the surface layers
+    with uw.ChunkBuilder(uw.Perlin(0)) as ref_b, uw.ChunkBuilder(uw.Perlin(0)) as b:
+        ref = ref_b.build(pos)
+        info = b.gather_create(1, len(pos), seg_vcap=ref.n_verts + 2, seg_icap=ref.n_inds)     # exactly enough
+        b.gather_attach(info, 0)
+        for rep in range(2):                                          # epochs advance; the arena is reused
+            b.gather_build(pos, 0)
+            res = b.gather_wait(descs_to_host=True)
+            assert res.epoch == rep + 1 and res.n_segments == 1
+            assert res.n_chunks == len(pos) and res.n_inds == ref.n_inds
+            assert res.segments[0]["n_mesh"] == int((ref.descs["index_count"] > 0).sum())
+            assert res.segments[0]["n_blank"] == int((ref.descs["flags"] & 1).sum())
+            descs, verts, inds = res.download()
+            _assert_same_chunks(descs, verts, inds, ref)
+            assert np.array_equal(res.host_descs().view(np.uint8), descs.view(np.uint8))
+        b.gather_detach()
+        b.gather_destroy()
+        assert np.array_equal(b.build(pos).descs["index_count"], ref.descs["index_count"])     # plain builds still work
+
+
+def test_three_producers_fill_three_segments(uw):
+    """Three contexts -- spread over the visible GPUs, so with >= 2 GPUs two of them write over NVLink -- each build
+    one slab of the request into its own segment of context 0's arenas."""
+    ndev = _device_count()
+    pos = uw.region.box_region((-4, 5), (-2, 2), (-3, 2))            # 9 x-columns: an uneven 3-way split
+    with uw.ChunkBuilder(uw.Perlin(3), device=0) as ref_b:
+        ref = ref_b.build(pos)
+    builders = [uw.ChunkBuilder(uw.Perlin(3), device=g % ndev) for g in range(3)]
+    try:
+        info = builders[0].gather_create(3, len(pos), seg_vcap=ref.n_verts, seg_icap=ref.n_inds)
+        for g, b in enumerate(builders):
+            b.gather_attach(info, g)
+        for g in (1, 2, 0):
+            f, c = uw.gather.slab_bounds(len(pos), 3, g)
+            builders[g].gather_build(pos[f:f + c], f)
+        res = builders[0].gather_wait()
+        for b in builders:
+            b.sync()
+        assert res.n_chunks == len(pos) and res.n_inds == ref.n_inds
+        assert [s["first_chunk"] for s in res.segments] == [uw.gather.slab_bounds(len(pos), 3, g)[0] for g in range(3)]
+        descs, verts, inds = res.download()
+        _assert_same_chunks(descs, verts, inds, ref)
+        for g in range(3):                                            # every chunk's buffers lie inside its producer's segment
+            f, c = uw.gather.slab_bounds(len(pos), 3, g)
+            d = descs[f:f + c]
+            d = d[d["index_count"] > 0]
+            assert (d["vert_offset"] >= g * res.seg_vcap).all() and (d["vert_offset"] + d["vert_count"] <= (g + 1) * res.seg_vcap).all()
+            assert (d["index_offset"] >= g * res.seg_icap).all() and (d["index_offset"] + d["index_count"] <= (g + 1) * res.seg_icap).all()
+    finally:
+        for b in builders[::-1]:
+            b.gather_detach()
+        for b in builders:
+            b.close()
+
+
+def test_multi_builder_region_equals_plain_build(uw):
+    """uw_multi_build over every visible GPU (one process): slabs, fused launches, gather, wait -- and a second,
+    larger request that makes it recreate the arena."""
+    ndev = min(_device_count(), 8)
+    small = uw.region.box_region((-2, 2), (-2, 2), (-3, 2))
+    large = uw.region.box_region((-8, 8), (-8, 8), (-4, 4))          # config 2
+    with uw.ChunkBuilder(uw.Perlin(0), device=0) as ref_b, uw.MultiBuilder(uw.Perlin(0), devices=list(range(ndev))) as mb:
+        for pos in (small, large, small):
+            ref = ref_b.build(pos)
+            res = mb.build(pos, descs_to_host=True, draw_to_host=True)
+            assert res.n_segments == ndev and res.n_chunks == len(pos) and res.n_inds == ref.n_inds
+            descs, verts, inds = res.download()
+            _assert_same_chunks(descs, verts, inds, ref)
+            assert np.array_equal(res.host_descs().view(np.uint8), descs.view(np.uint8))
+            # the draw list = exactly the descriptors of the chunks that ended with a mesh (any order inside a segment)
+            draw = res.host_draw()
+            meshed = descs[descs["index_count"] > 0]
+            assert res.n_draw == len(meshed) == len(draw)
+            key = lambda a: sorted(bytes(x) for x in a.view(np.uint8).reshape(len(a), 32))
+            assert key(draw) == key(meshed)
+            at = 0
+            for g, seg in enumerate(res.segments):                    # segment g's entries point into segment g
+                part = draw[at:at + seg["n_mesh"]]
+                assert (part["vert_offset"] // res.seg_vcap == g).all()
+                at += seg["n_mesh"]
+
+
+def test_segment_overflow_is_reported_and_multi_build_regrows(uw):
+    pos = uw.region.box_region((-4, 4), (-4, 4), (-1, 0))            # one surface layer: ~ 500 vertices per chunk
+    with uw.ChunkBuilder(uw.Perlin(0)) as b:
+        info = b.gather_create(1, len(pos), seg_vcap=1024, seg_icap=4096)
+        b.gather_attach(info, 0)
+        b.gather_build(pos, 0)
+        with pytest.raises(uw.UwError) as e:
+            b.sync()
+        assert e.value.status == 4 and "overflow" in str(e.value)     # UW_ERR_OOM
+        b.gather_detach()
+        b.gather_destroy()
+        ref = b.build(pos)
+    # uw_multi_build starts from the default estimate (192 vertices per chunk) and must grow for this request
+    dense = uw.region.box_region((-8, 8), (-8, 8), (-1, 0))
+    with uw.ChunkBuilder(uw.Perlin(0)) as ref_b, uw.MultiBuilder(uw.Perlin(0), devices=[0]) as mb:
+        ref = ref_b.build(dense)
+        assert ref.n_verts > len(dense) * 192 + 4096, "the request must exceed the default capacity for this test to bite"
+        res = mb.build(dense)
+        descs, verts, inds = res.download()
+        _assert_same_chunks(descs, verts, inds, ref)
+
+
+def _ipc_child(info_bytes, first, count, seed, q):
+    try:
+        import underwaterworld_b200 as uw
+        pos = uw.region.box_region((-3, 3), (-3, 3), (-3, 2))[first:first + count]
+        ndev = _device_count()
+        with uw.ChunkBuilder(uw.Perlin(seed), device=1 % ndev) as b:
+            b.gather_attach(uw.gather.info_from_bytes(info_bytes), 1)
+            b.gather_build(pos, first)
+            b.sync()
+            b.gather_detach()
+        q.put("ok")
+    except Exception as e:                                            # pragma: no cover
+        q.put(f"child failed: {type(e).__name__}: {e}")
+
+
+@pytest.mark.timeout(300)
+def test_producer_in_another_process_attaches_through_cuda_ipc(uw):
+    """One process per GPU (the torchrun layout of bench.py): the producer maps the rendering process's arena with
+    the cudaIpcMemHandle inside uw_gather_info and writes its segment from its own process (and, when a second GPU
+    is visible, from that GPU over NVLink)."""
+    pos = uw.region.box_region((-3, 3), (-3, 3), (-3, 2))
+    f1, c1 = uw.gather.slab_bounds(len(pos), 2, 1)
+    with uw.ChunkBuilder(uw.Perlin(5), device=0) as b:
+        ref = b.build(pos)
+        info = b.gather_create(2, len(pos), seg_vcap=ref.n_verts, seg_icap=ref.n_inds)
+        b.gather_attach(info, 0)
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        child = ctx.Process(target=_ipc_child, args=(uw.gather.info_to_bytes(info), f1, c1, 5, q))
+        child.start()
+        b.gather_build(pos[:f1], 0)
+        msg = q.get(timeout=240)
+        child.join(60)
+        assert msg == "ok", msg
+        res = b.gather_wait()
+        assert res.n_chunks == len(pos) and res.n_inds == ref.n_inds
+        descs, verts, inds = res.download()
+        _assert_same_chunks(descs, verts, inds, ref)
+        b.gather_detach()
+        b.gather_destroy()

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import MODE_FAITHFUL, MODE_FAST, FLAG_BLANK_EARLY, FLAG_HAS_MESH  # noqa: E402
 
-DENS_TOL = 2e-6       # FP32 factorised noise vs f64 reference (measured max 4.8e-7, tools/scratch/dens_err.py)
+DENS_TOL = 2e-6       # FP32 factorised noise vs f64 reference (measured max 4.8e-7, tools/dens_err.py)
 COL_TOL = 1e-6        # one pow(x, 2.4f) per vertex: the kernels' pow24_tab (<= 2 ulp) vs glibc powf
 GUARD_EPS = 1e-5      # default guard band of the library
 

@@ -61,35 +61,53 @@ def test_weak_scaling_regions_are_disjoint():
     assert not set(map(tuple, a)) & set(map(tuple, b))
 
 
-def _gather_worker(rank, world, port, out_dir):
+def _info_worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from underwaterworld_b200.gather import gather_meshes
-    rng = np.random.default_rng(rank)
-    n_chunks, n_verts, n_inds = 5 + rank, 100 * (rank + 1), 0 if rank == 1 else 300     # ragged, one rank has no indices
-    d = torch.from_numpy(rng.integers(0, 255, n_chunks * 32, dtype=np.uint8))
-    v = torch.from_numpy(rng.integers(0, 255, n_verts * 24, dtype=np.uint8))
-    i = torch.from_numpy(rng.integers(0, 255, n_inds * 2, dtype=np.uint8))
-    got = gather_meshes(d, v, i, dst=0)
-    if rank == 0:
-        assert got is not None and len(got) == world
-        for r, (gd, gv, gi) in enumerate(got):
-            rr = np.random.default_rng(r)
-            nc, nv, ni = 5 + r, 100 * (r + 1), 0 if r == 1 else 300
-            assert np.array_equal(gd.numpy(), rr.integers(0, 255, nc * 32, dtype=np.uint8))
-            assert np.array_equal(gv.numpy(), rr.integers(0, 255, nv * 24, dtype=np.uint8))
-            assert np.array_equal(gi.numpy(), rr.integers(0, 255, ni * 2, dtype=np.uint8))
-        open(os.path.join(out_dir, "ok"), "w").write("ok")
-    else:
-        assert got is None
+    from underwaterworld_b200 import _ffi, gather
+    info = None
+    if rank == 1:                                           # the rendering rank need not be rank 0
+        info = _ffi.UwGatherInfo()
+        info.abi_version, info.n_segments, info.device, info.index_bytes = 2, world, 1, 2
+        info.owner_pid, info.base, info.bytes = 4242, 0x7F0000000000, 1 << 30
+        info.off_descs, info.off_verts, info.off_inds = 256, 1 << 20, 1 << 29
+        info.n_chunks, info.seg_vcap, info.seg_icap = 524288, 12_000_000, 42_000_000
+        for k in range(64):
+            info.ipc_handle[k] = (7 * k + 1) & 0xFF
+    got = gather.broadcast_info(info, src=1)
+    # every rank derives its slab of the request from (n, world, rank) alone: no exchange on the data path
+    first, count = gather.slab_bounds(int(got.n_chunks), world, rank)
+    np.save(os.path.join(out_dir, f"info{rank}.npy"), np.frombuffer(gather.info_to_bytes(got), dtype=np.uint8))
+    np.save(os.path.join(out_dir, f"slab{rank}.npy"), np.array([first, count]))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(120)
-def test_mesh_gather_to_render_rank_gloo(tmp_path):
-    """Optional gather of finished meshes to the rendering rank: sizes by all_gather, ragged
-    payloads by send/recv; here over gloo with host tensors, on the GPU box over NCCL / NVLink."""
-    mp.spawn(_gather_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
-    assert (tmp_path / "ok").exists()
+def test_gather_info_reaches_every_rank_gloo(tmp_path):
+    """Setup of the one-sided mesh gather: the rendering rank's uw_gather_info (arena addresses, capacities,
+    CUDA IPC handle -- plain bytes) is broadcast once; afterwards every rank knows its segment and its slab of the
+    request.  Here over gloo; bench.py does the same under NCCL."""
+    world = 3
+    mp.spawn(_info_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    blobs = [np.load(tmp_path / f"info{r}.npy") for r in range(world)]
+    assert all(np.array_equal(b, blobs[1]) for b in blobs)
+    from underwaterworld_b200 import _ffi, gather
+    info = gather.info_from_bytes(blobs[0].tobytes())
+    assert (info.n_segments, info.device, info.owner_pid, info.n_chunks) == (3, 1, 4242, 524288)
+    assert bytes(info.ipc_handle) == bytes((7 * k + 1) & 0xFF for k in range(64))
+    slabs = [np.load(tmp_path / f"slab{r}.npy") for r in range(world)]
+    assert slabs[0][0] == 0 and all(slabs[r][0] + slabs[r][1] == slabs[r + 1][0] for r in range(world - 1))
+    assert slabs[-1][0] + slabs[-1][1] == 524288
+
+
+def test_gather_structs_match_the_header():
+    """ctypes mirrors of uw_gather_info / uw_gather_result have the C layout (no GPU needed: sizes follow from the
+    header's field list under the C ABI's natural alignment)."""
+    import ctypes as C
+    from underwaterworld_b200 import _ffi
+    assert C.sizeof(_ffi.UwGatherInfo) == 16 + 8 * 11 + 64
+    assert C.sizeof(_ffi.UwGatherSegment) == 48
+    assert C.sizeof(_ffi.UwGatherResult) == 8 + 24 + 24 + 16 + 8 + 24 + 48 * _ffi.UW_MAX_SEGMENTS
+    assert _ffi.UwGatherInfo.ipc_handle.offset == 104

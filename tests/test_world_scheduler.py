@@ -119,6 +119,34 @@ def test_world_update_batches_and_recheck_rule():
     assert w2.update(sub0, cam0, b2, max_batch=1) == 1 and w2.generate_count() > 100
 
 
+def test_start_up_phase_renders_without_the_distance_filter():
+    """world.rs:105-110: while should_full_build is set, build_full_step pushes EVERY not-blank chunk to
+    chunks_to_render (world.rs:117-119); build_step afterwards also demands dist_sq <= (VIEW_DIST + 1)^2
+    (world.rs:132-134).  The flag clears when the queue is empty or STOP_FULL_BUILD chunks exist."""
+    _, sub, cam = next(iter(W.scripted_flythrough(1, 0)))
+    sc = sub.chunk()
+    far = lambda p: sum((a - b) ** 2 for a, b in zip(p, sc)) > (W.VIEW_DIST + 1) ** 2
+    # start-up: one batch takes the whole queue -> everything with a mesh is rendered, far chunks included
+    w, b = W.World(), _StubBuilder()
+    assert w.should_full_build
+    w.update(sub, cam, b)
+    meshed = [p for p, c in w.chunks.items() if c.not_blank()]
+    assert sorted(w.chunks_to_render) == sorted(meshed)
+    assert any(far(p) for p in meshed), "the window must reach beyond VIEW_DIST + 1 for this test to bite"
+    assert not w.should_full_build                                   # queue empty -> phase over
+    # steady state: the same queue built with the flag cleared applies the distance filter
+    w2, b2 = W.World(), _StubBuilder()
+    w2.should_full_build = False
+    w2.update(sub, cam, b2)
+    assert sorted(w2.chunks_to_render) == sorted(p for p in meshed if not far(p))
+    # the phase also ends once STOP_FULL_BUILD chunks exist, even with a non-empty queue (world.rs:107)
+    w3, b3 = W.World(), _StubBuilder()
+    w3.update(sub, cam, b3, max_batch=W.STOP_FULL_BUILD - 1)
+    assert w3.should_full_build and w3.generate_count() > 0
+    w3.update(sub, cam, b3, max_batch=1)
+    assert not w3.should_full_build and w3.generate_count() > 0
+
+
 def test_camera_matrices():
     cam = W.Camera()
     m = cam.chunk_generation_frustum_matrix(90.0)

@@ -20,19 +20,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--frames-straight", type=int, default=600)
-    ap.add_argument("--frames-turn", type=int, default=600)
-    ap.add_argument("--cpu", action="store_true")
-    ap.add_argument("--out", default=None)
-    args = ap.parse_args()
-
+def flythrough(builder, frames_straight=600, frames_turn=600, cpu=False):
+    """Runs the scripted path against `builder` and returns the result record (bench.py calls this too)."""
     import underwaterworld_b200 as uw
     from underwaterworld_b200 import world as W, _ffi
 
+    class _A:
+        pass
+    args = _A()
+    args.frames_straight, args.frames_turn, args.cpu = frames_straight, frames_turn, cpu
     lib = uw.load_library()
-    builder = uw.ChunkBuilder(uw.Perlin(0))
     ctx = builder._ctx
     view = _ffi.UwBatchView()
 
@@ -86,6 +83,19 @@ def main():
         cpu = [1e6 * o.build_batch_timed(perm, pos, MODE_FAITHFUL, 1)["seconds"] for _, pos in batches]
         res["cpu_oracle_1thread_latency_us"] = {"p50": float(np.percentile(cpu, 50)), "p99": float(np.percentile(cpu, 99)),
                                                 "first_batch": cpu[0]}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames-straight", type=int, default=600)
+    ap.add_argument("--frames-turn", type=int, default=600)
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    import underwaterworld_b200 as uw
+    builder = uw.ChunkBuilder(uw.Perlin(0))
+    res = flythrough(builder, args.frames_straight, args.frames_turn, args.cpu)
     line = json.dumps(res)
     print(line)
     if args.out:

@@ -8,6 +8,8 @@ from .chunk import (Batch, Chunk, ChunkBuilder, ChunkMesh, Perlin, build_chunks,
                     ISO_LEVEL, PERLIN_OCTAVES)
 from ._ffi import UwError, load_library
 from . import region
+from . import gather
+from .gather import MultiBuilder, RegionGather
 
 __all__ = ["Batch", "Chunk", "ChunkBuilder", "ChunkMesh", "Perlin", "build_chunks", "UwError", "load_library",
-           "region", "CHUNK_SIZE", "INTERNAL_SIZE", "ISO_LEVEL", "PERLIN_OCTAVES"]
+           "region", "gather", "MultiBuilder", "RegionGather", "CHUNK_SIZE", "INTERNAL_SIZE", "ISO_LEVEL", "PERLIN_OCTAVES"]

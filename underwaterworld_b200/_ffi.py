@@ -60,6 +60,40 @@ class UwStageTimes(C.Structure):
     ]
 
 
+UW_MAX_SEGMENTS = 16
+GATHER_DESCS_TO_HOST = 0x1
+GATHER_DRAW_TO_HOST = 0x2
+
+
+class UwGatherInfo(C.Structure):
+    """uw_gather_info: plain bytes, handed from the rendering process to the producers."""
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("n_segments", C.c_uint32), ("device", C.c_int32), ("index_bytes", C.c_uint32),
+        ("owner_pid", C.c_uint64), ("base", C.c_uint64), ("bytes", C.c_uint64),
+        ("off_head", C.c_uint64), ("off_descs", C.c_uint64), ("off_verts", C.c_uint64), ("off_inds", C.c_uint64), ("off_draw", C.c_uint64),
+        ("n_chunks", C.c_uint64), ("seg_vcap", C.c_uint64), ("seg_icap", C.c_uint64),
+        ("ipc_handle", C.c_uint8 * 64),
+    ]
+
+
+class UwGatherSegment(C.Structure):
+    _fields_ = [
+        ("first_chunk", C.c_uint64), ("n_chunks", C.c_uint32), ("n_mesh", C.c_uint32), ("n_blank", C.c_uint32),
+        ("overflow", C.c_uint32), ("n_verts", C.c_uint64), ("n_inds", C.c_uint64), ("guard", C.c_uint64),
+    ]
+
+
+class UwGatherResult(C.Structure):
+    _fields_ = [
+        ("n_segments", C.c_uint32), ("epoch", C.c_uint32),
+        ("n_chunks", C.c_uint64), ("n_verts", C.c_uint64), ("n_inds", C.c_uint64),
+        ("d_descs", C.c_void_p), ("d_verts", C.c_void_p), ("d_inds", C.c_void_p),
+        ("seg_vcap", C.c_uint64), ("seg_icap", C.c_uint64),
+        ("h_descs", C.c_void_p), ("h_draw", C.c_void_p), ("d_draw", C.c_void_p), ("n_draw", C.c_uint64),
+        ("seg", UwGatherSegment * UW_MAX_SEGMENTS),
+    ]
+
+
 DESC_DTYPE = np.dtype([("pos", "<i4", (3,)), ("flags", "<u4"), ("vert_offset", "<u4"), ("vert_count", "<u4"),
                        ("index_offset", "<u4"), ("index_count", "<u4")])
 VERT_DTYPE = np.dtype([("pos", "<f4", (3,)), ("color", "<f4", (3,))])
@@ -73,6 +107,9 @@ EXPORTS = [
     "uw_build_device", "uw_sync", "uw_device_view_get",
     "uw_debug_densities", "uw_debug_cases", "uw_build_from_densities", "uw_iso_at",
     "uw_set_stream", "uw_get_stage_times", "uw_set_profiling", "uw_get_guard_count", "uw_debug_ffma_peak", "uw_export_arena_fd", "uw_debug_vertex_colors",
+    "uw_gather_create", "uw_gather_destroy", "uw_gather_attach", "uw_gather_detach", "uw_gather_build",
+    "uw_gather_build_device", "uw_gather_wait", "uw_slab_bounds",
+    "uw_multi_create", "uw_multi_build", "uw_multi_destroy", "uw_multi_last_error", "uw_debug_copy_to_host",
 ]
 
 _lib = None
@@ -125,5 +162,22 @@ def load_library() -> C.CDLL:
     lib.uw_debug_ffma_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.uw_debug_vertex_colors.argtypes = [vp, vp, vp, u32, vp]
     lib.uw_export_arena_fd.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    u64 = C.c_uint64
+    lib.uw_gather_create.argtypes = [vp, u32, u64, u64, u64, C.POINTER(UwGatherInfo)]
+    lib.uw_gather_destroy.argtypes = [vp]
+    lib.uw_gather_attach.argtypes = [vp, C.POINTER(UwGatherInfo), u32]
+    lib.uw_gather_detach.argtypes = [vp]
+    lib.uw_gather_build.argtypes = [vp, i32p, u32, u64]
+    lib.uw_gather_build_device.argtypes = [vp, vp, u32, u64]
+    lib.uw_gather_wait.argtypes = [vp, u32, C.POINTER(UwGatherResult)]
+    lib.uw_slab_bounds.argtypes = [u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    lib.uw_slab_bounds.restype = None
+    lib.uw_multi_create.argtypes = [C.POINTER(UwConfig), C.POINTER(C.c_int32), u32, C.POINTER(vp)]
+    lib.uw_multi_build.argtypes = [vp, i32p, u32, u32, C.POINTER(UwGatherResult)]
+    lib.uw_multi_destroy.argtypes = [vp]
+    lib.uw_multi_destroy.restype = None
+    lib.uw_multi_last_error.argtypes = [vp]
+    lib.uw_multi_last_error.restype = C.c_char_p
+    lib.uw_debug_copy_to_host.argtypes = [vp, u64, vp]
     _lib = lib
     return lib

@@ -277,6 +277,38 @@ class ChunkBuilder:
     def sync(self):
         self._check(self._lib.uw_sync(self._ctx))
 
+    # -- multi-GPU gather (include/uwcuda.h uw_gather_*; see gather.py) ---------------------------
+    def gather_create(self, n_segments: int, n_chunks: int, seg_vcap: int = 0, seg_icap: int = 0) -> _ffi.UwGatherInfo:
+        """This builder's GPU becomes the rendering side: arenas for n_chunks chunks in n_segments segments."""
+        info = _ffi.UwGatherInfo()
+        self._check(self._lib.uw_gather_create(self._ctx, n_segments, n_chunks, seg_vcap, seg_icap, C.byref(info)))
+        return info
+
+    def gather_destroy(self):
+        self._check(self._lib.uw_gather_destroy(self._ctx))
+
+    def gather_attach(self, info: _ffi.UwGatherInfo, segment: int):
+        self._check(self._lib.uw_gather_attach(self._ctx, C.byref(info), segment))
+
+    def gather_detach(self):
+        self._check(self._lib.uw_gather_detach(self._ctx))
+
+    def gather_build(self, positions, first_chunk: int):
+        """Chunk::new + build_full for the positions (host) into the attached segment; asynchronous."""
+        p = _as_positions(positions)
+        self._gather_pos = p                      # the library copies into its pinned staging before returning
+        self._check(self._lib.uw_gather_build(self._ctx, p.ctypes.data, p.shape[0], first_chunk))
+
+    def gather_build_device(self, d_positions_ptr: int, n: int, first_chunk: int):
+        self._check(self._lib.uw_gather_build_device(self._ctx, C.c_void_p(d_positions_ptr), n, first_chunk))
+
+    def gather_wait(self, descs_to_host: bool = False, draw_to_host: bool = False):
+        from .gather import GatherResult
+        out = _ffi.UwGatherResult()
+        flags = (_ffi.GATHER_DESCS_TO_HOST if descs_to_host else 0) | (_ffi.GATHER_DRAW_TO_HOST if draw_to_host else 0)
+        self._check(self._lib.uw_gather_wait(self._ctx, flags, C.byref(out)))
+        return GatherResult(out, 4 if self.index32 else 2)
+
     def device_view(self) -> _ffi.UwDeviceView:
         v = _ffi.UwDeviceView()
         self._check(self._lib.uw_device_view_get(self._ctx, C.byref(v)))

@@ -426,6 +426,26 @@ struct FusedSummary {
     BatchTotals totals;
 };
 
+// Multi-GPU gather (uw_gather_*): every segment of the render GPU's arenas has one 64-byte head.  The LAST CTA
+// of the fused kernel that filled the segment -- running on any GPU of the box, writing through NVLink peer
+// addresses -- stores its summary there, fences system-wide, then publishes the launch epoch: a consumer that
+// has seen head.epoch >= e may read everything the e-th build of that segment wrote.
+struct GatherHead {
+    FusedSummary sum;
+    uint32_t epoch, n_chunks;
+    uint32_t first_chunk_lo, first_chunk_hi;
+};
+static_assert(sizeof(GatherHead) == 64, "GatherHead is one 64-byte line");
+
+// Where a fused launch writes.  Default: the context's own arenas.  Attached to a gather segment: the render
+// GPU's arenas (peer or local addresses) with the segment's element offsets added to the descriptors.
+struct FusedOut {
+    uint32_t desc_vbase, desc_ibase;   // added to uw_chunk_desc::vert_offset / index_offset (segment base in the arena)
+    GatherHead* head;                  // nullable
+    uw_chunk_desc* drawlist;           // nullable: compact list of the descriptors of chunks that END WITH A MESH (completion order)
+    uint32_t epoch, first_chunk_lo, first_chunk_hi;
+};
+
 // Chunk hand-out for the persistent kernel.
 //
 // Request order (order == nullptr): tickets 0..n-1 walk the request list.
@@ -714,6 +734,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     if (hand && tid == NT - 1) *tk_out = ticket_fetch(*hand, tk_t);
 
     // ---- stage YZ -------------------------------------------------------------------------------
+    // lanes of this warp that own a column: taken while the warp is still converged, so that the votes at the end
+    // of the branch name their participants explicitly (the guard-band loop in between diverges)
+    const unsigned col_lanes = __ballot_sync(0xFFFFFFFFu, tid < L * L);
     if (tid < L * L) {
         const int i = tid / L, j = tid - i * L;
         float R0[NOCT], S0[NOCT], R1[NOCT], S1[NOCT], Cc[NOCT], Dd[NOCT];
@@ -784,8 +807,8 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         sm.mask[tid] = inside;
         // outside the guard band |iso - isl| >= eps > 0, so "all > isl" <=> no inside bit and no exact tie
         const bool all_gt = (inside == 0u) && !any_eq, any_lt = inside != 0u;
-        const bool w_all = __all_sync(__activemask(), all_gt), w_any = __any_sync(__activemask(), any_lt);
-        const bool w_solid = __all_sync(__activemask(), inside == (1u << L) - 1u);      // the all-full vote
+        const bool w_all = __all_sync(col_lanes, all_gt), w_any = __any_sync(col_lanes, any_lt);
+        const bool w_solid = __all_sync(col_lanes, inside == (1u << L) - 1u);           // the all-full vote
         if ((tid & 31) == 0 || tid == (L * L / 32) * 32) {
             if (!w_all) sm.red[0] = 0;
             if (w_any) sm.red[1] = 1;
@@ -2376,7 +2399,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
               float* __restrict__ dens_out /*nullable: debug tap*/, int ordered,
               uw_tri* __restrict__ tris /*nullable: UW_FLAG_TRIS*/, uint16_t* __restrict__ tri_cell /*nullable*/,
               uint4* __restrict__ order /*nullable: cost-ordered hand-out, [UW_NCLS][n]*/, int z_lo, int z_hi,
-              unsigned long long zcls, int analytic_skip, FusedSummary* __restrict__ sum_out) {
+              unsigned long long zcls, int analytic_skip, FusedSummary* __restrict__ sum_out,
+              const __grid_constant__ FusedOut fo) {
     using D = SpecDims<ST, NOCT>;
     BatchTotals* const totals = &ctr->totals;
     unsigned long long* const guard_count = &ctr->guard;
@@ -2504,17 +2528,24 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             d.pos[0] = px; d.pos[1] = py; d.pos[2] = pz;
             d.flags = ((fl & CF_ALL_GT) ? UW_CHUNK_BLANK_EARLY : 0u) | (ni > 0 ? UW_CHUNK_HAS_MESH : 0u)
                     | (nv > 65536u ? UW_CHUNK_U16_OVERFLOW : 0u);
-            d.vert_offset = (uint32_t)ev; d.vert_count = nv;
-            d.index_offset = (uint32_t)ei; d.index_count = ni;
+            d.vert_offset = (uint32_t)ev + fo.desc_vbase; d.vert_count = nv;
+            d.index_offset = (uint32_t)ei + fo.desc_ibase; d.index_count = ni;
             descs[chunk] = d;
-            if (ni > 0) atomicAdd(&totals->n_active, 1u);
+            if (ni > 0) {
+                const uint32_t slot = atomicAdd(&totals->n_active, 1u);
+                // the draw list (world.rs:117-121 keeps only not_blank chunks for rendering): 32 bytes per meshed chunk
+                if (fo.drawlist) fo.drawlist[slot] = d;
+            }
             if (fl & CF_ALL_GT) atomicAdd(&totals->n_blank, 1u);
             if (ordered && chunk == n - 1) {
                 totals->n_verts = ev + nv; totals->n_inds = ei + ni;
                 if (ev + nv > vcap || ei + ni > icap || ev + nv > 0xFFFFFFFFull || ei + ni > 0xFFFFFFFFull)
                     totals->overflow = 1u;
             }
-            if (!ordered && ni > 0 && (ev + nv > vcap || ei + ni > icap)) totals->overflow = 1u;
+            if (!ordered && ni > 0 && (ev + nv > vcap || ei + ni > icap)) atomicMax(&totals->overflow, 1u);
+            // completion-order packing keeps (vertices << 32 | indices) in ONE 64-bit counter: an index total beyond
+            // 2^32 would carry into the vertex half.  The chunk whose claim crosses the boundary sees it here.
+            if (!ordered && ni > 0 && (ei + ni > 0xFFFFFFFFull || ev + nv > 0xFFFFFFFFull)) atomicMax(&totals->overflow, 2u);
         }
         if (tid == D::NTF - 1) { sm.cur[0] = (int)nxt.chunk; sm.cur[1] = nxt.px; sm.cur[2] = nxt.py; sm.cur[3] = nxt.pz; }
         __syncthreads();                                   // chunk fully emitted, smem reusable, next ticket visible
@@ -2527,7 +2558,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // last CTA out resets the other control block for the next launch
     __syncthreads();                                       // every thread has seen TICKET_DONE in sm.cur[0]
     if (tid == 0) {
-        __threadfence();
+        if (fo.head) __threadfence_system();               // gather segment: the outputs may be another GPU's memory
+        else __threadfence();
         sm.cur[0] = (atomicAdd(&ctr->done, 1u) == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
@@ -2543,6 +2575,12 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             sm_out.totals.n_blank = atomicAdd(&ctr->totals.n_blank, 0u);
             sm_out.totals.n_mesh = 0;
             *sum_out = sm_out;                       // host-mapped memory: visible to the host at kernel completion
+            if (fo.head) {                           // gather segment: summary, system fence, then the epoch flag
+                fo.head->sum = sm_out; fo.head->n_chunks = n;
+                fo.head->first_chunk_lo = fo.first_chunk_lo; fo.head->first_chunk_hi = fo.first_chunk_hi;
+                __threadfence_system();
+                asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(&fo.head->epoch), "r"(fo.epoch) : "memory");
+            }
             ctr_next->ticket = 0; ctr_next->done = 0; ctr_next->classified = 0; ctr_next->cls_ticket = 0;
             for (int k = 0; k < UW_NCLS; ++k) ctr_next->cls_n[k] = 0;
             ctr_next->alloc = 0; ctr_next->guard = 0;
@@ -2550,6 +2588,34 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             ctr_next->totals = z;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Multi-GPU gather, consumer side (render GPU): wait until every segment's head carries the expected epoch.
+// One warp; lane s polls segment s with volatile (system-coherent, L1-bypassing) loads.  The producers are
+// fused-kernel launches on other GPUs of the box whose last CTA published the epoch after a system-wide
+// fence, so once the flags are seen (and this kernel's own fence has run) everything they wrote into the
+// arenas is visible to whatever follows on the stream.  status[0] = 0 ok, 1 timed out.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_gather_wait(const GatherHead* __restrict__ head, uint32_t n_segments,
+                                                    uint32_t epoch, unsigned long long timeout_ns,
+                                                    uint32_t* __restrict__ status) {
+    const uint32_t lane = threadIdx.x;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    bool ok = true;
+    for (uint32_t s = lane; s < n_segments; s += 32u) {
+        // epochs only grow; signed distance keeps the comparison valid across a wrap
+        while ((int32_t)(ld_volatile_u32(&head[s].epoch) - epoch) < 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (now - t0 > timeout_ns) { ok = false; break; }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+    const bool all_ok = __all_sync(0xFFFFFFFFu, ok);
+    if (lane == 0) status[0] = all_ok ? 0u : 1u;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -74,6 +74,7 @@ struct uw_ctx {
         uint32_t last_n = 0;
         const int32_t* last_pos_dev = nullptr;
         bool last_fused = false;
+        bool last_gather = false;       // the set's last build wrote into a gather segment (no local arenas, no regrow)
         bool pending = false;           // kernels enqueued, totals not yet validated
         BatchTotals result = {};        // validated totals of the last finished build
     } sets[2];
@@ -106,10 +107,10 @@ struct uw_ctx {
     typedef void (*emit32_fn_t)(DevCfg, const McTables*, const float*, const uw_chunk_desc*, const uint32_t*, const BatchTotals*, uw_vert*, uint32_t*, uw_tri*, uint16_t*);
     typedef void (*fused16_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint16_t*, unsigned long long,
-                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint4*, int, int, unsigned long long, int, FusedSummary*);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint4*, int, int, unsigned long long, int, FusedSummary*, FusedOut);
     typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint32_t*, unsigned long long,
-                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint4*, int, int, unsigned long long, int, FusedSummary*);
+                                 unsigned long long, float*, int, uw_tri*, uint16_t*, uint4*, int, int, unsigned long long, int, FusedSummary*, FusedOut);
     fused16_fn_t fused16_fn = nullptr;
     fused32_fn_t fused32_fn = nullptr;
     bool use_fused = false;
@@ -129,6 +130,29 @@ struct uw_ctx {
     int noise_threads = 192, fused_threads = 224, noise_blocks_per_sm = 1; size_t noise_smem = 0;
     int emit_blocks_per_sm = 1; size_t emit_smem = 0;
     int classify_blocks_per_sm = 1;
+
+    // multi-GPU gather (uw_gather_*): the arena this context OWNS as the rendering side ...
+    struct GatherArena {
+        bool alive = false;
+        uw_gather_info info = {};
+        char* base = nullptr;
+        GatherHead* h_head = nullptr;           // pinned
+        uint32_t* d_status = nullptr; uint32_t* h_status = nullptr;
+        uw_chunk_desc* h_descs = nullptr; size_t h_descs_cap = 0;   // pinned, UW_GATHER_DESCS_TO_HOST
+        uw_chunk_desc* h_draw = nullptr; size_t h_draw_cap = 0;     // pinned, UW_GATHER_DRAW_TO_HOST
+        uint32_t wait_epoch = 0;
+    } arena;
+    // ... and the segment this context WRITES as a producer (local, peer or IPC-mapped addresses)
+    struct GatherTarget {
+        bool active = false, ipc = false;
+        char* base = nullptr;                   // mapping of the arena allocation in this process
+        uw_gather_info info = {};
+        uint32_t segment = 0, epoch = 0;
+        uw_chunk_desc* descs = nullptr; uw_vert* verts = nullptr; char* inds = nullptr; GatherHead* head = nullptr;
+        uw_chunk_desc* draw = nullptr;
+    } gt;
+    uint64_t gather_first_chunk = 0;    // request index of the next gather build's first chunk
+    bool gather_build = false;          // the build being enqueued writes into the attached segment
 
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -266,7 +290,10 @@ static uw_status setup_tables(uw_ctx* c) {
             const bool solid_certain = tmax + 1.0f < cf.iso_level - margin;
             if (!blank_certain && !solid_certain) { if (!found) { lo = pz; found = true; } hi = pz; }
         }
-        if (found && lo > -4096 && hi < 4096) { c->z_lo = lo; c->z_hi = hi; } else { c->z_lo = 1; c->z_hi = 0; }
+        // "blank above, solid below" (answer_trivial) holds only if the terrace term grows with z: positive
+        // max_height and adj_z_mod.  Anything else keeps the range empty = unknown: no analytic skip, request-order hand-out.
+        const bool rising = cf.max_height > 0.0f && cf.adj_z_mod > 0.0f;
+        if (rising && found && lo > -4096 && hi < 4096) { c->z_lo = lo; c->z_hi = hi; } else { c->z_lo = 1; c->z_hi = 0; }
         // Rank those layers by how likely they are to hold surface: the noise term is roughly N(0, 0.25), so a
         // lattice level z contributes exp(-((iso - terrace(z)) / 0.25)^2 / 2).  Scheduling only (take_ticket).
         c->zcls = 0;
@@ -331,10 +358,15 @@ extern "C" const char* uw_last_error(const uw_ctx* ctx) {
     return ctx ? ctx->err.c_str() : g_create_error.c_str();
 }
 
+extern "C" uw_status uw_gather_detach(uw_ctx* c);
+extern "C" uw_status uw_gather_destroy(uw_ctx* c);
+
 extern "C" void uw_destroy(uw_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    uw_gather_detach(c);
+    uw_gather_destroy(c);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_axis); cudaFree(c->d_totals); cudaFree(c->d_guard); cudaFree(c->d_ctl);
     cudaFree(c->d_scan_part); cudaFree(c->d_scan_flag); cudaFree(c->d_scan_ctl);
@@ -830,12 +862,24 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     // heavy-first hand-out (scheduling only): provably trivial z layers are deferred inside the kernel; the
     // ordered-packing mode needs tickets == request order.  Only worth it when CTAs get just a few chunks each.
     uint4* d_order = (!c->ordered && c->z_hi >= c->z_lo && n > (uint32_t)grid && n <= c->order_cap) ? c->B().d_order : nullptr;
+    // where the outputs go: the context's own arenas, or the attached segment of the rendering GPU's arenas
+    uw_chunk_desc* o_descs = c->B().d_descs; uw_vert* o_verts = c->B().d_verts; void* o_inds = c->B().d_inds;
+    unsigned long long o_vcap = c->B().vcap, o_icap = c->B().icap;
+    FusedOut fo = {};
+    if (c->B().last_gather) {
+        const uw_ctx::GatherTarget& g = c->gt;
+        o_descs = g.descs + c->gather_first_chunk; o_verts = g.verts; o_inds = g.inds;
+        o_vcap = g.info.seg_vcap; o_icap = g.info.seg_icap;
+        fo.desc_vbase = (uint32_t)(g.segment * g.info.seg_vcap); fo.desc_ibase = (uint32_t)(g.segment * g.info.seg_icap);
+        fo.head = g.head; fo.epoch = g.epoch; fo.drawlist = g.draw;
+        fo.first_chunk_lo = (uint32_t)c->gather_first_chunk; fo.first_chunk_hi = (uint32_t)(c->gather_first_chunk >> 32);
+    }
     if (c->index32)
         c->fused32_fn<<<grid, c->fused_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
-            c->B().d_descs, c->B().d_verts, (uint32_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
+            o_descs, o_verts, (uint32_t*)o_inds, o_vcap, o_icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum, fo);
     else
         c->fused16_fn<<<grid, c->fused_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
-            c->B().d_descs, c->B().d_verts, (uint16_t*)c->B().d_inds, c->B().vcap, c->B().icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum);
+            o_descs, o_verts, (uint16_t*)o_inds, o_vcap, o_icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum, fo);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;
@@ -844,7 +888,9 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
 // enqueue the whole pipeline for n chunks whose positions are at d_pos (device), into the current buffer set
 static uw_status enqueue_build(uw_ctx* c, const int32_t* d_pos, uint32_t n, bool from_densities) {
     // initial output capacity guess: grows (and the emit stage is re-run) on overflow
-    uw_status st = ensure_outputs(c, (unsigned long long)n * 192 + 4096, (unsigned long long)n * 640 + 16384);
+    uw_status st = UW_OK;
+    c->B().last_gather = c->gather_build;
+    if (!c->gather_build) st = ensure_outputs(c, (unsigned long long)n * 192 + 4096, (unsigned long long)n * 640 + 16384);
     if (st != UW_OK) return st;
     const bool fused = c->use_fused && !from_densities;
     const bool keep = (c->cfg.flags & UW_FLAG_KEEP_DENSITIES) != 0;
@@ -899,7 +945,8 @@ static uw_status finish_build(uw_ctx* c) {
             guard = B.h_sum->guard;
             if (!c->ordered) {
                 t.n_verts = B.h_sum->alloc >> 32; t.n_inds = B.h_sum->alloc & 0xFFFFFFFFull;
-                if (t.n_verts > B.vcap || t.n_inds > B.icap) t.overflow = 1;
+                const unsigned long long vc = B.last_gather ? c->gt.info.seg_vcap : B.vcap, ic = B.last_gather ? c->gt.info.seg_icap : B.icap;
+                if ((t.n_verts > vc || t.n_inds > ic) && !t.overflow) t.overflow = 1;
             }
         } else {
             CU_TRY(c, cudaMemcpyAsync(c->h_totals, c->d_totals, sizeof(BatchTotals), cudaMemcpyDeviceToHost, c->copy_stream));
@@ -909,6 +956,18 @@ static uw_status finish_build(uw_ctx* c) {
             guard = *c->h_guard;
         }
         if (!t.overflow) break;
+        if (t.overflow >= 2)
+            return fail(c, UW_ERR_INVALID, "batch too large: packed vertex/index offsets exceed 32 bits; split the batch");
+        if (B.last_gather) {
+            // the segment belongs to the rendering side's arena: nothing to regrow here.  B.result keeps the sizes
+            // the build needs, so the owner (uw_multi_build does) can recreate the arena and build again.
+            if (t.n_verts <= c->gt.info.seg_vcap && t.n_inds <= c->gt.info.seg_icap) { t.n_verts = c->gt.info.seg_vcap + 1; }
+            B.result = t; B.pending = false;
+            char m[256];
+            snprintf(m, sizeof m, "gather segment overflow: the build needs %llu vertices / %llu indices, the segment holds %llu / %llu",
+                     t.n_verts, t.n_inds, (unsigned long long)c->gt.info.seg_vcap, (unsigned long long)c->gt.info.seg_icap);
+            return fail(c, UW_ERR_OOM, m);
+        }
         if (t.n_verts > 0xFFFFFFFFull || t.n_inds > 0xFFFFFFFFull)
             return fail(c, UW_ERR_INVALID, "batch too large: packed vertex/index offsets exceed 32 bits; split the batch");
         uw_status st = ensure_outputs(c, t.n_verts, t.n_inds);
@@ -942,12 +1001,27 @@ static uw_status finish_build(uw_ctx* c) {
 // batch of the fused path that is small enough to be latency-bound, the pinned staging buffer itself -- it is
 // mapped into the device's address space (UVA), every position is read exactly once (by the hand-out), and the
 // H2D copy's issue + completion latency would sit in front of the kernel.
-static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n, const int32_t** dev_pos = nullptr, bool zero_copy_ok = false) {
-    for (uint32_t i = 0; i < 3 * n; ++i) {
+static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n, const int32_t** dev_pos = nullptr, bool zero_copy_ok = false,
+                                 bool direct_ok = false) {
+    {
         // fast path validity: |16*pos| must stay exactly representable next to
         // the 2^-23-granular lattice offsets; also keeps pos*chunk_size inside i32 (chunk.rs:90-94)
-        if (pos[i] > (1 << 24) || pos[i] < -(1 << 24))
-            return fail(c, UW_ERR_INVALID, "chunk position out of supported range (|pos| <= 2^24)");
+        uint32_t bad = 0;                                  // branch-free so that the loop vectorises (1.5 M values for config 3)
+        const size_t m = (size_t)3 * n;
+        for (size_t i = 0; i < m; ++i) bad |= (uint32_t)(pos[i] + (1 << 24)) > (uint32_t)(2 << 24) ? 1u : 0u;
+        if (bad) return fail(c, UW_ERR_INVALID, "chunk position out of supported range (|pos| <= 2^24)");
+    }
+    // A request that already lives in pinned (page-locked) host memory is copied to the device straight from the
+    // caller's buffer -- no staging memcpy.  Only for calls whose contract keeps the buffer alive until completion
+    // (the blocking uw_build, uw_gather_build); uw_build_async copies, as its caller may reuse the array at once.
+    if (direct_ok && n >= 4096) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, pos) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+            if (dev_pos) *dev_pos = c->B().d_pos;
+            CU_TRY(c, cudaMemcpyAsync(c->B().d_pos, pos, (size_t)n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+            return UW_OK;
+        }
+        cudaGetLastError();
     }
     if ((size_t)n * 3 > c->B().h_pos_cap) {
         if (c->B().h_pos) cudaFreeHost(c->B().h_pos);
@@ -1075,7 +1149,7 @@ static uw_status build_common(uw_ctx* c, const int32_t* pos, const float* dens, 
     b->set = set;
     const int32_t* dev_pos = nullptr;
     uw_status st = ensure_chunks(c, n);
-    if (st == UW_OK) st = stage_positions(c, pos, n, &dev_pos, dens == nullptr);
+    if (st == UW_OK) st = stage_positions(c, pos, n, &dev_pos, dens == nullptr, !async);
     if (st == UW_OK && dens) {
         st = ensure_dens(c);
         const DevCfg& d = c->dcfg;
@@ -1195,6 +1269,362 @@ extern "C" uw_status uw_get_guard_count(uw_ctx* c, uint64_t* out) {
     if (!c || !out) return UW_ERR_INVALID;
     *out = c->guard_total;
     return UW_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU: gather arenas on the rendering GPU, producers that write into them over NVLink
+// ---------------------------------------------------------------------------------------
+#include <unistd.h>
+
+extern "C" void uw_slab_bounds(uint32_t n, uint32_t parts, uint32_t part, uint32_t* first, uint32_t* count) {
+    if (parts == 0) parts = 1;
+    const uint32_t base = n / parts, rem = n % parts;
+    const uint32_t lo = part * base + (part < rem ? part : rem);
+    if (first) *first = lo;
+    if (count) *count = base + (part < rem ? 1u : 0u);
+}
+
+static bool gather_supported(uw_ctx* c, const char* who) {
+    if (c->use_fused && !c->tris && !(c->cfg.flags & UW_FLAG_KEEP_DENSITIES)) return true;
+    fail(c, UW_ERR_UNSUPPORTED, std::string(who) + ": the gather path needs the fused kernel (internal_size 10 / 12, reference constants; "
+                                                   "no UW_FLAG_STAGED / TRIS / KEEP_DENSITIES / EXACT_F64)");
+    return false;
+}
+
+extern "C" uw_status uw_gather_destroy(uw_ctx* c) {
+    if (!c) return UW_ERR_INVALID;
+    uw_ctx::GatherArena& a = c->arena;
+    if (!a.alive) return UW_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (c->gt.active && !c->gt.ipc && c->gt.base == a.base) c->gt = uw_ctx::GatherTarget();
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(a.base); cudaFree(a.d_status);
+    if (a.h_head) cudaFreeHost(a.h_head);
+    if (a.h_status) cudaFreeHost(a.h_status);
+    if (a.h_descs) cudaFreeHost(a.h_descs);
+    if (a.h_draw) cudaFreeHost(a.h_draw);
+    a = uw_ctx::GatherArena();
+    return UW_OK;
+}
+
+extern "C" uw_status uw_gather_create(uw_ctx* c, uint32_t n_segments, uint64_t n_chunks, uint64_t seg_vcap, uint64_t seg_icap,
+                                      uw_gather_info* out) {
+    if (!c) return UW_ERR_INVALID;
+    if (!out || n_segments == 0 || n_segments > UW_MAX_SEGMENTS || n_chunks == 0)
+        return fail(c, UW_ERR_INVALID, "uw_gather_create: bad argument (1 <= n_segments <= UW_MAX_SEGMENTS, n_chunks > 0)");
+    if (!gather_supported(c, "uw_gather_create")) return UW_ERR_UNSUPPORTED;
+    if (c->arena.alive) { uw_status st = uw_gather_destroy(c); if (st != UW_OK) return st; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    const uint64_t per = (n_chunks + n_segments - 1) / n_segments;
+    if (seg_vcap == 0) seg_vcap = per * 192 + 4096;
+    if (seg_icap == 0) seg_icap = per * 640 + 16384;
+    seg_vcap = (seg_vcap + 1) & ~1ull;                     // segments start on 16-byte boundaries (2 x 24 B, 8 x 2 B)
+    seg_icap = (seg_icap + 7) & ~7ull;
+    if (seg_vcap * n_segments > 0xFFFFFFFFull || seg_icap * n_segments > 0xFFFFFFFFull)
+        return fail(c, UW_ERR_INVALID, "uw_gather_create: arena too large for 32-bit descriptor offsets; use fewer chunks per arena");
+    const size_t isz = c->index32 ? 4 : 2;
+    auto up = [](uint64_t v) { return (v + 255) & ~255ull; };
+    uw_gather_info g;
+    memset(&g, 0, sizeof g);
+    g.abi_version = UW_ABI_VERSION; g.n_segments = n_segments; g.device = c->device; g.index_bytes = (uint32_t)isz;
+    g.owner_pid = (uint64_t)getpid();
+    g.n_chunks = n_chunks; g.seg_vcap = seg_vcap; g.seg_icap = seg_icap;
+    g.off_head = 0;
+    g.off_descs = up(sizeof(GatherHead) * n_segments);
+    g.off_verts = up(g.off_descs + sizeof(uw_chunk_desc) * n_chunks);
+    g.off_inds = up(g.off_verts + sizeof(uw_vert) * seg_vcap * n_segments);
+    g.off_draw = up(g.off_inds + isz * seg_icap * n_segments);
+    g.bytes = up(g.off_draw + sizeof(uw_chunk_desc) * n_chunks * n_segments);
+    uw_ctx::GatherArena& a = c->arena;
+    CU_TRY(c, cudaMalloc((void**)&a.base, g.bytes));
+    cudaError_t e = cudaMemsetAsync(a.base, 0, g.off_descs, c->stream);           // heads: epoch 0
+    if (e == cudaSuccess) e = cudaMalloc((void**)&a.d_status, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&a.h_head, sizeof(GatherHead) * n_segments, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&a.h_status, sizeof(uint32_t), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) {
+        cudaIpcMemHandle_t h;
+        // other PROCESSES map the arena through this handle; it is optional (a box whose driver refuses IPC can still
+        // gather inside one process), so a failure only leaves the handle zeroed
+        if (cudaIpcGetMemHandle(&h, a.base) == cudaSuccess) { static_assert(sizeof h == 64, "cudaIpcMemHandle_t"); memcpy(g.ipc_handle, &h, 64); }
+        else cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        cudaFree(a.base); cudaFree(a.d_status);
+        if (a.h_head) cudaFreeHost(a.h_head);
+        if (a.h_status) cudaFreeHost(a.h_status);
+        a = uw_ctx::GatherArena();
+        return fail(c, e == cudaErrorMemoryAllocation ? UW_ERR_OOM : UW_ERR_CUDA, std::string("uw_gather_create: ") + cudaGetErrorString(e));
+    }
+    g.base = (uint64_t)(uintptr_t)a.base;
+    a.info = g; a.alive = true; a.wait_epoch = 0;
+    *out = g;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_gather_detach(uw_ctx* c) {
+    if (!c) return UW_ERR_INVALID;
+    if (!c->gt.active) return UW_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->gt.ipc && c->gt.base) cudaIpcCloseMemHandle(c->gt.base);
+    c->gt = uw_ctx::GatherTarget();
+    return UW_OK;
+}
+
+extern "C" uw_status uw_gather_attach(uw_ctx* c, const uw_gather_info* info, uint32_t segment) {
+    if (!c) return UW_ERR_INVALID;
+    if (!info || info->abi_version != UW_ABI_VERSION || segment >= info->n_segments || info->n_segments > UW_MAX_SEGMENTS)
+        return fail(c, UW_ERR_INVALID, "uw_gather_attach: bad info / segment");
+    if (!gather_supported(c, "uw_gather_attach")) return UW_ERR_UNSUPPORTED;
+    if (info->index_bytes != (c->index32 ? 4u : 2u))
+        return fail(c, UW_ERR_INVALID, "uw_gather_attach: index width differs from the arena's");
+    if (c->sets[0].busy || c->sets[1].busy || c->B().pending) return fail(c, UW_ERR_NOT_READY, "uw_gather_attach: a build is in flight");
+    { uw_status st = uw_gather_detach(c); if (st != UW_OK) return st; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    uw_ctx::GatherTarget g;
+    g.info = *info; g.segment = segment;
+    if (info->owner_pid == (uint64_t)getpid()) {
+        g.base = (char*)(uintptr_t)info->base;
+        if (info->device != c->device) {
+            int can = 0;
+            CU_TRY(c, cudaDeviceCanAccessPeer(&can, c->device, info->device));
+            if (!can) return fail(c, UW_ERR_UNSUPPORTED, "uw_gather_attach: no peer access between the producer and the render device");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(info->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(c, UW_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    } else {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, info->ipc_handle, 64);
+        void* p = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(c, UW_ERR_CUDA, std::string("uw_gather_attach: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+        g.base = (char*)p; g.ipc = true;
+    }
+    const size_t isz = info->index_bytes;
+    g.head = (GatherHead*)(g.base + info->off_head) + segment;
+    g.descs = (uw_chunk_desc*)(g.base + info->off_descs);
+    g.verts = (uw_vert*)(g.base + info->off_verts) + (size_t)segment * info->seg_vcap;
+    g.inds = g.base + info->off_inds + (size_t)segment * info->seg_icap * isz;
+    g.draw = (uw_chunk_desc*)(g.base + info->off_draw) + (size_t)segment * info->n_chunks;
+    // continue the segment's epoch count (an arena outlives re-attachments)
+    uint32_t ep = 0;
+    const cudaError_t e = cudaMemcpy(&ep, &g.head->epoch, sizeof ep, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        if (g.ipc) cudaIpcCloseMemHandle(g.base);
+        return fail(c, UW_ERR_CUDA, std::string("uw_gather_attach: reading the segment head: ") + cudaGetErrorString(e));
+    }
+    g.epoch = ep; g.active = true;
+    c->gt = g;
+    return UW_OK;
+}
+
+static uw_status gather_build_common(uw_ctx* c, const int32_t* pos, bool host_pos, uint32_t n, uint64_t first_chunk) {
+    if (!c) return UW_ERR_INVALID;
+    if (!c->gt.active) return fail(c, UW_ERR_INVALID, "uw_gather_build: no gather segment attached (uw_gather_attach)");
+    if (!pos && n) return fail(c, UW_ERR_INVALID, "uw_gather_build: null positions");
+    if (first_chunk + n > c->gt.info.n_chunks) return fail(c, UW_ERR_INVALID, "uw_gather_build: first_chunk + n exceeds the arena's descriptor capacity");
+    if (c->sets[0].busy || c->sets[1].busy) return fail(c, UW_ERR_NOT_READY, "uw_gather_build: an async host batch is in flight");
+    CU_TRY(c, cudaSetDevice(c->device));
+    // the previous build's totals must be validated before the set (and its pinned staging) is reused
+    if (c->B().pending) { uw_status st = finish_build(c); if (st != UW_OK) return st; }
+    uw_status st = ensure_chunks(c, n ? n : 1);
+    if (st != UW_OK) return st;
+    const int32_t* dev_pos = pos;
+    if (host_pos && n) { st = stage_positions(c, pos, n, &dev_pos, true, true); if (st != UW_OK) return st; }
+    c->gt.epoch += 1;
+    c->gather_first_chunk = first_chunk;
+    if (n == 0) {                                        // an empty slab still publishes its head
+        GatherHead h;
+        memset(&h, 0, sizeof h);
+        h.epoch = c->gt.epoch; h.first_chunk_lo = (uint32_t)first_chunk; h.first_chunk_hi = (uint32_t)(first_chunk >> 32);
+        CU_TRY(c, cudaMemcpyAsync(c->gt.head, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        c->B().last_n = 0; c->B().pending = false; c->B().result = BatchTotals{};
+        return UW_OK;
+    }
+    c->gather_build = true;
+    st = enqueue_build(c, dev_pos, n, false);
+    c->gather_build = false;
+    return st;
+}
+
+extern "C" uw_status uw_gather_build(uw_ctx* c, const int32_t* pos, uint32_t n, uint64_t first_chunk) {
+    return gather_build_common(c, pos, true, n, first_chunk);
+}
+extern "C" uw_status uw_gather_build_device(uw_ctx* c, const int32_t* d_pos, uint32_t n, uint64_t first_chunk) {
+    return gather_build_common(c, d_pos, false, n, first_chunk);
+}
+
+extern "C" uw_status uw_gather_wait(uw_ctx* c, uint32_t flags, uw_gather_result* out) {
+    if (!c) return UW_ERR_INVALID;
+    uw_ctx::GatherArena& a = c->arena;
+    if (!a.alive) return fail(c, UW_ERR_INVALID, "uw_gather_wait: this context owns no gather arena (uw_gather_create)");
+    if (!out) return fail(c, UW_ERR_INVALID, "uw_gather_wait: null result");
+    CU_TRY(c, cudaSetDevice(c->device));
+    // this context's own segment (if it produces one) is validated on the host like any other build
+    if (c->B().pending) { uw_status st = finish_build(c); if (st != UW_OK) return st; }
+    const uw_gather_info& g = a.info;
+    const uint32_t epoch = ++a.wait_epoch;
+    GatherHead* d_head = (GatherHead*)(a.base + g.off_head);
+    k_gather_wait<<<1, 32, 0, c->stream>>>(d_head, g.n_segments, epoch, 10ull * 1000 * 1000 * 1000, a.d_status);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(a.h_status, a.d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(a.h_head, d_head, sizeof(GatherHead) * g.n_segments, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (*a.h_status != 0) { --a.wait_epoch; return fail(c, UW_ERR_NOT_READY, "uw_gather_wait: timed out waiting for a segment (did every producer build?)"); }
+    memset(out, 0, sizeof *out);
+    out->n_segments = g.n_segments; out->epoch = epoch;
+    out->d_descs = a.base + g.off_descs; out->d_verts = a.base + g.off_verts; out->d_inds = a.base + g.off_inds;
+    out->seg_vcap = g.seg_vcap; out->seg_icap = g.seg_icap; out->d_draw = a.base + g.off_draw;
+    uint64_t hi_chunk = 0;
+    bool overflow = false;
+    for (uint32_t s = 0; s < g.n_segments; ++s) {
+        const GatherHead& h = a.h_head[s];
+        uw_gather_segment& o = out->seg[s];
+        o.first_chunk = (uint64_t)h.first_chunk_lo | ((uint64_t)h.first_chunk_hi << 32);
+        o.n_chunks = h.n_chunks; o.n_mesh = h.sum.totals.n_active; o.n_blank = h.sum.totals.n_blank;
+        o.guard = h.sum.guard;
+        if (c->ordered) { o.n_verts = h.sum.totals.n_verts; o.n_inds = h.sum.totals.n_inds; }
+        else { o.n_verts = h.sum.alloc >> 32; o.n_inds = h.sum.alloc & 0xFFFFFFFFull; }
+        o.overflow = (h.sum.totals.overflow || o.n_verts > g.seg_vcap || o.n_inds > g.seg_icap) ? 1u : 0u;
+        overflow |= o.overflow != 0;
+        out->n_chunks += o.n_chunks; out->n_verts += o.n_verts; out->n_inds += o.n_inds; out->n_draw += o.n_mesh;
+        if (o.n_chunks && o.first_chunk + o.n_chunks > hi_chunk) hi_chunk = o.first_chunk + o.n_chunks;
+    }
+    if (overflow) return fail(c, UW_ERR_OOM, "uw_gather_wait: a segment overflowed its capacity (see uw_gather_result.seg[].overflow); recreate the arena larger");
+    if ((flags & UW_GATHER_DESCS_TO_HOST) && hi_chunk) {
+        if (hi_chunk > a.h_descs_cap) {
+            if (a.h_descs) cudaFreeHost(a.h_descs);
+            a.h_descs = nullptr; a.h_descs_cap = 0;
+            CU_TRY(c, cudaHostAlloc((void**)&a.h_descs, sizeof(uw_chunk_desc) * (size_t)g.n_chunks, cudaHostAllocDefault));
+            a.h_descs_cap = (size_t)g.n_chunks;
+        }
+        CU_TRY(c, cudaMemcpyAsync(a.h_descs, a.base + g.off_descs, sizeof(uw_chunk_desc) * (size_t)hi_chunk, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        out->h_descs = a.h_descs;
+    }
+    if ((flags & UW_GATHER_DRAW_TO_HOST) && out->n_draw) {
+        if (out->n_draw > a.h_draw_cap) {
+            if (a.h_draw) cudaFreeHost(a.h_draw);
+            a.h_draw = nullptr; a.h_draw_cap = 0;
+            CU_TRY(c, cudaHostAlloc((void**)&a.h_draw, sizeof(uw_chunk_desc) * (size_t)g.n_chunks, cudaHostAllocDefault));
+            a.h_draw_cap = (size_t)g.n_chunks;
+        }
+        size_t at = 0;
+        for (uint32_t s = 0; s < g.n_segments; ++s) {
+            const size_t cnt = out->seg[s].n_mesh;
+            if (!cnt) continue;
+            CU_TRY(c, cudaMemcpyAsync(a.h_draw + at, (const uw_chunk_desc*)(a.base + g.off_draw) + (size_t)s * g.n_chunks,
+                                      sizeof(uw_chunk_desc) * cnt, cudaMemcpyDeviceToHost, c->stream));
+            at += cnt;
+        }
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        out->h_draw = a.h_draw;
+    }
+    return UW_OK;
+}
+
+extern "C" uw_status uw_debug_copy_to_host(const void* d_src, uint64_t bytes, void* h_dst) {
+    if ((!d_src || !h_dst) && bytes) return UW_ERR_INVALID;
+    if (bytes == 0) return UW_OK;
+    if (cudaMemcpy(h_dst, d_src, (size_t)bytes, cudaMemcpyDefault) != cudaSuccess) { cudaGetLastError(); return UW_ERR_CUDA; }
+    return UW_OK;
+}
+
+// ---- one process, G devices -----------------------------------------------------------------------------------
+struct uw_multi {
+    std::vector<uw_ctx*> ctx;            // ctx[0] renders
+    uw_gather_info info = {};
+    bool have_arena = false;
+    std::string err;
+};
+static thread_local std::string g_multi_error;
+
+static uw_status mfail(uw_multi* m, uw_status st, const std::string& msg) {
+    if (m) m->err = msg; else g_multi_error = msg;
+    return st;
+}
+
+extern "C" const char* uw_multi_last_error(const uw_multi* m) { return m ? m->err.c_str() : g_multi_error.c_str(); }
+
+extern "C" void uw_multi_destroy(uw_multi* m) {
+    if (!m) return;
+    for (size_t g = m->ctx.size(); g-- > 0;) if (m->ctx[g]) uw_gather_detach(m->ctx[g]);
+    if (!m->ctx.empty() && m->ctx[0]) uw_gather_destroy(m->ctx[0]);
+    for (auto* c : m->ctx) uw_destroy(c);
+    delete m;
+}
+
+extern "C" uw_status uw_multi_create(const uw_config* cfg, const int32_t* devices, uint32_t n_devices, uw_multi** out) {
+    if (!cfg || !out || !devices || n_devices == 0 || n_devices > UW_MAX_SEGMENTS)
+        return mfail(nullptr, UW_ERR_INVALID, "uw_multi_create: bad argument (1 <= n_devices <= UW_MAX_SEGMENTS)");
+    *out = nullptr;
+    for (uint32_t a = 0; a < n_devices; ++a)
+        for (uint32_t b = a + 1; b < n_devices; ++b)
+            if (devices[a] == devices[b]) return mfail(nullptr, UW_ERR_INVALID, "uw_multi_create: a device is listed twice");
+    uw_multi* m = new uw_multi();
+    for (uint32_t g = 0; g < n_devices; ++g) {
+        uw_config c = *cfg;
+        c.device = devices[g];
+        uw_ctx* ctx = nullptr;
+        const uw_status st = uw_create(&c, &ctx);
+        if (st != UW_OK) { g_multi_error = std::string("uw_multi_create: device ") + std::to_string(devices[g]) + ": " + uw_last_error(nullptr); uw_multi_destroy(m); return st; }
+        m->ctx.push_back(ctx);
+        if (!gather_supported(ctx, "uw_multi_create")) { g_multi_error = ctx->err; uw_multi_destroy(m); return UW_ERR_UNSUPPORTED; }
+    }
+    *out = m;
+    return UW_OK;
+}
+
+extern "C" uw_status uw_multi_build(uw_multi* m, const int32_t* pos, uint32_t n, uint32_t flags, uw_gather_result* out) {
+    if (!m) return UW_ERR_INVALID;
+    if (!out || (!pos && n)) return mfail(m, UW_ERR_INVALID, "uw_multi_build: null argument");
+    const uint32_t G = (uint32_t)m->ctx.size();
+    uw_ctx* r = m->ctx[0];
+    uint64_t vcap = 0, icap = 0;                          // 0 = the library's default estimate
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (!m->have_arena || m->info.n_chunks < (n ? n : 1u) || vcap > m->info.seg_vcap || icap > m->info.seg_icap) {
+            for (auto* c : m->ctx) { const uw_status st = uw_gather_detach(c); if (st != UW_OK) return mfail(m, st, c->err); }
+            m->have_arena = false;
+            uw_status st = uw_gather_create(r, G, n ? n : 1u, vcap, icap, &m->info);
+            if (st != UW_OK) return mfail(m, st, r->err);
+            for (uint32_t g = 0; g < G; ++g) {
+                st = uw_gather_attach(m->ctx[g], &m->info, g);
+                if (st != UW_OK) return mfail(m, st, m->ctx[g]->err);
+            }
+            m->have_arena = true;
+        }
+        // every device: pinned H2D of its slab + one fused launch, all asynchronous; device 0 last, so that the
+        // peers are already computing while the render device's own work is being enqueued
+        for (uint32_t k = 0; k < G; ++k) {
+            const uint32_t g = (k + 1) % G;
+            uint32_t first = 0, cnt = 0;
+            uw_slab_bounds(n, G, g, &first, &cnt);
+            const uw_status st = uw_gather_build(m->ctx[g], pos + 3 * (size_t)first, cnt, first);
+            if (st != UW_OK) return mfail(m, st, m->ctx[g]->err);
+        }
+        bool overflow = false;
+        unsigned long long need_v = 0, need_i = 0;
+        uw_status first_err = UW_OK; std::string first_msg;
+        for (uint32_t g = 0; g < G; ++g) {               // validate every producer on the host (overflow, CUDA errors)
+            const uw_status st = uw_sync(m->ctx[g]);
+            if (st == UW_ERR_OOM && m->ctx[g]->B().last_gather) {
+                overflow = true;
+                need_v = std::max(need_v, m->ctx[g]->B().result.n_verts); need_i = std::max(need_i, m->ctx[g]->B().result.n_inds);
+            } else if (st != UW_OK && first_err == UW_OK) { first_err = st; first_msg = m->ctx[g]->err; }
+        }
+        if (first_err != UW_OK) return mfail(m, first_err, first_msg);
+        const uw_status wst = uw_gather_wait(r, flags, out);
+        if (!overflow && wst == UW_OK) return UW_OK;
+        if (!overflow) return mfail(m, wst, r->err);
+        vcap = std::max<unsigned long long>(m->info.seg_vcap, need_v + need_v / 8 + 4096);
+        icap = std::max<unsigned long long>(m->info.seg_icap, need_i + need_i / 8 + 16384);
+        if (vcap == m->info.seg_vcap && icap == m->info.seg_icap) { vcap *= 2; icap *= 2; }
+    }
+    return mfail(m, UW_ERR_OOM, "uw_multi_build: segment overflow persisted");
 }
 
 // ---------------------------------------------------------------------------------------

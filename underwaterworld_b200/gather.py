@@ -1,83 +1,189 @@
-"""Optional gather of finished meshes to the rendering GPU.
+"""Multi-GPU region builds: slabs of the position list, meshes gathered on the rendering GPU.
 
-Chunks are independent, so the compute path has NO collective; the only cross-GPU traffic a renderer may
-want is "bring every rank's packed mesh to the GPU that draws".  With the NCCL backend the point-to-point
-transfers below run over NVLink / NVSwitch (peer copies measured at ~770 GB/s per direction on this pool);
-with gloo the same code moves host tensors (CPU tests).
+Chunks are independent (chunk.rs:89-129), so the compute path has NO collective: rank r builds slab r of the
+request.  The only cross-GPU traffic is the optional gather of the finished meshes to the GPU that draws, and it is
+fused into the build itself (include/uwcuda.h, uw_gather_*): the rendering GPU owns the arenas, every producer's
+fused kernel stores its vertices / indices / descriptors straight into its segment through NVLink peer addresses
+and publishes a per-segment head; the consumer waits for the heads on its own stream.  One-sided -- no NCCL, no
+rendezvous on the data path.
 
-    sizes  = all_gather([n_chunks, n_verts, n_inds])            24 bytes per rank
-    rank r = send(descs), send(verts), send(inds)  ->  dst      variable length, no padding
+Two ways to drive it:
 
-`device_batch_tensors` wraps the library's device arenas as torch uint8 tensors without copying
-(`__cuda_array_interface__`), so the sends read the kernel's output buffers directly.
+  * one process per GPU (torchrun): `RegionGather` -- rank `dst` creates the arena, the 168-byte `uw_gather_info`
+    travels to the other ranks once through torch.distributed (any backend; setup only), every rank attaches its
+    segment (CUDA IPC), then per build: `build()` on every rank, `wait()` on the rendering rank.
+  * one process, G GPUs: `MultiBuilder` (uw_multi_*), what a single-process caller such as the reference's
+    `World` (world.rs:113-123) would use.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+import ctypes as C
+from typing import Optional, Sequence
 
 import numpy as np
-import torch
-import torch.distributed as dist
 
-from ._ffi import DESC_DTYPE, VERT_DTYPE
-
-
-class _DevMem:
-    """Zero-copy view of raw device memory for torch.as_tensor."""
-
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+from . import _ffi
+from ._ffi import DESC_DTYPE, VERT_DTYPE, UwError
+from .chunk import ChunkBuilder, Perlin, _as_positions, INTERNAL_SIZE
 
 
-def device_batch_tensors(builder) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(descs, verts, inds) of the builder's last device-resident build as uint8 CUDA tensors (no copy).
-    Call after builder.sync(); valid until the next build on that builder."""
-    v = builder.device_view()
-    isz = 4 if v.d_inds32 else 2
-    iptr = v.d_inds32 or v.d_inds16
-
-    def wrap(ptr, nbytes):
-        if nbytes == 0 or not ptr:
-            return torch.empty(0, dtype=torch.uint8, device="cuda")
-        return torch.as_tensor(_DevMem(ptr, nbytes), device="cuda")
-
-    return (wrap(v.d_descs, v.n_chunks * DESC_DTYPE.itemsize), wrap(v.d_verts, v.n_verts * VERT_DTYPE.itemsize),
-            wrap(iptr, v.n_inds * isz))
+def slab_bounds(n: int, parts: int, part: int) -> tuple:
+    """(first, count) of contiguous slab `part` of `parts` of an n-chunk request; the remainder is spread one per
+    slab.  Mirror of uw_slab_bounds (the C function is what uw_multi_build uses; tests compare the two)."""
+    parts = max(1, parts)
+    base, rem = divmod(n, parts)
+    return part * base + min(part, rem), base + (1 if part < rem else 0)
 
 
-def gather_meshes(descs: torch.Tensor, verts: torch.Tensor, inds: torch.Tensor, dst: int = 0,
-                  group: Optional[dist.ProcessGroup] = None) -> Optional[List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]]:
-    """Bring every rank's (descs, verts, inds) byte tensors to rank `dst`.
+def info_to_bytes(info: _ffi.UwGatherInfo) -> bytes:
+    return bytes(C.string_at(C.addressof(info), C.sizeof(info)))
 
-    Returns, on `dst`, a list indexed by source rank (its own entry aliases the inputs); None elsewhere.
-    Descriptor offsets stay relative to the source rank's own vertex / index arrays."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    dev = descs.device
-    mine = torch.tensor([descs.numel(), verts.numel(), inds.numel()], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, mine, group=group)
-    ops = []
-    out = None
-    if rank != dst:
-        ops = [dist.P2POp(dist.isend, t.contiguous(), dst, group) for t in (descs, verts, inds) if t.numel()]
+
+def info_from_bytes(raw: bytes) -> _ffi.UwGatherInfo:
+    if len(raw) != C.sizeof(_ffi.UwGatherInfo):
+        raise ValueError("uw_gather_info blob has the wrong size")
+    return _ffi.UwGatherInfo.from_buffer_copy(raw)
+
+
+def broadcast_info(info: Optional[_ffi.UwGatherInfo], src: int = 0, group=None, device=None) -> _ffi.UwGatherInfo:
+    """Hand rank `src`'s uw_gather_info to every rank (setup, not data path).  Works over gloo (CPU tensor) and
+    NCCL (pass device="cuda")."""
+    import torch
+    import torch.distributed as dist
+    n = C.sizeof(_ffi.UwGatherInfo)
+    if dist.get_rank(group) == src:
+        t = torch.frombuffer(bytearray(info_to_bytes(info)), dtype=torch.uint8).clone()
     else:
-        out = []
-        for r in range(world):
-            if r == dst:
-                out.append((descs, verts, inds))
-                continue
-            bufs = [torch.empty(int(sizes[r][k].item()), dtype=torch.uint8, device=dev) for k in range(3)]
-            ops += [dist.P2POp(dist.irecv, b, r, group) for b in bufs if b.numel()]
-            out.append(tuple(bufs))
-    if ops:                                  # one batched group: the transfers run concurrently over NVLink
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-    return out
+        t = torch.zeros(n, dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=src, group=group)
+    return info_from_bytes(t.cpu().numpy().tobytes())
 
 
-def as_numpy_batch(descs: torch.Tensor, verts: torch.Tensor, inds: torch.Tensor, index32: bool = False):
-    """Host numpy views (structured dtypes) of a gathered (descs, verts, inds) byte triple."""
-    d = descs.cpu().numpy().view(DESC_DTYPE)
-    v = verts.cpu().numpy().view(VERT_DTYPE)
-    i = inds.cpu().numpy().view(np.uint32 if index32 else np.uint16)
-    return d, v, i
+class GatherResult:
+    """uw_gather_result with numpy conveniences."""
+
+    def __init__(self, raw: _ffi.UwGatherResult, index_bytes: int):
+        self.raw = raw
+        self.n_segments, self.epoch = raw.n_segments, raw.epoch
+        self.n_chunks, self.n_verts, self.n_inds, self.n_draw = raw.n_chunks, raw.n_verts, raw.n_inds, raw.n_draw
+        self.seg_vcap, self.seg_icap = raw.seg_vcap, raw.seg_icap
+        self.index_bytes = index_bytes
+        self.segments = [dict(first_chunk=s.first_chunk, n_chunks=s.n_chunks, n_mesh=s.n_mesh, n_blank=s.n_blank,
+                              n_verts=s.n_verts, n_inds=s.n_inds, guard=s.guard, overflow=s.overflow)
+                         for s in raw.seg[:raw.n_segments]]
+
+    def host_descs(self) -> Optional[np.ndarray]:
+        """The pinned host copy of the descriptors (UW_GATHER_DESCS_TO_HOST) as a structured array, or None."""
+        if not self.raw.h_descs:
+            return None
+        hi = max((s["first_chunk"] + s["n_chunks"] for s in self.segments if s["n_chunks"]), default=0)
+        buf = (C.c_uint8 * (hi * DESC_DTYPE.itemsize)).from_address(self.raw.h_descs)
+        return np.frombuffer(buf, dtype=DESC_DTYPE)
+
+    def host_draw(self) -> Optional[np.ndarray]:
+        """The pinned host copy of the draw list (UW_GATHER_DRAW_TO_HOST): descriptors of the chunks that ended with a
+        mesh, segment by segment, completion order inside a segment.  None if it was not requested (or is empty)."""
+        if not self.raw.h_draw:
+            return None
+        buf = (C.c_uint8 * (self.n_draw * DESC_DTYPE.itemsize)).from_address(self.raw.h_draw)
+        return np.frombuffer(buf, dtype=DESC_DTYPE)
+
+    def download(self):
+        """(descs, verts, inds) of the whole arena on the host -- verification only (plain cudaMemcpy of every
+        segment).  descs[i].vert_offset / index_offset index the returned verts / inds arrays."""
+        lib = _ffi.load_library()
+        hi = max((s["first_chunk"] + s["n_chunks"] for s in self.segments if s["n_chunks"]), default=0)
+        nseg = self.n_segments
+
+        def pull(ptr, count, dtype):
+            out = np.zeros(count, dtype=dtype)
+            if count:
+                st = lib.uw_debug_copy_to_host(C.c_void_p(ptr), out.nbytes, out.ctypes.data)
+                if st != _ffi.UW_OK:
+                    raise UwError(st, "uw_debug_copy_to_host failed")
+            return out
+
+        descs = pull(self.raw.d_descs, hi, DESC_DTYPE)
+        verts = pull(self.raw.d_verts, nseg * self.seg_vcap, VERT_DTYPE)
+        inds = pull(self.raw.d_inds, nseg * self.seg_icap, np.uint32 if self.index_bytes == 4 else np.uint16)
+        return descs, verts, inds
+
+
+class RegionGather:
+    """One process per GPU.  Every rank: `RegionGather(builder, rank, world, n_chunks, dst)` after
+    torch.distributed is initialised (collective: broadcasts the arena info), then `build(positions_of_my_slab,
+    first_chunk)` on every rank and `wait()` on rank `dst`."""
+
+    def __init__(self, builder: ChunkBuilder, rank: int, world: int, n_chunks: int, dst: int = 0,
+                 seg_vcap: int = 0, seg_icap: int = 0, group=None, bcast_device=None):
+        self.builder, self.rank, self.world, self.dst = builder, rank, world, dst
+        info = builder.gather_create(world, n_chunks, seg_vcap, seg_icap) if rank == dst else None
+        if world > 1:
+            info = broadcast_info(info, src=dst, group=group, device=bcast_device)
+        self.info = info
+        builder.gather_attach(info, rank)
+
+    def build(self, positions, first_chunk: int):
+        self.builder.gather_build(positions, first_chunk)
+
+    def build_device(self, d_positions_ptr: int, n: int, first_chunk: int):
+        self.builder.gather_build_device(d_positions_ptr, n, first_chunk)
+
+    def wait(self, descs_to_host: bool = False, draw_to_host: bool = False) -> GatherResult:
+        if self.rank != self.dst:
+            raise RuntimeError("RegionGather.wait() belongs to the rendering rank")
+        return self.builder.gather_wait(descs_to_host, draw_to_host)
+
+    def close(self):
+        self.builder.gather_detach()
+        if self.rank == self.dst:
+            self.builder.gather_destroy()
+
+
+class MultiBuilder:
+    """uw_multi_*: one process drives G GPUs; devices[0] renders."""
+
+    def __init__(self, perlin: Optional[Perlin] = None, devices: Sequence[int] = (0,), *, internal_size: int = INTERNAL_SIZE,
+                 index32: bool = False):
+        self._lib = _ffi.load_library()
+        cfg = _ffi.UwConfig()
+        self._lib.uw_config_default(C.byref(cfg))
+        cfg.internal_size = internal_size
+        cfg.seed = (perlin or Perlin()).seed()
+        cfg.flags = _ffi.FLAG_INDEX32 if index32 else 0
+        self.index_bytes = 4 if index32 else 2
+        devs = (C.c_int32 * len(devices))(*devices)
+        self._m = C.c_void_p()
+        st = self._lib.uw_multi_create(C.byref(cfg), devs, len(devices), C.byref(self._m))
+        if st != _ffi.UW_OK:
+            raise UwError(st, (self._lib.uw_multi_last_error(None) or b"").decode())
+        self.devices = list(devices)
+
+    def build(self, positions, descs_to_host: bool = False, draw_to_host: bool = False) -> GatherResult:
+        p = _as_positions(positions)
+        self._keep = p
+        out = _ffi.UwGatherResult()
+        flags = (_ffi.GATHER_DESCS_TO_HOST if descs_to_host else 0) | (_ffi.GATHER_DRAW_TO_HOST if draw_to_host else 0)
+        st = self._lib.uw_multi_build(self._m, p.ctypes.data, p.shape[0], flags, C.byref(out))
+        if st != _ffi.UW_OK:
+            raise UwError(st, (self._lib.uw_multi_last_error(self._m) or b"").decode())
+        return GatherResult(out, self.index_bytes)
+
+    def close(self):
+        if getattr(self, "_m", None) and self._m.value:
+            self._lib.uw_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

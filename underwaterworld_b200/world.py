@@ -33,6 +33,7 @@ RECHECK_NEARBY_DIST = 4.0
 RECHECK_NEARBY_ANGLE = 0.33
 VIEW_DIST = 4
 GENERATION_DIST = 5
+STOP_FULL_BUILD = GENERATION_DIST ** 3                       # world.rs:14
 KEEP_DIST = 6
 MAX_Z = 2
 MIN_Z = -2
@@ -199,6 +200,7 @@ class World:
     chunks_to_generate: List[Tuple[int, int, int]] = field(default_factory=list)   # in build order
     last_sub_pos: Optional[np.ndarray] = None
     last_sub_bearing: Optional[np.ndarray] = None
+    should_full_build: bool = True                            # world.rs:69,83: the start-up phase builds whole chunks
 
     def get_chunk(self, pos):
         return self.chunks.get(tuple(pos))
@@ -230,18 +232,31 @@ class World:
             del self.chunks[p]
 
     def build_batch(self, sub: Sub, builder: ChunkBuilder, max_batch: Optional[int] = None) -> int:
-        """Batched build_full_step (world.rs:113-123): pop up to max_batch positions, ONE GPU call."""
+        """Batched build_full_step / build_step (world.rs:113-145): pop up to max_batch positions, ONE GPU call.
+
+        Render-list rule, as in the reference: while `should_full_build` is set (start-up, world.rs:105-107) every
+        chunk that is not blank is drawn (build_full_step, world.rs:117-119, no distance test); afterwards
+        (build_step, world.rs:132-134) only chunks within VIEW_DIST + 1 of the sub's chunk.  The flag is cleared
+        once the queue is empty or STOP_FULL_BUILD chunks exist, evaluated after the batch like the reference does
+        after every chunk -- with a batch the phase can only end at a batch boundary, so a start-up batch larger than
+        what the reference would have built before the switch applies the start-up rule to all of it."""
         take = len(self.chunks_to_generate) if max_batch is None else min(max_batch, len(self.chunks_to_generate))
         if take == 0:
+            if self.should_full_build:
+                self.should_full_build = False                 # queue empty: world.rs:107
             return 0
         batch_pos, self.chunks_to_generate = self.chunks_to_generate[:take], self.chunks_to_generate[take:]
         batch = builder.build(np.array(batch_pos, dtype=np.int32))
         sc = sub.chunk()
+        full = self.should_full_build
         for i, p in enumerate(batch_pos):
             c = Chunk(p)._adopt(batch.chunk(i))
-            if c.not_blank() and sum((a - b) ** 2 for a, b in zip(p, sc)) <= (VIEW_DIST + 1) ** 2:   # world.rs:117-119,132-134
+            near = sum((a - b) ** 2 for a, b in zip(p, sc)) <= (VIEW_DIST + 1) ** 2
+            if c.not_blank() and (full or near):
                 self.chunks_to_render.append(p)
             self.chunks[p] = c
+        if full:
+            self.should_full_build = not (len(self.chunks_to_generate) == 0 or len(self.chunks) >= STOP_FULL_BUILD)
         return take
 
     def update(self, sub: Sub, camera: Camera, builder: ChunkBuilder, sub_reset: bool = False,

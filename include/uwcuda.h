@@ -202,6 +202,17 @@ uw_status   uw_build_from_densities(uw_ctx* ctx, const int32_t* chunk_pos_xyz, c
  * (x,y,z f64 triples, HOST) -> n floats (HOST).  SURVEY §8f-3. */
 uw_status   uw_iso_at(uw_ctx* ctx, const double* points_xyz, uint32_t n, float* out);
 
+/* Batched collision ray casts against the per-cell triangle lists (SURVEY §8f-1's consumer; replaces the per-boid loops of
+ * boid.rs:175-240).  Context created with UW_FLAG_TRIS; the rays are tested against the chunks of the context's LAST
+ * build (host or device-resident), whose triangle lists are still in HBM.  For ray i (origin, direction: n x 3 floats,
+ * HOST) the candidate triangles are exactly the ones the reference gathers: every built chunk within +-wall_range
+ * world units of the origin (boid.rs:177-208), and inside it the cells within +-wall_range cells of the origin's
+ * cell (Chunk::tris_around, chunk.rs:315-342).  Each is tested with util::Tri::intersects (util.rs:22-59) with
+ * range = wall_range; out_t[i] = the smallest Some(t), or -1 if every test returned None.  The reference's two uses
+ * follow from it: "heading for a collision" = (0 <= t < wall_range), "direction is safe" = (t == -1). */
+uw_status   uw_raycast_tris(uw_ctx* ctx, const float* origins_xyz, const float* dirs_xyz, uint32_t n_rays, int32_t wall_range,
+                            float* out_t);
+
 /* Vertex colour of chunk.rs:215-222 (util.rs:93-95 create_mix_ratio, :122-153 hsv_to_rgb, :106-112 to_srgb) for n
  * (world z, value level = corner_b index % 3) pairs (HOST) -> n RGB triples (HOST): the kernels' own colour code,
  * so the tests can sweep the whole hue range instead of the z values a mesh happens to hold. */

@@ -85,6 +85,11 @@ class Oracle:
             C.c_void_p, C.c_uint32, C.c_void_p,
         ]
         L.uwo_build_chunk.restype = C.c_int
+        L.uwo_vertex_pairs.argtypes = [C.POINTER(OracleConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.uwo_vertex_pairs.restype = C.c_int
+        L.uwo_raycast.argtypes = [C.POINTER(OracleConfig), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                  C.c_uint32, C.c_int32, C.c_void_p]
+        L.uwo_raycast.restype = None
         L.uwo_build_batch_timed.argtypes = [
             C.POINTER(OracleConfig), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int,
             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
@@ -178,6 +183,32 @@ class Oracle:
             r["tri_cell_start"] = tcs
             r["tris"] = tris[: tcs[-1]].copy()
         return r
+
+    def vertex_pairs(self, perm, pos, isos=None) -> np.ndarray:
+        """(n_verts, 2) lattice indices (x*L*L + y*L + z) of every vertex's ordered corner pair (corner_a, corner_b),
+        in vertex order -- Build::vert_pairs (chunk.rs:38)."""
+        perm = np.ascontiguousarray(perm, dtype=np.uint8)
+        p = np.asarray(pos, dtype=np.int32)
+        S = self.cfg.internal_size
+        cap = 5 * S * (S + 1) ** 2 + 16
+        out = np.zeros((cap, 2), dtype=np.uint32)
+        isos_in = None if isos is None else np.ascontiguousarray(isos, dtype=np.float32)
+        n = self.lib.uwo_vertex_pairs(C.byref(self.cfg), perm.ctypes.data, p.ctypes.data,
+                                      isos_in.ctypes.data if isos_in is not None else None, out.ctypes.data, cap)
+        assert n >= 0
+        return out[:n].copy()
+
+    def raycast(self, perm, chunk_positions, origins, dirs, wall_range=3) -> np.ndarray:
+        """Tri::intersects (util.rs:22-59) over the triangles boid.rs:175-208 gathers around every ray origin, out of
+        the given chunks: the smallest hit distance per ray, -1 where nothing is hit."""
+        perm = np.ascontiguousarray(perm, dtype=np.uint8)
+        cp = np.ascontiguousarray(chunk_positions, dtype=np.int32).reshape(-1, 3)
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        out = np.empty(len(o), dtype=np.float32)
+        self.lib.uwo_raycast(C.byref(self.cfg), perm.ctypes.data, cp.ctypes.data, len(cp), o.ctypes.data, d.ctypes.data,
+                             len(o), wall_range, out.ctypes.data)
+        return out
 
     def build_batch_timed(self, perm, positions, mode=MODE_FAITHFUL, nthreads=1):
         perm = np.ascontiguousarray(perm, dtype=np.uint8)

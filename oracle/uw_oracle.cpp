@@ -269,6 +269,7 @@ struct MeshOut {
     std::vector<uint8_t>  cases;    // per cell, scan order
     std::vector<uwo_tri>  tris;     // flattened per-cell triangle lists (cell scan order)
     std::vector<uint32_t> tri_cell_start;  // S^3 + 1 offsets into tris
+    std::vector<uint32_t> vpairs;   // per vertex: lattice index of corner_a, of corner_b (the reference's vert_pairs, chunk.rs:38)
 };
 
 // mode 0: FAITHFUL -- linear-search ordered-pair dedup (chunk.rs:233), colour per index
@@ -343,6 +344,7 @@ static void build_mesh(const uwo_config* c, const int32_t pos[3], const float* i
                 if (ind == vert_pairs.size()) {
                     vert_pairs.push_back(PairKey{{A[0], A[1], A[2]}, {B[0], B[1], B[2]}});
                     out.verts.push_back(v);
+                    out.vpairs.push_back((uint32_t)ia); out.vpairs.push_back((uint32_t)ib);
                 }
             } else {
                 // direction code of the ordered pair: +x,-x,+y,-y(unused),+z,-z
@@ -355,6 +357,7 @@ static void build_mesh(const uwo_config* c, const int32_t pos[3], const float* i
                     uwo_vertex_color(c, world_z, cb, v.color);
                     slot = (int32_t)out.verts.size();
                     out.verts.push_back(v);
+                    out.vpairs.push_back((uint32_t)ia); out.vpairs.push_back((uint32_t)ib);
                 }
                 ind = (size_t)slot;
             }
@@ -518,6 +521,113 @@ int uwo_build_chunk(const uwo_config* c, const uint8_t* perm, const int32_t pos[
         if (tri_cell_start_out) memcpy(tri_cell_start_out, out.tri_cell_start.data(), sizeof(uint32_t) * (S * S * S + 1));
     }
     return rc;
+}
+
+// The ordered corner pair behind every vertex (Build::vert_pairs, chunk.rs:38,233-240) as lattice indices
+// x*L*L + y*L + z, two per vertex, in vertex order -- lets the tests bound each vertex's position error by the
+// conditioning of ITS edge, (iso_b - iso_a).  Returns the vertex count, or -1 if cap (in vertices) is too small.
+int uwo_vertex_pairs(const uwo_config* c, const uint8_t* perm, const int32_t pos[3], const float* isos_in,
+                     uint32_t* pairs_out, uint32_t cap) {
+    const size_t S = (size_t)c->internal_size, L = S + 1;
+    std::vector<float> isos(L * L * L);
+    if (isos_in) isos.assign(isos_in, isos_in + L * L * L);
+    else uwo_densities(c, perm, pos, isos.data());
+    bool blank = true;
+    for (float v : isos) if (!(v > c->iso_level)) { blank = false; break; }
+    if (blank) return 0;
+    MeshOut out;
+    build_mesh(c, pos, isos.data(), 1, false, out);
+    const size_t nv = out.verts.size();
+    if (nv > cap) return -1;
+    memcpy(pairs_out, out.vpairs.data(), sizeof(uint32_t) * 2 * nv);
+    return (int)nv;
+}
+
+// ---------------------------------------------------------------------------------------
+// Collision ray casts (SURVEY 8f-1's consumer): util::Tri::intersects (util.rs:22-59) over the triangles
+// Chunk::tris_around (chunk.rs:315-342) returns for the chunks boid.rs:175-208 visits.  cgmath (un-vendored,
+// cgmath 0.18 per the reference's Cargo.toml) is restated from its published source: dot = (x*x' + y*y') + z*z',
+// cross = (y z' - z y', z x' - x z', x y' - y x'), vector * scalar and +/- element-wise; f32, unfused.
+// PARITY UNPINNED for this function: the shipped wasm's copy of boid.rs was not executed (see wasm_forensics.py).
+// ---------------------------------------------------------------------------------------
+static inline float dot3(const float a[3], const float b[3]) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+static inline void cross3(const float a[3], const float b[3], float o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// util.rs:22-59.  Returns t, or -1 for None.
+float uwo_tri_intersects(const uwo_tri* tr, const float pos[3], const float dir[3], float range) {
+    const float EPSILON = 1e-5f;                                        // util.rs:3
+    const float dot_normal_dir = dot3(tr->normal, dir);
+    if (fabsf(dot_normal_dir) < EPSILON) return -1.0f;
+    const float d0[3] = { tr->verts[0][0] - pos[0], tr->verts[0][1] - pos[1], tr->verts[0][2] - pos[2] };
+    const float t = dot3(tr->normal, d0) / dot_normal_dir;
+    if (t < 0.0f || t > range) return -1.0f;
+    const float ip[3] = { pos[0] + dir[0] * t, pos[1] + dir[1] * t, pos[2] + dir[2] * t };
+    const float* v0 = tr->verts[0]; const float* v1 = tr->verts[1]; const float* v2 = tr->verts[2];
+    const float e0[3] = { v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2] };
+    const float e1[3] = { v2[0] - v1[0], v2[1] - v1[1], v2[2] - v1[2] };
+    const float e2[3] = { v0[0] - v2[0], v0[1] - v2[1], v0[2] - v2[2] };
+    const float p0[3] = { ip[0] - v0[0], ip[1] - v0[1], ip[2] - v0[2] };
+    const float p1[3] = { ip[0] - v1[0], ip[1] - v1[1], ip[2] - v1[2] };
+    const float p2[3] = { ip[0] - v2[0], ip[1] - v2[1], ip[2] - v2[2] };
+    float n0[3], n1[3], n2[3];
+    cross3(e0, p0, n0); cross3(e1, p1, n1); cross3(e2, p2, n2);
+    const float q0 = dot3(n0, tr->normal), q1 = dot3(n1, tr->normal), q2 = dot3(n2, tr->normal);
+    return (q0 >= 0.0f && q1 >= 0.0f && q2 >= 0.0f) ? t : -1.0f;
+}
+
+// For every ray: the triangles boid.rs:175-208 gathers around its origin (chunks within +-wall_range world units,
+// cells within +-wall_range cells: Chunk::tris_around) out of the given chunks, each tested with Tri::intersects
+// (range = wall_range as f32, boid.rs:221); out_t = the smallest Some(t), or -1 if every test returned None.
+void uwo_raycast(const uwo_config* c, const uint8_t* perm, const int32_t* chunk_pos, uint32_t n_chunks,
+                 const float* origins, const float* dirs, uint32_t n_rays, int32_t wall_range, float* out_t) {
+    const size_t S = (size_t)c->internal_size, L = S + 1, NC = S * S * S;
+    struct Built { int32_t pos[3]; std::vector<uwo_tri> tris; std::vector<uint32_t> start; };
+    std::vector<Built> built(n_chunks);
+    for (uint32_t i = 0; i < n_chunks; ++i) {
+        Built& b = built[i];
+        memcpy(b.pos, chunk_pos + 3 * (size_t)i, sizeof b.pos);
+        b.start.assign(NC + 1, 0);
+        std::vector<float> isos(L * L * L);
+        uwo_densities(c, perm, b.pos, isos.data());
+        bool blank = true;
+        for (float v : isos) if (!(v > c->iso_level)) { blank = false; break; }
+        if (blank) continue;
+        MeshOut out;
+        build_mesh(c, b.pos, isos.data(), 1, true, out);
+        b.tris = out.tris; b.start = out.tri_cell_start;
+    }
+    const float cs = (float)c->chunk_size, wr = (float)wall_range;
+    for (uint32_t r = 0; r < n_rays; ++r) {
+        const float* p = origins + 3 * (size_t)r;
+        const float* d = dirs + 3 * (size_t)r;
+        int32_t ws[3], we[3];
+        for (int k = 0; k < 3; ++k) { ws[k] = (int32_t)floorf((p[k] - wr) / cs); we[k] = (int32_t)floorf((p[k] + wr) / cs); }   // boid.rs:177-183
+        float best = -1.0f;
+        for (int32_t a = ws[0]; a <= we[0]; ++a) for (int32_t b = ws[1]; b <= we[1]; ++b) for (int32_t cc = ws[2]; cc <= we[2]; ++cc) {
+            const Built* bc = nullptr;
+            for (const Built& q : built) if (q.pos[0] == a && q.pos[1] == b && q.pos[2] == cc) { bc = &q; break; }   // world.get_chunk
+            if (!bc) continue;
+            const int32_t cp[3] = { a, b, cc };
+            int32_t lo[3], hi[3];
+            for (int k = 0; k < 3; ++k) {
+                const float local = p[k] - (float)cp[k] * cs;                 // boid.rs:186,190,201
+                const float pct = local / cs;
+                const int32_t mid = (int32_t)floorf(pct * (float)c->internal_size);   // chunk.rs:316-318
+                lo[k] = std::max(mid - wall_range, 0); hi[k] = std::min(mid + wall_range, (int32_t)c->internal_size);
+            }
+            for (int32_t x = lo[0]; x <= hi[0]; ++x) for (int32_t y = lo[1]; y <= hi[1]; ++y) for (int32_t z = lo[2]; z <= hi[2]; ++z) {
+                if (x >= (int32_t)S || y >= (int32_t)S || z >= (int32_t)S) continue;   // no such key in the map
+                const size_t cell = ((size_t)x * S + y) * S + z;
+                for (uint32_t j = bc->start[cell]; j < bc->start[cell + 1]; ++j) {
+                    const float t = uwo_tri_intersects(&bc->tris[j], p, d, wr);
+                    if (t >= 0.0f && (best < 0.0f || t < best)) best = t;
+                }
+            }
+        }
+        out_t[r] = best;
+    }
 }
 
 // CPU baseline driver: builds n chunks exactly as World::build_full_step does one by one

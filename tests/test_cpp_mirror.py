@@ -63,7 +63,10 @@ def test_cpp_mirror_matches_oracle(exe, oracle12):
             mm = re.search(r"verts=(\d+) inds_hash=([0-9a-f]+) pos0=(\S+)", m.group(6))
             assert int(mm.group(1)) == len(r["verts"])
             assert int(mm.group(2), 16) == _fnv(r["inds"].astype(np.uint16).tobytes())
-            assert abs(float.fromhex(mm.group(3)) - float(r["verts"]["pos"][0][0])) < 5e-2
+            vp = oracle12.vertex_pairs(perm, pos)[0]                     # per-edge position bound, as in test_gpu_parity._pos_bound
+            gap = abs(float(r["isos"][vp[1]]) - float(r["isos"][vp[0]]))
+            bound = 1e-5 + (16.0 / 12.0) * min(1.0, 2e-6 / max(gap - 4e-6, 1e-300))
+            assert abs(float.fromhex(mm.group(3)) - float(r["verts"]["pos"][0][0])) <= bound
         else:
             assert f"blank_early={r['flags'] & 1}" in m.group(6)
     assert n == 5

@@ -198,3 +198,69 @@ def test_producer_in_another_process_attaches_through_cuda_ipc(uw):
         _assert_same_chunks(descs, verts, inds, ref)
         b.gather_detach()
         b.gather_destroy()
+
+
+def test_staged_stores_give_the_same_buffers_as_register_stores(uw):
+    """Producers that write into ANOTHER GPU's memory leave vertices and indices through shared memory as whole
+    16-byte vectors (FusedOut::staged_stores); the GPU's own HBM is written straight from registers.  Same chunks,
+    same bytes -- UW_STAGED_STORES=1 forces the staged path for a local arena so one GPU can compare the two,
+    including chunks with more indices than one staging tile holds."""
+    pos = uw.region.config_positions("spawn")
+    with uw.ChunkBuilder(uw.Perlin(0), ordered=True) as b:
+        want = b.build(pos)
+    os.environ["UW_STAGED_STORES"] = "1"
+    try:
+        with uw.ChunkBuilder(uw.Perlin(0), ordered=True) as b:
+            got = b.build(pos)
+        with uw.ChunkBuilder(uw.Perlin(0), ordered=True, index32=True) as b:
+            got32 = b.build(pos)
+    finally:
+        del os.environ["UW_STAGED_STORES"]
+    assert want.descs["index_count"].max() > 3072                      # more than one u16 staging tile
+    assert np.array_equal(got.descs.view(np.uint8), want.descs.view(np.uint8))
+    assert np.array_equal(got.inds, want.inds) and np.array_equal(got.verts.view(np.uint8), want.verts.view(np.uint8))
+    for i in range(0, len(pos), 7):
+        a, w = got32.chunk(i), want.chunk(i)
+        assert np.array_equal(a.inds, w.inds.astype(np.uint32)) and np.array_equal(a.verts.view(np.uint8), w.verts.view(np.uint8))
+
+
+def test_raycast_against_collision_triangles_matches_the_reference_loops(uw):
+    """uw_raycast_tris (SURVEY 8f-1's consumer) against the oracle's restatement of boid.rs:175-240 +
+    Chunk::tris_around (chunk.rs:315-342) + Tri::intersects (util.rs:22-59): the smallest hit distance of every
+    ray, bit for bit (same candidate triangles, same f32 operation order), -1 where the reference finds None."""
+    from oracle import Oracle
+    o = Oracle(12)
+    perm = o.perm_table(0)
+    pos = uw.region.box_region((-2, 2), (-2, 2), (-2, 1))              # 48 chunks around the surface
+    rng = np.random.default_rng(7)
+    n = 6000
+    org = rng.uniform([-34, -34, -34], [34, 34, 18], size=(n, 3)).astype(np.float32)     # some origins outside every built chunk
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # boids sit near the surface: pull most origins close to a vertex of the mesh.  The exact-f64 builder's triangles
+    # are bit-identical to the oracle's (test_collision_tris_bit_exact), so its hit distances must be too.
+    with uw.ChunkBuilder(uw.Perlin(0), tris=True, exact_f64=True) as b:
+        batch = b.build(pos)
+        verts, _ = batch.compact()
+        pick = rng.integers(0, len(verts), size=n - 500)
+        org[500:] = verts["pos"][pick] + rng.normal(scale=1.5, size=(n - 500, 3)).astype(np.float32)
+        got = b.raycast_tris(org, d, 3)
+        again = b.raycast_tris(org[:100], d[:100], 3)                   # the chunk table is reused
+        wide = b.raycast_tris(org[:800], d[:800], 5)
+    want = o.raycast(perm, pos, org, d, 3)
+    assert (want >= 0).sum() > 1000 and (want < 0).sum() > 1000
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(again, got[:100])
+    assert np.array_equal(wide.view(np.uint32), o.raycast(perm, pos, org[:800], d[:800], 5).view(np.uint32))
+    # the shipped FP32 path: same triangles up to the stated vertex tolerance -> same hits except for rays that graze
+    # an edge, same distances within that tolerance
+    with uw.ChunkBuilder(uw.Perlin(0), tris=True) as b:
+        b.build(pos)
+        fast = b.raycast_tris(org, d, 3)
+    both = (fast >= 0) & (want >= 0)
+    assert ((fast >= 0) != (want >= 0)).sum() <= 0.005 * n
+    assert np.abs(fast[both] - want[both]).max() < 1e-3
+    with uw.ChunkBuilder(uw.Perlin(0)) as plain:
+        plain.build(pos[:2])
+        with pytest.raises(uw.UwError):
+            plain.raycast_tris(org[:1], d[:1])                          # needs UW_FLAG_TRIS

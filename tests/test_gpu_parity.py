@@ -27,6 +27,35 @@ def _bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
+def _pos_bound(oracle, perm, chunk_pos, r, dens_tol=DENS_TOL):
+    """Per-vertex bound on |GPU position - oracle position| for the FP32 noise path, from the
+    conditioning of the vertex's OWN edge: t = (iso - a) / (b - a) (chunk.rs:203) with a, b each off by at most
+    dens_tol moves by |dt| <= dens_tol / (|b - a| - 2 dens_tol) (and t stays inside [0, 1]); the vertex moves
+    size_scale * |dt| along the edge; on top come the f32 roundings of the lerp and of the final `+ chunk_offset`
+    (an ulp of the world coordinate each).  r = the oracle's result for the chunk (its isos are the f64-derived
+    reference densities); the ordered corner pairs come from the oracle's vert_pairs."""
+    S = oracle.cfg.internal_size
+    vp = oracle.vertex_pairs(perm, chunk_pos)
+    assert len(vp) == len(r["verts"])
+    isos = r["isos"].astype(np.float64)
+    gap = np.abs(isos[vp[:, 1]] - isos[vp[:, 0]])
+    dt = np.minimum(1.0, dens_tol / np.maximum(gap - 2.0 * dens_tol, 1e-300))
+    ss = float(np.float32(16.0) / np.float32(S))
+    ulp = np.spacing(np.abs(r["verts"]["pos"]).max(axis=1).astype(np.float32)).astype(np.float64)
+    return 2.0 * ulp + 2e-6 + ss * dt
+
+
+def _padv(n):
+    """A chunk's vertex allocation in the packed arena: rounded up to an even count (16-byte aligned start)."""
+    return (n + 1) // 2 * 2
+
+
+def _padi(n, index_bytes=2):
+    """A chunk's index allocation: rounded up to a multiple of 16 bytes."""
+    per = 16 // index_bytes
+    return (n + per - 1) // per * per
+
+
 @pytest.fixture(scope="module")
 def uw():
     import underwaterworld_b200 as m
@@ -55,8 +84,8 @@ def _oracle_batch(o, perm, positions, mode=MODE_FAST, isos=None):
             for i, p in enumerate(positions)]
 
 
-def _check_batch(batch, refs, *, exact_positions, ordered=True):
-    """Compare a GPU batch with per-chunk oracle results."""
+def _check_batch(batch, refs, *, exact_positions, ordered=True, bound=None):
+    """Compare a GPU batch with per-chunk oracle results.  bound(i, r) -> per-vertex position bound (FP32 path)."""
     assert len(batch) == len(refs)
     vo = io = 0
     for i, r in enumerate(refs):
@@ -72,10 +101,11 @@ def _check_batch(batch, refs, *, exact_positions, ordered=True):
             if exact_positions:
                 assert np.array_equal(_bits(m.verts["pos"]), _bits(r["verts"]["pos"])), f"positions chunk {i}"
             else:
-                np.testing.assert_allclose(m.verts["pos"], r["verts"]["pos"], rtol=0, atol=5e-2)
+                err = np.abs(m.verts["pos"].astype(np.float64) - r["verts"]["pos"]).max(axis=1)
+                assert (err <= bound(i, r)).all(), f"positions chunk {i}: {err.max()}"
             np.testing.assert_allclose(m.verts["color"], r["verts"]["color"], rtol=0, atol=COL_TOL if exact_positions else 5e-3)
-        vo += len(r["verts"])
-        io += len(r["inds"])
+        vo += _padv(len(r["verts"]))
+        io += _padi(len(r["inds"]), batch.inds.dtype.itemsize)
     assert batch.n_verts == vo and batch.n_inds == io
 
 
@@ -198,9 +228,13 @@ def test_full_build_fast_path_topology_bit_exact(uw, oracle12, seed):
     _check_batch(batch, refs_g, exact_positions=True)
     errs = np.concatenate([np.abs(batch.chunk(i).verts["pos"] - r["verts"]["pos"]).max(axis=1)
                            for i, r in enumerate(refs) if len(r["verts"])])
+    bounds = np.concatenate([_pos_bound(oracle12, perm, tuple(int(v) for v in pos[i]), r)
+                             for i, r in enumerate(refs) if len(r["verts"])])
+    assert (errs <= bounds).all(), f"per-edge position bound violated: worst ratio {np.max(errs / bounds)}"
+    assert np.median(bounds) < 1e-4, "the bound itself must be tight in bulk"
     cerr = np.concatenate([np.abs(batch.chunk(i).verts["color"] - r["verts"]["color"]).max(axis=1)
                            for i, r in enumerate(refs) if len(r["verts"])])
-    assert np.median(errs) < 5e-6 and np.quantile(errs, 0.99) < 1e-4 and errs.max() < 5e-2
+    assert np.median(errs) < 5e-6 and np.quantile(errs, 0.99) < 1e-4
     assert np.quantile(cerr, 0.99) < 1e-5 and cerr.max() < 5e-3
     assert guards < 0.001 * len(pos) * 2197
 
@@ -221,7 +255,7 @@ def test_spawn_config_config2(uw, builder12, oracle12):
         assert np.array_equal(m.inds.astype(np.uint32), r["inds"]), f"chunk {p}"
         assert len(m.verts) == len(r["verts"])
         n_mesh += m.not_blank()
-        io += len(r["inds"]); vo += len(r["verts"])
+        io += _padi(len(r["inds"])); vo += _padv(len(r["verts"]))
     assert batch.n_inds == io and batch.n_verts == vo and n_mesh > 100
     # provably trivial layers
     z = pos[:, 2]
@@ -258,12 +292,12 @@ def test_default_unordered_packing_is_a_valid_partition(uw, builder12, builder12
             assert np.array_equal(a.inds, b.inds) and np.array_equal(a.verts.view(np.uint8), b.verts.view(np.uint8))
         d = got.descs[got.descs["index_count"] > 0]
         o = np.argsort(d["vert_offset"])
-        assert d["vert_offset"][o][0] == 0 and np.array_equal(d["vert_offset"][o][1:], np.cumsum(d["vert_count"][o])[:-1])
+        assert d["vert_offset"][o][0] == 0 and np.array_equal(d["vert_offset"][o][1:], np.cumsum(_padv(d["vert_count"][o]))[:-1])
         o = np.argsort(d["index_offset"])
-        assert d["index_offset"][o][0] == 0 and np.array_equal(d["index_offset"][o][1:], np.cumsum(d["index_count"][o])[:-1])
+        assert d["index_offset"][o][0] == 0 and np.array_equal(d["index_offset"][o][1:], np.cumsum(_padi(d["index_count"][o]))[:-1])
 
 
-def test_golden_reference_binary_chunks_s10(uw, golden_dir):
+def test_golden_reference_binary_chunks_s10(uw, golden_dir, oracle10):
     """The reference's own shipped binary (INTERNAL_SIZE=10): GPU vs tests/golden/ref_wasm_chunks_s10.npz."""
     g = np.load(os.path.join(golden_dir, "ref_wasm_chunks_s10.npz"))
     for exact in (True, False):
@@ -283,8 +317,12 @@ def test_golden_reference_binary_chunks_s10(uw, golden_dir):
                 if exact:
                     assert np.array_equal(_bits(m.verts["pos"]), _bits(want_v[:, :3]))
                     np.testing.assert_allclose(m.verts["color"], want_v[:, 3:], rtol=0, atol=COL_TOL)
-                else:
-                    np.testing.assert_allclose(m.verts["pos"], want_v[:, :3], rtol=0, atol=5e-2)
+                else:                                            # FP32 path: per-edge bound from the binary's own densities
+                    rv = np.zeros(len(want_v), dtype=m.verts.dtype)
+                    rv["pos"] = want_v[:, :3]
+                    ref = dict(isos=g[f"isos_{ci}"], verts=rv)
+                    bound = _pos_bound(oracle10, oracle10.perm_table(int(seed)), (int(x), int(y), int(z)), ref)
+                    assert (np.abs(m.verts["pos"].astype(np.float64) - want_v[:, :3]).max(axis=1) <= bound).all()
             else:
                 assert m.num_inds() == 0 and not m.not_blank()
                 assert m.blank_early == (calls == 1)
@@ -386,7 +424,8 @@ def test_index32_and_async(uw, oracle12):
         batch = b.wait(h)
     assert batch.inds.dtype == np.uint32
     refs = _oracle_batch(oracle12, perm, pos, MODE_FAST)
-    assert np.array_equal(batch.inds, np.concatenate([r["inds"] for r in refs]))
+    assert np.array_equal(batch.compact()[1], np.concatenate([r["inds"] for r in refs]))
+    assert np.all(batch.descs["index_offset"] % 4 == 0)           # 16-byte aligned chunk allocations, u32 indices
 
 
 def test_two_async_batches_overlap(uw, builder12):
@@ -461,88 +500,157 @@ def test_large_batch_properties(uw, builder12):
     batch = builder12.build(pos)
     d = batch.descs
     assert np.array_equal(d["pos"], pos)
-    assert np.array_equal(d["vert_offset"][1:], np.cumsum(d["vert_count"])[:-1])
-    assert np.array_equal(d["index_offset"][1:], np.cumsum(d["index_count"])[:-1])
-    assert batch.n_inds % 3 == 0 and np.all(d["index_count"] % 3 == 0)
+    # request-order packing; every chunk starts on a 16-byte boundary (even vertex count, 8 u16 indices)
+    assert np.array_equal(d["vert_offset"][1:], np.cumsum(_padv(d["vert_count"]))[:-1])
+    assert np.array_equal(d["index_offset"][1:], np.cumsum(_padi(d["index_count"]))[:-1])
+    assert np.all(d["vert_offset"] % 2 == 0) and np.all(d["index_offset"] % 8 == 0)
+    assert np.all(d["index_count"] % 3 == 0)
+    verts, inds = batch.compact()
     # every index addresses a vertex of its own chunk, and every vertex is referenced
     owner = np.repeat(np.arange(len(d)), d["index_count"])
-    assert np.all(batch.inds < d["vert_count"][owner])
-    used = np.zeros(batch.n_verts, dtype=bool)
-    used[batch.inds.astype(np.int64) + d["vert_offset"][owner]] = True
+    assert np.all(inds < d["vert_count"][owner])
+    vfirst = (np.cumsum(d["vert_count"]) - d["vert_count"]).astype(np.int64)
+    used = np.zeros(len(verts), dtype=bool)
+    used[inds.astype(np.int64) + vfirst[owner]] = True
     assert used.all()
     # vertices lie inside their chunk's bounding box (chunk.rs:224-229)
     vown = np.repeat(np.arange(len(d)), d["vert_count"])
     lo = (d["pos"][vown] * 16).astype(np.float32)
-    p = batch.verts["pos"]
+    p = verts["pos"]
     assert np.all(p >= lo - 1e-4) and np.all(p <= lo + 16.0 + 1e-4)
     with uw.ChunkBuilder(uw.Perlin(0), exact_f64=True, ordered=True) as bx:
         exact = bx.build(pos)
-    assert np.array_equal(exact.inds, batch.inds) and np.array_equal(exact.descs, batch.descs)
-    np.testing.assert_allclose(batch.verts["pos"], exact.verts["pos"], rtol=0, atol=5e-2)
+    xverts, xinds = exact.compact()
+    assert np.array_equal(xinds, inds) and np.array_equal(exact.descs, batch.descs)
+    # FP32 path against the exact-f64 path on 7168 chunks: tiny in bulk; an ill-conditioned edge (|iso_b - iso_a| of the
+    # order of the density tolerance) may move its vertex, never by more than the edge it sits on (per-edge bound:
+    # test_full_build_fast_path_topology_bit_exact)
+    perr = np.abs(verts["pos"] - xverts["pos"]).max(axis=1)
+    assert np.median(perr) < 5e-6 and np.quantile(perr, 0.999) < 1e-3 and perr.max() <= 16.0 / 12.0 + 1e-3
+
+
+def _device_region_stats(uw, torch, builder, d_pos, n, index_bytes=2):
+    """One device-resident build of n chunks, analysed with torch ON the device.  Checks the size-independent
+    properties (arena packing is a partition into 16-byte aligned ranges, every index addresses a vertex of its own
+    chunk, every vertex is referenced, pad entries are zero) and returns order-free per-chunk content."""
+    from underwaterworld_b200.gather import device_batch_tensors
+    builder.build_device(d_pos.data_ptr(), n)
+    builder.sync()
+    descs, verts, inds = device_batch_tensors(builder)
+    d = descs.view(torch.int32).reshape(-1, 8).to(torch.int64)
+    vo, vc, io, ic = d[:, 4], d[:, 5], d[:, 6], d[:, 7]
+    flags = d[:, 3]
+    per16 = 16 // index_bytes
+    pvc, pic = (vc + 1) // 2 * 2, (ic + per16 - 1) // per16 * per16         # what a chunk occupies in the arenas
+    nv, ni = verts.numel() // 24, inds.numel() // index_bytes
+    assert int(pvc.sum()) == nv and int(pic.sum()) == ni and bool((ic % 3 == 0).all())
+    assert bool(((flags & 2) != 0).eq(ic > 0).all())
+    act = torch.nonzero(ic > 0).flatten()
+    order = act[torch.argsort(vo[act])]
+    # the packed arenas are partitioned by the surface chunks' (padded) ranges, whatever the packing order
+    assert int(vo[order[0]]) == 0 and bool((vo[order][1:] == (vo[order] + pvc[order])[:-1]).all())
+    iorder = act[torch.argsort(io[act])]
+    assert int(io[iorder[0]]) == 0 and bool((io[iorder][1:] == (io[iorder] + pic[iorder])[:-1]).all())
+    assert bool((vo[act] % 2 == 0).all()) and bool((io[act] % per16 == 0).all())
+    # per index slot: owner chunk (by arena order), real entry or pad, local range check, vertex usage
+    i_owner = torch.repeat_interleave(iorder, pic[iorder])
+    i_real = (torch.arange(ni, device="cuda") - io[i_owner]) < ic[i_owner]
+    idx = (inds.view(torch.int16).to(torch.int64) & 0xFFFF) if index_bytes == 2 else (inds.view(torch.int32).to(torch.int64) & 0xFFFFFFFF)
+    assert bool((idx[i_real] < vc[i_owner][i_real]).all())
+    v_owner = torch.repeat_interleave(order, pvc[order])
+    v_real = (torch.arange(nv, device="cuda") - vo[v_owner]) < vc[v_owner]
+    used = torch.zeros(nv, dtype=torch.bool, device="cuda")
+    used[idx[i_real] + vo[i_owner][i_real]] = True
+    assert bool((used == v_real).all())                                  # every real vertex referenced, no pad referenced
+    del used
+    vf = verts.view(torch.float32).reshape(-1, 6)
+    lo = (d[v_owner, 0:3] * 16).to(torch.float32)
+    assert bool((vf[v_real, 0:3] >= lo[v_real] - 1e-4).all()) and bool((vf[v_real, 0:3] <= lo[v_real] + 16.0 + 1e-4).all())
+    assert bool((vf[v_real, 3:6] >= 0).all()) and bool((vf[v_real, 3:6] <= 1).all())
+    # order-free per-chunk content sums (bit patterns as integers) over the real entries
+    vsum = torch.zeros(n, dtype=torch.int64, device="cuda")
+    vsum.index_add_(0, v_owner[v_real], verts.view(torch.int32).reshape(-1, 6).to(torch.int64).sum(dim=1)[v_real])
+    isum = torch.zeros(n, dtype=torch.int64, device="cuda")
+    isum.index_add_(0, i_owner[i_real], (idx * ((torch.arange(ni, device="cuda") - io[i_owner]) % 8191 + 1))[i_real])   # position-weighted
+    return dict(pos=d[:, 0:3].clone(), flags=flags.clone(), vc=vc.clone(), ic=ic.clone(), vo=vo.clone(), io=io.clone(),
+                vsum=vsum, isum=isum, nv=nv, ni=ni, verts=vf, v_owner=v_owner, v_real=v_real, order=order)
 
 
 def test_config3_full_region_invariants_on_device(uw):
     """BASELINE config 3 at full size (524 288 chunks, one launch, outputs stay in HBM): size-independent
-    properties checked with torch on the device -- arena packing is a partition, every index addresses a vertex
-    of its own chunk, every vertex is referenced and lies inside its chunk, provably blank / solid layers end the
+    properties checked with torch on the device (see _device_region_stats), provably blank / solid layers end the
     way the reference ends them, two runs (different completion orders) agree chunk by chunk, and the
     analytic-skip variant produces the same descriptors and the same per-chunk content."""
     import torch
-    from underwaterworld_b200.gather import device_batch_tensors
     pos = uw.region.config_positions("large")
     assert len(pos) == 524288
     d_pos = torch.from_numpy(pos).cuda()
-
-    def run(builder):
-        builder.build_device(d_pos.data_ptr(), len(pos))
-        builder.sync()
-        descs, verts, inds = device_batch_tensors(builder)
-        d = descs.view(torch.int32).reshape(-1, 8).to(torch.int64)
-        vo, vc, io, ic = d[:, 4], d[:, 5], d[:, 6], d[:, 7]
-        flags = d[:, 3]
-        nv, ni = verts.numel() // 24, inds.numel() // 2
-        assert int(vc.sum()) == nv and int(ic.sum()) == ni and bool((ic % 3 == 0).all())
-        assert bool(((flags & 2) != 0).eq(ic > 0).all())
-        act = torch.nonzero(ic > 0).flatten()
-        order = act[torch.argsort(vo[act])]
-        # the packed arenas are partitioned by the surface chunks' ranges (completion order)
-        assert int(vo[order[0]]) == 0 and bool((vo[order][1:] == (vo[order] + vc[order])[:-1]).all())
-        iorder = act[torch.argsort(io[act])]
-        assert int(io[iorder[0]]) == 0 and bool((io[iorder][1:] == (io[iorder] + ic[iorder])[:-1]).all())
-        # per index: owner chunk (by arena order), local range check, vertex usage
-        i_owner = torch.repeat_interleave(iorder, ic[iorder])
-        idx = inds.view(torch.int16).to(torch.int64) & 0xFFFF
-        assert bool((idx < vc[i_owner]).all())
-        used = torch.zeros(nv, dtype=torch.bool, device="cuda")
-        used[idx + vo[i_owner]] = True
-        assert bool(used.all())
-        del used
-        v_owner = torch.repeat_interleave(order, vc[order])
-        vf = verts.view(torch.float32).reshape(-1, 6)
-        lo = (d[v_owner, 0:3] * 16).to(torch.float32)
-        assert bool((vf[:, 0:3] >= lo - 1e-4).all()) and bool((vf[:, 0:3] <= lo + 16.0 + 1e-4).all())
-        assert bool((vf[:, 3:6] >= 0).all()) and bool((vf[:, 3:6] <= 1).all())
-        # order-free per-chunk content sums (bit patterns as integers)
-        vsum = torch.zeros(len(pos), dtype=torch.int64, device="cuda")
-        vsum.index_add_(0, v_owner, verts.view(torch.int32).reshape(-1, 6).to(torch.int64).sum(dim=1))
-        isum = torch.zeros(len(pos), dtype=torch.int64, device="cuda")
-        isum.index_add_(0, i_owner, idx)
-        return dict(pos=d[:, 0:3].clone(), flags=flags.clone(), vc=vc.clone(), ic=ic.clone(), vsum=vsum, isum=isum, nv=nv, ni=ni)
-
+    keys = ("flags", "vc", "ic", "vsum", "isum")
     with uw.ChunkBuilder(uw.Perlin(0)) as b:
-        a = run(b)
-        c = run(b)
+        a = {k: v for k, v in _device_region_stats(uw, torch, b, d_pos, len(pos)).items() if k in keys + ("pos", "nv", "ni")}
+        c = {k: v for k, v in _device_region_stats(uw, torch, b, d_pos, len(pos)).items() if k in keys}
     assert bool((a["pos"].cpu() == torch.from_numpy(pos).to(torch.int64)).all())
     z = a["pos"][:, 2]
     assert bool((a["flags"][z >= 2] == 1).all())                 # provably blank: early-out, no mesh (chunk.rs:276-280)
     assert bool((a["flags"][z <= -4] == 0).all())                # provably solid: mesh stage runs, emits nothing
     assert a["nv"] > 20_000_000 and a["ni"] > 80_000_000
-    for k in ("flags", "vc", "ic", "vsum", "isum"):
+    for k in keys:
         assert bool((a[k] == c[k]).all()), k
     with uw.ChunkBuilder(uw.Perlin(0), analytic_skip=True) as s:
-        e = run(s)
-    for k in ("pos", "flags", "vc", "ic", "vsum", "isum"):
+        e = _device_region_stats(uw, torch, s, d_pos, len(pos))
+    for k in ("pos",) + keys:
         assert bool((a[k] == e[k]).all()), k
+
+
+def _compare_fp32_with_exact(uw, torch, pos, internal_size, index_bytes):
+    """The shipped path (FP32 factorised noise + f64 guard band) against UW_FLAG_EXACT_F64 (every sample in f64,
+    reference operation order: bit-exact densities, see test_densities_exact_mode_bit_exact) over a WHOLE region,
+    on the device: flags, counts and the complete index content of every chunk must be identical; vertex positions
+    are compared vertex by vertex (both paths number vertices identically, so chunk-local vertex k is the same edge)."""
+    d_pos = torch.from_numpy(pos).cuda()
+    n = len(pos)
+    with uw.ChunkBuilder(uw.Perlin(0), internal_size=internal_size, exact_f64=True) as bx:
+        x = _device_region_stats(uw, torch, bx, d_pos, n, index_bytes)
+        # compacted vertex positions in (chunk, local vertex) order
+        xkey = (x["v_owner"] * (1 << 22) + (torch.arange(x["nv"], device="cuda") - x["vo"][x["v_owner"]]))[x["v_real"]]
+        xpos = x["verts"][x["v_real"], 0:3][torch.argsort(xkey)].clone()
+        xcol = x["verts"][x["v_real"], 3:6][torch.argsort(xkey)].clone()
+        x = {k: x[k] for k in ("flags", "vc", "ic", "isum", "nv", "ni")}
+    with uw.ChunkBuilder(uw.Perlin(0), internal_size=internal_size) as bf:
+        f = _device_region_stats(uw, torch, bf, d_pos, n, index_bytes)
+        guards = bf.guard_count()
+        fkey = (f["v_owner"] * (1 << 22) + (torch.arange(f["nv"], device="cuda") - f["vo"][f["v_owner"]]))[f["v_real"]]
+        fpos = f["verts"][f["v_real"], 0:3][torch.argsort(fkey)]
+        fcol = f["verts"][f["v_real"], 3:6][torch.argsort(fkey)]
+    for k in ("flags", "vc", "ic", "isum"):                        # topology: bit-exact, every chunk
+        assert bool((f[k] == x[k]).all()), f"{k}: {int((f[k] != x[k]).sum())} chunks differ"
+    assert f["nv"] == x["nv"] and f["ni"] == x["ni"]
+    perr = (fpos - xpos).abs().amax(dim=1)
+    cerr = (fcol - xcol).abs().amax(dim=1)
+    return dict(n_verts=int(f["vc"].sum()), n_inds=int(f["ic"].sum()), guards=int(guards), pos_err_max=float(perr.max()),
+                pos_err_median=float(perr.median()), pos_err_p999=float(torch.quantile(perr[:: max(1, len(perr) // 4_000_000)], 0.999)),
+                n_pos_err_gt_1e4=int((perr > 1e-4).sum()), col_err_max=float(cerr.max()))
+
+
+def test_config3_whole_region_fp32_path_matches_exact_f64_path(uw):
+    """Parity at scale (VERDICT r01 'what is weak' #1): all 524 288 chunks of BASELINE config 3."""
+    import torch
+    r = _compare_fp32_with_exact(uw, torch, uw.region.config_positions("large"), 12, 2)
+    print("config 3, FP32+guard vs exact f64:", r)
+    assert r["n_verts"] > 20_000_000 and r["n_inds"] > 80_000_000 and r["guards"] > 0
+    size_scale = 16.0 / 12.0
+    assert r["pos_err_median"] < 5e-6 and r["pos_err_p999"] < 1e-3 and r["pos_err_max"] <= size_scale + 1e-3
+    assert r["n_pos_err_gt_1e4"] < 1e-3 * r["n_verts"]
+    assert r["col_err_max"] <= 0.35      # colour follows world z; bounded by the hue gradient over one cell
+
+
+def test_config4_whole_region_fp32_path_matches_exact_f64_path(uw):
+    """The same at BASELINE config 4: the 2048-chunk region at 64^3 cells per chunk (u32 indices)."""
+    import torch
+    r = _compare_fp32_with_exact(uw, torch, uw.region.config_positions("spawn"), 64, 4)
+    print("config 4, FP32+guard vs exact f64:", r)
+    assert r["n_verts"] > 10_000_000 and r["n_inds"] > 40_000_000
+    assert r["pos_err_median"] < 5e-6 and r["pos_err_p999"] < 1e-3 and r["pos_err_max"] <= 0.25 + 1e-3
 
 
 def test_exportable_arenas_round_trip_through_a_file_descriptor(uw, builder12):

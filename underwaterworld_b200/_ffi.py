@@ -109,7 +109,7 @@ EXPORTS = [
     "uw_set_stream", "uw_get_stage_times", "uw_set_profiling", "uw_get_guard_count", "uw_debug_ffma_peak", "uw_export_arena_fd", "uw_debug_vertex_colors",
     "uw_gather_create", "uw_gather_destroy", "uw_gather_attach", "uw_gather_detach", "uw_gather_build",
     "uw_gather_build_device", "uw_gather_wait", "uw_slab_bounds",
-    "uw_multi_create", "uw_multi_build", "uw_multi_destroy", "uw_multi_last_error", "uw_debug_copy_to_host",
+    "uw_multi_create", "uw_multi_build", "uw_multi_destroy", "uw_multi_last_error", "uw_debug_copy_to_host", "uw_raycast_tris",
 ]
 
 _lib = None
@@ -179,5 +179,6 @@ def load_library() -> C.CDLL:
     lib.uw_multi_last_error.argtypes = [vp]
     lib.uw_multi_last_error.restype = C.c_char_p
     lib.uw_debug_copy_to_host.argtypes = [vp, u64, vp]
+    lib.uw_raycast_tris.argtypes = [vp, vp, vp, u32, C.c_int32, vp]
     _lib = lib
     return lib

@@ -99,6 +99,18 @@ class Batch:
     def n_inds(self) -> int:
         return int(self.inds.shape[0])
 
+    def compact(self):
+        """(verts, inds) with every chunk's buffers concatenated tightly in chunk order.  The packed arrays themselves
+        start every chunk on a 16-byte boundary (allocations are padded to an even vertex count / a multiple of 16
+        bytes of indices), so they hold a few unused pad entries between chunks."""
+        def ranges(off, cnt):
+            cnt = cnt.astype(np.int64)
+            tot = int(cnt.sum())
+            start = np.repeat(off.astype(np.int64) - (np.cumsum(cnt) - cnt), cnt)
+            return start + np.arange(tot, dtype=np.int64)
+        d = self.descs
+        return self.verts[ranges(d["vert_offset"], d["vert_count"])], self.inds[ranges(d["index_offset"], d["index_count"])]
+
     def chunk(self, i: int) -> ChunkMesh:
         d = self.descs[i]
         vo, vc, io, ic = int(d["vert_offset"]), int(d["vert_count"]), int(d["index_offset"]), int(d["index_count"])
@@ -333,6 +345,18 @@ class ChunkBuilder:
         p = _as_positions(positions)
         out = np.empty((p.shape[0], self.S ** 3), dtype=np.uint8)
         self._check(self._lib.uw_debug_cases(self._ctx, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def raycast_tris(self, origins, dirs, wall_range: int = 3) -> np.ndarray:
+        """Batched Tri::intersects (util.rs:22-59) the way boid.rs:175-240 uses it, against the collision triangles of
+        this builder's LAST build (ChunkBuilder(tris=True)): per ray the smallest hit distance t, -1 where no candidate
+        triangle is hit.  `heading for a collision` = (0 <= t < wall_range); `direction is safe` = (t == -1)."""
+        o = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, 3)
+        if o.shape != d.shape:
+            raise ValueError("origins and dirs must have the same shape")
+        out = np.empty(o.shape[0], dtype=np.float32)
+        self._check(self._lib.uw_raycast_tris(self._ctx, o.ctypes.data, d.ctypes.data, o.shape[0], wall_range, out.ctypes.data))
         return out
 
     def iso_at(self, points) -> np.ndarray:

@@ -44,6 +44,8 @@ struct DevCfg {
     int cs_pow2, mod_pow2;             // chunk_size / adj_z_mod are powers of two: exact reciprocal multiplies
     double inv_chunk_size;             // 1 / chunk_size (exact when cs_pow2)
     float inv_adj_z_mod;               // 1 / adj_z_mod  (exact when mod_pow2)
+    const float* terr_tab;             // [terr_nz][16]: terrace term - 1 per (chunk z layer, lattice index), see k_terrace_table
+    int terr_z0, terr_nz;              // layers terr_z0 .. terr_z0 + terr_nz - 1 are tabulated (others are computed in place)
     int G[UW_MAX_OCT];                 // lattice points per axis per octave = 2^o + 2
     int lat_base[UW_MAX_OCT + 1];      // prefix of G^3
     int x_base[UW_MAX_OCT + 1];        // prefix of L*G^2
@@ -648,29 +650,75 @@ struct SpecDims {
 template <int ST, int NOCT>
 struct SpecSmem {
     using D = SpecDims<ST, NOCT>;
-    float4 lat[D::LAT];
     float4 X[D::XN];
-    // lat + X (+ this pad) are dead after the noise stages; the fused kernel reuses the region for the
-    // vertex-id table of K4 (L^3 * 5 u16)
+    // X (+ this pad) is dead after the noise stages; the fused kernel reuses the region for the vertex-id table of K4
+    // (L^3 * 5 u16).  lat is NOT part of it: it is dead after stage X already, and the fused kernel's spare warp hashes
+    // the NEXT chunk's lattice into it while this chunk's columns are walked (see noise_chunk_spec, PF) -- those
+    // gradients must survive this chunk's K2..K4.
     static constexpr int VID_BYTES = D::L * D::L * D::L * 5 * 2;
-    static constexpr int PAD0 = VID_BYTES > (D::LAT + D::XN) * 16 ? ((VID_BYTES - (D::LAT + D::XN) * 16 + 15) / 16) * 16 : 16;
+    static constexpr int PAD0 = VID_BYTES > D::XN * 16 ? ((VID_BYTES - D::XN * 16 + 15) / 16) * 16 : 16;
     static constexpr int PAD = PAD0 > D::GTOP * 16 ? PAD0 : D::GTOP * 16;   // >= one X row: see stage X (PRUNE)
     unsigned char xpad[PAD];
+    float4 lat[D::LAT];
     float dens[D::DSTRIDE];
     float4 grad[16];
     float4 axis[NOCT][D::L + 1];   // (d, d - 1, fade(d), -) per octave and lattice index
-    float terr[32];            // adj_z - fmod(adj_z, mod): exact multiple of the terrace step
+    float terr[2][16];         // adj_z - fmod(adj_z, mod) - 1 of this chunk / the prefetched next chunk
     uint32_t mask[D::L * D::L + 3];
     uint8_t perm[256];
     int red[4];
 };
+static_assert(SpecDims<12, 3>::L <= 16 && SpecDims<10, 3>::L <= 16, "terr rows hold 16 entries");
+
+// terrace term of perlin_util.rs:27-28, minus 1: every octave value is carried as u = v / (2 lim) + 1/2 in [0, 1]
+// (see stage YZ) and sum_o lim_o = 1.  Tabulated per z layer at context creation by the SAME device function
+// (k_terrace_table), so a table hit is bit-identical to the in-place evaluation.
+__device__ __forceinline__ float terrace_minus_one(const DevCfg& cfg, int k, int pz) {
+    float adj, fm;
+    terrace_terms(cfg, k, pz, adj, fm);
+    return __fsub_rn(__fsub_rn(adj, fm), 1.0f);
+}
+__device__ __forceinline__ float terrace_lookup(const DevCfg& cfg, int k, int pz) {
+    const unsigned dz = (unsigned)(pz - cfg.terr_z0);
+    if (cfg.terr_tab != nullptr && dz < (unsigned)cfg.terr_nz) return __ldg(cfg.terr_tab + dz * 16u + (unsigned)k);
+    return terrace_minus_one(cfg, k, pz);
+}
+__global__ void __launch_bounds__(256) k_terrace_table(DevCfg cfg, float* __restrict__ tab, int z0, int nz) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nz * 16; t += gridDim.x * blockDim.x) {
+        const int k = t & 15;
+        tab[t] = k < cfg.L ? terrace_minus_one(cfg, k, z0 + (t >> 4)) : 0.f;
+    }
+}
+
+// stage H of one chunk for the items t = first, first + step, ...: the gradient vector of every touched noise-lattice point
+template <int ST, int NOCT>
+__device__ __forceinline__ void noise_stage_h(SpecSmem<ST, NOCT>& sm, int px, int py, int pz, int first, int step) {
+    using D = SpecDims<ST, NOCT>;
+#pragma unroll
+    for (int o = 0; o < NOCT; ++o) {
+        const int G = D::G(o), F = 1 << o, base = D::lat_base(o);
+        for (int t = first; t < G * G * G; t += step) {
+            const int cx = t / (G * G), r = t - cx * G * G, cy = r / G, cz = r - cy * G;
+            const uint32_t h = sm.perm[sm.perm[sm.perm[(F * px + cx) & 255] ^ ((F * py + cy) & 255)] ^ ((F * pz + cz) & 255)];
+            sm.lat[base + t] = sm.grad[h & 15u];
+        }
+    }
+}
 
 // stages H, X, YZ for one chunk; leaves densities in sm.dens and column sign masks in sm.mask.
 // Returns (block-uniform) CF_ALL_GT | CF_ANY_LT.  All threads must call; ends with a barrier.
-template <int ST, int NOCT, int NT /*threads of the CTA: SpecDims::NT or ::NTF*/>
+//
+// PF (fused kernel, NT = NTF: one warp more than the columns need): while warps 0..5 walk the columns of THIS chunk
+// (stage YZ, the longest stage), the spare warp hashes the NEXT chunk's lattice (stage H) and looks up its terrace
+// terms -- lat is dead after stage X, the next ticket is known by then.  The next call then starts at stage X
+// (lat_ready): one block barrier and the whole hash-chain latency (3 dependent shared-memory loads per lattice point,
+// 14 % of the kernel's stall samples at config 3, 58 % of them at the barrier) leave the per-chunk critical path.
+// tb = which half of sm.terr belongs to this chunk (the prefetch writes the other one).
+template <int ST, int NOCT, int NT /*threads of the CTA: SpecDims::NT or ::NTF*/, bool PF = false>
 __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const AxisTables& tab, SpecSmem<ST, NOCT>& sm,
                                                      int px, int py, int pz, unsigned long long* guard_count PHASE_ARG,
-                                                     const Handout* hand = nullptr, Ticket* tk_out = nullptr) {
+                                                     const Handout* hand = nullptr, Ticket* tk_out = nullptr,
+                                                     int tb = 0, bool lat_ready = false) {
     using D = SpecDims<ST, NOCT>;
     constexpr int L = D::L;
     const int tid = threadIdx.x;
@@ -679,25 +727,13 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     uint32_t tk_t = 0;
     if (hand && tid == NT - 1) tk_t = ticket_begin(*hand);
 
-    // ---- stage H --------------------------------------------------------------------------------
-#pragma unroll
-    for (int o = 0; o < NOCT; ++o) {
-        const int G = D::G(o), F = 1 << o, base = D::lat_base(o);
-        for (int t = tid; t < G * G * G; t += NT) {
-            const int cx = t / (G * G), r = t - cx * G * G, cy = r / G, cz = r - cy * G;
-            const uint32_t h = sm.perm[sm.perm[sm.perm[(F * px + cx) & 255] ^ ((F * py + cy) & 255)] ^ ((F * pz + cz) & 255)];
-            sm.lat[base + t] = sm.grad[h & 15u];
-        }
+    // ---- stage H (skipped when the previous call's spare warp has done it) ------------------------------
+    if (!(PF && lat_ready)) {                      // block-uniform
+        noise_stage_h<ST, NOCT>(sm, px, py, pz, tid, NT);
+        if (tid >= NT - 32 && tid - (NT - 32) < L)   // terrace term perlin_util.rs:27-28 (last warp: it has idle lanes later)
+            sm.terr[tb][tid - (NT - 32)] = terrace_lookup(cfg, tid - (NT - 32), pz);
+        __syncthreads();
     }
-    if (tid >= NT - 32 && tid - (NT - 32) < L) {   // terrace term perlin_util.rs:27-28 (last warp: it has idle lanes later)
-        float adj, fm;
-        terrace_terms(cfg, tid - (NT - 32), pz, adj, fm);
-        // minus 1: every octave value is carried as u = v / (2 lim) + 1/2 in [0, 1] (see stage YZ) and
-        // sum_o lim_o = 1
-        sm.terr[tid - (NT - 32)] = __fsub_rn(__fsub_rn(adj, fm), 1.0f);
-    }
-    if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; sm.red[2] = 1; }
-    __syncthreads();
     PHASE_MARK(11);
 
     // ---- stage X --------------------------------------------------------------------------------
@@ -729,9 +765,12 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     // PRUNE: a column with j = S reads the X row "one past" its last kept row with weight ~ 1e-22; that is row 0 of
     // the next x-plane / the next octave (finite values) or, for the very last one, this pad row: keep it finite
     if (D::PRUNE && tid < D::GTOP) sm.X[D::XN + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; sm.red[2] = 1; }
     __syncthreads();
     PHASE_MARK(12);
-    if (hand && tid == NT - 1) *tk_out = ticket_fetch(*hand, tk_t);
+    Ticket nx;
+    nx.chunk = TICKET_DONE; nx.px = nx.py = nx.pz = 0;
+    if (hand && tid == NT - 1) { nx = ticket_fetch(*hand, tk_t); if (!PF) *tk_out = nx; }
 
     // ---- stage YZ -------------------------------------------------------------------------------
     // lanes of this warp that own a column: taken while the warp is still converged, so that the votes at the end
@@ -765,7 +804,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         float nearest = 3.0e38f;                  // min |iso - iso_level| of the column: one FMNMX per sample
 #pragma unroll
         for (int k = 0; k < L; ++k) {
-            float total = sm.terr[k];                                    // terrace term - 1
+            float total = sm.terr[tb][k];                                // terrace term - 1
 #pragma unroll
             for (int o = 0; o < NOCT; ++o) {
                 const int c = D::cell(o, k);
@@ -814,6 +853,16 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             if (w_any) sm.red[1] = 1;
             if (!w_solid) sm.red[2] = 0;
         }
+    } else if (PF && tid >= NT - 32) {
+        // the spare warp: stage H + terrace terms of the NEXT chunk (its ticket sits in lane 31's registers)
+        const int lane = tid - (NT - 32);
+        const uint32_t nchunk = __shfl_sync(0xFFFFFFFFu, nx.chunk, 31);
+        const int npx = __shfl_sync(0xFFFFFFFFu, nx.px, 31), npy = __shfl_sync(0xFFFFFFFFu, nx.py, 31), npz = __shfl_sync(0xFFFFFFFFu, nx.pz, 31);
+        if (nchunk != TICKET_DONE) {
+            noise_stage_h<ST, NOCT>(sm, npx, npy, npz, lane, 32);
+            if (lane < L) sm.terr[tb ^ 1][lane] = terrace_lookup(cfg, lane, npz);
+        }
+        if (lane == 31) *tk_out = nx;
     }
     __syncthreads();
     return (sm.red[0] ? CF_ALL_GT : 0u) | (sm.red[1] ? CF_ANY_LT : 0u) | (sm.red[2] ? CF_ALL_LT : 0u);
@@ -852,6 +901,16 @@ k_noise_spec(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTab
 // Shared extraction helpers (small path): sign bits -> per-column masks -> cases
 // ---------------------------------------------------------------------------------------
 struct ChunkCounts { uint32_t n_verts, n_inds, flags, pad; };
+
+// Every chunk's range of the packed arenas starts on a 16-byte boundary: vertex allocations are rounded up to an
+// even count (2 x 24 B), index allocations to a multiple of 16 bytes.  That is what lets the emit stage write whole
+// 16-byte vectors (shared-memory staged, warp-contiguous) -- to HBM or, in the gather path, over NVLink into another
+// GPU's memory, where partial-sector stores cost a full packet each.  Descriptors carry the exact counts.
+#define UW_VSTAGE_VERTS 16                               // vertices per warp and staging round
+#define UW_VSTAGE_BYTES (UW_VSTAGE_VERTS * 24)
+__host__ __device__ __forceinline__ uint32_t pad_verts(uint32_t nv) { return (nv + 1u) & ~1u; }
+template <typename IndexT>
+__host__ __device__ __forceinline__ uint32_t pad_inds(uint32_t ni) { return (ni + (16u / sizeof(IndexT)) - 1u) & ~((16u / (uint32_t)sizeof(IndexT)) - 1u); }
 
 __device__ __forceinline__ uint32_t own_mask_of(int x, int y, int z) {
     // SURVEY App. B.4 ownership table: edges this cell is the FIRST (scan order) holder of
@@ -1197,7 +1256,7 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restr
                                                       BatchTotals* __restrict__ totals,
                                                       unsigned long long vcap, unsigned long long icap,
                                                       ScanPart* __restrict__ part, uint32_t* __restrict__ flag,
-                                                      ScanCtl* __restrict__ ctl, uint32_t epoch) {
+                                                      ScanCtl* __restrict__ ctl, uint32_t epoch, uint32_t ipad_mask) {
     __shared__ uint32_t s_w[4][32];
     __shared__ unsigned long long s_c[2][32];
     __shared__ uint32_t s_ca[2][32];
@@ -1213,8 +1272,10 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restr
     if (idx < n) { px = pos[3 * idx]; py = pos[3 * idx + 1]; pz = pos[3 * idx + 2]; }
     const uint32_t act = c.y > 0 ? 1u : 0u, blank = (idx < n && (c.z & CF_ALL_GT)) ? 1u : 0u;
 
-    // tile-local inclusive scans of (verts, inds, active, blank)
-    uint32_t xv = c.x, xi = c.y, xa = act | (blank << 16);
+    // tile-local inclusive scans of (verts, inds, active, blank); a chunk OCCUPIES padded counts (16-byte aligned
+    // allocations, see pad_verts / pad_inds), its descriptor carries the exact ones
+    const uint32_t pv = pad_verts(c.x), pi = (c.y + ipad_mask) & ~ipad_mask;
+    uint32_t xv = pv, xi = pi, xa = act | (blank << 16);
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, xv, d), b = __shfl_up_sync(0xFFFFFFFFu, xi, d),
@@ -1241,8 +1302,8 @@ __global__ void __launch_bounds__(1024) k_scan_chunks(const ChunkCounts* __restr
         }
     }
     __syncthreads();
-    const uint32_t lv = (warp ? s_w[0][warp - 1] : 0u) + xv - c.x;          // exclusive, tile-local
-    const uint32_t li = (warp ? s_w[1][warp - 1] : 0u) + xi - c.y;
+    const uint32_t lv = (warp ? s_w[0][warp - 1] : 0u) + xv - pv;           // exclusive, tile-local
+    const uint32_t li = (warp ? s_w[1][warp - 1] : 0u) + xi - pi;
     const uint32_t la = ((warp ? s_w[2][warp - 1] : 0u) + xa - (act | (blank << 16))) & 0xFFFFu;
     const uint32_t tile_v = s_w[0][31], tile_i = s_w[1][31], tile_a = s_w[2][31] & 0xFFFFu, tile_b = s_w[2][31] >> 16;
 
@@ -1446,7 +1507,7 @@ __device__ __forceinline__ void owner_of(int e, int x, int y, int z, int& ox, in
 // ---------------------------------------------------------------------------------------
 #define UW_SMALL_MAX_CELLS ((UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1) * (UW_SMALL_MAX_L - 1))
 #ifndef UW_VLIST_CAP
-#define UW_VLIST_CAP 3072
+#define UW_VLIST_CAP 2816    // (3072 before the lattice table moved out of the region K4's vertex-id table aliases)
 #endif
 #define UW_EDGE_KINDS 5      // +x, -x, +y, +z, -z  (-y never occurs: edges 8..11 all run +y)
 
@@ -1455,7 +1516,12 @@ struct EmitSmem {
     uint16_t* vlist; uint16_t* vid; uint8_t* cs; uint32_t* lut; uint16_t* eoff;
     const float* powtab;            // McTables::powtab in shared memory
     const uint64_t* rows;           // McTables::rows in shared memory (the L1 left beside 4 x 55 KB of shared memory does not keep it)
+    // Output staging (see emit_verts / emit_indices): both alias tables that are dead by then.
+    float* vstage;                  // = vbase region (dead after D1): UW_VSTAGE_BYTES per warp
+    void* istage;                   // = vlist region (dead after D2): UW_VLIST_CAP * 2 bytes
 };
+
+
 
 // per edge: (corner_a lattice offset) * 5 + direction kind, for lattice size L
 __device__ __forceinline__ void fill_edge_offsets(uint16_t* eoff, int L) {
@@ -1473,13 +1539,14 @@ __host__ __device__ inline size_t emit_smem_bytes(const DevCfg& cfg) {
     size_t b = (size_t)cfg.dens_stride * 4;
     b += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
     b += ((size_t)cfg.L2 + 3) / 4 * 16;
-    b += cells2 * 2 * 3;
+    b += cells2 * 2 * 2;
+    b += (cells2 * 2 > 8 * UW_VSTAGE_BYTES ? cells2 * 2 : 8 * UW_VSTAGE_BYTES);      // vbase, reused as the vertex staging of 8 warps
     b += UW_VLIST_CAP * 2;
     b += (((size_t)cfg.L3 * UW_EDGE_KINDS + 7) & ~(size_t)7) * 2;
     b += 256 * 4 + 16 * 2;
     b += 256 * 8 + 48 * 4;
     b += (cells + 15) & ~(size_t)15;
-    return b;
+    return b + 16;                                       // alignment slack of the staging regions
 }
 
 __device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned char* base) {
@@ -1490,10 +1557,12 @@ __device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned 
     s.powtab = (const float*)base;  base += 48 * 4;
     s.bits = (uint32_t*)base;     base += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
     s.mask = (uint32_t*)base;     base += ((size_t)cfg.L2 + 3) / 4 * 16;
-    s.vbase = (uint16_t*)base;    base += cells2 * 2;
+    base = (unsigned char*)(((uintptr_t)base + 15) & ~(uintptr_t)15);           // the staging regions hold 16-byte vectors
+    s.vbase = (uint16_t*)base;    s.vstage = (float*)base;
+    base += (cells2 * 2 > 8 * UW_VSTAGE_BYTES ? cells2 * 2 : 8 * UW_VSTAGE_BYTES);
     s.ibase = (uint16_t*)base;    base += cells2 * 2;
     s.alist = (uint16_t*)base;    base += cells2 * 2;
-    s.vlist = (uint16_t*)base;    base += UW_VLIST_CAP * 2;
+    s.vlist = (uint16_t*)base;    s.istage = (void*)base;    base += UW_VLIST_CAP * 2;
     s.vid = (uint16_t*)base;      base += (((size_t)cfg.L3 * UW_EDGE_KINDS + 7) & ~(size_t)7) * 2;
     s.lut = (uint32_t*)base;      base += 256 * 4;
     s.eoff = (uint16_t*)base;     base += 16 * 2;
@@ -1507,7 +1576,8 @@ struct ChunkShape { uint32_t n_vert, n_ind, n_act; };
 template <int ST>
 __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const EmitSmem& s, uint32_t* s_w,
                                                    uint16_t* __restrict__ tri_cell = nullptr,
-                                                   unsigned long long* alloc_ctr = nullptr, unsigned long long* packed = nullptr) {
+                                                   unsigned long long* alloc_ctr = nullptr, unsigned long long* packed = nullptr,
+                                                   int index_pad_mask = 7 /* 16 / sizeof(IndexT) - 1 */) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int S = ST > 0 ? ST : cfg.S, L = S + 1, ncol = S * S;
 
@@ -1536,7 +1606,8 @@ __device__ __forceinline__ ChunkShape emit_prepare(const DevCfg& cfg, const Emit
     block_scan2(nva, ni, eva, ei, tva, ti, s_w);
     // completion-order packing: claim this chunk's range of the arenas now (one 64-bit atomic); the
     // round trip hides under phases C and D1
-    if (alloc_ctr && tid == 0 && ti > 0) *packed = atomicAdd(alloc_ctr, ((unsigned long long)(tva & 0xFFFFu) << 32) | ti);
+    if (alloc_ctr && tid == 0 && ti > 0)
+        *packed = atomicAdd(alloc_ctr, ((unsigned long long)pad_verts(tva & 0xFFFFu) << 32) | (ti + (uint32_t)index_pad_mask & ~(uint32_t)index_pad_mask));
 
     if (tri_cell && col < ncol) {        // per-cell triangle offsets (the reference's per-cell Vec<Tri>, chunk.rs:167-174)
         uint32_t rt = ei;
@@ -1596,49 +1667,133 @@ __device__ __forceinline__ void emit_fill(const DevCfg& cfg, const McTables* __r
     }
 }
 
-// D2: one thread per vertex of the tile
-template <int ST>
+// D2: one thread per vertex of the tile.  The vertices leave through shared memory: a warp parks 16 of its 32
+// vertices (384 B) in its staging slot and writes them as 24 consecutive 16-byte vectors, twice -- whole sectors,
+// warp-contiguous, instead of 3 x 8-byte stores per lane at a 24-byte stride (which touch every 32-byte sector of
+// the run three times with a third of it each: measured 331 GB/s over NVLink against ~2x that for full vectors).
+// vout + v0 is 16-byte aligned (allocations start on even vertex counts); a tile's odd tail writes one pad vertex.
+template <int ST, bool STAGED>
 __device__ __forceinline__ void emit_verts(const DevCfg& cfg, const EmitSmem& s, const ChunkShape sh, uint32_t v0,
                                            int px, int py, int pz, uw_vert* __restrict__ vout) {
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int S = ST > 0 ? ST : cfg.S;
     const int offx = px * cfg.chunk_size, offy = py * cfg.chunk_size, offz = pz * cfg.chunk_size;
     const uint32_t cnt = min((uint32_t)UW_VLIST_CAP, sh.n_vert - v0);
-    for (uint32_t t = tid; t < cnt; t += NT) {
-        const uint32_t ent = s.vlist[t];
-        const int cell = ent & 0xFFF, e = ent >> 12;
-        const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+    float* stage = s.vstage + warp * (UW_VSTAGE_BYTES / 4);
+    for (uint32_t base = 0; base < cnt; base += NT) {
+        const uint32_t w0 = base + warp * 32u;                       // first vertex of this warp's group
+        if (w0 >= cnt) break;                                        // warp-uniform
+        const uint32_t t = w0 + lane;
         float v[6];
-        make_vertex(cfg, s.dens, x, y, z, e, offx, offy, offz, v, s.powtab);
-        float2* dst = reinterpret_cast<float2*>(vout + v0 + t);
-        dst[0] = make_float2(v[0], v[1]); dst[1] = make_float2(v[2], v[3]); dst[2] = make_float2(v[4], v[5]);
+        if (t < cnt) {
+            const uint32_t ent = s.vlist[t];
+            const int cell = ent & 0xFFF, e = ent >> 12;
+            const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+            make_vertex(cfg, s.dens, x, y, z, e, offx, offy, offz, v, s.powtab);
+        }
+        // Straight from registers (3 x 8-byte stores per lane) when the arena is this GPU's own HBM -- the L2 merges the
+        // partial sectors and the staging costs more issue slots than it saves (measured, profiles/r02_ab_staged_stores.txt:
+        // +7 % at 32 768 chunks) -- and for multi-tile chunks (> UW_VLIST_CAP vertices, worst-case fields only), whose
+        // staging slots alias vbase, which the fill pass of the NEXT tile still reads.
+        if (!STAGED || sh.n_vert > (uint32_t)UW_VLIST_CAP) {
+            // t == cnt on an odd LAST tile: the allocation's pad vertex, zeroed so that the used extent of the arena is defined
+            if (t < cnt || (t == cnt && (cnt & 1u) && v0 + cnt == sh.n_vert)) {
+                if (t == cnt) { v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = 0.f; }
+                float2* dst = reinterpret_cast<float2*>(vout + v0 + t);
+                dst[0] = make_float2(v[0], v[1]); dst[1] = make_float2(v[2], v[3]); dst[2] = make_float2(v[4], v[5]);
+            }
+            continue;
+        }
+        const uint32_t wcnt = min(32u, cnt - w0);
+        float4* gdst = reinterpret_cast<float4*>(vout + v0 + w0);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (wcnt <= 16u * half) break;                           // warp-uniform
+            const uint32_t hcnt = min(16u, wcnt - 16u * half);
+            if ((lane >> 4) == half && t <= cnt) {                    // t == cnt: the pad vertex of an odd tail, zeroed
+                if (t == cnt) { v[0] = v[1] = v[2] = v[3] = v[4] = v[5] = 0.f; }
+                float2* d = reinterpret_cast<float2*>(stage + (lane & 15) * 6);
+                d[0] = make_float2(v[0], v[1]); d[1] = make_float2(v[2], v[3]); d[2] = make_float2(v[4], v[5]);
+            }
+            __syncwarp();
+            const uint32_t n16 = (pad_verts(hcnt) * 3u) >> 1;        // 24 B per vertex = 1.5 vectors
+            if ((uint32_t)lane < n16) gdst[half * 24 + lane] = reinterpret_cast<const float4*>(stage)[lane];
+            __syncwarp();
+        }
     }
 }
 
-// E: indices; every slot is one table lookup keyed by the ordered lattice pair
-template <int ST, typename IndexT>
+// E: indices; every slot is one table lookup keyed by the ordered lattice pair.  The chunk's index buffer is
+// assembled in shared memory (s.istage aliases the vertex list, dead after D2) and leaves as whole 16-byte vectors in
+// one linear sweep; chunks with more indices than the staging holds take several tiles.  iout is 16-byte aligned
+// (index allocations are padded), the last vector may carry up to 7 pad entries inside the chunk's own allocation.
+// ALL threads must call; contains block barriers; the caller has a barrier between D2 and this.
+template <int ST, typename IndexT, bool STAGED>
 __device__ __forceinline__ void emit_indices(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
                                              const ChunkShape sh, IndexT* __restrict__ iout) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const int S = ST > 0 ? ST : cfg.S, L = S + 1;
-    for (uint32_t a = tid; a < sh.n_act; a += NT) {
-        const int cell = s.alist[a];
-        const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
-        const uint64_t row = s.rows[s.cs[cell]];
-        const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
-        const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
-        IndexT* dst = iout + s.ibase[a];
-        const uint16_t* vid = s.vid + lbase;
+    constexpr uint32_t TILE = UW_VLIST_CAP * 2 / sizeof(IndexT), PER16 = 16 / sizeof(IndexT);
+    IndexT* stage = reinterpret_cast<IndexT*>(s.istage);
+    if constexpr (!STAGED) {                                         // own HBM: per-cell runs straight from registers
+        for (uint32_t a = tid; a < sh.n_act; a += NT) {
+            const int cell = s.alist[a];
+            const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+            const uint64_t row = s.rows[s.cs[cell]];
+            const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
+            const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
+            IndexT* dst = iout + s.ibase[a];
+            const uint16_t* vid = s.vid + lbase;
 #pragma unroll
-        for (int k = 0; k < 15; k += 3) {                              // a triangle at a time: three independent lookups in flight
-            const uint32_t e0 = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
-            if (e0 == 15u) break;
-            const uint32_t e1 = ((k + 1 < 8 ? rlo : rhi) >> (4 * ((k + 1) & 7))) & 15u;
-            const uint32_t e2 = ((k + 2 < 8 ? rlo : rhi) >> (4 * ((k + 2) & 7))) & 15u;
-            const uint32_t o0 = s.eoff[e0], o1 = s.eoff[e1], o2 = s.eoff[e2];
-            const IndexT i0 = (IndexT)vid[o0], i1 = (IndexT)vid[o1], i2 = (IndexT)vid[o2];   // `ind as u16`, chunk.rs:243
-            dst[k] = i0; dst[k + 1] = i1; dst[k + 2] = i2;
+            for (int k = 0; k < 15; k += 3) {                        // a triangle at a time: three independent lookups in flight
+                const uint32_t e0 = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
+                if (e0 == 15u) break;
+                const uint32_t e1 = ((k + 1 < 8 ? rlo : rhi) >> (4 * ((k + 1) & 7))) & 15u;
+                const uint32_t e2 = ((k + 2 < 8 ? rlo : rhi) >> (4 * ((k + 2) & 7))) & 15u;
+                const uint32_t o0 = s.eoff[e0], o1 = s.eoff[e1], o2 = s.eoff[e2];
+                const IndexT i0 = (IndexT)vid[o0], i1 = (IndexT)vid[o1], i2 = (IndexT)vid[o2];   // `ind as u16`, chunk.rs:243
+                dst[k] = i0; dst[k + 1] = i1; dst[k + 2] = i2;
+            }
         }
+        if ((uint32_t)tid < PER16 && sh.n_ind + tid < pad_inds<IndexT>(sh.n_ind)) iout[sh.n_ind + tid] = (IndexT)0;   // pad entries, defined
+        return;
+    }
+    for (uint32_t lo = 0; lo < sh.n_ind; lo += TILE) {
+        const uint32_t hi = min(lo + TILE, sh.n_ind);
+        if (lo) __syncthreads();                                     // previous tile fully copied out
+        for (uint32_t a = tid; a < sh.n_act; a += NT) {
+            const uint32_t ib = s.ibase[a];
+            if (ib >= hi || ib + 15u <= lo) continue;                // the cell's run (<= 15 indices) misses this tile
+            const int cell = s.alist[a];
+            const int x = cell / (S * S), r = cell - x * S * S, y = r / S, z = r - y * S;
+            const uint64_t row = s.rows[s.cs[cell]];
+            const uint32_t rlo = (uint32_t)row, rhi = (uint32_t)(row >> 32);
+            const int lbase = ((x * L + y) * L + z) * UW_EDGE_KINDS;
+            const uint16_t* vid = s.vid + lbase;
+            const bool inside = ib >= lo && ib + 15u <= hi;          // common case: no per-entry range test
+#pragma unroll
+            for (int k = 0; k < 15; k += 3) {                        // a triangle at a time: three independent lookups in flight
+                const uint32_t e0 = ((k < 8 ? rlo : rhi) >> (4 * (k & 7))) & 15u;
+                if (e0 == 15u) break;
+                const uint32_t e1 = ((k + 1 < 8 ? rlo : rhi) >> (4 * ((k + 1) & 7))) & 15u;
+                const uint32_t e2 = ((k + 2 < 8 ? rlo : rhi) >> (4 * ((k + 2) & 7))) & 15u;
+                const uint32_t o0 = s.eoff[e0], o1 = s.eoff[e1], o2 = s.eoff[e2];
+                const IndexT i0 = (IndexT)vid[o0], i1 = (IndexT)vid[o1], i2 = (IndexT)vid[o2];   // `ind as u16`, chunk.rs:243
+                const uint32_t q = ib + k - lo;                      // may wrap below lo: the range tests catch it
+                if (inside) { stage[q] = i0; stage[q + 1] = i1; stage[q + 2] = i2; }
+                else {
+                    if (ib + k >= lo && ib + k < hi) stage[q] = i0;
+                    if (ib + k + 1 >= lo && ib + k + 1 < hi) stage[q + 1] = i1;
+                    if (ib + k + 2 >= lo && ib + k + 2 < hi) stage[q + 2] = i2;
+                }
+            }
+        }
+        const uint32_t n16 = (hi - lo + PER16 - 1) / PER16;
+        if ((uint32_t)tid < PER16 && hi - lo + tid < n16 * PER16) stage[hi - lo + tid] = (IndexT)0;   // pad entries of the last vector
+        __syncthreads();
+        uint4* gdst = reinterpret_cast<uint4*>(iout + lo);
+        const uint4* src = reinterpret_cast<const uint4*>(stage);
+        for (uint32_t t = tid; t < n16; t += NT) gdst[t] = src[t];
     }
 }
 
@@ -1679,19 +1834,20 @@ __device__ __forceinline__ void emit_tris(const DevCfg& cfg, const McTables* __r
     }
 }
 
-// everything after the first fill + barrier
-template <int ST, typename IndexT>
+// everything after the first fill + barrier.  ALL threads must call (block barriers inside).
+template <int ST, typename IndexT, bool STAGED>
 __device__ __forceinline__ void emit_rest(const DevCfg& cfg, const McTables* __restrict__ mc, const EmitSmem& s,
                                           const ChunkShape sh, int px, int py, int pz,
                                           uw_vert* __restrict__ vout, IndexT* __restrict__ iout) {
-    emit_verts<ST>(cfg, s, sh, 0, px, py, pz, vout);
+    emit_verts<ST, STAGED>(cfg, s, sh, 0, px, py, pz, vout);
     for (uint32_t v0 = UW_VLIST_CAP; v0 < sh.n_vert; v0 += UW_VLIST_CAP) {
         __syncthreads();
         emit_fill<ST>(cfg, mc, s, sh, v0);
         __syncthreads();
-        emit_verts<ST>(cfg, s, sh, v0, px, py, pz, vout);
+        emit_verts<ST, STAGED>(cfg, s, sh, v0, px, py, pz, vout);
     }
-    emit_indices<ST, IndexT>(cfg, mc, s, sh, iout);
+    if (STAGED) __syncthreads();                       // the vertex list is dead: its memory becomes the index staging
+    emit_indices<ST, IndexT, STAGED>(cfg, mc, s, sh, iout);
 }
 
 template <int ST, typename IndexT>
@@ -1726,7 +1882,7 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ DevC
         const ChunkShape sh = emit_prepare<ST>(cfg, s, s_w, tri_cell ? tri_cell + (size_t)chunk * (ncell + 1) : nullptr);
         emit_fill<ST>(cfg, mc, s, sh, 0);
         __syncthreads();
-        emit_rest<ST, IndexT>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
+        emit_rest<ST, IndexT, false>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], verts + d.vert_offset, inds + d.index_offset);
         if (tris) emit_tris<ST>(cfg, mc, s, sh, d.pos[0], d.pos[1], d.pos[2], tris + d.index_offset / 3u);
         __syncthreads();
     }
@@ -2319,8 +2475,10 @@ struct ScanSlot { unsigned long long v, i; };     // bits 63..62: 0 = empty, 1 =
 template <int ST, int NOCT>
 struct FusedSmem {
     SpecSmem<ST, NOCT> n;                             // n.lat / n.X are dead after K1 and reused by K4 (vid)
-    uint16_t vlist[UW_VLIST_CAP];
-    uint16_t vbase[ST * ST * ST + 8];                 // vbase / ibase / alist: one entry per SURFACE cell (worst case: all)
+    static constexpr int VSTAGE_U16 = (SpecDims<ST, NOCT>::NTF / 32) * (UW_VSTAGE_BYTES / 2);
+    alignas(16) uint16_t vlist[UW_VLIST_CAP];         // K4 vertex list; dead after D2 -> index staging (emit_indices)
+    // vbase / ibase / alist: one entry per SURFACE cell (worst case: all).  vbase is dead after D1 -> vertex staging
+    alignas(16) uint16_t vbase[ST * ST * ST + 8 > VSTAGE_U16 ? ST * ST * ST + 8 : VSTAGE_U16];
     uint16_t ibase[ST * ST * ST + 8];
     uint16_t alist[ST * ST * ST + 8];
     uint64_t rows[256];
@@ -2387,7 +2545,13 @@ __device__ __forceinline__ void lookback_block(ScanSlot* st, uint32_t c, unsigne
 #ifndef UW_FUSED_MINB
 #define UW_FUSED_MINB 4
 #endif
-template <int ST, int NOCT, typename IndexT>
+#ifndef UW_FUSED_PREFETCH_H          // the spare warp hashes the next chunk's lattice during stage YZ (A/B switch)
+#define UW_FUSED_PREFETCH_H (UW_FUSED_EXTRA_WARPS == 1)
+#endif
+// PEER: the output arenas are another GPU's memory (gather path): vertices and indices leave through shared memory
+// as whole 16-byte vectors (see emit_verts / emit_indices).  A separate instantiation, so that the kernel that writes
+// the GPU's own HBM is exactly the register-store code (both in one kernel cost the local path 7 %, measured).
+template <int ST, int NOCT, typename IndexT, bool PEER>
 __global__ void __launch_bounds__(SpecDims<ST, NOCT>::NTF, UW_FUSED_MINB)
 k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTables tab,
               const uint8_t* __restrict__ g_perm, const McTables* __restrict__ mc,
@@ -2413,13 +2577,14 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     // lat and X are adjacent members of SpecSmem)
     EmitSmem es;
     es.dens = sm.n.dens; es.bits = nullptr; es.mask = sm.n.mask;
-    es.vid = reinterpret_cast<uint16_t*>(sm.n.lat);
+    es.vid = reinterpret_cast<uint16_t*>(sm.n.X);
     es.vlist = sm.vlist; es.vbase = sm.vbase; es.ibase = sm.ibase; es.alist = sm.alist;
     es.cs = sm.cs; es.lut = sm.lut; es.eoff = sm.eoff; es.rows = sm.rows; es.powtab = sm.powtab;
+    es.vstage = reinterpret_cast<float*>(sm.vbase); es.istage = sm.vlist;
     using NS = SpecSmem<ST, NOCT>;
-    static_assert(offsetof(NS, X) == offsetof(NS, lat) + sizeof(sm.n.lat), "lat and X must be adjacent");
     static_assert(offsetof(NS, xpad) == offsetof(NS, X) + sizeof(sm.n.X), "X and xpad must be adjacent");
-    static_assert(sizeof(sm.n.lat) + sizeof(sm.n.X) + sizeof(sm.n.xpad) >= (size_t)L * L * L * UW_EDGE_KINDS * 2, "vid must fit");
+    static_assert(sizeof(sm.n.X) + sizeof(sm.n.xpad) >= (size_t)L * L * L * UW_EDGE_KINDS * 2, "vid must fit");
+    static_assert(sizeof(FusedSmem<ST, NOCT>) <= (233472 / UW_FUSED_MINB) - 1024, "shared memory budget of UW_FUSED_MINB CTAs per SM");
 
     // first ticket; later ones are requested inside K1 (see noise_chunk_spec) and published at the end of
     // the iteration, so chunks are still handed out on demand (committing a whole chunk ahead was measured
@@ -2460,6 +2625,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     long long t_phase = clock64();
     if (tid == 0 && blockIdx.x < 1024) { g_cta[blockIdx.x][0] = gtimer(); g_cta[blockIdx.x][2] = 0; g_cta[blockIdx.x][3] = 0; }
 #endif
+    int tb = 0;                                            // half of sm.n.terr that belongs to the current chunk
+    bool lat_ready = false;                                // the previous iteration's spare warp has run stage H for this chunk
     while (true) {
         const uint32_t chunk = (uint32_t)sm.cur[0];
         if (chunk == TICKET_DONE) break;
@@ -2469,8 +2636,9 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         nxt.chunk = TICKET_DONE; nxt.px = nxt.py = nxt.pz = 0;
 
         // ---- K1 ---------------------------------------------------------------------------------
-        const uint32_t fl = noise_chunk_spec<ST, NOCT, D::NTF>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS,
-                                                       &hand, &nxt);
+        const uint32_t fl = noise_chunk_spec<ST, NOCT, D::NTF, UW_FUSED_PREFETCH_H != 0>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS,
+                                                       &hand, &nxt, tb, lat_ready);
+        tb ^= 1; lat_ready = true;
         PHASE_MARK(1);                                     // K1 noise
         if (dens_out) {
             float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);
@@ -2484,8 +2652,9 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         unsigned long long packed = 0;
         if ((fl & (CF_ANY_LT | CF_ALL_LT)) == CF_ANY_LT)   // all-empty and all-full chunks skip K2..K4 (north_star's ballot skip)
             sh = emit_prepare<ST>(cfg, es, sm.w, tri_cell ? tri_cell + (size_t)chunk * (ST * ST * ST + 1) : nullptr,
-                                  ordered ? nullptr : &ctr->alloc, &packed);
+                                  ordered ? nullptr : &ctr->alloc, &packed, (int)(16 / sizeof(IndexT)) - 1);
         const uint32_t nv = sh.n_vert, ni = sh.n_ind;
+        const uint32_t nv_pad = pad_verts(nv), ni_pad = pad_inds<IndexT>(ni);   // what the chunk occupies in the arenas
         PHASE_MARK(2);                                     // K2 prepare
 
         // ---- K3: this chunk's offsets in the packed arenas ------------------------------------------------
@@ -2498,13 +2667,13 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         if (ordered) {
             if (tid == 0) {
                 const unsigned long long tag = chunk == 0 ? SCAN_PFX : SCAN_AGG;
-                atomicExch(&scan[chunk].v, tag | nv);
-                atomicExch(&scan[chunk].i, tag | ni);
+                atomicExch(&scan[chunk].v, tag | nv_pad);
+                atomicExch(&scan[chunk].i, tag | ni_pad);
             }
             if (chunk > 0) lookback_block(scan, chunk, ev, ei, sm.part);
             if (tid == 0 && chunk > 0) {
-                atomicExch(&scan[chunk].v, SCAN_PFX | (ev + nv));
-                atomicExch(&scan[chunk].i, SCAN_PFX | (ei + ni));
+                atomicExch(&scan[chunk].v, SCAN_PFX | (ev + nv_pad));
+                atomicExch(&scan[chunk].i, SCAN_PFX | (ei + ni_pad));
             }
             packed = (ev << 32) | ei;
         }
@@ -2517,8 +2686,8 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             __syncthreads();
             PHASE_MARK(4);                                 // K4 D1 fill
             ev = sm.part[0] >> 32; ei = sm.part[0] & 0xFFFFFFFFull;
-            if (ev + nv <= vcap && ei + ni <= icap) {
-                emit_rest<ST, IndexT>(cfg, mc, es, sh, px, py, pz, verts + ev, inds + ei);
+            if (ev + nv_pad <= vcap && ei + ni_pad <= icap) {              // block-uniform
+                emit_rest<ST, IndexT, PEER>(cfg, mc, es, sh, px, py, pz, verts + ev, inds + ei);
                 if (tris) emit_tris<ST>(cfg, mc, es, sh, px, py, pz, tris + ei / 3u);
             }
             PHASE_MARK(5);                                 // K4 D2 + E (thread 0's own share)
@@ -2538,14 +2707,14 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             }
             if (fl & CF_ALL_GT) atomicAdd(&totals->n_blank, 1u);
             if (ordered && chunk == n - 1) {
-                totals->n_verts = ev + nv; totals->n_inds = ei + ni;
-                if (ev + nv > vcap || ei + ni > icap || ev + nv > 0xFFFFFFFFull || ei + ni > 0xFFFFFFFFull)
+                totals->n_verts = ev + nv_pad; totals->n_inds = ei + ni_pad;
+                if (ev + nv_pad > vcap || ei + ni_pad > icap || ev + nv_pad > 0xFFFFFFFFull || ei + ni_pad > 0xFFFFFFFFull)
                     totals->overflow = 1u;
             }
-            if (!ordered && ni > 0 && (ev + nv > vcap || ei + ni > icap)) atomicMax(&totals->overflow, 1u);
+            if (!ordered && ni > 0 && (ev + nv_pad > vcap || ei + ni_pad > icap)) atomicMax(&totals->overflow, 1u);
             // completion-order packing keeps (vertices << 32 | indices) in ONE 64-bit counter: an index total beyond
             // 2^32 would carry into the vertex half.  The chunk whose claim crosses the boundary sees it here.
-            if (!ordered && ni > 0 && (ei + ni > 0xFFFFFFFFull || ev + nv > 0xFFFFFFFFull)) atomicMax(&totals->overflow, 2u);
+            if (!ordered && ni > 0 && (ei + ni_pad > 0xFFFFFFFFull || ev + nv_pad > 0xFFFFFFFFull)) atomicMax(&totals->overflow, 2u);
         }
         if (tid == D::NTF - 1) { sm.cur[0] = (int)nxt.chunk; sm.cur[1] = nxt.px; sm.cur[2] = nxt.py; sm.cur[3] = nxt.pz; }
         __syncthreads();                                   // chunk fully emitted, smem reusable, next ticket visible
@@ -2587,6 +2756,119 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             BatchTotals z; z.n_verts = 0; z.n_inds = 0; z.n_active = 0; z.overflow = 0; z.n_blank = 0; z.n_mesh = 0;
             ctr_next->totals = z;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Collision ray casts against the per-cell triangle lists (SURVEY 8f-1's consumer): util::Tri::intersects
+// (util.rs:22-59) over the triangles Chunk::tris_around (chunk.rs:315-342) returns for the chunks a boid visits
+// (boid.rs:175-208), for a whole flock of rays at once.  cgmath's operation order, f32, unfused.
+//   k_chunk_table : chunk position -> chunk index of the last build (open addressing; the key is compared against
+//                   the descriptor's position, so the table holds indices only)
+//   k_raycast     : one warp per ray.  At most 2 x 2 x 2 chunks lie within +-wall_range world units (wall_range <
+//                   chunk_size); lanes stride over the (<= (2 wall_range + 1)^3) cells of each, walk the cell's
+//                   triangles, keep the smallest hit distance; warp min; -1 = every test returned None.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pos_hash(int x, int y, int z) {
+    uint32_t h = (uint32_t)x * 0x9E3779B1u ^ (uint32_t)y * 0x85EBCA77u ^ (uint32_t)z * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    return h;
+}
+
+__global__ void __launch_bounds__(256) k_chunk_table(const uw_chunk_desc* __restrict__ descs, uint32_t n,
+                                                     uint32_t* __restrict__ table, uint32_t mask) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uw_chunk_desc d = descs[i];
+        uint32_t slot = pos_hash(d.pos[0], d.pos[1], d.pos[2]) & mask;
+        while (atomicCAS(&table[slot], 0u, i + 1u) != 0u) slot = (slot + 1u) & mask;     // table is >= 2n slots: terminates
+    }
+}
+
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));     // cgmath: (x x' + y y') + z z'
+}
+
+// util.rs:22-59; returns t or -1 (None)
+__device__ __forceinline__ float tri_intersects(const uw_tri& tr, float px, float py, float pz, float dx, float dy, float dz, float range) {
+    const float nx = tr.normal[0], ny = tr.normal[1], nz = tr.normal[2];
+    const float dnd = dot3_rn(nx, ny, nz, dx, dy, dz);
+    if (fabsf(dnd) < 1e-5f) return -1.0f;
+    const float t = __fdiv_rn(dot3_rn(nx, ny, nz, __fsub_rn(tr.verts[0][0], px), __fsub_rn(tr.verts[0][1], py), __fsub_rn(tr.verts[0][2], pz)), dnd);
+    if (t < 0.0f || t > range) return -1.0f;
+    const float ix = __fadd_rn(px, __fmul_rn(dx, t)), iy = __fadd_rn(py, __fmul_rn(dy, t)), iz = __fadd_rn(pz, __fmul_rn(dz, t));
+    float q[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float* a = tr.verts[k];
+        const float* b = tr.verts[k == 2 ? 0 : k + 1];
+        const float ex = __fsub_rn(b[0], a[0]), ey = __fsub_rn(b[1], a[1]), ez = __fsub_rn(b[2], a[2]);
+        const float wx = __fsub_rn(ix, a[0]), wy = __fsub_rn(iy, a[1]), wz = __fsub_rn(iz, a[2]);
+        const float cx = __fsub_rn(__fmul_rn(ey, wz), __fmul_rn(ez, wy));
+        const float cy = __fsub_rn(__fmul_rn(ez, wx), __fmul_rn(ex, wz));
+        const float cz = __fsub_rn(__fmul_rn(ex, wy), __fmul_rn(ey, wx));
+        q[k] = dot3_rn(cx, cy, cz, nx, ny, nz);
+    }
+    return (q[0] >= 0.0f && q[1] >= 0.0f && q[2] >= 0.0f) ? t : -1.0f;
+}
+
+__global__ void __launch_bounds__(256) k_raycast(const __grid_constant__ DevCfg cfg, const uw_chunk_desc* __restrict__ descs,
+                                                 const uw_tri* __restrict__ tris, const uint16_t* __restrict__ tri_cell,
+                                                 const uint32_t* __restrict__ table, uint32_t mask,
+                                                 const float* __restrict__ origins, const float* __restrict__ dirs,
+                                                 uint32_t n_rays, int wall_range, float* __restrict__ out_t) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const int S = cfg.S, NC1 = S * S * S + 1;
+    const float cs = (float)cfg.chunk_size, wr = (float)wall_range;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rays; r += warps) {
+        const float px = origins[3 * r], py = origins[3 * r + 1], pz = origins[3 * r + 2];
+        const float dx = dirs[3 * r], dy = dirs[3 * r + 1], dz = dirs[3 * r + 2];
+        const float p[3] = {px, py, pz};
+        int ws[3], we[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                                    // boid.rs:177-183
+            ws[k] = (int)floorf(__fdiv_rn(__fsub_rn(p[k], wr), cs));
+            we[k] = (int)floorf(__fdiv_rn(__fadd_rn(p[k], wr), cs));
+        }
+        float best = 3.0e38f;
+        for (int a = ws[0]; a <= we[0]; ++a) for (int b = ws[1]; b <= we[1]; ++b) for (int c = ws[2]; c <= we[2]; ++c) {
+            // world.get_chunk((a, b, c)): warp-uniform probe
+            uint32_t slot = pos_hash(a, b, c) & mask, ci = 0xFFFFFFFFu;
+            for (;;) {
+                const uint32_t e = table[slot];
+                if (e == 0u) break;
+                const uw_chunk_desc& d = descs[e - 1u];
+                if (d.pos[0] == a && d.pos[1] == b && d.pos[2] == c) { ci = e - 1u; break; }
+                slot = (slot + 1u) & mask;
+            }
+            if (ci == 0xFFFFFFFFu) continue;
+            const uint32_t nind = descs[ci].index_count;
+            if (nind == 0u) continue;
+            const uw_tri* ctris = tris + descs[ci].index_offset / 3u;
+            const uint16_t* cstart = tri_cell + (size_t)ci * NC1;
+            const int cp[3] = {a, b, c};
+            int lo[3], hi[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {                                // boid.rs:186-203, chunk.rs:316-326
+                const float local = __fsub_rn(p[k], __fmul_rn((float)cp[k], cs));
+                const int mid = (int)floorf(__fmul_rn(__fdiv_rn(local, cs), (float)S));
+                lo[k] = max(mid - wall_range, 0); hi[k] = min(min(mid + wall_range, S), S - 1);   // cells == S hold nothing
+            }
+            const int ny = hi[1] - lo[1] + 1, nz = hi[2] - lo[2] + 1, ncell = (hi[0] - lo[0] + 1) * ny * nz;
+            if (hi[0] < lo[0] || ny <= 0 || nz <= 0) continue;
+            for (int q = (int)lane; q < ncell; q += 32) {
+                const int x = lo[0] + q / (ny * nz), rem = q % (ny * nz), y = lo[1] + rem / nz, z = lo[2] + rem % nz;
+                const int cell = (x * S + y) * S + z;
+                const uint32_t t0 = cstart[cell], t1 = cstart[cell + 1];
+                for (uint32_t j = t0; j < t1; ++j) {
+                    const float t = tri_intersects(ctris[j], px, py, pz, dx, dy, dz, wr);
+                    if (t >= 0.0f) best = fminf(best, t);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+        if (lane == 0) out_t[r] = best < 3.0e38f ? best : -1.0f;
     }
 }
 

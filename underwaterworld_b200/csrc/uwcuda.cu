@@ -40,6 +40,7 @@ struct uw_ctx {
     bool big_fast_noise = false;            // FP32 plane-tiled noise available for this configuration
     size_t big_noise_smem = 0; int big_noise_blocks_per_sm = 1;
     McTables* d_mc = nullptr;
+    float* d_terr_tab = nullptr;            // terrace terms per z layer (DevCfg::terr_tab)
 
     bool tris = false;              // UW_FLAG_TRIS: per-cell collision triangles
     bool exportable = false;        // UW_FLAG_EXPORTABLE: output arenas are VMM allocations with fd handles
@@ -111,8 +112,8 @@ struct uw_ctx {
     typedef void (*fused32_fn_t)(DevCfg, AxisTables, const uint8_t*, const McTables*, const int32_t*, uint32_t, ScanSlot*,
                                  FusedControl*, FusedControl*, uw_chunk_desc*, uw_vert*, uint32_t*, unsigned long long,
                                  unsigned long long, float*, int, uw_tri*, uint16_t*, uint4*, int, int, unsigned long long, int, FusedSummary*, FusedOut);
-    fused16_fn_t fused16_fn = nullptr;
-    fused32_fn_t fused32_fn = nullptr;
+    fused16_fn_t fused16_fn = nullptr, fused16_peer_fn = nullptr;     // *_peer_fn: staged 16-byte stores (another GPU's memory)
+    fused32_fn_t fused32_fn = nullptr, fused32_peer_fn = nullptr;
     bool use_fused = false;
     int z_lo = 1, z_hi = 0;         // chunk z layers that can hold surface (empty range = unknown: request-order hand-out)
     unsigned long long zcls = 0;    // hand-out class of layer z_lo + i in bits 4i..4i+3 (0 = most likely to hold surface)
@@ -151,8 +152,16 @@ struct uw_ctx {
         uw_chunk_desc* descs = nullptr; uw_vert* verts = nullptr; char* inds = nullptr; GatherHead* head = nullptr;
         uw_chunk_desc* draw = nullptr;
     } gt;
+    bool force_staged = false;          // UW_STAGED_STORES=1 in the environment: staged stores for local arenas too (A/B measurements)
     uint64_t gather_first_chunk = 0;    // request index of the next gather build's first chunk
     bool gather_build = false;          // the build being enqueued writes into the attached segment
+
+    // grow-only device scratch shared by the point-query style entry points (uw_iso_at, uw_raycast_tris,
+    // uw_debug_vertex_colors): no cudaMalloc / cudaFree per call
+    char* d_scratch = nullptr; size_t d_scratch_cap = 0;
+    // uw_raycast_tris: chunk position -> chunk index of the last build
+    uint32_t* d_ray_table = nullptr; uint32_t ray_table_cap = 0, ray_table_mask = 0;
+    uint64_t build_serial = 0, ray_table_serial = ~0ull; int ray_table_set = -1;
 
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -370,6 +379,7 @@ extern "C" void uw_destroy(uw_ctx* c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_perm); cudaFree(c->d_mc); cudaFree(c->d_axis); cudaFree(c->d_totals); cudaFree(c->d_guard); cudaFree(c->d_ctl);
     cudaFree(c->d_scan_part); cudaFree(c->d_scan_flag); cudaFree(c->d_scan_ctl);
+    cudaFree(c->d_scratch); cudaFree(c->d_ray_table); cudaFree(c->d_terr_tab);
     for (auto& b : c->sets) {
         cudaFree(b.d_pos); cudaFree(b.d_dens); cudaFree(b.d_counts); cudaFree(b.d_quarters); cudaFree(b.d_descs); cudaFree(b.d_active);
         cudaFree(b.d_cases);
@@ -420,6 +430,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         c->err = b; return bail(UW_ERR_NO_DEVICE);
     }
     c->num_sms = prop.multiProcessorCount;
+    { const char* e = getenv("UW_STAGED_STORES"); c->force_staged = e && e[0] == '1'; }
     c->host_ptr_ok = prop.unifiedAddressing && prop.canMapHostMemory;
     c->index32 = (cfg->flags & UW_FLAG_INDEX32) != 0 || cfg->internal_size > 22;
     // FP32 factorisation needs chunk-independent fractional parts: chunk_size a power of two
@@ -485,6 +496,16 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
     if (!cu(cudaHostAlloc(&c->h_guard, sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc guard")) return bail(UW_ERR_OOM);
     for (auto& ev : c->ev) if (!cu(cudaEventCreate(&ev), "cudaEventCreate")) return bail(UW_ERR_CUDA);
 
+    // terrace terms of the z layers around the origin, tabulated by the device function the kernels would otherwise
+    // evaluate per chunk (f64 coordinate, IEEE division, fmod): bit-identical by construction
+    if (c->dcfg.L <= 16) {
+        const int z0 = -256, nz = 512;
+        if (!cu(cudaMalloc(&c->d_terr_tab, (size_t)nz * 16 * sizeof(float)), "cudaMalloc terrace table")) return bail(UW_ERR_OOM);
+        k_terrace_table<<<32, 256, 0, c->stream>>>(c->dcfg, c->d_terr_tab, z0, nz);
+        if (!cu(cudaGetLastError(), "k_terrace_table") || !cu(cudaStreamSynchronize(c->stream), "k_terrace_table")) return bail(UW_ERR_CUDA);
+        c->dcfg.terr_tab = c->d_terr_tab; c->dcfg.terr_z0 = z0; c->dcfg.terr_nz = nz;
+    }
+
     // launch geometry / kernel selection
     const DevCfg& d = c->dcfg;
     if (c->big_path) {
@@ -525,12 +546,14 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         if (spec_ok(SpecDims<12, 3>())) {
             c->noise_fn = k_noise_spec<12, 3>; c->spec_noise = true;
             c->noise_threads = SpecDims<12, 3>::NT; c->fused_threads = SpecDims<12, 3>::NTF; c->noise_smem = sizeof(SpecSmem<12, 3>);
-            c->fused16_fn = k_build_fused<12, 3, uint16_t>; c->fused32_fn = k_build_fused<12, 3, uint32_t>;
+            c->fused16_fn = k_build_fused<12, 3, uint16_t, false>; c->fused32_fn = k_build_fused<12, 3, uint32_t, false>;
+            c->fused16_peer_fn = k_build_fused<12, 3, uint16_t, true>; c->fused32_peer_fn = k_build_fused<12, 3, uint32_t, true>;
             c->fused_smem = sizeof(FusedSmem<12, 3>);
         } else if (spec_ok(SpecDims<10, 3>())) {
             c->noise_fn = k_noise_spec<10, 3>; c->spec_noise = true;
             c->noise_threads = SpecDims<10, 3>::NT; c->fused_threads = SpecDims<10, 3>::NTF; c->noise_smem = sizeof(SpecSmem<10, 3>);
-            c->fused16_fn = k_build_fused<10, 3, uint16_t>; c->fused32_fn = k_build_fused<10, 3, uint32_t>;
+            c->fused16_fn = k_build_fused<10, 3, uint16_t, false>; c->fused32_fn = k_build_fused<10, 3, uint32_t, false>;
+            c->fused16_peer_fn = k_build_fused<10, 3, uint16_t, true>; c->fused32_peer_fn = k_build_fused<10, 3, uint32_t, true>;
             c->fused_smem = sizeof(FusedSmem<10, 3>);
         }
         c->use_fused = c->spec_noise && !(cfg->flags & UW_FLAG_STAGED);
@@ -547,7 +570,9 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
                   cu(set_attr((const void*)c->emit32_fn, c->emit_smem), "attr emit32");
         if (ok && c->fused16_fn)
             ok = cu(set_attr((const void*)c->fused16_fn, c->fused_smem), "attr fused16") &&
-                 cu(set_attr((const void*)c->fused32_fn, c->fused_smem), "attr fused32");
+                 cu(set_attr((const void*)c->fused32_fn, c->fused_smem), "attr fused32") &&
+                 cu(set_attr((const void*)c->fused16_peer_fn, c->fused_smem), "attr fused16 peer") &&
+                 cu(set_attr((const void*)c->fused32_peer_fn, c->fused_smem), "attr fused32 peer");
         if (!ok) return bail(UW_ERR_CUDA);
         int nb = 1;
         if (c->fused16_fn && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)c->fused16_fn, c->fused_threads, c->fused_smem) == cudaSuccess && nb > 0)
@@ -801,7 +826,8 @@ static uw_status launch_scan(uw_ctx* c, const int32_t* d_pos, uint32_t n) {
         c->scan_epoch = 1;
     }
     k_scan_chunks<<<tiles, 1024, 0, c->stream>>>(c->B().d_counts, d_pos, n, c->B().d_descs, c->B().d_active, c->d_totals,
-                                                 c->B().vcap, c->B().icap, c->d_scan_part, c->d_scan_flag, c->d_scan_ctl, c->scan_epoch);
+                                                 c->B().vcap, c->B().icap, c->d_scan_part, c->d_scan_flag, c->d_scan_ctl, c->scan_epoch,
+                                                 c->index32 ? 3u : 7u);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     return UW_OK;
@@ -866,19 +892,21 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
     uw_chunk_desc* o_descs = c->B().d_descs; uw_vert* o_verts = c->B().d_verts; void* o_inds = c->B().d_inds;
     unsigned long long o_vcap = c->B().vcap, o_icap = c->B().icap;
     FusedOut fo = {};
+    bool peer = c->force_staged;
     if (c->B().last_gather) {
         const uw_ctx::GatherTarget& g = c->gt;
         o_descs = g.descs + c->gather_first_chunk; o_verts = g.verts; o_inds = g.inds;
         o_vcap = g.info.seg_vcap; o_icap = g.info.seg_icap;
         fo.desc_vbase = (uint32_t)(g.segment * g.info.seg_vcap); fo.desc_ibase = (uint32_t)(g.segment * g.info.seg_icap);
         fo.head = g.head; fo.epoch = g.epoch; fo.drawlist = g.draw;
+        peer = g.ipc || g.info.device != c->device || c->force_staged;                          // NVLink: whole 16-byte vectors
         fo.first_chunk_lo = (uint32_t)c->gather_first_chunk; fo.first_chunk_hi = (uint32_t)(c->gather_first_chunk >> 32);
     }
     if (c->index32)
-        c->fused32_fn<<<grid, c->fused_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
+        (peer ? c->fused32_peer_fn : c->fused32_fn)<<<grid, c->fused_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
             o_descs, o_verts, (uint32_t*)o_inds, o_vcap, o_icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum, fo);
     else
-        c->fused16_fn<<<grid, c->fused_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
+        (peer ? c->fused16_peer_fn : c->fused16_fn)<<<grid, c->fused_threads, c->fused_smem, c->stream>>>(d, c->tab, c->d_perm, c->d_mc, d_pos, n, c->B().d_scan, ctl, ctl_next,
             o_descs, o_verts, (uint16_t*)o_inds, o_vcap, o_icap, d_dens_out, c->ordered ? 1 : 0, c->B().d_tris, c->B().d_tri_cell, d_order, c->z_lo, c->z_hi, c->zcls, (c->cfg.flags & UW_FLAG_ANALYTIC_SKIP) ? 1 : 0, c->B().h_sum, fo);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
@@ -927,6 +955,20 @@ static uw_status enqueue_build(uw_ctx* c, const int32_t* d_pos, uint32_t n, bool
     if (c->profiling) CU_TRY(c, cudaEventRecord(c->ev[4], c->stream));
     CU_TRY(c, cudaEventRecord(c->B().done, c->stream));
     c->B().last_n = n; c->B().last_pos_dev = d_pos; c->B().pending = true;
+    c->build_serial++;
+    return UW_OK;
+}
+
+static uw_status scratch_get(uw_ctx* c, size_t bytes, char** out) {
+    if (bytes > c->d_scratch_cap) {
+        size_t cap = c->d_scratch_cap ? c->d_scratch_cap : (1 << 16);
+        while (cap < bytes) cap *= 2;
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->d_scratch) { cudaFree(c->d_scratch); c->d_scratch = nullptr; c->d_scratch_cap = 0; }
+        CU_TRY(c, cudaMalloc((void**)&c->d_scratch, cap));
+        c->d_scratch_cap = cap;
+    }
+    *out = c->d_scratch;
     return UW_OK;
 }
 
@@ -1682,21 +1724,62 @@ extern "C" uw_status uw_iso_at(uw_ctx* c, const double* pts, uint32_t n, float* 
     if ((!pts || !out) && n) return fail(c, UW_ERR_INVALID, "uw_iso_at: null argument");
     if (n == 0) return UW_OK;
     CU_TRY(c, cudaSetDevice(c->device));
-    double* d_pts = nullptr; float* d_out = nullptr;
-    CU_TRY(c, cudaMalloc(&d_pts, (size_t)n * 3 * sizeof(double)));
-    cudaError_t e = cudaMalloc(&d_out, (size_t)n * sizeof(float));
-    if (e != cudaSuccess) { cudaFree(d_pts); return fail(c, UW_ERR_OOM, "uw_iso_at: cudaMalloc failed"); }
-    e = cudaMemcpyAsync(d_pts, pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) {
+    char* base = nullptr;
+    const size_t pts_bytes = ((size_t)n * 3 * sizeof(double) + 255) & ~(size_t)255;
+    { uw_status st = scratch_get(c, pts_bytes + (size_t)n * sizeof(float), &base); if (st != UW_OK) return st; }
+    double* d_pts = (double*)base; float* d_out = (float*)(base + pts_bytes);
+    CU_TRY(c, cudaMemcpyAsync(d_pts, pts, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    unsigned blocks = (n + 255) / 256;
+    if (blocks > (unsigned)c->num_sms * 8) blocks = c->num_sms * 8;
+    k_iso_points<<<blocks, 256, 0, c->stream>>>(c->dcfg, c->d_perm, d_pts, n, d_out);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return UW_OK;
+}
+
+extern "C" uw_status uw_raycast_tris(uw_ctx* c, const float* origins, const float* dirs, uint32_t n_rays, int32_t wall_range, float* out_t) {
+    if (!c) return UW_ERR_INVALID;
+    if ((!origins || !dirs || !out_t) && n_rays) return fail(c, UW_ERR_INVALID, "uw_raycast_tris: null argument");
+    if (!c->tris) return fail(c, UW_ERR_UNSUPPORTED, "uw_raycast_tris: the context was not created with UW_FLAG_TRIS");
+    if (wall_range < 0 || wall_range >= c->cfg.chunk_size)
+        return fail(c, UW_ERR_INVALID, "uw_raycast_tris: wall_range must be in [0, chunk_size)");
+    if (n_rays == 0) return UW_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (c->sets[0].busy || c->sets[1].busy) return fail(c, UW_ERR_NOT_READY, "uw_raycast_tris: an async batch is in flight");
+    if (c->B().pending) { uw_status st = finish_build(c); if (st != UW_OK) return st; }
+    const uint32_t n = c->B().last_n;
+    if (n == 0) { for (uint32_t i = 0; i < n_rays; ++i) out_t[i] = -1.0f; return UW_OK; }
+    if (c->ray_table_serial != c->build_serial || c->ray_table_set != c->cur) {           // first query after a build: index its chunks
+        uint32_t cap = 1024;
+        while (cap < 2u * n) cap *= 2;
+        if (cap > c->ray_table_cap) {
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            if (c->d_ray_table) { cudaFree(c->d_ray_table); c->d_ray_table = nullptr; c->ray_table_cap = 0; }
+            CU_TRY(c, cudaMalloc((void**)&c->d_ray_table, (size_t)cap * sizeof(uint32_t)));
+            c->ray_table_cap = cap;
+        }
+        c->ray_table_mask = cap - 1;
+        CU_TRY(c, cudaMemsetAsync(c->d_ray_table, 0, (size_t)cap * sizeof(uint32_t), c->stream));
         unsigned blocks = (n + 255) / 256;
         if (blocks > (unsigned)c->num_sms * 8) blocks = c->num_sms * 8;
-        k_iso_points<<<blocks, 256, 0, c->stream>>>(c->dcfg, c->d_perm, d_pts, n, d_out);
-        e = cudaGetLastError();
+        k_chunk_table<<<blocks, 256, 0, c->stream>>>(c->B().d_descs, n, c->d_ray_table, c->ray_table_mask);
+        CU_TRY(c, cudaGetLastError());
+        c->ray_table_serial = c->build_serial; c->ray_table_set = c->cur;
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_pts); cudaFree(d_out);
-    if (e != cudaSuccess) return fail(c, UW_ERR_CUDA, std::string("uw_iso_at: ") + cudaGetErrorString(e));
+    char* base = nullptr;
+    const size_t vb = ((size_t)n_rays * 3 * sizeof(float) + 255) & ~(size_t)255;
+    { uw_status st = scratch_get(c, 2 * vb + (size_t)n_rays * sizeof(float), &base); if (st != UW_OK) return st; }
+    float* d_o = (float*)base; float* d_d = (float*)(base + vb); float* d_t = (float*)(base + 2 * vb);
+    CU_TRY(c, cudaMemcpyAsync(d_o, origins, (size_t)n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(d_d, dirs, (size_t)n_rays * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    unsigned long long blocks = ((unsigned long long)n_rays * 32 + 255) / 256;
+    if (blocks > (unsigned long long)c->num_sms * 8) blocks = (unsigned long long)c->num_sms * 8;
+    k_raycast<<<(unsigned)blocks, 256, 0, c->stream>>>(c->dcfg, c->B().d_descs, c->B().d_tris, c->B().d_tri_cell, c->d_ray_table, c->ray_table_mask,
+                                                      d_o, d_d, n_rays, wall_range, d_t);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out_t, d_t, (size_t)n_rays * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
     return UW_OK;
 }
 
@@ -1705,23 +1788,18 @@ extern "C" uw_status uw_debug_vertex_colors(uw_ctx* c, const float* world_z, con
     if ((!world_z || !level || !out_rgb) && n) return fail(c, UW_ERR_INVALID, "uw_debug_vertex_colors: null argument");
     if (n == 0) return UW_OK;
     CU_TRY(c, cudaSetDevice(c->device));
-    float* d_z = nullptr; uint32_t* d_l = nullptr; float* d_o = nullptr;
-    cudaError_t e = cudaMalloc(&d_z, (size_t)n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d_l, (size_t)n * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&d_o, (size_t)n * 12);
-    if (e != cudaSuccess) { cudaFree(d_z); cudaFree(d_l); cudaFree(d_o); return fail(c, UW_ERR_OOM, "uw_debug_vertex_colors: cudaMalloc failed"); }
-    e = cudaMemcpyAsync(d_z, world_z, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_l, level, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) {
-        unsigned blocks = (n + 255) / 256;
-        if (blocks > (unsigned)c->num_sms * 8) blocks = c->num_sms * 8;
-        k_vertex_colors<<<blocks, 256, 0, c->stream>>>(c->dcfg, c->d_mc, d_z, d_l, n, d_o);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_z); cudaFree(d_l); cudaFree(d_o);
-    if (e != cudaSuccess) return fail(c, UW_ERR_CUDA, std::string("uw_debug_vertex_colors: ") + cudaGetErrorString(e));
+    char* base = nullptr;
+    const size_t a = ((size_t)n * 4 + 255) & ~(size_t)255;
+    { uw_status st = scratch_get(c, 2 * a + (size_t)n * 12, &base); if (st != UW_OK) return st; }
+    float* d_z = (float*)base; uint32_t* d_l = (uint32_t*)(base + a); float* d_o = (float*)(base + 2 * a);
+    CU_TRY(c, cudaMemcpyAsync(d_z, world_z, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(d_l, level, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    unsigned blocks = (n + 255) / 256;
+    if (blocks > (unsigned)c->num_sms * 8) blocks = c->num_sms * 8;
+    k_vertex_colors<<<blocks, 256, 0, c->stream>>>(c->dcfg, c->d_mc, d_z, d_l, n, d_o);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(out_rgb, d_o, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
     return UW_OK;
 }
 

@@ -61,6 +61,30 @@ def broadcast_info(info: Optional[_ffi.UwGatherInfo], src: int = 0, group=None, 
     return info_from_bytes(t.cpu().numpy().tobytes())
 
 
+class _DevMem:
+    """Zero-copy view of raw device memory for torch.as_tensor (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def device_batch_tensors(builder):
+    """(descs, verts, inds) of the builder's last device-resident build as uint8 CUDA tensors that alias the
+    library's arenas (no copy).  Call after builder.sync(); valid until the next build on that builder."""
+    import torch
+    v = builder.device_view()
+    isz = 4 if v.d_inds32 else 2
+    iptr = v.d_inds32 or v.d_inds16
+
+    def wrap(ptr, nbytes):
+        if nbytes == 0 or not ptr:
+            return torch.empty(0, dtype=torch.uint8, device="cuda")
+        return torch.as_tensor(_DevMem(ptr, nbytes), device="cuda")
+
+    return (wrap(v.d_descs, v.n_chunks * DESC_DTYPE.itemsize), wrap(v.d_verts, v.n_verts * VERT_DTYPE.itemsize),
+            wrap(iptr, v.n_inds * isz))
+
+
 class GatherResult:
     """uw_gather_result with numpy conveniences."""
 

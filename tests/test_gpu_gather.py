@@ -264,3 +264,34 @@ def test_raycast_against_collision_triangles_matches_the_reference_loops(uw):
         plain.build(pos[:2])
         with pytest.raises(uw.UwError):
             plain.raycast_tris(org[:1], d[:1])                          # needs UW_FLAG_TRIS
+
+
+def test_pinned_requests_skip_the_host_scan_and_are_validated_on_the_device(uw):
+    """A request of >= 4096 chunks in page-locked memory goes to the device straight from the caller's buffer and is
+    not scanned on the host; the fused kernel checks every position it fetches (|pos| <= 2^24) and
+    the build fails with UW_ERR_INVALID at its wait -- through uw_build and through uw_gather_build alike."""
+    import torch
+    pos = uw.region.box_region((-16, 16), (-16, 16), (-4, 4))          # 8192 chunks
+    pin = torch.from_numpy(pos.copy()).pin_memory()
+    good = pin.numpy()
+    with uw.ChunkBuilder(uw.Perlin(0)) as b, uw.ChunkBuilder(uw.Perlin(0)) as ref_b:
+        ref = ref_b.build(pos)                                          # pageable: staged + scanned on the host
+        got = b.build(good)                                             # pinned: direct
+        assert np.array_equal(got.descs["index_count"], ref.descs["index_count"])
+        bad = torch.from_numpy(pos.copy()).pin_memory()
+        bad.numpy()[5000, 1] = (1 << 24) + 1
+        with pytest.raises(uw.UwError) as e:
+            b.build(bad.numpy())
+        assert e.value.status == 1 and "out of supported range" in str(e.value)      # UW_ERR_INVALID
+        assert np.array_equal(b.build(good).descs["index_count"], ref.descs["index_count"])   # the context recovers
+        info = b.gather_create(1, len(pos), seg_vcap=ref.n_verts, seg_icap=ref.n_inds)
+        b.gather_attach(info, 0)
+        b.gather_build(bad.numpy(), 0)
+        with pytest.raises(uw.UwError) as e:
+            b.sync()
+        assert e.value.status == 1
+        b.gather_build(good, 0)
+        res = b.gather_wait()
+        assert res.n_inds == ref.n_inds
+        b.gather_detach()
+        b.gather_destroy()

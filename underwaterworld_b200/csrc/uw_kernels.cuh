@@ -461,6 +461,8 @@ struct FusedOut {
 // depend on the order.
 struct Ticket { uint32_t chunk; int px, py, pz; };
 #define TICKET_DONE 0xFFFFFFFFu
+#define UW_POS_LIMIT (1 << 24)       // |chunk position| <= 2^24: SURVEY App. A.6 (exact lattice offsets), pos * 16 inside i32
+#define UW_OVERFLOW_BAD_POS 3u       // BatchTotals::overflow code: a position of the request is out of range
 
 struct Handout {
     FusedControl* ctr; const int32_t* pos; uint32_t n;
@@ -469,6 +471,14 @@ struct Handout {
     int z_lo, z_hi; unsigned long long zcls;   // class of layer z_lo + i in bits 4i..4i+3
     uw_chunk_desc* skip;               // UW_FLAG_ANALYTIC_SKIP: provably trivial chunks are answered without being handed out
 };
+
+// Requests handed over in pinned memory are not scanned on the host (6 MB for config 3: 0.3-0.8 ms of one core);
+// the thread that fetches a ticket checks its position instead and the batch fails with UW_ERR_INVALID at its wait.
+__device__ __forceinline__ void check_position(FusedControl* ctr, int px, int py, int pz) {
+    const unsigned lim = 2u * UW_POS_LIMIT;
+    if ((unsigned)(px + UW_POS_LIMIT) > lim || (unsigned)(py + UW_POS_LIMIT) > lim || (unsigned)(pz + UW_POS_LIMIT) > lim)
+        atomicMax(&ctr->totals.overflow, UW_OVERFLOW_BAD_POS);
+}
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
@@ -501,7 +511,7 @@ __device__ __forceinline__ void handout_classify(const Handout& h) {
         const uint32_t c = c0 + threadIdx.x;
         int px = 0, py = 0, pz = 0;
         bool valid = c < h.n;
-        if (valid) { px = h.pos[3 * c]; py = h.pos[3 * c + 1]; pz = h.pos[3 * c + 2]; }
+        if (valid) { px = h.pos[3 * c]; py = h.pos[3 * c + 1]; pz = h.pos[3 * c + 2]; check_position(h.ctr, px, py, pz); }
         if (valid && answer_trivial(h, c, px, py, pz)) valid = false;
         const int dz = pz - h.z_lo;
         const uint32_t cls = (pz < h.z_lo || pz > h.z_hi) ? UW_NCLS - 1 : dz < 16 ? (uint32_t)((h.zcls >> (4 * dz)) & 15ull) : UW_NCLS - 2;
@@ -550,6 +560,7 @@ __device__ __noinline__ Ticket take_ticket(const Handout& h) {
         const uint32_t c = atomicAdd(&h.ctr->ticket, 1u);
         if (c >= h.n) return tk;
         tk.px = h.pos[3 * c]; tk.py = h.pos[3 * c + 1]; tk.pz = h.pos[3 * c + 2];
+        check_position(h.ctr, tk.px, tk.py, tk.pz);
         if (answer_trivial(h, c, tk.px, tk.py, tk.pz)) continue;
         tk.chunk = c;
         return tk;
@@ -577,6 +588,7 @@ __device__ __forceinline__ Ticket ticket_fetch(const Handout& h, uint32_t t) {
     }
     if (t < h.n) {
         tk.px = h.pos[3 * t]; tk.py = h.pos[3 * t + 1]; tk.pz = h.pos[3 * t + 2];
+        check_position(h.ctr, tk.px, tk.py, tk.pz);
         if (h.skip) {                                  // UW_FLAG_ANALYTIC_SKIP: may have to move on to the next ticket (blocking)
             if (answer_trivial(h, t, tk.px, tk.py, tk.pz)) return take_ticket(h);
         }

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <limits.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -153,6 +154,7 @@ struct uw_ctx {
         uw_chunk_desc* draw = nullptr;
     } gt;
     bool force_staged = false;          // UW_STAGED_STORES=1 in the environment: staged stores for local arenas too (A/B measurements)
+    bool force_direct = false;          // UW_STAGED_STORES=0: register stores even into another GPU's memory (A/B measurements)
     uint64_t gather_first_chunk = 0;    // request index of the next gather build's first chunk
     bool gather_build = false;          // the build being enqueued writes into the attached segment
 
@@ -430,7 +432,7 @@ extern "C" uw_status uw_create(const uw_config* cfg, uw_ctx** out) {
         c->err = b; return bail(UW_ERR_NO_DEVICE);
     }
     c->num_sms = prop.multiProcessorCount;
-    { const char* e = getenv("UW_STAGED_STORES"); c->force_staged = e && e[0] == '1'; }
+    { const char* e = getenv("UW_STAGED_STORES"); c->force_staged = e && e[0] == '1'; c->force_direct = e && e[0] == '0'; }
     c->host_ptr_ok = prop.unifiedAddressing && prop.canMapHostMemory;
     c->index32 = (cfg->flags & UW_FLAG_INDEX32) != 0 || cfg->internal_size > 22;
     // FP32 factorisation needs chunk-independent fractional parts: chunk_size a power of two
@@ -899,7 +901,7 @@ static uw_status launch_fused(uw_ctx* c, const int32_t* d_pos, uint32_t n, float
         o_vcap = g.info.seg_vcap; o_icap = g.info.seg_icap;
         fo.desc_vbase = (uint32_t)(g.segment * g.info.seg_vcap); fo.desc_ibase = (uint32_t)(g.segment * g.info.seg_icap);
         fo.head = g.head; fo.epoch = g.epoch; fo.drawlist = g.draw;
-        peer = g.ipc || g.info.device != c->device || c->force_staged;                          // NVLink: whole 16-byte vectors
+        peer = (g.ipc || g.info.device != c->device || c->force_staged) && !c->force_direct;     // NVLink: whole 16-byte vectors
         fo.first_chunk_lo = (uint32_t)c->gather_first_chunk; fo.first_chunk_hi = (uint32_t)(c->gather_first_chunk >> 32);
     }
     if (c->index32)
@@ -998,8 +1000,8 @@ static uw_status finish_build(uw_ctx* c) {
             guard = *c->h_guard;
         }
         if (!t.overflow) break;
-        if (t.overflow >= 2)
-            return fail(c, UW_ERR_INVALID, "batch too large: packed vertex/index offsets exceed 32 bits; split the batch");
+        if (t.overflow >= 3) { B.pending = false; return fail(c, UW_ERR_INVALID, "chunk position out of supported range (|pos| <= 2^24)"); }
+        if (t.overflow >= 2) { B.pending = false; return fail(c, UW_ERR_INVALID, "batch too large: packed vertex/index offsets exceed 32 bits; split the batch"); }
         if (B.last_gather) {
             // the segment belongs to the rendering side's arena: nothing to regrow here.  B.result keeps the sizes
             // the build needs, so the owner (uw_multi_build does) can recreate the arena and build again.
@@ -1045,18 +1047,11 @@ static uw_status finish_build(uw_ctx* c) {
 // H2D copy's issue + completion latency would sit in front of the kernel.
 static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n, const int32_t** dev_pos = nullptr, bool zero_copy_ok = false,
                                  bool direct_ok = false) {
-    {
-        // fast path validity (SURVEY App. A.6): |16*pos| must stay exactly representable next to
-        // the 2^-23-granular lattice offsets; also keeps pos*chunk_size inside i32 (chunk.rs:90-94)
-        uint32_t bad = 0;                                  // branch-free so that the loop vectorises (1.5 M values for config 3)
-        const size_t m = (size_t)3 * n;
-        for (size_t i = 0; i < m; ++i) bad |= (uint32_t)(pos[i] + (1 << 24)) > (uint32_t)(2 << 24) ? 1u : 0u;
-        if (bad) return fail(c, UW_ERR_INVALID, "chunk position out of supported range (|pos| <= 2^24)");
-    }
     // A request that already lives in pinned (page-locked) host memory is copied to the device straight from the
-    // caller's buffer -- no staging memcpy.  Only for calls whose contract keeps the buffer alive until completion
+    // caller's buffer -- no staging memcpy, no host-side scan (the fused kernel validates the positions as it fetches
+    // them and the batch fails at its wait).  Only for calls whose contract keeps the buffer alive until completion
     // (the blocking uw_build, uw_gather_build); uw_build_async copies, as its caller may reuse the array at once.
-    if (direct_ok && n >= 4096) {
+    if (direct_ok && n >= 4096 && c->use_fused) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, pos) == cudaSuccess && at.type == cudaMemoryTypeHost) {
             if (dev_pos) *dev_pos = c->B().d_pos;
@@ -1064,6 +1059,14 @@ static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n, cons
             return UW_OK;
         }
         cudaGetLastError();
+    }
+    {
+        // fast path validity (SURVEY App. A.6): |16*pos| must stay exactly representable next to
+        // the 2^-23-granular lattice offsets; also keeps pos*chunk_size inside i32 (chunk.rs:90-94)
+        int32_t mx = INT32_MIN, mn = INT32_MAX;            // min / max reductions vectorise
+        const size_t m = (size_t)3 * n;
+        for (size_t i = 0; i < m; ++i) { mx = pos[i] > mx ? pos[i] : mx; mn = pos[i] < mn ? pos[i] : mn; }
+        if (n && (mx > (1 << 24) || mn < -(1 << 24))) return fail(c, UW_ERR_INVALID, "chunk position out of supported range (|pos| <= 2^24)");
     }
     if ((size_t)n * 3 > c->B().h_pos_cap) {
         if (c->B().h_pos) cudaFreeHost(c->B().h_pos);
@@ -1191,7 +1194,7 @@ static uw_status build_common(uw_ctx* c, const int32_t* pos, const float* dens, 
     b->set = set;
     const int32_t* dev_pos = nullptr;
     uw_status st = ensure_chunks(c, n);
-    if (st == UW_OK) st = stage_positions(c, pos, n, &dev_pos, dens == nullptr, !async);
+    if (st == UW_OK) st = stage_positions(c, pos, n, &dev_pos, dens == nullptr, !async && dens == nullptr);
     if (st == UW_OK && dens) {
         st = ensure_dens(c);
         const DevCfg& d = c->dcfg;

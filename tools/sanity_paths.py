@@ -34,3 +34,26 @@ with uw.ChunkBuilder(uw.Perlin(0), internal_size=10, staged=True) as s10, uw.Chu
 with uw.ChunkBuilder(uw.Perlin(0), analytic_skip=True) as b:
     print("analytic skip, cost order:", b.build(big).n_inds == fb.n_inds)
 print("done 2")
+# round 2 paths: gather segments (local + forced staged stores), uw_multi_build, draw list, collision ray casts
+import os
+with uw.ChunkBuilder(uw.Perlin(0)) as b:
+    ref = b.build(big)
+    info = b.gather_create(1, len(big), seg_vcap=ref.n_verts, seg_icap=ref.n_inds)
+    b.gather_attach(info, 0)
+    b.gather_build(big, 0)
+    res = b.gather_wait(descs_to_host=True, draw_to_host=True)
+    print("gather (one local segment, register stores):", res.n_inds == ref.n_inds, res.n_draw)
+    b.gather_detach(); b.gather_destroy()
+os.environ["UW_STAGED_STORES"] = "1"
+with uw.ChunkBuilder(uw.Perlin(0), ordered=True) as b, uw.ChunkBuilder(uw.Perlin(0), index32=True) as b32:
+    st = b.build(big)
+    print("staged 16-byte stores (u16):", st.n_inds == ob.n_inds if 'ob' in dir() else st.n_inds, " u32:", b32.build(pos).n_inds)
+del os.environ["UW_STAGED_STORES"]
+with uw.MultiBuilder(uw.Perlin(0), devices=[0]) as mb:
+    print("uw_multi_build:", mb.build(big, draw_to_host=True).n_inds == ref.n_inds)
+with uw.ChunkBuilder(uw.Perlin(0), tris=True) as b:
+    b.build(pos)
+    rng = np.random.default_rng(0)
+    o = rng.uniform(-30, 30, size=(512, 3)).astype(np.float32); d = rng.normal(size=(512, 3)).astype(np.float32)
+    print("raycast hits:", int((b.raycast_tris(o, d, 3) >= 0).sum()))
+print("done 3")

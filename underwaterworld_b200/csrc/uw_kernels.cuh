@@ -757,7 +757,15 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         // that the reference's clamp to [-1, 1] becomes the .sat of the last FFMA of stage YZ; the shift rides on
         // the value component through the y and z lerps (weights sum to 1), the slopes are only scaled
         const float sc = 1.1547005383792515f * 0.5f;
-        for (int t = tid; t < L * G * G; t += NT) {
+        // Items are dealt round-robin ACROSS the octaves (thread rotation = items of the octaves before this one, mod NT):
+        // no warp takes more than ceil(all items / NT) rounds -- 3 instead of 4 for warps 0-1 at S = 12 -- without a
+        // per-item octave selection (measured slower in round 1).  The slowest warp sets the time of the barrier below.
+#ifndef UW_NO_X_ROTATION
+        const int rot = D::x_base(o) % NT;                      // folds: the octave loop is unrolled
+#else
+        const int rot = 0;
+#endif
+        for (int t = tid >= rot ? tid - rot : tid - rot + NT; t < L * G * G; t += NT) {
             const int i = t / (G * G), r = t - i * G * G;
             const int c = (i << o) / ST;
             const int c1 = D::PRUNE ? min(c + 1, G - 1) : c + 1;         // i = S: weight ~ 1e-22 on a plane that is not kept

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """A/B timing of kernel variants in ONE gpurun call.
 
-    python tools/ab.py libA.so libB.so ...        (a name may carry builder kwargs: lib.so@{"staged":true})
+    python tools/ab.py libA.so libB.so ...        (a name may carry builder kwargs and environment settings:
+                                                   lib.so@{"staged":true}   lib.so@@UW_FUSED_PIPE=0,UW_X=1)
 
 Each variant runs in its own subprocess (UWCUDA_LIB), interleaved over several rounds, on three workloads:
 config 2 (2048 chunks, L2 flushed, per launch), 32 768 chunks (back to back) and config 3 (524 288 chunks, one
@@ -56,9 +57,13 @@ def main():
     for rnd in range(3):
         for l in libs:
             env = dict(os.environ)
-            name, _, kw = l.partition("@")
+            name, _, rest = l.partition("@")
+            kw, _, envs = rest.partition("@")
             env["UWCUDA_LIB"] = os.path.abspath(name)
             env["UW_KW"] = kw or "{}"
+            for a in filter(None, envs.split(",")):
+                k, _, v = a.partition("=")
+                env[k] = v
             out = subprocess.run([sys.executable, "-c", WORKER], env=env, capture_output=True, text=True)
             try:
                 res[l].append(json.loads(out.stdout.strip().splitlines()[-1]))
@@ -69,7 +74,7 @@ def main():
         if not r:
             continue
         med = lambda k: float(np.median([x[k] for x in r if k in x])) if any(k in x for x in r) else float("nan")
-        print(f"{os.path.basename(l):44s} config2 {med('c2_median_us'):7.2f} us (min {min(x['c2_min_us'] for x in r):6.2f})   "
+        print(f"{os.path.basename(l.split('@')[0]) + ' ' + '@'.join(l.split('@')[1:]):44s} config2 {med('c2_median_us'):7.2f} us (min {min(x['c2_min_us'] for x in r):6.2f})   "
               f"32768 {med('n32768_us'):8.1f} us   config3 {med('c3_us'):9.1f} us   ni={r[0]['c2_ni']}/{r[0].get('n32768_ni')}/{r[0].get('c3_ni')}")
 
 

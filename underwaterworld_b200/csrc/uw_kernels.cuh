@@ -879,8 +879,18 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         const uint32_t nchunk = __shfl_sync(0xFFFFFFFFu, nx.chunk, 31);
         const int npx = __shfl_sync(0xFFFFFFFFu, nx.px, 31), npy = __shfl_sync(0xFFFFFFFFu, nx.py, 31), npz = __shfl_sync(0xFFFFFFFFu, nx.pz, 31);
         if (nchunk != TICKET_DONE) {
+#ifndef UW_NO_TERR_FIRST
+            // global table load first: its latency hides under the hash rounds (the barrier that ends stage YZ waits for
+            // this warp: -2.6 % at config 3, profiles/r02_ab_terr_first.txt; writing the six hash rounds out for more
+            // loads in flight costs registers and was slower, +4 %)
+            float tv = 0.f;
+            if (lane < L) tv = terrace_lookup(cfg, lane, npz);
+            noise_stage_h<ST, NOCT>(sm, npx, npy, npz, lane, 32);
+            if (lane < L) sm.terr[tb ^ 1][lane] = tv;
+#else
             noise_stage_h<ST, NOCT>(sm, npx, npy, npz, lane, 32);
             if (lane < L) sm.terr[tb ^ 1][lane] = terrace_lookup(cfg, lane, npz);
+#endif
         }
         if (lane == 31) *tk_out = nx;
     }

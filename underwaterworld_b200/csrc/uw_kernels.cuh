@@ -1580,23 +1580,26 @@ __host__ __device__ inline size_t emit_smem_bytes(const DevCfg& cfg) {
 }
 
 __device__ __forceinline__ EmitSmem emit_smem_carve(const DevCfg& cfg, unsigned char* base) {
+    // offsets are kept as integers relative to `base` (16-byte aligned dynamic shared memory): rounding a POINTER through
+    // uintptr_t would hide the address space from the compiler and turn every access behind it into a generic load
     const size_t cells = (size_t)cfg.S * cfg.S * cfg.S, cells2 = (cells + 7) & ~(size_t)7;
     EmitSmem s;
-    s.dens = (float*)base;        base += (size_t)cfg.dens_stride * 4;       // multiple of 16 bytes
-    s.rows = (const uint64_t*)base; base += 256 * 8;
-    s.powtab = (const float*)base;  base += 48 * 4;
-    s.bits = (uint32_t*)base;     base += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
-    s.mask = (uint32_t*)base;     base += ((size_t)cfg.L2 + 3) / 4 * 16;
-    base = (unsigned char*)(((uintptr_t)base + 15) & ~(uintptr_t)15);           // the staging regions hold 16-byte vectors
-    s.vbase = (uint16_t*)base;    s.vstage = (float*)base;
-    base += (cells2 * 2 > 8 * UW_VSTAGE_BYTES ? cells2 * 2 : 8 * UW_VSTAGE_BYTES);
-    s.ibase = (uint16_t*)base;    base += cells2 * 2;
-    s.alist = (uint16_t*)base;    base += cells2 * 2;
-    s.vlist = (uint16_t*)base;    s.istage = (void*)base;    base += UW_VLIST_CAP * 2;
-    s.vid = (uint16_t*)base;      base += (((size_t)cfg.L3 * UW_EDGE_KINDS + 7) & ~(size_t)7) * 2;
-    s.lut = (uint32_t*)base;      base += 256 * 4;
-    s.eoff = (uint16_t*)base;     base += 16 * 2;
-    s.cs = (uint8_t*)base;
+    size_t o = 0;
+    s.dens = (float*)(base + o);          o += (size_t)cfg.dens_stride * 4;       // multiple of 16 bytes
+    s.rows = (const uint64_t*)(base + o); o += 256 * 8;
+    s.powtab = (const float*)(base + o);  o += 48 * 4;
+    s.bits = (uint32_t*)(base + o);       o += ((size_t)(cfg.L3 + 31) / 32 + 2) * 4;
+    s.mask = (uint32_t*)(base + o);       o += ((size_t)cfg.L2 + 3) / 4 * 16;
+    o = (o + 15) & ~(size_t)15;                                                    // the staging regions hold 16-byte vectors
+    s.vbase = (uint16_t*)(base + o);      s.vstage = (float*)(base + o);
+    o += (cells2 * 2 > 8 * UW_VSTAGE_BYTES ? cells2 * 2 : 8 * UW_VSTAGE_BYTES);
+    s.ibase = (uint16_t*)(base + o);      o += cells2 * 2;
+    s.alist = (uint16_t*)(base + o);      o += cells2 * 2;
+    s.vlist = (uint16_t*)(base + o);      s.istage = (void*)(base + o);    o += UW_VLIST_CAP * 2;
+    s.vid = (uint16_t*)(base + o);        o += (((size_t)cfg.L3 * UW_EDGE_KINDS + 7) & ~(size_t)7) * 2;
+    s.lut = (uint32_t*)(base + o);        o += 256 * 4;
+    s.eoff = (uint16_t*)(base + o);       o += 16 * 2;
+    s.cs = (uint8_t*)(base + o);
     return s;
 }
 

@@ -267,9 +267,9 @@ def run_ours(args):
     first, n = G.slab_bounds(n_total, world, rank)
     # the request lives in PINNED host memory (the contract's "host->device copy from pinned host memory"): the library
     # then copies it to the device straight from this buffer
-    pos_pin = torch.from_numpy(np.ascontiguousarray(whole[first:first + n])).pin_memory()
-    pos = pos_pin.numpy()
+    whole_pin = torch.from_numpy(whole).pin_memory()           # every rank keeps the request; its slab is a slice of it
     del whole
+    pos = whole_pin.numpy()[first:first + n]
     builder = uw.ChunkBuilder(uw.Perlin(SEED), internal_size=S, device=local)
     stream = torch.cuda.current_stream()
     builder.set_stream(stream.cuda_stream)
@@ -301,32 +301,49 @@ def run_ours(args):
         my_verts, my_inds = int(dv.n_verts), int(dv.n_inds)
 
         # ---- e2e: host positions -> meshes in the rendering GPU's arenas (rank 0) + draw list on the host ----------
-        rg = G.RegionGather(builder, rank, world, n_total, dst=0, bcast_device="cuda" if world > 1 else None)
+        # Gather-aware partition: the rendering rank's own output does not cross NVLink, so when the gather is bound by
+        # its NVLink ingress (N = 8) it takes a larger slab.  The share adapts during the warm-up steps from every
+        # rank's build time (RegionGather.feedback: one small all_reduce between steps, never inside a timed step) and
+        # is frozen for the timed ones.  Segments are sized for half the region each.
+        half = (n_total + 1) // 2
+        rg = G.RegionGather(builder, rank, world, n_total, dst=0, seg_vcap=half * 192 + 4096, seg_icap=half * 640 + 16384,
+                            bcast_device="cuda" if world > 1 else None)
         res = None
-        for i in range(W):
+        WG = max(W, 8) if world > 1 else W
+        for i in range(WG):
+            gf, gn = rg.plan(n_total)
+            gpos = whole_pin.numpy()[gf:gf + gn]
             flush.fill_(i & 0xFF)
             barrier()
-            rg.build(pos, first)
+            t0 = time.perf_counter()
+            rg.build(gpos, gf)
+            builder.sync()                                   # this rank's kernel (for the balance; not done in timed steps)
+            mine = time.perf_counter() - t0
             if rank == 0:
                 res = rg.wait(draw_to_host=True)
-            builder.sync()
+            if i < WG - 2:
+                rg.feedback(mine, device="cuda" if world > 1 else None)
+        gf, gn = rg.plan(n_total)
+        gpos = whole_pin.numpy()[gf:gf + gn]
         e2e_t = []
         for i in range(K):
             flush.fill_(i & 0xFF)
             barrier()
             t0 = time.perf_counter()
-            rg.build(pos, first)
+            rg.build(gpos, gf)
             if rank == 0:
                 res = rg.wait(draw_to_host=True)
             builder.sync()
             e2e_t.append(time.perf_counter() - t0)
         barrier()
         e2e_steps = rmax(np.array(e2e_t))                    # per step: the slowest rank (rank 0 waits for all)
+        render_share = rg.render_share
         if rank == 0:
             g_verts, g_inds = int(res.n_verts), int(res.n_inds)
             g_mesh = sum(s["n_mesh"] for s in res.segments)
             g_blank = sum(s["n_blank"] for s in res.segments)
             g_guard = sum(s["guard"] for s in res.segments)
+            g_counts = [int(s["n_chunks"]) for s in res.segments]
             assert res.n_chunks == n_total
         rg.close()
 
@@ -492,6 +509,9 @@ def run_ours(args):
                             "of the draw list (descriptors of the chunks that ended with a mesh) and the heads into pinned host memory",
                     "timing": "host perf_counter per step on every rank (barrier, build, wait/sync), MAX over ranks per step, mean over K",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "render_share": render_share if render_share > 0 else 1.0 / world, "chunks_per_rank": g_counts,
+                    "partition": "gather-aware: the rendering rank's slab grows until it finishes with the slowest producer "
+                                 "(adapted over the warm-up steps, frozen for the timed ones); value uses the even split",
                     "mesh_bytes_to_render_gpu": 24 * g_verts + 2 * g_inds,
                     "nvlink_bytes_per_step": (24 * (g_verts - int(res.segments[0]["n_verts"])) + 2 * (g_inds - int(res.segments[0]["n_inds"]))
                                               + 32 * (n_total - int(res.segments[0]["n_chunks"]))) if world > 1 else 0},

@@ -308,6 +308,14 @@ uw_status   uw_gather_wait(uw_ctx* render_ctx, uint32_t flags, uw_gather_result*
 /* Contiguous slab `part` of `parts` of a list of n chunks (remainder spread one per slab) -- the partition
  * uw_multi_build and bench.py use. */
 void        uw_slab_bounds(uint32_t n, uint32_t parts, uint32_t part, uint32_t* first, uint32_t* count);
+/* Gather-aware partition: the rendering GPU's own output does not cross NVLink, so when the gather is bound by the
+ * rendering GPU's ingress (8 GPUs: 706 MB into one GPU) its slab should be larger.  Slab `render_part` holds
+ * render_permille / 1000 of the n chunks (never less than an even share), the other slabs share the rest evenly; slabs
+ * stay contiguous and in part order.  render_permille = 0: the even split of uw_slab_bounds.  uw_multi_build adapts the
+ * share from the kernel times it measures (render GPU against the slowest producer); gather.RegionGather does the same
+ * for one process per GPU. */
+void        uw_slab_bounds_weighted(uint32_t n, uint32_t parts, uint32_t part, uint32_t render_part, uint32_t render_permille,
+                                    uint32_t* first, uint32_t* count);
 
 /* One process, G GPUs: devices[0] renders.  uw_multi_build = World::build_full_step for a whole region
  * (world.rs:113-123) -- slabs, G fused launches (each GPU's H2D + kernel on its own stream), meshes gathered into
@@ -316,6 +324,8 @@ void        uw_slab_bounds(uint32_t n, uint32_t parts, uint32_t part, uint32_t* 
 typedef struct uw_multi uw_multi;
 uw_status   uw_multi_create(const uw_config* cfg, const int32_t* devices, uint32_t n_devices, uw_multi** out);
 uw_status   uw_multi_build(uw_multi* m, const int32_t* chunk_pos_xyz, uint32_t n, uint32_t flags, uw_gather_result* out);
+/* The rendering GPU's current share of a request in 1/1000 (0 = even split so far); adapts over successive builds. */
+uint32_t    uw_multi_render_share(const uw_multi* m);
 void        uw_multi_destroy(uw_multi* m);
 const char* uw_multi_last_error(const uw_multi* m);           /* m may be NULL: last create error             */
 /* Verification aid: blocking copy of `bytes` of device memory (any device of the process: unified addressing) to the

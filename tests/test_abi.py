@@ -114,3 +114,31 @@ def test_chunk_mirror_host_logic():
     c._adopt(mesh)
     assert c.not_blank() and c.num_inds() == 3 and len(c.verts_buffer_slice()) == 3
     assert uw.Perlin(2 ** 32 + 5).seed() == 5
+
+
+def test_weighted_slab_bounds_mirror_the_library(lib):
+    """Gather-aware partition (uw_slab_bounds_weighted, pure host arithmetic): the Python mirror RegionGather.plan uses
+    equals the C function uw_multi_build uses; slabs tile the request in part order; the rendering slab never gets less
+    than an even share."""
+    from underwaterworld_b200 import gather
+    for n, parts, rp, pm in [(524288, 8, 0, 232), (524288, 8, 0, 0), (100, 4, 2, 500), (7, 3, 0, 400), (2048, 8, 0, 100),
+                             (10, 2, 1, 900), (0, 4, 0, 300), (5, 1, 0, 700), (1000, 5, 4, 1000)]:
+        cover, counts = 0, []
+        for p in range(parts):
+            f, c = C.c_uint32(), C.c_uint32()
+            lib.uw_slab_bounds_weighted(n, parts, p, rp, pm, C.byref(f), C.byref(c))
+            assert (f.value, c.value) == gather.slab_bounds_weighted(n, parts, p, rp, pm)
+            assert f.value == cover
+            cover += c.value
+            counts.append(c.value)
+        assert cover == n
+        if parts > 1 and pm * parts > 1000:
+            assert counts[rp] == (n * min(pm, 1000) + 500) // 1000 and counts[rp] >= n // parts
+    # the balance controller: moves towards equal finish times, stays within [even, 1/2], holds when balanced
+    s = 0.0
+    for _ in range(12):
+        t_r = max(s, 1 / 8) * 3.8
+        t_o = max((1 - max(s, 1 / 8)) / 7 * 3.8, (1 - max(s, 1 / 8)) * 1.14)
+        s = gather.balance_share(s, 8, t_r, t_o)
+    assert 0.20 < s < 0.26
+    assert gather.balance_share(0.3, 4, 1.0, 1.02) == 0.3 and gather.balance_share(0.0, 4, 2.0, 1.0) == 0.25

@@ -136,6 +136,28 @@ def test_multi_builder_region_equals_plain_build(uw):
                 at += seg["n_mesh"]
 
 
+def test_multi_builder_adapts_the_render_share_without_changing_results(uw):
+    """uw_multi_build balances the rendering GPU's slab against the slowest producer over successive requests
+    (gather-aware partition); whatever the split, every chunk's buffers stay those of the plain build."""
+    import ctypes as C
+    ndev = min(_device_count(), 8)
+    pos = uw.region.box_region((-24, 24), (-24, 24), (-6, 4))        # 23 040 chunks
+    with uw.ChunkBuilder(uw.Perlin(0), device=0) as ref_b, uw.MultiBuilder(uw.Perlin(0), devices=list(range(ndev))) as mb:
+        ref = ref_b.build(pos)
+        shares = []
+        for _ in range(5):
+            res = mb.build(pos)
+            shares.append(mb._lib.uw_multi_render_share(mb._m))
+            assert res.n_chunks == len(pos) and res.n_inds == ref.n_inds
+        descs, verts, inds = res.download()
+        _assert_same_chunks(descs, verts, inds, ref)
+        assert [s["first_chunk"] for s in res.segments] == [uw.gather.slab_bounds_weighted(len(pos), ndev, g, 0, shares[-2])[0] for g in range(ndev)]
+        if ndev == 1:
+            assert shares == [0] * 5
+        else:
+            assert all(0 <= s <= 500 for s in shares)
+
+
 def test_segment_overflow_is_reported_and_multi_build_regrows(uw):
     pos = uw.region.box_region((-4, 4), (-4, 4), (-1, 0))            # one surface layer: ~ 500 vertices per chunk
     with uw.ChunkBuilder(uw.Perlin(0)) as b:

@@ -109,7 +109,7 @@ EXPORTS = [
     "uw_set_stream", "uw_get_stage_times", "uw_set_profiling", "uw_get_guard_count", "uw_debug_ffma_peak", "uw_export_arena_fd", "uw_debug_vertex_colors",
     "uw_gather_create", "uw_gather_destroy", "uw_gather_attach", "uw_gather_detach", "uw_gather_build",
     "uw_gather_build_device", "uw_gather_wait", "uw_slab_bounds",
-    "uw_multi_create", "uw_multi_build", "uw_multi_destroy", "uw_multi_last_error", "uw_debug_copy_to_host", "uw_raycast_tris",
+    "uw_multi_create", "uw_multi_build", "uw_multi_destroy", "uw_multi_last_error", "uw_debug_copy_to_host", "uw_raycast_tris", "uw_slab_bounds_weighted", "uw_multi_render_share",
 ]
 
 _lib = None
@@ -172,6 +172,10 @@ def load_library() -> C.CDLL:
     lib.uw_gather_wait.argtypes = [vp, u32, C.POINTER(UwGatherResult)]
     lib.uw_slab_bounds.argtypes = [u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
     lib.uw_slab_bounds.restype = None
+    lib.uw_slab_bounds_weighted.argtypes = [u32, u32, u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+    lib.uw_slab_bounds_weighted.restype = None
+    lib.uw_multi_render_share.argtypes = [vp]
+    lib.uw_multi_render_share.restype = C.c_uint32
     lib.uw_multi_create.argtypes = [C.POINTER(UwConfig), C.POINTER(C.c_int32), u32, C.POINTER(vp)]
     lib.uw_multi_build.argtypes = [vp, i32p, u32, u32, C.POINTER(UwGatherResult)]
     lib.uw_multi_destroy.argtypes = [vp]

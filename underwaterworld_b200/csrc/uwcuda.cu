@@ -1329,6 +1329,26 @@ extern "C" void uw_slab_bounds(uint32_t n, uint32_t parts, uint32_t part, uint32
     if (count) *count = base + (part < rem ? 1u : 0u);
 }
 
+extern "C" void uw_slab_bounds_weighted(uint32_t n, uint32_t parts, uint32_t part, uint32_t render_part, uint32_t render_permille,
+                                        uint32_t* first, uint32_t* count) {
+    if (parts <= 1 || render_part >= parts || (unsigned long long)render_permille * parts <= 1000ull) {
+        uw_slab_bounds(n, parts, part, first, count);
+        return;
+    }
+    if (render_permille > 1000) render_permille = 1000;
+    const uint32_t cr = (uint32_t)(((unsigned long long)n * render_permille + 500ull) / 1000ull);
+    const uint32_t rest = n - cr, others = parts - 1;
+    const uint32_t base = rest / others, rem = rest % others;
+    uint32_t lo = 0, cnt = 0;
+    for (uint32_t p = 0, k = 0; p <= part; ++p) {           // k = index among the non-render slabs
+        lo += cnt;
+        if (p == render_part) cnt = cr;
+        else { cnt = base + (k < rem ? 1u : 0u); ++k; }
+    }
+    if (first) *first = lo;
+    if (count) *count = cnt;
+}
+
 static bool gather_supported(uw_ctx* c, const char* who) {
     if (c->use_fused && !c->tris && !(c->cfg.flags & UW_FLAG_KEEP_DENSITIES)) return true;
     fail(c, UW_ERR_UNSUPPORTED, std::string(who) + ": the gather path needs the fused kernel (internal_size 10 / 12, reference constants; "
@@ -1491,7 +1511,9 @@ static uw_status gather_build_common(uw_ctx* c, const int32_t* pos, bool host_po
         return UW_OK;
     }
     c->gather_build = true;
+    cudaEventRecord(c->ev[0], c->stream);                 // kernel time of this producer (uw_multi_build balances on it)
     st = enqueue_build(c, dev_pos, n, false);
+    cudaEventRecord(c->ev[4], c->stream);
     c->gather_build = false;
     return st;
 }
@@ -1584,6 +1606,7 @@ struct uw_multi {
     std::vector<uw_ctx*> ctx;            // ctx[0] renders
     uw_gather_info info = {};
     bool have_arena = false;
+    double render_share = 0.0;           // fraction of a request the rendering GPU builds itself; 0 = even split
     std::string err;
 };
 static thread_local std::string g_multi_error;
@@ -1594,6 +1617,22 @@ static uw_status mfail(uw_multi* m, uw_status st, const std::string& msg) {
 }
 
 extern "C" const char* uw_multi_last_error(const uw_multi* m) { return m ? m->err.c_str() : g_multi_error.c_str(); }
+extern "C" uint32_t uw_multi_render_share(const uw_multi* m) { return m ? (uint32_t)(m->render_share * 1000.0 + 0.5) : 0u; }
+
+// One step of the gather-aware balance: the rendering GPU's kernel ran t_render ms, the slowest other producer t_other ms
+// (a producer whose stores wait for the rendering GPU's NVLink ingress runs longer than its compute alone).  Moves the
+// share by the square root of the ratio; even split <= share <= 1/2.
+static double balance_share(double share, uint32_t parts, double t_render, double t_other) {
+    const double even = 1.0 / (double)parts;
+    if (parts < 2 || !(t_render > 0.0) || !(t_other > 0.0)) return share;
+    double s = share > 0.0 ? share : even;
+    const double ratio = t_other / t_render;
+    if (ratio > 0.95 && ratio < 1.05) return s;
+    s *= sqrt(ratio);
+    if (s < even) s = even;
+    if (s > 0.5) s = 0.5;
+    return s;
+}
 
 extern "C" void uw_multi_destroy(uw_multi* m) {
     if (!m) return;
@@ -1647,7 +1686,7 @@ extern "C" uw_status uw_multi_build(uw_multi* m, const int32_t* pos, uint32_t n,
         for (uint32_t k = 0; k < G; ++k) {
             const uint32_t g = (k + 1) % G;
             uint32_t first = 0, cnt = 0;
-            uw_slab_bounds(n, G, g, &first, &cnt);
+            uw_slab_bounds_weighted(n, G, g, 0, (uint32_t)(m->render_share * 1000.0 + 0.5), &first, &cnt);
             const uw_status st = uw_gather_build(m->ctx[g], pos + 3 * (size_t)first, cnt, first);
             if (st != UW_OK) return mfail(m, st, m->ctx[g]->err);
         }
@@ -1663,7 +1702,20 @@ extern "C" uw_status uw_multi_build(uw_multi* m, const int32_t* pos, uint32_t n,
         }
         if (first_err != UW_OK) return mfail(m, first_err, first_msg);
         const uw_status wst = uw_gather_wait(r, flags, out);
-        if (!overflow && wst == UW_OK) return UW_OK;
+        if (!overflow && wst == UW_OK) {
+            if (G >= 2 && n >= 4096u * G) {               // adapt the rendering GPU's share for the next request
+                float t_r = 0.f, t_o = 0.f;
+                cudaSetDevice(r->device);
+                if (cudaEventElapsedTime(&t_r, r->ev[0], r->ev[4]) != cudaSuccess) { cudaGetLastError(); t_r = 0.f; }
+                for (uint32_t g = 1; g < G; ++g) {
+                    float t = 0.f;
+                    cudaSetDevice(m->ctx[g]->device);
+                    if (cudaEventElapsedTime(&t, m->ctx[g]->ev[0], m->ctx[g]->ev[4]) == cudaSuccess) t_o = std::max(t_o, t); else cudaGetLastError();
+                }
+                m->render_share = balance_share(m->render_share, G, t_r, t_o);
+            }
+            return UW_OK;
+        }
         if (!overflow) return mfail(m, wst, r->err);
         vcap = std::max<unsigned long long>(m->info.seg_vcap, need_v + need_v / 8 + 4096);
         icap = std::max<unsigned long long>(m->info.seg_icap, need_i + need_i / 8 + 16384);

@@ -35,6 +35,39 @@ def slab_bounds(n: int, parts: int, part: int) -> tuple:
     return part * base + min(part, rem), base + (1 if part < rem else 0)
 
 
+def slab_bounds_weighted(n: int, parts: int, part: int, render_part: int, render_permille: int) -> tuple:
+    """Gather-aware partition (mirror of uw_slab_bounds_weighted): slab `render_part` holds render_permille / 1000 of
+    the request (never less than an even share), the other slabs share the rest evenly, contiguous and in part order."""
+    if parts <= 1 or render_part >= parts or render_permille * parts <= 1000:
+        return slab_bounds(n, parts, part)
+    render_permille = min(render_permille, 1000)
+    cr = (n * render_permille + 500) // 1000
+    base, rem = divmod(n - cr, parts - 1)
+    lo = cnt = k = 0
+    for p in range(part + 1):
+        lo += cnt
+        if p == render_part:
+            cnt = cr
+        else:
+            cnt = base + (1 if k < rem else 0)
+            k += 1
+    return lo, cnt
+
+
+def balance_share(share: float, parts: int, t_render: float, t_other: float) -> float:
+    """One step of the gather-aware balance (mirror of the library's): the rendering GPU's kernel ran t_render, the
+    slowest other producer t_other (a producer whose stores wait for the rendering GPU's NVLink ingress runs longer than
+    its compute alone).  Moves the share by the square root of the ratio; even split <= share <= 1/2."""
+    even = 1.0 / parts
+    if parts < 2 or not (t_render > 0.0) or not (t_other > 0.0):
+        return share
+    s = share if share > 0.0 else even
+    ratio = t_other / t_render
+    if 0.95 < ratio < 1.05:
+        return s
+    return min(0.5, max(even, s * ratio ** 0.5))
+
+
 def info_to_bytes(info: _ffi.UwGatherInfo) -> bytes:
     return bytes(C.string_at(C.addressof(info), C.sizeof(info)))
 
@@ -148,6 +181,27 @@ class RegionGather:
             info = broadcast_info(info, src=dst, group=group, device=bcast_device)
         self.info = info
         builder.gather_attach(info, rank)
+        self.group = group
+        self.render_share = 0.0                           # the rendering rank's fraction of a request; 0 = even split
+
+    def plan(self, n: int) -> tuple:
+        """(first, count) of this rank's slab of an n-chunk request under the current render share."""
+        return slab_bounds_weighted(n, self.world, self.rank, self.dst, int(self.render_share * 1000.0 + 0.5))
+
+    def feedback(self, my_kernel_seconds: float, device=None) -> float:
+        """Collective (control plane, between builds): every rank reports how long its last build took; the rendering
+        rank's share moves towards the point where it finishes together with the slowest producer."""
+        if self.world < 2:
+            return self.render_share
+        import torch
+        import torch.distributed as dist
+        t = torch.zeros(self.world, dtype=torch.float64, device=device or "cpu")
+        t[self.rank] = my_kernel_seconds
+        dist.all_reduce(t, group=self.group)
+        ts = t.cpu().tolist()
+        others = max(x for r, x in enumerate(ts) if r != self.dst)
+        self.render_share = balance_share(self.render_share, self.world, ts[self.dst], others)
+        return self.render_share
 
     def build(self, positions, first_chunk: int):
         self.builder.gather_build(positions, first_chunk)

@@ -293,7 +293,7 @@ def test_pinned_requests_skip_the_host_scan_and_are_validated_on_the_device(uw):
     not scanned on the host; the fused kernel checks every position it fetches (|pos| <= 2^24) and
     the build fails with UW_ERR_INVALID at its wait -- through uw_build and through uw_gather_build alike."""
     import torch
-    pos = uw.region.box_region((-16, 16), (-16, 16), (-4, 4))          # 8192 chunks
+    pos = uw.region.box_region((-16, 16), (-16, 16), (-6, 6))          # 12 288 chunks: beyond the cost-ordered range
     pin = torch.from_numpy(pos.copy()).pin_memory()
     good = pin.numpy()
     with uw.ChunkBuilder(uw.Perlin(0)) as b, uw.ChunkBuilder(uw.Perlin(0)) as ref_b:

@@ -1051,7 +1051,7 @@ static uw_status stage_positions(uw_ctx* c, const int32_t* pos, uint32_t n, cons
     // caller's buffer -- no staging memcpy, no host-side scan (the fused kernel validates the positions as it fetches
     // them and the batch fails at its wait).  Only for calls whose contract keeps the buffer alive until completion
     // (the blocking uw_build, uw_gather_build); uw_build_async copies, as its caller may reuse the array at once.
-    if (direct_ok && n >= 4096 && c->use_fused) {
+    if (direct_ok && n >= 4096 && (size_t)n > c->order_cap && c->use_fused) {   // (smaller batches: zero-copy hand-out below)
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, pos) == cudaSuccess && at.type == cudaMemoryTypeHost) {
             if (dev_pos) *dev_pos = c->B().d_pos;
@@ -1669,6 +1669,12 @@ extern "C" uw_status uw_multi_build(uw_multi* m, const int32_t* pos, uint32_t n,
     const uint32_t G = (uint32_t)m->ctx.size();
     uw_ctx* r = m->ctx[0];
     uint64_t vcap = 0, icap = 0;                          // 0 = the library's default estimate
+    if (G >= 2) {
+        // the rendering GPU's slab may grow to half the request (gather-aware partition): size the segments for that
+        // from the start, unless 32-bit descriptor offsets would not cover G such segments
+        const uint64_t per = ((uint64_t)n + 1) / 2, v = per * 192 + 4096, i = per * 640 + 16384;
+        if (v * G <= 0xFFFFFFFFull && i * G <= 0xFFFFFFFFull) { vcap = v; icap = i; }
+    }
     for (int attempt = 0; attempt < 4; ++attempt) {
         if (!m->have_arena || m->info.n_chunks < (n ? n : 1u) || vcap > m->info.seg_vcap || icap > m->info.seg_icap) {
             for (auto* c : m->ctx) { const uw_status st = uw_gather_detach(c); if (st != UW_OK) return mfail(m, st, c->err); }

@@ -15,7 +15,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "underwaterworld_b200", "lib", "libuwcuda.so")
+LIB = os.environ.get("UWCUDA_LIB") or os.path.join(ROOT, "underwaterworld_b200", "lib", "libuwcuda.so")
 
 
 def sass_lines(mangled_sub):

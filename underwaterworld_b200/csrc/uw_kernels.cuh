@@ -657,6 +657,13 @@ struct SpecDims {
     __host__ __device__ static constexpr float tab_w(int o, int k) { return (float)cfade(axis_frac(o, k)); }
     __host__ __device__ static constexpr int tab_c(int o, int k) { return (int)cfloor(axis_p(o, k)); }
     static constexpr int LAT = lat_base(NOCT), XN = x_base(NOCT), GTOP = G(NOCT - 1);
+    // Stage X by cell groups (see noise_chunk_spec): when the finest octave's noise cells hold a whole number GS of
+    // samples (S = 12, 3 octaves: 4 cells of 3), the samples i = q GS .. q GS + GS - 1 lie in ONE cell of every octave,
+    // c = (q << o) >> (NOCT - 1), so one thread can lerp them all from a single pair of lattice points.
+    static constexpr int NGRP = 1 << (NOCT - 1), GS = ST / NGRP;
+    __host__ __device__ static constexpr int g2_base(int o) { int b = 0; for (int q = 0; q < o; ++q) b += G(q) * G(q); return b; }   // prefix of G^2
+    static constexpr int SG2 = g2_base(NOCT);
+    static constexpr bool XGROUPED = PRUNE && (ST % NGRP == 0) && GS >= 2;
 };
 
 template <int ST, int NOCT>
@@ -750,13 +757,71 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
 
     // ---- stage X --------------------------------------------------------------------------------
     constexpr float inv_max = 1.0f / (2.0f - 1.0f / (float)(1 << (NOCT - 1)));
+    // the octave value is carried normalised to its clamp range and shifted: u = v * (2/sqrt(3)) / 2 + 1/2, so
+    // that the reference's clamp to [-1, 1] becomes the .sat of the last FFMA of stage YZ; the shift rides on
+    // the value component through the y and z lerps (weights sum to 1), the slopes are only scaled
+    const float sc = 1.1547005383792515f * 0.5f;
+    auto xlerp = [&](const float4 g0, const float4 g1, const float4 ax) {
+        const float d = ax.x, d1 = ax.y, w = ax.z;
+        const float q0 = g0.x * d, q1 = g1.x * d1;
+        float4 e;
+        e.x = fmaf(fmaf(w, q1 - q0, q0), sc, 0.5f);
+        e.y = fmaf(w, g1.y - g0.y, g0.y) * sc;
+        e.z = fmaf(w, g1.z - g0.z, g0.z) * sc;
+        e.w = 0.f;
+        return e;
+    };
+#ifdef UW_X_GROUPED     // measured, not kept (profiles/r02_ab_x_grouped_not_kept.txt): -3.5 % warp-instructions, +1.9 % time at config 3
+    constexpr int XITEMS = D::NGRP * D::SG2;                   // (cell group q, octave, lattice (cy, cz)) items, q-major
+    constexpr int XTOP0 = NT >= ((XITEMS + 31) & ~31) + D::SG2 ? ((XITEMS + 31) & ~31) : XITEMS;   // tops start a warp if room
+    constexpr bool XG = D::XGROUPED && XTOP0 + D::SG2 <= NT;
+#else
+    constexpr int XITEMS = 0, XTOP0 = 0;
+    constexpr bool XG = false;
+#endif
+    if constexpr (XG) {
+        // ONE round: thread (q, o, r) loads its two lattice points once and writes the GS x-samples of cell group q;
+        // SG2 more threads write the chunk's last sample plane (i = S: both points are the plane G - 1, weight ~ 0 on
+        // the pruned one).  Same operations per output as the per-(o, i, r) loop below, a third of its loads and index
+        // arithmetic, and no warp takes more than one round.
+        int u = -1, q = 0;
+        int xt = tid;
+#ifndef UW_X_HOIST
+        // keep the (chunk-independent) item decode inside the chunk loop: hoisted, its results are spilled to local
+        // memory by the 72-register budget and reloaded at the head of this stage's dependent chain
+        asm volatile("" : "+r"(xt));
+#endif
+        const bool top = xt >= XTOP0;
+        if (xt < XITEMS) { q = xt / D::SG2; u = xt - q * D::SG2; }
+        else if (top && xt < XTOP0 + D::SG2) u = xt - XTOP0;
+        if (u >= 0) {
+            int o = 0, r = u, G2 = D::G(0) * D::G(0), lb = D::lat_base(0), xb = D::x_base(0);
+#pragma unroll
+            for (int p = 1; p < NOCT; ++p)
+                if (u >= D::g2_base(p)) { o = p; r = u - D::g2_base(p); G2 = D::G(p) * D::G(p); lb = D::lat_base(p); xb = D::x_base(p); }
+            const float4* axo = sm.axis[o];
+            float4* xo = sm.X + xb + r;
+            if (!top) {
+                const int c = (q << o) >> (NOCT - 1);
+                const float4 g0 = sm.lat[lb + c * G2 + r];
+                const float4 g1 = sm.lat[lb + (c + 1) * G2 + r];
+                // all loads first, then the arithmetic, then the stores: the GS outputs are independent chains
+                float4 ax[D::GS], e[D::GS];
+#pragma unroll
+                for (int m = 0; m < D::GS; ++m) ax[m] = axo[q * D::GS + m];
+#pragma unroll
+                for (int m = 0; m < D::GS; ++m) e[m] = xlerp(g0, g1, ax[m]);
+#pragma unroll
+                for (int m = 0; m < D::GS; ++m) xo[(q * D::GS + m) * G2] = e[m];
+            } else {
+                const float4 g = sm.lat[lb + (G2 << o) + r];              // plane G - 1 = 2^o
+                xo[ST * G2] = xlerp(g, g, axo[ST]);
+            }
+        }
+    } else {
 #pragma unroll
     for (int o = 0; o < NOCT; ++o) {
         const int G = D::G(o), lb = D::lat_base(o), xb = D::x_base(o);
-        // the octave value is carried normalised to its clamp range and shifted: u = v * (2/sqrt(3)) / 2 + 1/2, so
-        // that the reference's clamp to [-1, 1] becomes the .sat of the last FFMA of stage YZ; the shift rides on
-        // the value component through the y and z lerps (weights sum to 1), the slopes are only scaled
-        const float sc = 1.1547005383792515f * 0.5f;
         // Items are dealt round-robin ACROSS the octaves (thread rotation = items of the octaves before this one, mod NT):
         // no warp takes more than ceil(all items / NT) rounds -- 3 instead of 4 for warps 0-1 at S = 12 -- without a
         // per-item octave selection (measured slower in round 1).  The slowest warp sets the time of the barrier below.
@@ -769,18 +834,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             const int i = t / (G * G), r = t - i * G * G;
             const int c = (i << o) / ST;
             const int c1 = D::PRUNE ? min(c + 1, G - 1) : c + 1;         // i = S: weight ~ 1e-22 on a plane that is not kept
-            const float4 g0 = sm.lat[lb + c * G * G + r];
-            const float4 g1 = sm.lat[lb + c1 * G * G + r];
-            const float4 ax = sm.axis[o][i];
-            const float d = ax.x, d1 = ax.y, w = ax.z;
-            const float q0 = g0.x * d, q1 = g1.x * d1;
-            float4 e;
-            e.x = fmaf(fmaf(w, q1 - q0, q0), sc, 0.5f);
-            e.y = fmaf(w, g1.y - g0.y, g0.y) * sc;
-            e.z = fmaf(w, g1.z - g0.z, g0.z) * sc;
-            e.w = 0.f;
-            sm.X[xb + t] = e;
+            sm.X[xb + t] = xlerp(sm.lat[lb + c * G * G + r], sm.lat[lb + c1 * G * G + r], sm.axis[o][i]);
         }
+    }
     }
     // PRUNE: a column with j = S reads the X row "one past" its last kept row with weight ~ 1e-22; that is row 0 of
     // the next x-plane / the next octave (finite values) or, for the very last one, this pad row: keep it finite

@@ -33,5 +33,5 @@ regions = [
     f"K4_indices:{inds0}-{tris0 - 1}", f"K4_tris:{tris0}-{rest0 - 1}", f"hand_out:{hand0}-{hand1}", f"loop_body:{fused0}-{fused1}",
 ]
 kern = sys.argv[2] if len(sys.argv) > 2 else "k_build_fused"
-mangled = sys.argv[3] if len(sys.argv) > 3 else "k_build_fusedILi12ELi3Et"
+mangled = sys.argv[3] if len(sys.argv) > 3 else "k_build_fusedILi12ELi3EtLb0"
 subprocess.check_call([sys.executable, os.path.join(ROOT, "tools/ncu_regions.py"), sys.argv[1], kern, mangled] + regions)

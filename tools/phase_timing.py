@@ -5,7 +5,8 @@ import underwaterworld_b200 as uw
 lib = uw.load_library()
 pos = uw.region.config_positions("spawn")
 N = int(os.environ.get("N", "2048"))
-if N != 2048: pos = np.ascontiguousarray(uw.region.box_region((-16, 16), (-16, 16), (-4, 4))[:N])
+ZR = int(os.environ.get("ZR", "4"))
+if N != 2048: pos = np.ascontiguousarray(uw.region.box_region((-16, 16), (-16, 16), (-ZR, ZR))[:N])
 d_pos = torch.from_numpy(pos).cuda()
 b = uw.ChunkBuilder(uw.Perlin(0))
 for i in range(3): b.build_device(d_pos.data_ptr(), len(pos))
@@ -22,6 +23,7 @@ names = ["ticket+pos", "K1 noise", "K2 prepare", "K3 offsets", "K4 D1 fill", "K4
 tot = v[:7].sum() + v[11] + v[12]
 print(f"chunks {n/R:.0f} per build, active {nact/R:.0f}, any_lt {nany/R:.0f}; total cycles/chunk {tot/n:.0f}")
 print(f"  K1 split: H {v[11]/n:.0f}  X {v[12]/n:.0f}  YZ {v[1]/n:.0f} cycles/chunk")
+print(f"  end of stage YZ: spare warp last in {100*v[15]/n:.1f}% of the chunks, by {v[13]/max(v[15],1):.0f} cycles on average; otherwise the columns are last by {v[14]/max(n-v[15],1):.0f}")
 for i, nm in enumerate(names):
     denom = nact if i in (4, 5) else (nany if i == 2 else n)
     print(f"  {nm:14s} {100*v[i]/tot:5.1f}%   avg cycles per (relevant) chunk {v[i]/max(denom,1):8.0f}")

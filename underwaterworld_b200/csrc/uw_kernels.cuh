@@ -663,6 +663,7 @@ struct SpecDims {
     static constexpr int NGRP = 1 << (NOCT - 1), GS = ST / NGRP;
     __host__ __device__ static constexpr int g2_base(int o) { int b = 0; for (int q = 0; q < o; ++q) b += G(q) * G(q); return b; }   // prefix of G^2
     static constexpr int SG2 = g2_base(NOCT);
+    __host__ __device__ static constexpr int h_rounds() { int r = 0; for (int o = 0; o < NOCT; ++o) r += (G(o) * G(o) * G(o) + 31) / 32; return r; }
     static constexpr bool XGROUPED = PRUNE && (ST % NGRP == 0) && GS >= 2;
 };
 
@@ -686,6 +687,14 @@ struct SpecSmem {
     uint32_t mask[D::L * D::L + 3];
     uint8_t perm[256];
     int red[4];
+    // fused kernel: (chunk index, chunk position) of the current ticket [tb] and of the next one [tb ^ 1].  Kept here,
+    // not in registers: nothing in K1 needs them on its fast path (the guard band, the descriptor and K4 read them when
+    // they get there), and the registers they would hold across the whole iteration are what ptxas otherwise spills --
+    // the reloads sat at the head of stages X and YZ (4 % of the stall samples at config 3).
+    int ticket[2][4];
+#ifdef UW_PHASE_TIMING
+    uint32_t arrive[7];        // clock() of every warp's arrival at the barrier that ends stage YZ
+#endif
 };
 static_assert(SpecDims<12, 3>::L <= 16 && SpecDims<10, 3>::L <= 16, "terr rows hold 16 entries");
 
@@ -724,33 +733,94 @@ __device__ __forceinline__ void noise_stage_h(SpecSmem<ST, NOCT>& sm, int px, in
     }
 }
 
+// stage H of one chunk by ONE warp (the fused kernel's spare warp).  tools/phase_timing.py: with the loop above the
+// spare warp is the LAST to reach the barrier that ends stage YZ in ~87 % of the chunks, by ~600 cycles: 6 rounds of
+// (3 dependent table loads + gradient load + store), one after the other.  Same hash, factorised: perm[perm[X] ^ Y]
+// takes only G^2 values per octave (38 in all) -- one lane each, handed round by shuffle -- and the G^3 last-level
+// steps (one table load, the gradient load, the store) are branch-free (lanes past the end repeat the last point), so
+// the rounds are independent instruction streams the scheduler can overlap.
+template <int ST, int NOCT>
+__device__ __forceinline__ void noise_stage_h_warp(SpecSmem<ST, NOCT>& sm, int px, int py, int pz, int lane_in) {
+    using D = SpecDims<ST, NOCT>;
+    constexpr int OT = NOCT - 1, GT = D::G(OT), NLOW = D::g2_base(OT);
+    static_assert(GT * GT <= 32 && NLOW <= 32, "the second-level hashes of the top octave / of the others fit one warp each");
+    int lane = lane_in;
+    asm volatile("" : "+r"(lane));      // keep the index arithmetic here: hoisted out of the chunk loop it is spilled
+    uint32_t hb_top, hb_low;
+    {
+        const int l = lane < GT * GT ? lane : GT * GT - 1;
+        const int cx = l / GT, cy = l - cx * GT;
+        hb_top = sm.perm[sm.perm[((px << OT) + cx) & 255] ^ (((py << OT) + cy) & 255)];
+    }
+    {
+        int o = 0, cx = 0, cy = 0;
+#pragma unroll
+        for (int p = 0; p < OT; ++p) {
+            const int r = lane - D::g2_base(p);
+            if (r >= 0 && r < D::G(p) * D::G(p)) { o = p; cx = r / D::G(p); cy = r - cx * D::G(p); }
+        }
+        hb_low = sm.perm[sm.perm[((px << o) + cx) & 255] ^ (((py << o) + cy) & 255)];
+    }
+    // three passes over the rounds (second-level value + last table load, gradient load, store): written apart so that
+    // the loads of all rounds are in flight together instead of one round waiting for the previous round's store
+    constexpr int NR = D::h_rounds();
+    uint32_t hh[NR];
+    int dst[NR];
+    {
+        int k = 0;
+#pragma unroll
+        for (int o = 0; o < NOCT; ++o) {
+            const int G = D::G(o), base = D::lat_base(o);
+#pragma unroll
+            for (int t0 = 0; t0 < G * G * G; t0 += 32, ++k) {
+                const int t = t0 + lane;
+                const int tt = t < G * G * G ? t : G * G * G - 1;
+                const int cxy = tt / G, cz = tt - cxy * G;                   // cxy = cx G + cy
+                const uint32_t hb = __shfl_sync(0xFFFFFFFFu, o == OT ? hb_top : hb_low, (o == OT ? 0 : D::g2_base(o)) + cxy);
+                hh[k] = sm.perm[hb ^ (((pz << o) + cz) & 255)];
+                dst[k] = base + tt;
+            }
+        }
+    }
+    float4 gg[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) gg[k] = sm.grad[hh[k] & 15u];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) sm.lat[dst[k]] = gg[k];
+}
+
 // stages H, X, YZ for one chunk; leaves densities in sm.dens and column sign masks in sm.mask.
 // Returns (block-uniform) CF_ALL_GT | CF_ANY_LT.  All threads must call; ends with a barrier.
 //
 // PF (fused kernel, NT = NTF: one warp more than the columns need): while warps 0..5 walk the columns of THIS chunk
 // (stage YZ, the longest stage), the spare warp hashes the NEXT chunk's lattice (stage H) and looks up its terrace
-// terms -- lat is dead after stage X, the next ticket is known by then.  The next call then starts at stage X
-// (lat_ready): one block barrier and the whole hash-chain latency (3 dependent shared-memory loads per lattice point,
+// terms -- lat is dead after stage X, the next ticket is known by then.  Every call then starts at stage X (the
+// caller hashes the lattice of its first chunk itself): one block barrier and the whole hash-chain latency (3 dependent shared-memory loads per lattice point,
 // 14 % of the kernel's stall samples at config 3, 58 % of them at the barrier) leave the per-chunk critical path.
 // tb = which half of sm.terr belongs to this chunk (the prefetch writes the other one).
 template <int ST, int NOCT, int NT /*threads of the CTA: SpecDims::NT or ::NTF*/, bool PF = false>
 __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const AxisTables& tab, SpecSmem<ST, NOCT>& sm,
-                                                     int px, int py, int pz, unsigned long long* guard_count PHASE_ARG,
-                                                     const Handout* hand = nullptr, Ticket* tk_out = nullptr,
-                                                     int tb = 0, bool lat_ready = false) {
+                                                     int px_arg, int py_arg, int pz_arg, unsigned long long* guard_count PHASE_ARG,
+                                                     const Handout* hand = nullptr,
+                                                     int tb = 0) {
     using D = SpecDims<ST, NOCT>;
     constexpr int L = D::L;
     const int tid = threadIdx.x;
+    // with a hand-out (fused kernel) the chunk position is read from sm.ticket[tb] where it is needed
+    const volatile int* const cur = sm.ticket[tb];
+    auto PX = [&]() { return hand ? cur[1] : px_arg; };
+    auto PY = [&]() { return hand ? cur[2] : py_arg; };
+    auto PZ = [&]() { return hand ? cur[3] : pz_arg; };
     // the NEXT chunk's ticket: atomic issued here, (chunk, position) loads after stage X, values first touched by
     // the caller at the end of the iteration -- see ticket_begin / ticket_fetch
     uint32_t tk_t = 0;
     if (hand && tid == NT - 1) tk_t = ticket_begin(*hand);
 
     // ---- stage H (skipped when the previous call's spare warp has done it) ------------------------------
-    if (!(PF && lat_ready)) {                      // block-uniform
-        noise_stage_h<ST, NOCT>(sm, px, py, pz, tid, NT);
+    if (!PF) {
+        noise_stage_h<ST, NOCT>(sm, PX(), PY(), PZ(), tid, NT);
         if (tid >= NT - 32 && tid - (NT - 32) < L)   // terrace term perlin_util.rs:27-28 (last warp: it has idle lanes later)
-            sm.terr[tb][tid - (NT - 32)] = terrace_lookup(cfg, tid - (NT - 32), pz);
+            sm.terr[tb][tid - (NT - 32)] = terrace_lookup(cfg, tid - (NT - 32), PZ());
         __syncthreads();
     }
     PHASE_MARK(11);
@@ -830,7 +900,13 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
 #else
         const int rot = 0;
 #endif
-        for (int t = tid >= rot ? tid - rot : tid - rot + NT; t < L * G * G; t += NT) {
+#ifndef UW_K1_HOIST
+        int xtid = tid;
+        asm volatile("" : "+r"(xtid));          // see stage YZ: keep the item index arithmetic inside the chunk loop
+#else
+        const int xtid = tid;
+#endif
+        for (int t = xtid >= rot ? xtid - rot : xtid - rot + NT; t < L * G * G; t += NT) {
             const int i = t / (G * G), r = t - i * G * G;
             const int c = (i << o) / ST;
             const int c1 = D::PRUNE ? min(c + 1, G - 1) : c + 1;         // i = S: weight ~ 1e-22 on a plane that is not kept
@@ -844,16 +920,27 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; sm.red[2] = 1; }
     __syncthreads();
     PHASE_MARK(12);
-    Ticket nx;
-    nx.chunk = TICKET_DONE; nx.px = nx.py = nx.pz = 0;
-    if (hand && tid == NT - 1) { nx = ticket_fetch(*hand, tk_t); if (!PF) *tk_out = nx; }
+    // the next ticket goes to sm.ticket[tb ^ 1]: by the last thread here, or (PF) by the spare warp's last lane below
+    if (!PF && hand && tid == NT - 1) {
+        const Ticket nx = ticket_fetch(*hand, tk_t);
+        sm.ticket[tb ^ 1][0] = (int)nx.chunk; sm.ticket[tb ^ 1][1] = nx.px; sm.ticket[tb ^ 1][2] = nx.py; sm.ticket[tb ^ 1][3] = nx.pz;
+    }
 
     // ---- stage YZ -------------------------------------------------------------------------------
     // lanes of this warp that own a column: taken while the warp is still converged, so that the votes at the end
     // of the branch name their participants explicitly (the guard-band loop in between diverges)
     const unsigned col_lanes = __ballot_sync(0xFFFFFFFFu, tid < L * L);
     if (tid < L * L) {
-        const int i = tid / L, j = tid - i * L;
+        // the column's indices and table pointers do not depend on the chunk: hoisted out of the chunk loop by the
+        // compiler they do not fit the 72-register budget and come back as local-memory reloads at the head of this
+        // stage (37 % L1 misses) -- recomputing them here is ~15 instructions per column
+#ifndef UW_K1_HOIST
+        int ytid = tid;
+        asm volatile("" : "+r"(ytid));
+#else
+        const int ytid = tid;
+#endif
+        const int i = ytid / L, j = ytid - i * L;
         float R0[NOCT], S0[NOCT], R1[NOCT], S1[NOCT], Cc[NOCT], Dd[NOCT];
         const float4* xrow[NOCT];
         float dy[NOCT], dy1[NOCT], wy[NOCT];
@@ -874,13 +961,19 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             R = fmaf(wy[o], A1 - A0, A0);
             Sz = fmaf(wy[o], E1.z - E0.z, E0.z);
         };
-        float* out = sm.dens + tid * L;
+        float* out = sm.dens + ytid * L;
         const float isl = cfg.iso_level, eps = cfg.guard_eps;
         uint32_t signs = 0;                       // bit (L-1-k) <- (iso_k < iso_level), shifted in MSB-first
         float nearest = 3.0e38f;                  // min |iso - iso_level| of the column: one FMNMX per sample
+        float4 terr4 = make_float4(0.f, 0.f, 0.f, 0.f); (void)terr4;
 #pragma unroll
         for (int k = 0; k < L; ++k) {
+#ifndef UW_NO_TERR_VEC4               // one 16-byte load per four samples (-0.4 % at config 3 once the spare warp is off the critical path)
+            if ((k & 3) == 0) terr4 = reinterpret_cast<const float4*>(sm.terr[tb])[k >> 2];
+            float total = (k & 3) == 0 ? terr4.x : (k & 3) == 1 ? terr4.y : (k & 3) == 2 ? terr4.z : terr4.w;
+#else
             float total = sm.terr[tb][k];                                // terrace term - 1
+#endif
 #pragma unroll
             for (int o = 0; o < NOCT; ++o) {
                 const int c = D::cell(o, k);
@@ -913,13 +1006,13 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         while (near) {                                                   // rare: exact f64 re-evaluation
             const int k = __ffs(near) - 1;
             near &= near - 1;
-            const float iso = x_iso_lattice(cfg, sm.perm, px, py, pz, i, j, k);
+            const float iso = x_iso_lattice(cfg, sm.perm, PX(), PY(), PZ(), i, j, k);
             out[k] = iso;
             inside = (inside & ~(1u << k)) | ((iso < isl) ? (1u << k) : 0u);
             any_eq |= (iso == isl);
             atomicAdd(guard_count, 1ull);
         }
-        sm.mask[tid] = inside;
+        sm.mask[ytid] = inside;
         // outside the guard band |iso - isl| >= eps > 0, so "all > isl" <=> no inside bit and no exact tie
         const bool all_gt = (inside == 0u) && !any_eq, any_lt = inside != 0u;
         const bool w_all = __all_sync(col_lanes, all_gt), w_any = __any_sync(col_lanes, any_lt);
@@ -930,10 +1023,16 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             if (!w_solid) sm.red[2] = 0;
         }
     } else if (PF && tid >= NT - 32) {
-        // the spare warp: stage H + terrace terms of the NEXT chunk (its ticket sits in lane 31's registers)
+        // the spare warp: the NEXT chunk's ticket (last lane -> sm.ticket[tb ^ 1]), then its stage H + terrace terms
         const int lane = tid - (NT - 32);
-        const uint32_t nchunk = __shfl_sync(0xFFFFFFFFu, nx.chunk, 31);
-        const int npx = __shfl_sync(0xFFFFFFFFu, nx.px, 31), npy = __shfl_sync(0xFFFFFFFFu, nx.py, 31), npz = __shfl_sync(0xFFFFFFFFu, nx.pz, 31);
+        volatile int* const nxt = sm.ticket[tb ^ 1];
+        if (lane == 31) {
+            const Ticket nx = ticket_fetch(*hand, tk_t);
+            nxt[0] = (int)nx.chunk; nxt[1] = nx.px; nxt[2] = nx.py; nxt[3] = nx.pz;
+        }
+        __syncwarp();
+        const uint32_t nchunk = (uint32_t)nxt[0];
+        const int npx = nxt[1], npy = nxt[2], npz = nxt[3];
         if (nchunk != TICKET_DONE) {
 #ifndef UW_NO_TERR_FIRST
             // global table load first: its latency hides under the hash rounds (the barrier that ends stage YZ waits for
@@ -941,16 +1040,32 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
             // loads in flight costs registers and was slower, +4 %)
             float tv = 0.f;
             if (lane < L) tv = terrace_lookup(cfg, lane, npz);
+#ifndef UW_NO_H_WARP
+            noise_stage_h_warp<ST, NOCT>(sm, npx, npy, npz, lane);
+#else
             noise_stage_h<ST, NOCT>(sm, npx, npy, npz, lane, 32);
+#endif
             if (lane < L) sm.terr[tb ^ 1][lane] = tv;
 #else
             noise_stage_h<ST, NOCT>(sm, npx, npy, npz, lane, 32);
             if (lane < L) sm.terr[tb ^ 1][lane] = terrace_lookup(cfg, lane, npz);
 #endif
         }
-        if (lane == 31) *tk_out = nx;
     }
+#ifdef UW_PHASE_TIMING
+    if (PF && (tid & 31) == 0 && (tid >> 5) < 7) sm.arrive[tid >> 5] = (uint32_t)clock();
+#endif
     __syncthreads();
+#ifdef UW_PHASE_TIMING
+    if (PF && tid == 0 && NT == 224) {         // who is last at the barrier: the column warps (0..5) or the spare warp (6)?
+        int32_t col = 0;
+        const uint32_t base = sm.arrive[0];
+        for (int w = 1; w < 6; ++w) col = max(col, (int32_t)(sm.arrive[w] - base));
+        const int32_t d = (int32_t)(sm.arrive[6] - base) - col;
+        if (d > 0) { atomicAdd(&g_phase[13], (unsigned long long)d); atomicAdd(&g_phase[15], 1ull); }
+        else atomicAdd(&g_phase[14], (unsigned long long)(-d));
+    }
+#endif
     return (sm.red[0] ? CF_ALL_GT : 0u) | (sm.red[1] ? CF_ANY_LT : 0u) | (sm.red[2] ? CF_ALL_LT : 0u);
 }
 
@@ -2577,7 +2692,7 @@ struct FusedSmem {
     uint8_t cs[((ST * ST * ST + 15) / 16) * 16];
     uint32_t w[64];
     unsigned long long part[4 * 8];
-    int cur[4];                                       // current ticket: chunk index, chunk position
+    int last;                                         // set in the CTA that leaves the launch last
     uint32_t hand[UW_NCLS + 1];                       // cost-ordered hand-out: class-list prefix sums, ready flag
     Handout handout;
 };
@@ -2707,27 +2822,31 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
     if (tid == D::NTF - 1) {
         if (order) handout_ready(hand);
         const Ticket t0 = ticket_fetch(hand, t_first);
-        sm.cur[0] = (int)t0.chunk; sm.cur[1] = t0.px; sm.cur[2] = t0.py; sm.cur[3] = t0.pz;
+        sm.n.ticket[0][0] = (int)t0.chunk; sm.n.ticket[0][1] = t0.px; sm.n.ticket[0][2] = t0.py; sm.n.ticket[0][3] = t0.pz;
     }
     __syncthreads();
 #ifdef UW_PHASE_TIMING
     long long t_phase = clock64();
     if (tid == 0 && blockIdx.x < 1024) { g_cta[blockIdx.x][0] = gtimer(); g_cta[blockIdx.x][2] = 0; g_cta[blockIdx.x][3] = 0; }
 #endif
-    int tb = 0;                                            // half of sm.n.terr that belongs to the current chunk
-    bool lat_ready = false;                                // the previous iteration's spare warp has run stage H for this chunk
+    int tb = 0;                                            // half of sm.n.terr / sm.n.ticket that belongs to the current chunk
+    // PF: every iteration finds its lattice hashed (by the previous iteration's spare warp); the first one by all threads here
+    constexpr bool PFH = UW_FUSED_PREFETCH_H != 0;
+    if (PFH && (uint32_t)sm.n.ticket[0][0] != TICKET_DONE) {           // block-uniform
+        const int px = sm.n.ticket[0][1], py = sm.n.ticket[0][2], pz = sm.n.ticket[0][3];
+        noise_stage_h<ST, NOCT>(sm.n, px, py, pz, tid, D::NTF);
+        if (tid >= D::NTF - 32 && tid - (D::NTF - 32) < L) sm.n.terr[0][tid - (D::NTF - 32)] = terrace_lookup(cfg, tid - (D::NTF - 32), pz);
+        __syncthreads();
+    }
     while (true) {
-        const uint32_t chunk = (uint32_t)sm.cur[0];
+        const volatile int* const cur = sm.n.ticket[tb];   // this chunk's ticket; K1 leaves the next one in ticket[tb ^ 1]
+        const uint32_t chunk = (uint32_t)cur[0];
         if (chunk == TICKET_DONE) break;
-        const int px = sm.cur[1], py = sm.cur[2], pz = sm.cur[3];
         PHASE_MARK(0);                                     // ticket + position
-        Ticket nxt;
-        nxt.chunk = TICKET_DONE; nxt.px = nxt.py = nxt.pz = 0;
 
         // ---- K1 ---------------------------------------------------------------------------------
-        const uint32_t fl = noise_chunk_spec<ST, NOCT, D::NTF, UW_FUSED_PREFETCH_H != 0>(cfg, tab, sm.n, px, py, pz, guard_count PHASE_PASS,
-                                                       &hand, &nxt, tb, lat_ready);
-        tb ^= 1; lat_ready = true;
+        const uint32_t fl = noise_chunk_spec<ST, NOCT, D::NTF, PFH>(cfg, tab, sm.n, 0, 0, 0, guard_count PHASE_PASS, &hand, tb);
+        tb ^= 1;
         PHASE_MARK(1);                                     // K1 noise
         if (dens_out) {
             float4* dst = reinterpret_cast<float4*>(dens_out + (size_t)chunk * D::DSTRIDE);
@@ -2776,6 +2895,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             PHASE_MARK(4);                                 // K4 D1 fill
             ev = sm.part[0] >> 32; ei = sm.part[0] & 0xFFFFFFFFull;
             if (ev + nv_pad <= vcap && ei + ni_pad <= icap) {              // block-uniform
+                const int px = cur[1], py = cur[2], pz = cur[3];
                 emit_rest<ST, IndexT, PEER>(cfg, mc, es, sh, px, py, pz, verts + ev, inds + ei);
                 if (tris) emit_tris<ST>(cfg, mc, es, sh, px, py, pz, tris + ei / 3u);
             }
@@ -2783,7 +2903,7 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
         }
         if (tid == 0) {
             uw_chunk_desc d;
-            d.pos[0] = px; d.pos[1] = py; d.pos[2] = pz;
+            d.pos[0] = cur[1]; d.pos[1] = cur[2]; d.pos[2] = cur[3];
             d.flags = ((fl & CF_ALL_GT) ? UW_CHUNK_BLANK_EARLY : 0u) | (ni > 0 ? UW_CHUNK_HAS_MESH : 0u)
                     | (nv > 65536u ? UW_CHUNK_U16_OVERFLOW : 0u);
             d.vert_offset = (uint32_t)ev + fo.desc_vbase; d.vert_count = nv;
@@ -2805,7 +2925,6 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             // 2^32 would carry into the vertex half.  The chunk whose claim crosses the boundary sees it here.
             if (!ordered && ni > 0 && (ei + ni_pad > 0xFFFFFFFFull || ev + nv_pad > 0xFFFFFFFFull)) atomicMax(&totals->overflow, 2u);
         }
-        if (tid == D::NTF - 1) { sm.cur[0] = (int)nxt.chunk; sm.cur[1] = nxt.px; sm.cur[2] = nxt.py; sm.cur[3] = nxt.pz; }
         __syncthreads();                                   // chunk fully emitted, smem reusable, next ticket visible
         PHASE_MARK(6);                                     // tail: descriptor + waiting for the other warps
 #ifdef UW_PHASE_TIMING
@@ -2814,14 +2933,14 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
 #endif
     }
     // last CTA out resets the other control block for the next launch
-    __syncthreads();                                       // every thread has seen TICKET_DONE in sm.cur[0]
+    __syncthreads();                                       // every thread has seen TICKET_DONE
     if (tid == 0) {
         if (fo.head) __threadfence_system();               // gather segment: the outputs may be another GPU's memory
         else __threadfence();
-        sm.cur[0] = (atomicAdd(&ctr->done, 1u) == gridDim.x - 1) ? 1 : 0;
+        sm.last = (atomicAdd(&ctr->done, 1u) == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
-    if (sm.cur[0]) {
+    if (sm.last) {
         if (tid == 0) {
             FusedSummary sm_out;                     // every other CTA fenced its writes before bumping `done`
             sm_out.alloc = atomicAdd(&ctr->alloc, 0ull);

@@ -686,7 +686,7 @@ struct SpecSmem {
     float terr[2][16];         // adj_z - fmod(adj_z, mod) - 1 of this chunk / the prefetched next chunk
     uint32_t mask[D::L * D::L + 3];
     uint8_t perm[256];
-    int red[4];
+    int red[2][3];             // block votes of the chunk [tb]: all samples > iso_level, any inside, all inside
     // fused kernel: (chunk index, chunk position) of the current ticket [tb] and of the next one [tb ^ 1].  Kept here,
     // not in registers: nothing in K1 needs them on its fast path (the guard band, the descriptor and K4 read them when
     // they get there), and the registers they would hold across the whole iteration are what ptxas otherwise spills --
@@ -841,7 +841,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         e.w = 0.f;
         return e;
     };
-#ifdef UW_X_GROUPED     // measured, not kept (profiles/r02_ab_x_grouped_not_kept.txt): -3.5 % warp-instructions, +1.9 % time at config 3
+#ifndef UW_NO_X_GROUPED
     constexpr int XITEMS = D::NGRP * D::SG2;                   // (cell group q, octave, lattice (cy, cz)) items, q-major
     constexpr int XTOP0 = NT >= ((XITEMS + 31) & ~31) + D::SG2 ? ((XITEMS + 31) & ~31) : XITEMS;   // tops start a warp if room
     constexpr bool XG = D::XGROUPED && XTOP0 + D::SG2 <= NT;
@@ -917,7 +917,7 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
     // PRUNE: a column with j = S reads the X row "one past" its last kept row with weight ~ 1e-22; that is row 0 of
     // the next x-plane / the next octave (finite values) or, for the very last one, this pad row: keep it finite
     if (D::PRUNE && tid < D::GTOP) sm.X[D::XN + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid == 0) { sm.red[0] = 1; sm.red[1] = 0; sm.red[2] = 1; }
+    if (tid == 0) { sm.red[tb][0] = 1; sm.red[tb][1] = 0; sm.red[tb][2] = 1; }
     __syncthreads();
     PHASE_MARK(12);
     // the next ticket goes to sm.ticket[tb ^ 1]: by the last thread here, or (PF) by the spare warp's last lane below
@@ -1018,9 +1018,9 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         const bool w_all = __all_sync(col_lanes, all_gt), w_any = __any_sync(col_lanes, any_lt);
         const bool w_solid = __all_sync(col_lanes, inside == (1u << L) - 1u);           // the all-full vote
         if ((tid & 31) == 0 || tid == (L * L / 32) * 32) {
-            if (!w_all) sm.red[0] = 0;
-            if (w_any) sm.red[1] = 1;
-            if (!w_solid) sm.red[2] = 0;
+            if (!w_all) sm.red[tb][0] = 0;
+            if (w_any) sm.red[tb][1] = 1;
+            if (!w_solid) sm.red[tb][2] = 0;
         }
     } else if (PF && tid >= NT - 32) {
         // the spare warp: the NEXT chunk's ticket (last lane -> sm.ticket[tb ^ 1]), then its stage H + terrace terms
@@ -1066,7 +1066,8 @@ __device__ __forceinline__ uint32_t noise_chunk_spec(const DevCfg& cfg, const Ax
         else atomicAdd(&g_phase[14], (unsigned long long)(-d));
     }
 #endif
-    return (sm.red[0] ? CF_ALL_GT : 0u) | (sm.red[1] ? CF_ANY_LT : 0u) | (sm.red[2] ? CF_ALL_LT : 0u);
+    // (the flags alternate with tb: a caller that skips its end-of-chunk barrier may be resetting the next chunk's word already)
+    return (sm.red[tb][0] ? CF_ALL_GT : 0u) | (sm.red[tb][1] ? CF_ANY_LT : 0u) | (sm.red[tb][2] ? CF_ALL_LT : 0u);
 }
 
 template <int ST, int NOCT>
@@ -2925,7 +2926,14 @@ k_build_fused(const __grid_constant__ DevCfg cfg, const __grid_constant__ AxisTa
             // 2^32 would carry into the vertex half.  The chunk whose claim crosses the boundary sees it here.
             if (!ordered && ni > 0 && (ei + ni_pad > 0xFFFFFFFFull || ev + nv_pad > 0xFFFFFFFFull)) atomicMax(&totals->overflow, 2u);
         }
-        __syncthreads();                                   // chunk fully emitted, smem reusable, next ticket visible
+        // chunk fully emitted, shared memory reusable.  A chunk without K2..K4 (all empty / all full: most of a region)
+        // needs no barrier here: its next ticket became visible at the barrier that ended K1, the vote flags, the ticket
+        // slots and the terrace terms alternate between chunks, and everything else K1 writes is ordered by K1's own
+        // barriers -- the other warps start the next chunk's stage X while warp 0 writes the descriptor.
+#ifndef UW_NO_LIGHT_SKIP
+        if (dens_out != nullptr || (fl & (CF_ANY_LT | CF_ALL_LT)) == CF_ANY_LT)        // block-uniform
+#endif
+        __syncthreads();
         PHASE_MARK(6);                                     // tail: descriptor + waiting for the other warps
 #ifdef UW_PHASE_TIMING
         if (tid == 0) { atomicAdd(&g_phase[8], 1ull); if (ni > 0) atomicAdd(&g_phase[9], 1ull); if (fl & CF_ANY_LT) atomicAdd(&g_phase[10], 1ull);

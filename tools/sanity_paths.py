@@ -33,6 +33,12 @@ with uw.ChunkBuilder(uw.Perlin(0), internal_size=10, staged=True) as s10, uw.Chu
     print("S=10 staged == fused:", s10.build(pos).n_inds == f10.build(pos).n_inds)
 with uw.ChunkBuilder(uw.Perlin(0), analytic_skip=True) as b:
     print("analytic skip, cost order:", b.build(big).n_inds == fb.n_inds)
+# a tall region in request order (n > 9472): ~25 chunks per CTA, most of them without a mesh -- runs of chunks that skip
+# the end-of-chunk barrier, with the spare warp hashing ahead and the vote flags / ticket slots alternating
+tall = uw.region.box_region((-12, 12), (-12, 12), (-13, 13))  # 14 976 chunks
+with uw.ChunkBuilder(uw.Perlin(0)) as b, uw.ChunkBuilder(uw.Perlin(0), staged=True) as s:
+    fb2, sb2 = b.build(tall), s.build(tall)
+    print("tall region (request order, barrier-free mesh-less chunks): fused == staged:", fb2.n_inds == sb2.n_inds and fb2.n_verts == sb2.n_verts, fb2.n_inds)
 print("done 2")
 # round 2 paths: gather segments (local + forced staged stores), uw_multi_build, draw list, collision ray casts
 import os

@@ -302,27 +302,34 @@ def run_ours(args):
 
         # ---- e2e: host positions -> meshes in the rendering GPU's arenas (rank 0) + draw list on the host ----------
         # Gather-aware partition: the rendering rank's own output does not cross NVLink, so when the gather is bound by
-        # its NVLink ingress (N = 8) it takes a larger slab.  The share adapts during the warm-up steps from every
-        # rank's build time (RegionGather.feedback: one small all_reduce between steps, never inside a timed step) and
-        # is frozen for the timed ones.  Segments are sized for half the region each.
+        # its NVLink ingress (N = 8) it takes a larger slab.  The share is chosen during the warm-up steps by measuring
+        # whole steps under a handful of candidate shares (RegionGather.tune: one small all_reduce between steps, never
+        # inside a timed step) and is frozen for the timed ones.  Segments are sized for half the region each.
         half = (n_total + 1) // 2
         rg = G.RegionGather(builder, rank, world, n_total, dst=0, seg_vcap=half * 192 + 4096, seg_icap=half * 640 + 16384,
                             bcast_device="cuda" if world > 1 else None)
         res = None
-        WG = max(W, 8) if world > 1 else W
-        for i in range(WG):
+        step_no = [0]
+
+        def e2e_step():
+            nonlocal res
             gf, gn = rg.plan(n_total)
             gpos = whole_pin.numpy()[gf:gf + gn]
-            flush.fill_(i & 0xFF)
+            flush.fill_(step_no[0] & 0xFF)
+            step_no[0] += 1
             barrier()
             t0 = time.perf_counter()
             rg.build(gpos, gf)
-            builder.sync()                                   # this rank's kernel (for the balance; not done in timed steps)
-            mine = time.perf_counter() - t0
             if rank == 0:
                 res = rg.wait(draw_to_host=True)
-            if i < WG - 2:
-                rg.feedback(mine, device="cuda" if world > 1 else None)
+            builder.sync()
+            return time.perf_counter() - t0
+
+        if world > 1:
+            # measured search over a handful of render shares (two cold steps, then two steps per candidate), warm-up only
+            rg.tune(e2e_step, device="cuda")
+        for i in range(W):
+            e2e_step()
         gf, gn = rg.plan(n_total)
         gpos = whole_pin.numpy()[gf:gf + gn]
         e2e_t = []
@@ -510,8 +517,10 @@ def run_ours(args):
                     "timing": "host perf_counter per step on every rank (barrier, build, wait/sync), MAX over ranks per step, mean over K",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "render_share": render_share if render_share > 0 else 1.0 / world, "chunks_per_rank": g_counts,
-                    "partition": "gather-aware: the rendering rank's slab grows until it finishes with the slowest producer "
-                                 "(adapted over the warm-up steps, frozen for the timed ones); value uses the even split",
+                    "share_search_ms": [[round(a, 4), round(1e3 * b, 4)] for a, b in getattr(rg, "tune_trace", [])],
+                    "partition": "gather-aware: the rendering rank takes a larger slab (its output does not cross NVLink); the share is "
+                                 "the fastest of a handful of candidates measured over the warm-up steps (RegionGather.tune), "
+                                 "frozen for the timed ones; value uses the even split",
                     "mesh_bytes_to_render_gpu": 24 * g_verts + 2 * g_inds,
                     "nvlink_bytes_per_step": (24 * (g_verts - int(res.segments[0]["n_verts"])) + 2 * (g_inds - int(res.segments[0]["n_inds"]))
                                               + 32 * (n_total - int(res.segments[0]["n_chunks"]))) if world > 1 else 0},

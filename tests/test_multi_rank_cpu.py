@@ -111,3 +111,40 @@ def test_gather_structs_match_the_header():
     assert C.sizeof(_ffi.UwGatherSegment) == 48
     assert C.sizeof(_ffi.UwGatherResult) == 8 + 24 + 24 + 16 + 8 + 24 + 48 * _ffi.UW_MAX_SEGMENTS
     assert _ffi.UwGatherInfo.ipc_handle.offset == 104
+
+
+def _tune_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from underwaterworld_b200 import gather
+    rg = gather.RegionGather.__new__(gather.RegionGather)      # control-plane logic only: no builder, no GPU
+    rg.world, rank_, rg.dst, rg.group, rg.render_share = 8, rank, 0, None, 0.0
+    rg.rank = rank_
+    calls = []
+
+    def run_step():
+        # a step is as slow as its slowest rank: the rendering rank's compute grows with its share, the producers'
+        # ingress-bound stores shrink with it; rank 1 plays "slowest producer"
+        calls.append(rg.render_share)
+        return 3.25 * rg.render_share if rank == 0 else 1.03 * (1.0 - rg.render_share)
+
+    best = rg.tune(run_step)
+    np.save(os.path.join(out_dir, f"tune{rank}.npy"), np.array([best, len(calls)] + rg.candidate_shares()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_render_share_search_picks_the_fastest_candidate_gloo(tmp_path):
+    """RegionGather.tune (bench.py's warm-up): every rank measures whole steps under each candidate share, the step time
+    is the MAX over ranks, the fastest share wins on every rank alike."""
+    world = 2
+    mp.spawn(_tune_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = np.load(tmp_path / "tune0.npy"), np.load(tmp_path / "tune1.npy")
+    cands = a[2:].tolist()
+    assert cands == b[2:].tolist() and cands[0] == 0.125 and max(cands) <= 0.5 and len(cands) == 7
+    assert a[0] == b[0]                                            # same decision everywhere
+    model = [max(3.25 * s, 1.03 * (1.0 - s)) for s in cands]
+    assert a[0] == cands[int(np.argmin(model))]                    # 0.25 for these constants (optimum 0.24)
+    assert a[1] == b[1] == 2 + 2 * len(cands)                      # two cold steps, two per candidate

@@ -2147,10 +2147,12 @@ k_noise_big(const __grid_constant__ DevCfg cfg, const float4* __restrict__ g_axi
         const int px = pos[3 * chunk], py = pos[3 * chunk + 1], pz = pos[3 * chunk + 2];
 
         // ---- stage H ----------------------------------------------------------------------------
+        int htid = tid;
+        asm volatile("" : "+r"(htid));       // lattice indices recomputed per unit: hoisted, they are spilled (cf. noise_chunk_spec)
 #pragma unroll
         for (int o = 0; o < NOCT; ++o) {
             const int G = D::G(o), F = 1 << o, base = D::lat_base(o);
-            for (int t = tid; t < G * G * G; t += NT) {
+            for (int t = htid; t < G * G * G; t += NT) {
                 const int cx = t / (G * G), r = t - cx * G * G, cy = r / G, cz = r - cy * G;
                 const uint32_t h = sm.perm[sm.perm[sm.perm[(F * px + cx) & 255] ^ ((F * py + cy) & 255)] ^ ((F * pz + cz) & 255)];
                 sm.lat[base + t] = sm.grad[h & 15u];

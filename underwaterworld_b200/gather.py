@@ -203,6 +203,41 @@ class RegionGather:
         self.render_share = balance_share(self.render_share, self.world, ts[self.dst], others)
         return self.render_share
 
+    def candidate_shares(self, steps: int = 7, growth: float = 0.25) -> list:
+        """Render shares worth measuring: the even split and `steps - 1` larger ones (the rendering rank's own output does
+        not cross NVLink, so its slab only ever grows), capped at one half."""
+        even = 1.0 / max(self.world, 1)
+        return sorted({min(0.5, even * (1.0 + growth * k)) for k in range(steps)})
+
+    def tune(self, run_step, candidates=None, repeats: int = 2, cold: int = 2, device=None) -> float:
+        """Collective (control plane, warm-up only): measure whole steps under each candidate render share and keep the
+        fastest.  `run_step()` runs ONE complete request under the current share on this rank (plan, build, the
+        rendering rank's wait, sync) and returns its seconds; the step time is the maximum over ranks.  The one-step
+        controller (`feedback`) equalises kernel times, which stops short of the optimum when the rendering GPU's own
+        kernel is slowed by the traffic arriving over NVLink; a direct search over a handful of shares does not care."""
+        if self.world < 2:
+            return self.render_share
+        import torch
+        import torch.distributed as dist
+        cands = list(candidates) if candidates is not None else self.candidate_shares()
+        best, best_t = self.render_share, float("inf")
+        self.tune_trace = []                                   # [(share, seconds)]: what the search saw
+        self.render_share = cands[0]
+        for _ in range(cold):
+            run_step()
+        for sh in cands:
+            self.render_share = sh
+            t_min = float("inf")
+            for _ in range(repeats):
+                t = torch.tensor([run_step()], dtype=torch.float64, device=device or "cpu")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+                t_min = min(t_min, float(t.cpu()[0]))
+            self.tune_trace.append((sh, t_min))
+            if t_min < best_t:
+                best, best_t = sh, t_min
+        self.render_share = best
+        return best
+
     def build(self, positions, first_chunk: int):
         self.builder.gather_build(positions, first_chunk)
 

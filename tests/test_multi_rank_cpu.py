@@ -145,6 +145,8 @@ def test_render_share_search_picks_the_fastest_candidate_gloo(tmp_path):
     cands = a[2:].tolist()
     assert cands == b[2:].tolist() and cands[0] == 0.125 and max(cands) <= 0.5 and len(cands) == 7
     assert a[0] == b[0]                                            # same decision everywhere
-    model = [max(3.25 * s, 1.03 * (1.0 - s)) for s in cands]
-    assert a[0] == cands[int(np.argmin(model))]                    # 0.25 for these constants (optimum 0.24)
-    assert a[1] == b[1] == 2 + 2 * len(cands)                      # two cold steps, two per candidate
+    model = lambda s: max(3.25 * s, 1.03 * (1.0 - s))
+    coarse = cands[int(np.argmin([model(s) for s in cands]))]      # 0.21875 for these constants (optimum 0.2407)
+    half = 0.5 * (cands[1] - cands[0])
+    assert a[0] == min([coarse, coarse - half, coarse + half], key=model) == 0.234375          # refined towards it
+    assert a[1] == b[1] == 2 + 2 * (len(cands) + 2)                # two cold steps, two per candidate, two refinements

@@ -209,7 +209,7 @@ class RegionGather:
         even = 1.0 / max(self.world, 1)
         return sorted({min(0.5, even * (1.0 + growth * k)) for k in range(steps)})
 
-    def tune(self, run_step, candidates=None, repeats: int = 2, cold: int = 2, device=None) -> float:
+    def tune(self, run_step, candidates=None, repeats: int = 2, cold: int = 2, device=None, refine: bool = True) -> float:
         """Collective (control plane, warm-up only): measure whole steps under each candidate render share and keep the
         fastest.  `run_step()` runs ONE complete request under the current share on this rank (plan, build, the
         rendering rank's wait, sync) and returns its seconds; the step time is the maximum over ranks.  The one-step
@@ -225,7 +225,9 @@ class RegionGather:
         self.render_share = cands[0]
         for _ in range(cold):
             run_step()
-        for sh in cands:
+
+        def measure(sh):
+            nonlocal best, best_t
             self.render_share = sh
             t_min = float("inf")
             for _ in range(repeats):
@@ -235,6 +237,15 @@ class RegionGather:
             self.tune_trace.append((sh, t_min))
             if t_min < best_t:
                 best, best_t = sh, t_min
+
+        for sh in cands:
+            measure(sh)
+        if refine and len(cands) > 1:                          # one refinement pass: half a grid step either side of the best
+            half = 0.5 * min(b - a for a, b in zip(cands, cands[1:]))
+            centre = best
+            for sh in (centre - half, centre + half):
+                if cands[0] <= sh <= 0.5 and all(abs(sh - c) > 1e-9 for c in cands):
+                    measure(sh)
         self.render_share = best
         return best
 

@@ -699,6 +699,26 @@ def test_exportable_arenas_round_trip_through_a_file_descriptor(uw, builder12):
         builder12.export_arena_fd(0)                                   # not created with the flag
 
 
+def test_tall_region_runs_of_mesh_less_chunks_agree_across_pipelines(uw):
+    """A tall request-order region (n > 9472, ~25 chunks per CTA, 4 of 5 of them without a mesh): in the fused kernel
+    such chunks take no end-of-chunk barrier, the spare warp hashes the next lattice while the columns are walked, and
+    tickets / vote flags / terrace terms alternate between two shared-memory slots.  Same chunks, three pipelines
+    (fused, fused with request-order packing, staged kernels with densities in HBM; plus the density tap, which keeps
+    every barrier): per chunk byte-identical."""
+    pos = uw.region.box_region((-12, 12), (-12, 12), (-13, 13))       # 14 976 chunks
+    outs = []
+    for kw in (dict(), dict(ordered=True), dict(staged=True), dict(keep_densities=True)):
+        with uw.ChunkBuilder(uw.Perlin(3), **kw) as b:
+            batch = b.build(pos)
+            outs.append((batch.descs.copy(), *batch.compact()))
+    d0, v0, i0 = outs[0]
+    assert int((d0["index_count"] > 0).sum()) > 1000 and int((d0["index_count"] == 0).sum()) > 10000
+    for d, v, i in outs[1:]:
+        for f in ("pos", "flags", "vert_count", "index_count"):
+            assert np.array_equal(d[f], d0[f]), f
+        assert v.tobytes() == v0.tobytes() and i.tobytes() == i0.tobytes()
+
+
 def test_keep_densities_tap_of_the_fused_kernel(uw):
     """UW_FLAG_KEEP_DENSITIES: the fused kernel also writes its shared-memory density field to HBM (the default
     path never materialises it and reports a NULL pointer); it equals the stand-alone noise kernel's output."""

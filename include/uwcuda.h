@@ -311,11 +311,33 @@ void        uw_slab_bounds(uint32_t n, uint32_t parts, uint32_t part, uint32_t* 
 /* Gather-aware partition: the rendering GPU's own output does not cross NVLink, so when the gather is bound by the
  * rendering GPU's ingress (8 GPUs: 706 MB into one GPU) its slab should be larger.  Slab `render_part` holds
  * render_permille / 1000 of the n chunks (never less than an even share), the other slabs share the rest evenly; slabs
- * stay contiguous and in part order.  render_permille = 0: the even split of uw_slab_bounds.  uw_multi_build adapts the
- * share from the kernel times it measures (render GPU against the slowest producer); gather.RegionGather does the same
- * for one process per GPU. */
+ * stay contiguous and in part order.  render_permille = 0: the even split of uw_slab_bounds.  uw_multi_build chooses the
+ * share by a search over successive requests (uw_share_search_next); gather.RegionGather.tune measures a handful of
+ * candidate shares during warm-up for one process per GPU. */
 void        uw_slab_bounds_weighted(uint32_t n, uint32_t parts, uint32_t part, uint32_t render_part, uint32_t render_permille,
                                     uint32_t* first, uint32_t* count);
+
+/* Choosing the rendering GPU's share over successive requests (what uw_multi_build does internally; exported so that
+ * other drivers -- one process per GPU -- can run the same search and so that it can be tested without a GPU).
+ * A damped hill climb on the measured cost of a whole request (any unit that is comparable between requests, e.g.
+ * seconds per chunk of the slowest GPU): start at the even split, grow the share while the cost falls, turn round and
+ * halve the step when it rises, settle on the cheapest share seen once the step is down to 1/64 of an even share, and
+ * start over if the cost at that share later rises by more than 10 % (another workload).  Equalising the GPUs' kernel times instead stops short of the optimum, because the
+ * rendering GPU's own kernel is slowed by the traffic arriving over NVLink (profiles/r02_gather_scaling.txt).
+ * Zero-initialise the state; uw_share_search_next records the cost measured AT state->share (the first two costs are
+ * discarded: cold requests) and returns the share to use for the next request (even split <= share <= 1/2; 0 when parts < 2). */
+typedef struct uw_share_search {
+    double   share;       /* share the next cost will be measured at; 0 = not started (even split)            */
+    double   step;        /* current step                                                                     */
+    double   last_cost;   /* cost at the previous share; 0 = none yet                                         */
+    double   best_share;  /* cheapest share seen so far ...                                                   */
+    double   best_cost;   /* ... and its cost                                                                 */
+    int32_t  dir;         /* +1 / -1                                                                           */
+    uint32_t moves;       /* requests seen                                                                     */
+    uint32_t settled;     /* 1 = the step has shrunk to 1/64 of an even share: holding best_share             */
+    uint32_t reserved;
+} uw_share_search;
+double      uw_share_search_next(uw_share_search* state, uint32_t parts, double cost);
 
 /* One process, G GPUs: devices[0] renders.  uw_multi_build = World::build_full_step for a whole region
  * (world.rs:113-123) -- slabs, G fused launches (each GPU's H2D + kernel on its own stream), meshes gathered into

@@ -142,3 +142,28 @@ def test_weighted_slab_bounds_mirror_the_library(lib):
         s = gather.balance_share(s, 8, t_r, t_o)
     assert 0.20 < s < 0.26
     assert gather.balance_share(0.3, 4, 1.0, 1.02) == 0.3 and gather.balance_share(0.0, 4, 2.0, 1.0) == 0.25
+    # the search uw_multi_build runs between requests (uw_share_search_next, a pure function of its state): the C
+    # function and its Python mirror take the same steps; on a model of the 8-GPU gather (the rendering GPU's kernel is
+    # slowed by the traffic arriving over NVLink, the producers are ingress-bound) it settles at the cost minimum, where
+    # equalising kernel times (above) would stop early
+    for parts, model in ((8, lambda f: max(3.25 * f * (1.0 + 1.2 * (1.0 - f)), 1.03 * (1.0 - f))),
+                         (4, lambda f: max(3.25 * f, 0.82 * (1.0 - f) / 3 * 4, 1.03 * (1.0 - f))),
+                         (2, lambda f: 1.0 + f)):
+        st, mirror = _ffi.UwShareSearch(), {}
+        share = lib.uw_share_search_next(C.byref(st), parts, 0.0)          # not started: the even split
+        assert share == gather.share_search_next(mirror, parts, 0.0) == 1.0 / parts
+        seen = []
+        for k in range(40):
+            cost = model(share) * (1.0 + 0.004 * ((k * 7919) % 5 - 2))       # +-0.8 % measurement noise
+            seen.append((cost, share))
+            share = lib.uw_share_search_next(C.byref(st), parts, cost)
+            assert share == gather.share_search_next(mirror, parts, cost)
+            assert 1.0 / parts <= share <= 0.5
+        grid = [1.0 / parts + k * (0.5 - 1.0 / parts) / 400 for k in range(401)]
+        best = min(grid, key=model)
+        assert abs(share - best) <= 0.02 and model(share) <= model(best) * 1.03, (parts, share, best)
+        assert st.settled == 1 and share == st.best_share                   # ... and stays there
+        # another workload (everything 30 % slower): the search starts over from where it is
+        assert lib.uw_share_search_next(C.byref(st), parts, 1.3 * model(share)) == gather.share_search_next(mirror, parts, 1.3 * model(share))
+        assert st.settled == 0 or parts == 2
+    assert lib.uw_share_search_next(C.byref(_ffi.UwShareSearch()), 1, 1.0) == 0.0 and C.sizeof(_ffi.UwShareSearch) == 56

@@ -109,10 +109,16 @@ EXPORTS = [
     "uw_set_stream", "uw_get_stage_times", "uw_set_profiling", "uw_get_guard_count", "uw_debug_ffma_peak", "uw_export_arena_fd", "uw_debug_vertex_colors",
     "uw_gather_create", "uw_gather_destroy", "uw_gather_attach", "uw_gather_detach", "uw_gather_build",
     "uw_gather_build_device", "uw_gather_wait", "uw_slab_bounds",
-    "uw_multi_create", "uw_multi_build", "uw_multi_destroy", "uw_multi_last_error", "uw_debug_copy_to_host", "uw_raycast_tris", "uw_slab_bounds_weighted", "uw_multi_render_share",
+    "uw_multi_create", "uw_multi_build", "uw_multi_destroy", "uw_multi_last_error", "uw_debug_copy_to_host", "uw_raycast_tris", "uw_slab_bounds_weighted", "uw_multi_render_share", "uw_share_search_next",
 ]
 
 _lib = None
+
+
+class UwShareSearch(C.Structure):
+    """uw_share_search (include/uwcuda.h): state of the render-share search; zero-initialised = not started."""
+    _fields_ = [("share", C.c_double), ("step", C.c_double), ("last_cost", C.c_double), ("best_share", C.c_double),
+                ("best_cost", C.c_double), ("dir", C.c_int32), ("moves", C.c_uint32), ("settled", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class UwError(RuntimeError):
@@ -176,6 +182,8 @@ def load_library() -> C.CDLL:
     lib.uw_slab_bounds_weighted.restype = None
     lib.uw_multi_render_share.argtypes = [vp]
     lib.uw_multi_render_share.restype = C.c_uint32
+    lib.uw_share_search_next.argtypes = [C.POINTER(UwShareSearch), u32, C.c_double]
+    lib.uw_share_search_next.restype = C.c_double
     lib.uw_multi_create.argtypes = [C.POINTER(UwConfig), C.POINTER(C.c_int32), u32, C.POINTER(vp)]
     lib.uw_multi_build.argtypes = [vp, i32p, u32, u32, C.POINTER(UwGatherResult)]
     lib.uw_multi_destroy.argtypes = [vp]

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <limits.h>
 #include <string.h>
+#include <chrono>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -1607,6 +1608,7 @@ struct uw_multi {
     uw_gather_info info = {};
     bool have_arena = false;
     double render_share = 0.0;           // fraction of a request the rendering GPU builds itself; 0 = even split
+    uw_share_search search = {};         // state of the search that chooses it (uw_share_search_next)
     std::string err;
 };
 static thread_local std::string g_multi_error;
@@ -1619,19 +1621,34 @@ static uw_status mfail(uw_multi* m, uw_status st, const std::string& msg) {
 extern "C" const char* uw_multi_last_error(const uw_multi* m) { return m ? m->err.c_str() : g_multi_error.c_str(); }
 extern "C" uint32_t uw_multi_render_share(const uw_multi* m) { return m ? (uint32_t)(m->render_share * 1000.0 + 0.5) : 0u; }
 
-// One step of the gather-aware balance: the rendering GPU's kernel ran t_render ms, the slowest other producer t_other ms
-// (a producer whose stores wait for the rendering GPU's NVLink ingress runs longer than its compute alone).  Moves the
-// share by the square root of the ratio; even split <= share <= 1/2.
-static double balance_share(double share, uint32_t parts, double t_render, double t_other) {
-    const double even = 1.0 / (double)parts;
-    if (parts < 2 || !(t_render > 0.0) || !(t_other > 0.0)) return share;
-    double s = share > 0.0 ? share : even;
-    const double ratio = t_other / t_render;
-    if (ratio > 0.95 && ratio < 1.05) return s;
-    s *= sqrt(ratio);
-    if (s < even) s = even;
-    if (s > 0.5) s = 0.5;
-    return s;
+// include/uwcuda.h: damped hill climb on the measured cost of a whole request
+extern "C" double uw_share_search_next(uw_share_search* s, uint32_t parts, double cost) {
+    if (!s) return 0.0;
+    if (parts < 2) { s->share = 0.0; return 0.0; }
+    const double even = 1.0 / (double)parts, min_step = even / 64.0;
+    auto clamp = [&](double x) { return x < even ? even : x > 0.5 ? 0.5 : x; };
+    auto restart = [&](double from) {
+        s->share = from; s->step = even / 4.0; s->dir = 1; s->last_cost = 0.0; s->best_share = from; s->best_cost = 0.0; s->settled = 0;
+    };
+    if (!(s->share > 0.0)) { restart(even); s->moves = 0; }
+    if (!(cost > 0.0)) return s->share;
+    if (++s->moves <= 2) return s->share;                  // the first two requests are cold (allocation, first touch): not evidence
+    if (s->settled) {                                      // holding the cheapest share: only watch for another workload
+        if (cost > s->best_cost * 1.10) { restart(s->share); s->last_cost = s->best_cost = cost; s->share = clamp(s->share + s->step); }
+        else if (cost < s->best_cost) s->best_cost = cost;
+        return s->share;
+    }
+    if (!(s->best_cost > 0.0) || cost < s->best_cost) { s->best_cost = cost; s->best_share = s->share; }
+    if (s->last_cost > 0.0) {
+        if (cost > s->last_cost * 1.01) { s->dir = -s->dir; s->step *= 0.5; }        // worse: turn round, smaller step
+        else if (!(cost < s->last_cost * 0.99)) s->step *= 0.5;                       // flat: refine
+    }
+    s->last_cost = cost;
+    if (s->step < min_step) { s->settled = 1; s->share = s->best_share; return s->share; }
+    double next = clamp(s->share + (double)s->dir * s->step);
+    if (next == s->share) { s->dir = -s->dir; next = clamp(s->share + (double)s->dir * s->step); }   // at a bound: look the other way
+    s->share = next;
+    return next;
 }
 
 extern "C" void uw_multi_destroy(uw_multi* m) {
@@ -1689,6 +1706,7 @@ extern "C" uw_status uw_multi_build(uw_multi* m, const int32_t* pos, uint32_t n,
         }
         // every device: pinned H2D of its slab + one fused launch, all asynchronous; device 0 last, so that the
         // peers are already computing while the render device's own work is being enqueued
+        const auto t_begin = std::chrono::steady_clock::now();
         for (uint32_t k = 0; k < G; ++k) {
             const uint32_t g = (k + 1) % G;
             uint32_t first = 0, cnt = 0;
@@ -1709,16 +1727,11 @@ extern "C" uw_status uw_multi_build(uw_multi* m, const int32_t* pos, uint32_t n,
         if (first_err != UW_OK) return mfail(m, first_err, first_msg);
         const uw_status wst = uw_gather_wait(r, flags, out);
         if (!overflow && wst == UW_OK) {
-            if (G >= 2 && n >= 4096u * G) {               // adapt the rendering GPU's share for the next request
-                float t_r = 0.f, t_o = 0.f;
-                cudaSetDevice(r->device);
-                if (cudaEventElapsedTime(&t_r, r->ev[0], r->ev[4]) != cudaSuccess) { cudaGetLastError(); t_r = 0.f; }
-                for (uint32_t g = 1; g < G; ++g) {
-                    float t = 0.f;
-                    cudaSetDevice(m->ctx[g]->device);
-                    if (cudaEventElapsedTime(&t, m->ctx[g]->ev[0], m->ctx[g]->ev[4]) == cudaSuccess) t_o = std::max(t_o, t); else cudaGetLastError();
-                }
-                m->render_share = balance_share(m->render_share, G, t_r, t_o);
+            if (G >= 2 && n >= 4096u * G) {               // choose the rendering GPU's share for the next request
+                // cost of this request = its wall time per chunk (enqueue .. every mesh landed and the heads read), measured
+                // at the share it ran with; the search hands back the share for the next request
+                const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+                m->render_share = uw_share_search_next(&m->search, G, secs / (double)n);
             }
             return UW_OK;
         }

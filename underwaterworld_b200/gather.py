@@ -68,6 +68,55 @@ def balance_share(share: float, parts: int, t_render: float, t_other: float) -> 
     return min(0.5, max(even, s * ratio ** 0.5))
 
 
+def share_search_next(state: dict, parts: int, cost: float) -> float:
+    """Mirror of uw_share_search_next (what uw_multi_build runs between requests): damped hill climb on the measured
+    cost of a whole request; settles on the cheapest share seen, starts over when the cost there rises by > 10 %.
+    `state` = {} to start; returns the share for the next request."""
+    if parts < 2:
+        state["share"] = 0.0
+        return 0.0
+    even = 1.0 / parts
+    min_step = even / 64.0
+    clamp = lambda x: even if x < even else 0.5 if x > 0.5 else x
+
+    def restart(frm):
+        state.update(share=frm, step=even / 4.0, dir=1, last_cost=0.0, best_share=frm, best_cost=0.0, settled=0)
+
+    if not state.get("share", 0.0) > 0.0:
+        restart(even)
+        state["moves"] = 0
+    if not cost > 0.0:
+        return state["share"]
+    state["moves"] += 1
+    if state["moves"] <= 2:                                # cold requests are not evidence
+        return state["share"]
+    if state["settled"]:
+        if cost > state["best_cost"] * 1.10:
+            restart(state["share"])
+            state["last_cost"] = state["best_cost"] = cost
+            state["share"] = clamp(state["share"] + state["step"])
+        elif cost < state["best_cost"]:
+            state["best_cost"] = cost
+        return state["share"]
+    if not state["best_cost"] > 0.0 or cost < state["best_cost"]:
+        state["best_cost"], state["best_share"] = cost, state["share"]
+    if state["last_cost"] > 0.0:
+        if cost > state["last_cost"] * 1.01:
+            state["dir"], state["step"] = -state["dir"], state["step"] * 0.5
+        elif not cost < state["last_cost"] * 0.99:
+            state["step"] *= 0.5
+    state["last_cost"] = cost
+    if state["step"] < min_step:
+        state["settled"], state["share"] = 1, state["best_share"]
+        return state["share"]
+    nxt = clamp(state["share"] + state["dir"] * state["step"])
+    if nxt == state["share"]:
+        state["dir"] = -state["dir"]
+        nxt = clamp(state["share"] + state["dir"] * state["step"])
+    state["share"] = nxt
+    return nxt
+
+
 def info_to_bytes(info: _ffi.UwGatherInfo) -> bytes:
     return bytes(C.string_at(C.addressof(info), C.sizeof(info)))
 

@@ -224,3 +224,86 @@ def test_table_driven_pow24_scheme_is_within_two_ulp():
     ulp = np.abs(got.astype(np.float64) - want) / np.spacing(want.astype(f32)).astype(np.float64)
     assert ulp.max() <= 2.5, ulp.max()
     assert (ulp > 1.0).mean() < 0.01
+
+
+def test_factorised_lattice_hash_of_the_spare_warp(oracle12):
+    """noise_stage_h_warp (uw_kernels.cuh): the lattice hash perm[perm[perm[X] ^ Y] ^ Z] of every touched lattice point,
+    factorised -- one lane per (octave, cx, cy) computes perm[perm[X] ^ Y] (25 lanes for the top octave, 4 + 9 for the
+    others), the G^3 last-level lookups take it by shuffle from lane (cx G + cy) [+ the octave's offset], six rounds of
+    32 lanes, lanes past the end repeating the last point.  Restated lane by lane in numpy against the direct triple
+    lookup the other kernels (and the reference, through the noise crate's PermutationTable::hash) use."""
+    perm = oracle12.perm_table(0).astype(np.int64)
+    NOCT, OT = 3, 2
+    G = [(1 << o) + 1 for o in range(NOCT)]                          # PRUNE: 2, 3, 5 lattice planes per axis
+    g2_base = [0, 4, 13]
+    lat_base = [0, 8, 35]
+    lane = np.arange(32)
+    for px, py, pz in ((0, 0, 0), (3, -2, 1), (-70000, 123456, -5), (2 ** 24, -(2 ** 24), 255)):
+        # second level
+        l = np.minimum(lane, G[OT] ** 2 - 1)
+        cx, cy = l // G[OT], l % G[OT]
+        hb_top = perm[perm[((px << OT) + cx) & 255] ^ (((py << OT) + cy) & 255)]
+        o_of = np.zeros(32, dtype=np.int64); cxl = np.zeros(32, dtype=np.int64); cyl = np.zeros(32, dtype=np.int64)
+        for p in range(OT):
+            r = lane - g2_base[p]
+            sel = (r >= 0) & (r < G[p] ** 2)
+            o_of[sel], cxl[sel], cyl[sel] = p, r[sel] // G[p], r[sel] % G[p]
+        hb_low = perm[perm[((px << o_of) + cxl) & 255] ^ (((py << o_of) + cyl) & 255)]
+        # last level, round by round
+        got = np.full(160, -1, dtype=np.int64)
+        rounds = 0
+        for o in range(NOCT):
+            n = G[o] ** 3
+            for t0 in range(0, n, 32):
+                tt = np.minimum(t0 + lane, n - 1)
+                cxy, cz = tt // G[o], tt % G[o]
+                src = (0 if o == OT else g2_base[o]) + cxy
+                assert src.max() < 32
+                hb = (hb_top if o == OT else hb_low)[src]
+                got[lat_base[o] + tt] = perm[hb ^ (((pz << o) + cz) & 255)]
+                rounds += 1
+        assert rounds == 6
+        want = np.empty(160, dtype=np.int64)
+        for o in range(NOCT):
+            F = 1 << o
+            for t in range(G[o] ** 3):
+                cx, r = divmod(t, G[o] ** 2)
+                cy, cz = divmod(r, G[o])
+                want[lat_base[o] + t] = perm[perm[perm[(F * px + cx) & 255] ^ ((F * py + cy) & 255)] ^ ((F * pz + cz) & 255)]
+        assert np.array_equal(got, want)
+
+
+def test_stage_x_by_cell_groups_covers_every_x_sample_once():
+    """Stage X of the S = 12 kernels (noise_chunk_spec, XG): thread (q, octave, r) handles the three samples
+    i = 3q .. 3q + 2 from ONE pair of lattice planes, c = (q << o) >> 2 and c + 1; 38 more threads write the last sample
+    plane i = 12 from plane G - 1 alone.  Restated in numpy: the (octave, i, r) items are covered exactly once, with the
+    lattice planes the per-item loop uses ((i << o) / 12 and min(c + 1, G - 1))."""
+    S, NOCT, NG, GS = 12, 3, 4, 3
+    G = [(1 << o) + 1 for o in range(NOCT)]
+    g2 = [g * g for g in G]
+    g2_base = [0, 4, 13]
+    SG2 = sum(g2)                                                    # 38
+    seen = {}
+    for tid in range(NG * SG2):                                      # the triple items, q-major
+        q, u = divmod(tid, SG2)
+        o = max(p for p in range(NOCT) if u >= g2_base[p])
+        r = u - g2_base[o]
+        assert 0 <= r < g2[o]
+        c = (q << o) >> (NOCT - 1)
+        for m in range(GS):
+            i = q * GS + m
+            assert (o, i, r) not in seen
+            seen[(o, i, r)] = (c, c + 1)
+    for t in range(SG2):                                             # the last sample plane
+        o = max(p for p in range(NOCT) if t >= g2_base[p])
+        r = t - g2_base[o]
+        assert (o, S, r) not in seen
+        seen[(o, S, r)] = (1 << o, 1 << o)
+    want = {}
+    for o in range(NOCT):
+        for i in range(S + 1):
+            c = (i << o) // S
+            for r in range(g2[o]):
+                want[(o, i, r)] = (c, min(c + 1, G[o] - 1))
+    assert seen == want and len(seen) == 13 * SG2 == 494
+    assert NG * SG2 == 152 and 160 + SG2 <= 224 and 152 + SG2 <= 192    # one round: fused (224 threads) and staged (192)
